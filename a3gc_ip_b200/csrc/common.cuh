@@ -1,0 +1,83 @@
+// Shared declarations of the a3gc_b200 library (internal; the public surface is include/a3gc_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include "../../include/a3gc_b200.h"
+
+namespace a3gc {
+
+constexpr int kNodes = A3GC_NODES;   // 15 graph nodes
+constexpr int kNodesPad = 16;        // node dimension padded to 16 (index 15 is always zero)
+
+// ---- error plumbing (thread-local message, no exceptions across the ABI) -------------
+void set_error(const char* fmt, ...);
+int64_t& launch_counter();
+
+inline int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return A3GC_ERR_CUDA;
+}
+
+#define A3GC_CUDA_TRY(expr)                                  \
+  do {                                                       \
+    cudaError_t _e = (expr);                                 \
+    if (_e != cudaSuccess) return ::a3gc::cuda_fail(_e, #expr); \
+  } while (0)
+
+// check the launch that was just issued
+#define A3GC_LAUNCH_CHECK(name)                              \
+  do {                                                       \
+    ::a3gc::launch_counter() += 1;                           \
+    cudaError_t _e = cudaGetLastError();                     \
+    if (_e != cudaSuccess) return ::a3gc::cuda_fail(_e, "launch " name); \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// tanh via exp: |err| ~ 1e-7 relative, well inside the 1e-4 parity budget; saturates cleanly.
+__device__ __forceinline__ float tanhf_(float x) {
+  float e = __expf(-2.0f * fabsf(x));
+  float r = (1.0f - e) / (1.0f + e);
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float apply_act(float v, int act) {
+  return act == A3GC_ACT_TANH ? tanhf_(v) : (act == A3GC_ACT_RELU ? fmaxf(v, 0.0f) : v);
+}
+
+// ---- SIMT (fp32 CUDA-core) engine: simt_kernels.cu -------------------------------------
+struct LayerArgs {
+  int variant;
+  int num_dirs;
+  const a3gc_cell_params* cells;   // host array [num_dirs]
+  int reverse[2];
+  const float* x;
+  int64_t x_stride_b, x_stride_t;
+  const float* h0[2];
+  const float* c0[2];
+  float* y;
+  int64_t y_stride_b, y_stride_t, y_ld;
+  float* hT[2];
+  float* cT[2];
+  int64_t batch, steps;
+  int f_in, hidden, out_act;
+  int precision;
+};
+
+size_t simt_layer_workspace_bytes(int variant, int f_in, int hidden, int num_dirs);
+int simt_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t stream);
+int simt_gc_forward(const a3gc_gc_params* p, const float* x, float* y, int64_t frames, int f_in,
+                    int f_out, int act, cudaStream_t stream);
+int simt_prepare_input(const float* acc, const float* ori, const float* acc_mean, const float* acc_std,
+                       const float* ori_mean, const float* ori_std, float* x, int64_t frames, int ld_x,
+                       cudaStream_t stream);
+int simt_concat_stage_input(const float* x, const float* pos, float* dst, int64_t frames, cudaStream_t stream);
+
+// ---- tensor-core (tcgen05) engine: tc_kernels.cu ----------------------------------------
+bool tc_layer_supported(int variant, int f_in, int hidden, int precision);
+size_t tc_layer_workspace_bytes(int variant, int64_t batch, int64_t steps, int f_in, int hidden, int num_dirs, int precision);
+int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+}  // namespace a3gc

@@ -1,0 +1,665 @@
+// SIMT (fp32 CUDA-core) engine of the A3GC-IP hot path: works for every variant and every shape,
+// is the shape-generic path behind A3GC_ENGINE_SIMT / AUTO, and the on-device cross-check for the
+// tcgen05 engine.  Math follows net_aagc.py:61-66 (AAGC), :103-126 / :178-217 / :266-303 (LSTM cells),
+// :343-368 (G-GRU) with the graph mix applied on the accumulator side:  P (S W^T) == (P S) W^T.
+//
+// Data layout in shared memory: every activation operand is kept as [sequence][feature k][16 nodes]
+// (node index fastest, padded 15 -> 16 with a zero), so that one (sequence, hidden-unit) task reads
+// the 16 node values of feature k as four broadcast 128-bit loads and owns all 15 nodes of its
+// column -- which makes the 15x15 adjacency mix a purely in-register operation.
+#include "common.cuh"
+
+namespace a3gc {
+namespace {
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------------------------------
+// weight packing (global -> workspace).  k-major so that consecutive hidden units are contiguous.
+// ------------------------------------------------------------------------------------------
+struct LstmPacked {
+  float4* Wg4;     // [(F+H)][H] float4 = (i, f, c, o) weights of unit j at input feature k
+  float* Wa_t;     // [H][H]  Wa_t[k][j] = attention_w [j][k]
+  float* Wh_t;     // [H][H]
+  float* Wq_t;     // [H][H]
+  float* P;        // [4][16][16] zero-padded mixing matrices, P_g[m][n]
+  float4* bias4;   // [H]
+  float* bs;       // [H]
+  float* u;        // [H]
+  float* bu;       // [16]
+};
+
+struct GruPacked {
+  float* Wg_t;     // [H][H]   Wg_t[k][j] = gcn_kernel[j][k]
+  float4* Win4;    // [F][H]   (r_in, u_in, c_in, 0)
+  float4* Whid4;   // [H][H]   (r_hid, u_hid, 0, c_hid)
+  float* P;        // [16][16] P[n][m] = adjacency[m][n]   (used transposed, net_aagc.py:348)
+  float4* bias4;   // [H]      (b_r, b_u, b_c, 0)
+};
+
+size_t lstm_packed_floats(int F, int H) {
+  return (size_t)(F + H) * H * 4 + 3 * (size_t)H * H + 4 * 256 + (size_t)H * 4 + H + H + 16;
+}
+size_t gru_packed_floats(int F, int H) {
+  return (size_t)H * H + (size_t)F * H * 4 + (size_t)H * H * 4 + 256 + (size_t)H * 4;
+}
+
+LstmPacked carve_lstm(float* base, int F, int H) {
+  LstmPacked p;
+  float* q = base;
+  p.Wg4 = reinterpret_cast<float4*>(q); q += (size_t)(F + H) * H * 4;
+  p.bias4 = reinterpret_cast<float4*>(q); q += (size_t)H * 4;
+  p.Wa_t = q; q += (size_t)H * H;
+  p.Wh_t = q; q += (size_t)H * H;
+  p.Wq_t = q; q += (size_t)H * H;
+  p.P = q; q += 4 * 256;
+  p.bs = q; q += H;
+  p.u = q; q += H;
+  p.bu = q; q += 16;
+  return p;
+}
+GruPacked carve_gru(float* base, int F, int H) {
+  GruPacked p;
+  float* q = base;
+  p.Win4 = reinterpret_cast<float4*>(q); q += (size_t)F * H * 4;
+  p.Whid4 = reinterpret_cast<float4*>(q); q += (size_t)H * H * 4;
+  p.bias4 = reinterpret_cast<float4*>(q); q += (size_t)H * 4;
+  p.Wg_t = q; q += (size_t)H * H;
+  p.P = q; q += 256;
+  return p;
+}
+
+__global__ void pack_lstm_kernel(a3gc_cell_params cp, LstmPacked out, int F, int H, int variant) {
+  const int K = F + H;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = tid; i < (int64_t)K * H; i += stride) {
+    int k = (int)(i / H), j = (int)(i % H);
+    size_t src = (size_t)j * K + k;
+    out.Wg4[i] = make_float4(cp.gcn_kernel[0][src], cp.gcn_kernel[1][src], cp.gcn_kernel[2][src], cp.gcn_kernel[3][src]);
+  }
+  for (int64_t i = tid; i < H; i += stride)
+    out.bias4[i] = make_float4(cp.gcn_bias[0][i], cp.gcn_bias[1][i], cp.gcn_bias[2][i], cp.gcn_bias[3][i]);
+  for (int64_t i = tid; i < 4 * 256; i += stride) {
+    int g = (int)(i / 256), m = (int)((i % 256) / 16), n = (int)(i % 16);
+    float v = 0.f;
+    if (m < kNodes && n < kNodes) {
+      // A3GC / AAGC: z = adjacency_g @ S (einsum 'bnf,nm->bmf' with adjacency.t(), net_aagc.py:183)
+      // AGC:         z = adjacency^T @ S (einsum 'nm,bmf->bnf' with adjacency.t(), net_aagc.py:271)
+      v = (variant == A3GC_VARIANT_AGC) ? cp.adjacency[0][n * kNodes + m] : cp.adjacency[g][m * kNodes + n];
+    }
+    out.P[i] = v;
+  }
+  if (cp.attention_w != nullptr) {
+    for (int64_t i = tid; i < (int64_t)H * H; i += stride) {
+      int k = (int)(i / H), j = (int)(i % H);
+      size_t src = (size_t)j * H + k;
+      out.Wa_t[i] = cp.attention_w[src];
+      out.Wh_t[i] = cp.attention_wh[src];
+      out.Wq_t[i] = cp.attention_wq[src];
+    }
+    for (int64_t i = tid; i < H; i += stride) {
+      out.bs[i] = cp.attention_bs[i];
+      out.u[i] = cp.attention_u[i];
+    }
+    for (int64_t i = tid; i < 16; i += stride) out.bu[i] = i < kNodes ? cp.attention_bu[i] : 0.f;
+  }
+}
+
+__global__ void pack_gru_kernel(a3gc_cell_params cp, GruPacked out, int F, int H) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = tid; i < (int64_t)F * H; i += stride) {
+    int k = (int)(i / H), j = (int)(i % H);
+    size_t src = (size_t)j * F + k;
+    out.Win4[i] = make_float4(cp.dense_in_w[0][src], cp.dense_in_w[1][src], cp.dense_in_w[2][src], 0.f);
+  }
+  for (int64_t i = tid; i < (int64_t)H * H; i += stride) {
+    int k = (int)(i / H), j = (int)(i % H);
+    size_t src = (size_t)j * H + k;
+    out.Whid4[i] = make_float4(cp.dense_hid_w[0][src], cp.dense_hid_w[1][src], 0.f, cp.dense_hid_w[2][src]);
+    out.Wg_t[i] = cp.g_gcn_kernel[src];
+  }
+  for (int64_t i = tid; i < H; i += stride)
+    out.bias4[i] = make_float4(cp.dense_in_b[0][i], cp.dense_in_b[1][i], cp.dense_in_b[2][i], 0.f);
+  for (int64_t i = tid; i < 256; i += stride) {
+    int n = (int)(i / 16), m = (int)(i % 16);
+    out.P[i] = (m < kNodes && n < kNodes) ? cp.g_adjacency[m * kNodes + n] : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+// acc[g][n] += sum_k act[k][n] * w[k].{x,y,z,w}[g]   (act: shared [K][16];  w: global, stride ldw float4)
+__device__ __forceinline__ void accum4(float (&acc)[4][16], const float* __restrict__ act,
+                                       const float4* __restrict__ w, int K, int ldw) {
+#pragma unroll 2
+  for (int k = 0; k < K; ++k) {
+    const float4 wv = __ldg(w + (size_t)k * ldw);
+    const float4* a4 = reinterpret_cast<const float4*>(act + k * kNodesPad);
+    float a[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 v = a4[q];
+      a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+    }
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      acc[0][n] = fmaf(wv.x, a[n], acc[0][n]);
+      acc[1][n] = fmaf(wv.y, a[n], acc[1][n]);
+      acc[2][n] = fmaf(wv.z, a[n], acc[2][n]);
+      acc[3][n] = fmaf(wv.w, a[n], acc[3][n]);
+    }
+  }
+}
+
+__device__ __forceinline__ void accum1(float (&acc)[16], const float* __restrict__ act,
+                                       const float* __restrict__ w, int K, int ldw) {
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float wv = __ldg(w + (size_t)k * ldw);
+    const float4* a4 = reinterpret_cast<const float4*>(act + k * kNodesPad);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 v = a4[q];
+      acc[4 * q] = fmaf(wv, v.x, acc[4 * q]);
+      acc[4 * q + 1] = fmaf(wv, v.y, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(wv, v.z, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(wv, v.w, acc[4 * q + 3]);
+    }
+  }
+}
+
+// out[m] = sum_n P[m][n] * in[n], m, n < 15 (P: shared [16][16], broadcast reads)
+__device__ __forceinline__ void mix15(const float (&in)[16], const float* __restrict__ P, float (&out)[16]) {
+#pragma unroll
+  for (int m = 0; m < kNodes; ++m) {
+    const float4* p4 = reinterpret_cast<const float4*>(P + m * 16);
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 pv = p4[q];
+      s = fmaf(pv.x, in[4 * q], s);
+      s = fmaf(pv.y, in[4 * q + 1], s);
+      s = fmaf(pv.z, in[4 * q + 2], s);
+      s = fmaf(pv.w, in[4 * q + 3], s);   // P[m][15] == 0
+    }
+    out[m] = s;
+  }
+  out[15] = 0.f;
+}
+
+__device__ __forceinline__ void store16(float* dst, const float (&v)[16]) {
+  float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) d4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+__device__ __forceinline__ void load16(float (&v)[16], const float* src) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float4 t = s4[q];
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  }
+}
+
+struct DirPtrs {
+  const float* h0; const float* c0; float* hT; float* cT; int reverse;
+};
+struct LayerGeom {
+  const float* x; int64_t sxb, sxt;
+  float* y; int64_t syb, syt, yld;
+  int B, T, F, H, out_act, BT;
+};
+
+// state [B,15,H] (global) -> [seq][j][16] (shared); zero when src == nullptr or b >= B
+__device__ void load_state(float* dst, const float* src, int b0, const LayerGeom& g) {
+  for (int i = threadIdx.x; i < g.BT * g.H * kNodesPad; i += blockDim.x) {
+    int n = i % kNodesPad, j = (i / kNodesPad) % g.H, s = i / (kNodesPad * g.H);
+    int b = b0 + s;
+    float v = 0.f;
+    if (src != nullptr && n < kNodes && b < g.B) v = src[((size_t)b * kNodes + n) * g.H + j];
+    dst[i] = v;
+  }
+}
+__device__ void store_state(float* dst, const float* src, int b0, const LayerGeom& g) {
+  if (dst == nullptr) return;
+  for (int i = threadIdx.x; i < g.BT * kNodes * g.H; i += blockDim.x) {
+    int j = i % g.H, n = (i / g.H) % kNodes, s = i / (g.H * kNodes);
+    int b = b0 + s;
+    if (b < g.B) dst[((size_t)b * kNodes + n) * g.H + j] = src[((size_t)s * g.H + j) * kNodesPad + n];
+  }
+}
+// x[b, t, n, k] (global) -> xbuf[seq][k][16]; row 15 zero
+__device__ void load_x(float* xbuf, int b0, int t, const LayerGeom& g) {
+  const int per_seq = kNodesPad * g.F;
+  for (int i = threadIdx.x; i < g.BT * per_seq; i += blockDim.x) {
+    int k = i % g.F, n = (i / g.F) % kNodesPad, s = i / per_seq;
+    int b = b0 + s;
+    float v = 0.f;
+    if (n < kNodes && b < g.B) v = __ldg(g.x + (size_t)b * g.sxb + (size_t)t * g.sxt + (size_t)n * g.F + k);
+    xbuf[((size_t)s * g.F + k) * kNodesPad + n] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LSTM family time loop: one CTA = BT sequences of one direction, all T steps
+// ------------------------------------------------------------------------------------------
+template <bool ATT>
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_layer_kernel(LstmPacked w0, LstmPacked w1, DirPtrs d0, DirPtrs d1, LayerGeom g) {
+  extern __shared__ __align__(16) float smem[];
+  const LstmPacked w = blockIdx.y == 0 ? w0 : w1;
+  const DirPtrs d = blockIdx.y == 0 ? d0 : d1;
+  const int H = g.H, F = g.F, BT = g.BT;
+  const int KX = F > H ? F : H;
+  float* hbuf = smem;                                  // [2][BT][H][16]
+  float* cbuf = hbuf + (size_t)2 * BT * H * kNodesPad; // [BT][H][16]
+  float* xbuf = cbuf + (size_t)BT * H * kNodesPad;     // [BT][KX][16]  (x_t; reused as attention scratch)
+  float* qbuf = xbuf + (size_t)BT * KX * kNodesPad;    // [BT][H]
+  float* sbuf = qbuf + (size_t)BT * H;                 // [BT][H]
+  float* abuf = sbuf + (size_t)BT * H;                 // [BT][16]
+  float* Pbuf = abuf + (size_t)BT * kNodesPad;         // [4][16][16]
+  const int b0 = blockIdx.x * BT;
+  const int y_off = blockIdx.y * H;
+
+  load_state(hbuf, d.h0, b0, g);
+  load_state(cbuf, d.c0, b0, g);
+  for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) Pbuf[i] = w.P[i];
+  int cur = 0;
+  const int ntask = BT * H;
+
+  for (int step = 0; step < g.T; ++step) {
+    const int t = d.reverse ? g.T - 1 - step : step;
+    float* hcur = hbuf + (size_t)cur * BT * H * kNodesPad;
+    float* hnxt = hbuf + (size_t)(cur ^ 1) * BT * H * kNodesPad;
+    __syncthreads();                 // previous step done with xbuf / hbuf
+    load_x(xbuf, b0, t, g);
+    __syncthreads();
+
+    for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+      const int s = task / H, j = task % H;
+      float acc[4][16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int n = 0; n < 16; ++n) acc[q][n] = 0.f;
+      accum4(acc, xbuf + (size_t)s * F * kNodesPad, w.Wg4 + j, F, H);
+      accum4(acc, hcur + (size_t)s * H * kNodesPad, w.Wg4 + (size_t)F * H + j, H, H);
+      const float4 bias = w.bias4[j];
+      float tmp[16], cs[16];
+      load16(cs, cbuf + ((size_t)s * H + j) * kNodesPad);
+      mix15(acc[0], Pbuf, tmp);                        // i
+#pragma unroll
+      for (int m = 0; m < kNodes; ++m) acc[0][m] = sigmoidf_(tmp[m] + bias.x);
+      mix15(acc[2], Pbuf + 512, tmp);                  // c (candidate)
+#pragma unroll
+      for (int m = 0; m < kNodes; ++m) acc[0][m] *= tanhf_(tmp[m] + bias.z);
+      mix15(acc[1], Pbuf + 256, tmp);                  // f
+#pragma unroll
+      for (int m = 0; m < kNodes; ++m) cs[m] = fmaf(sigmoidf_(tmp[m] + bias.y), cs[m], acc[0][m]);
+      cs[15] = 0.f;
+      mix15(acc[3], Pbuf + 768, tmp);                  // o
+      float hy[16];
+#pragma unroll
+      for (int m = 0; m < kNodes; ++m) hy[m] = sigmoidf_(tmp[m] + bias.w) * tanhf_(cs[m]);
+      hy[15] = 0.f;
+      store16(cbuf + ((size_t)s * H + j) * kNodesPad, cs);
+      store16(hnxt + ((size_t)s * H + j) * kNodesPad, hy);
+      if (!ATT) {
+        const int b = b0 + s;
+        if (b < g.B) {
+          float* yp = g.y + (size_t)b * g.syb + (size_t)t * g.syt + y_off + j;
+#pragma unroll
+          for (int m = 0; m < kNodes; ++m) yp[(size_t)m * g.yld] = apply_act(hy[m], g.out_act);
+        }
+      }
+    }
+
+    if (ATT) {
+      __syncthreads();
+      // s[seq][k] = sum over nodes of hy  (q_t = relu((sum_n hy_n) W_a^T), net_aagc.py:200)
+      for (int i = threadIdx.x; i < ntask; i += blockDim.x) {
+        float v[16];
+        load16(v, hnxt + (size_t)i * kNodesPad);
+        float sum = 0.f;
+#pragma unroll
+        for (int n = 0; n < kNodes; ++n) sum += v[n];
+        sbuf[i] = sum;
+      }
+      __syncthreads();
+      for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+        const int s = task / H, j = task % H;
+        float q = 0.f;
+        const float* sv = sbuf + (size_t)s * H;
+        for (int k = 0; k < H; ++k) q = fmaf(sv[k], __ldg(w.Wa_t + (size_t)k * H + j), q);
+        qbuf[task] = fmaxf(q, 0.f);
+      }
+      __syncthreads();
+      for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+        const int s = task / H, j = task % H;
+        float e[16];
+#pragma unroll
+        for (int n = 0; n < 16; ++n) e[n] = 0.f;
+        accum1(e, hnxt + (size_t)s * H * kNodesPad, w.Wh_t + j, H, H);
+        float wq = w.bs[j];
+        const float* qv = qbuf + (size_t)s * H;
+        for (int k = 0; k < H; ++k) wq = fmaf(qv[k], __ldg(w.Wq_t + (size_t)k * H + j), wq);
+        const float uj = w.u[j];
+#pragma unroll
+        for (int n = 0; n < kNodes; ++n) e[n] = tanhf_(e[n] + wq) * uj;
+        e[15] = 0.f;
+        store16(xbuf + ((size_t)s * KX + j) * kNodesPad, e);     // scratch [seq][j][16]
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < BT * kNodesPad; i += blockDim.x) {
+        const int s = i / kNodesPad, n = i % kNodesPad;
+        float a = 0.f;
+        if (n < kNodes) {
+          const float* ev = xbuf + (size_t)s * KX * kNodesPad + n;
+          for (int j = 0; j < H; ++j) a += ev[(size_t)j * kNodesPad];
+          a = 1.0f + sigmoidf_(a + w.bu[n]);                     // hy + hy * a_t  (net_aagc.py:212-213)
+        }
+        abuf[i] = a;
+      }
+      __syncthreads();
+      for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+        const int s = task / H, j = task % H;
+        float hy[16], av[16];
+        load16(hy, hnxt + (size_t)task * kNodesPad);
+        load16(av, abuf + (size_t)s * kNodesPad);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) hy[m] *= av[m];
+        store16(hnxt + (size_t)task * kNodesPad, hy);
+        const int b = b0 + s;
+        if (b < g.B) {
+          float* yp = g.y + (size_t)b * g.syb + (size_t)t * g.syt + y_off + j;
+#pragma unroll
+          for (int m = 0; m < kNodes; ++m) yp[(size_t)m * g.yld] = apply_act(hy[m], g.out_act);
+        }
+      }
+    }
+    cur ^= 1;
+  }
+  __syncthreads();
+  store_state(d.hT, hbuf + (size_t)cur * BT * H * kNodesPad, b0, g);
+  store_state(d.cT, cbuf, b0, g);
+}
+
+// ------------------------------------------------------------------------------------------
+// G-GRU time loop
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+gru_layer_kernel(GruPacked w0, GruPacked w1, DirPtrs d0, DirPtrs d1, LayerGeom g) {
+  extern __shared__ __align__(16) float smem[];
+  const GruPacked w = blockIdx.y == 0 ? w0 : w1;
+  const DirPtrs d = blockIdx.y == 0 ? d0 : d1;
+  const int H = g.H, F = g.F, BT = g.BT;
+  float* hbuf = smem;                                    // [2][BT][H][16]
+  float* mbuf = hbuf + (size_t)2 * BT * H * kNodesPad;   // [BT][H][16]  message
+  float* xbuf = mbuf + (size_t)BT * H * kNodesPad;       // [BT][F][16]
+  float* Pbuf = xbuf + (size_t)BT * F * kNodesPad;       // [16][16]
+  const int b0 = blockIdx.x * BT;
+  const int y_off = blockIdx.y * H;
+  load_state(hbuf, d.h0, b0, g);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) Pbuf[i] = w.P[i];
+  int cur = 0;
+  const int ntask = BT * H;
+  for (int step = 0; step < g.T; ++step) {
+    const int t = d.reverse ? g.T - 1 - step : step;
+    float* hcur = hbuf + (size_t)cur * BT * H * kNodesPad;
+    float* hnxt = hbuf + (size_t)(cur ^ 1) * BT * H * kNodesPad;
+    __syncthreads();
+    load_x(xbuf, b0, t, g);
+    // msg = adjacency^T (h W_g^T)   (net_aagc.py:347-348)
+    for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+      const int s = task / H, j = task % H;
+      float m[16], msg[16];
+#pragma unroll
+      for (int n = 0; n < 16; ++n) m[n] = 0.f;
+      accum1(m, hcur + (size_t)s * H * kNodesPad, w.Wg_t + j, H, H);
+      mix15(m, Pbuf, msg);
+      store16(mbuf + (size_t)task * kNodesPad, msg);
+    }
+    __syncthreads();
+    for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+      const int s = task / H, j = task % H;
+      float acc[4][16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int n = 0; n < 16; ++n) acc[q][n] = 0.f;
+      accum4(acc, xbuf + (size_t)s * F * kNodesPad, w.Win4 + j, F, H);       // r, u, c_in
+      accum4(acc, mbuf + (size_t)s * H * kNodesPad, w.Whid4 + j, H, H);      // r, u, -, c_hid
+      const float4 bias = w.bias4[j];
+      float hold[16], hy[16];
+      load16(hold, hcur + (size_t)task * kNodesPad);
+#pragma unroll
+      for (int n = 0; n < kNodes; ++n) {
+        const float r = sigmoidf_(acc[0][n] + bias.x);
+        const float u = sigmoidf_(acc[1][n] + bias.y);
+        const float c = tanhf_(acc[2][n] + bias.z + r * acc[3][n]);
+        hy[n] = u * hold[n] + (1.0f - u) * c;                                  // net_aagc.py:364
+      }
+      hy[15] = 0.f;
+      store16(hnxt + (size_t)task * kNodesPad, hy);
+      const int b = b0 + s;
+      if (b < g.B) {
+        float* yp = g.y + (size_t)b * g.syb + (size_t)t * g.syt + y_off + j;
+#pragma unroll
+        for (int n = 0; n < kNodes; ++n) yp[(size_t)n * g.yld] = hy[n];        // returns (h, h): no activation
+      }
+    }
+    cur ^= 1;
+  }
+  __syncthreads();
+  store_state(d.hT, hbuf + (size_t)cur * BT * H * kNodesPad, b0, g);
+}
+
+// ------------------------------------------------------------------------------------------
+// AAGC graph convolution: y = act((adj @ x) @ W^T + b)    (net_aagc.py:61-66)
+// one CTA processes FR frames at a time: stage x, mix over nodes, then 15*f_out dot products
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+gc_kernel(a3gc_gc_params p, const float* __restrict__ x, float* __restrict__ y, int64_t frames,
+          int f_in, int f_out, int act, int FR) {
+  extern __shared__ __align__(16) float smem[];
+  float* adj = smem;                       // [15][16]
+  float* xs = adj + 256;                   // [FR][15][f_in]
+  float* xm = xs + (size_t)FR * kNodes * f_in;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    int m = i / 16, n = i % 16;
+    adj[i] = (m < kNodes && n < kNodes) ? p.adj[m * kNodes + n] : 0.f;
+  }
+  const int per_frame = kNodes * f_in;
+  for (int64_t f0 = (int64_t)blockIdx.x * FR; f0 < frames; f0 += (int64_t)gridDim.x * FR) {
+    const int nf = (int)((frames - f0) < FR ? (frames - f0) : FR);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nf * per_frame; i += blockDim.x) xs[i] = __ldg(x + (size_t)f0 * per_frame + i);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nf * per_frame; i += blockDim.x) {
+      const int k = i % f_in, m = (i / f_in) % kNodes, fr = i / per_frame;
+      const float* col = xs + (size_t)fr * per_frame + k;
+      float s = 0.f;
+#pragma unroll
+      for (int n = 0; n < kNodes; ++n) s = fmaf(adj[m * 16 + n], col[n * f_in], s);
+      xm[i] = s;
+    }
+    __syncthreads();
+    const int outs = nf * kNodes * f_out;
+    for (int i = threadIdx.x; i < outs; i += blockDim.x) {
+      const int o = i % f_out, row = i / f_out;      // row = fr*15 + m
+      const float* a = xm + (size_t)row * f_in;
+      const float* wr = p.gcn_kernel + (size_t)o * f_in;
+      float s = p.gcn_bias[o];
+      for (int k = 0; k < f_in; ++k) s = fmaf(a[k], __ldg(wr + k), s);
+      y[((size_t)f0 * kNodes + row) * f_out + o] = apply_act(s, act);
+    }
+  }
+}
+
+// prepare_input (evaluate_a3gc_tp.py:64-94): one thread per (frame, node, channel<12)
+__global__ void prepare_input_kernel(const float* __restrict__ acc, const float* __restrict__ ori,
+                                     const float* acc_mean, const float* acc_std, const float* ori_mean,
+                                     const float* ori_std, float* __restrict__ x, int64_t frames, int ld_x) {
+  // node -> IMU index; input_joints = [3, 4, 13, 14, 10]  (evaluate_a3gc_tp.py:65)
+  const int64_t total = frames * kNodes * 12;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % 12), n = (int)((i / 12) % kNodes);
+    const int64_t f = i / (12 * kNodes);
+    int imu = -1;
+    switch (n) { case 3: imu = 0; break; case 4: imu = 1; break; case 13: imu = 2; break; case 14: imu = 3; break; case 10: imu = 4; break; default: break; }
+    float v = 0.f;
+    if (imu >= 0) {
+      if (c < 3) {
+        const int ch = imu * 3 + c;
+        v = acc[f * 18 + ch];
+        if (acc_mean != nullptr) v = (v - acc_mean[ch]) / acc_std[ch];
+      } else {
+        const int ch = imu * 9 + (c - 3);
+        v = ori[f * 54 + ch];
+        if (ori_mean != nullptr) v = (v - ori_mean[ch]) / ori_std[ch];
+      }
+    }
+    x[(f * kNodes + n) * ld_x + c] = v;
+  }
+}
+
+__global__ void concat_stage_input_kernel(const float* __restrict__ x, const float* __restrict__ pos,
+                                          float* __restrict__ dst, int64_t rows) {
+  const int64_t total = rows * 15;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % 15);
+    const int64_t r = i / 15;
+    dst[i] = c < 12 ? x[r * 12 + c] : pos[r * 3 + (c - 12)];
+  }
+}
+
+int max_optin_smem() {
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
+  return v;
+}
+
+}  // namespace
+
+size_t simt_layer_workspace_bytes(int variant, int f_in, int hidden, int num_dirs) {
+  size_t per = variant == A3GC_VARIANT_GGRU ? gru_packed_floats(f_in, hidden) : lstm_packed_floats(f_in, hidden);
+  return (size_t)num_dirs * align_up(per * sizeof(float), 256);
+}
+
+int simt_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  const int F = a.f_in, H = a.hidden;
+  const size_t need = simt_layer_workspace_bytes(a.variant, F, H, a.num_dirs);
+  if (ws_bytes < need || ws == nullptr) {
+    set_error("a3gc_layer_forward: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+    return A3GC_ERR_WORKSPACE;
+  }
+  const int smem_max = max_optin_smem();
+  if (smem_max <= 0) { set_error("no CUDA device"); return A3GC_ERR_NO_DEVICE; }
+  const bool gru = a.variant == A3GC_VARIANT_GGRU;
+  const bool att = a.variant == A3GC_VARIANT_A3GC || a.variant == A3GC_VARIANT_AGC;
+  const int KX = F > H ? F : H;
+  // shared-memory bytes as a function of the batch tile
+  auto smem_bytes = [&](int bt) -> size_t {
+    size_t fl = gru ? ((size_t)3 * bt * H * 16 + (size_t)bt * F * 16 + 256)
+                    : ((size_t)3 * bt * H * 16 + (size_t)bt * KX * 16 + (size_t)2 * bt * H + (size_t)bt * 16 + 1024);
+    return fl * sizeof(float);
+  };
+  int BT = 8;
+  while (BT > 1 && smem_bytes(BT) > (size_t)smem_max) --BT;
+  // do not leave SMs idle when the batch is small: shrink the tile until the grid covers the chip
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  while (BT > 1 && ((a.batch + BT - 1) / BT) * a.num_dirs < sms) --BT;
+  if (smem_bytes(BT) > (size_t)smem_max) {
+    set_error("SIMT engine: hidden=%d f_in=%d needs %zu bytes of shared memory (> %d)", H, F, smem_bytes(1), smem_max);
+    return A3GC_ERR_UNSUPPORTED;
+  }
+  char* base = static_cast<char*>(ws);
+  const size_t per = need / a.num_dirs;
+  DirPtrs dp[2] = {};
+  for (int d = 0; d < a.num_dirs; ++d) {
+    dp[d].h0 = a.h0[d]; dp[d].c0 = a.c0[d]; dp[d].hT = a.hT[d]; dp[d].cT = a.cT[d]; dp[d].reverse = a.reverse[d];
+  }
+  LayerGeom g;
+  g.x = a.x; g.sxb = a.x_stride_b; g.sxt = a.x_stride_t;
+  g.y = a.y; g.syb = a.y_stride_b; g.syt = a.y_stride_t; g.yld = a.y_ld;
+  g.B = (int)a.batch; g.T = (int)a.steps; g.F = F; g.H = H; g.out_act = a.out_act; g.BT = BT;
+  dim3 grid((unsigned)((a.batch + BT - 1) / BT), (unsigned)a.num_dirs);
+  const size_t smem = smem_bytes(BT);
+  if (gru) {
+    GruPacked pk[2];
+    for (int d = 0; d < a.num_dirs; ++d) {
+      pk[d] = carve_gru(reinterpret_cast<float*>(base + d * per), F, H);
+      pack_gru_kernel<<<64, 256, 0, stream>>>(a.cells[d], pk[d], F, H);
+      A3GC_LAUNCH_CHECK("pack_gru_kernel");
+    }
+    if (a.num_dirs == 1) pk[1] = pk[0];
+    A3GC_CUDA_TRY(cudaFuncSetAttribute(gru_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gru_layer_kernel<<<grid, kThreads, smem, stream>>>(pk[0], pk[1], dp[0], dp[1], g);
+    A3GC_LAUNCH_CHECK("gru_layer_kernel");
+  } else {
+    LstmPacked pk[2];
+    for (int d = 0; d < a.num_dirs; ++d) {
+      pk[d] = carve_lstm(reinterpret_cast<float*>(base + d * per), F, H);
+      pack_lstm_kernel<<<64, 256, 0, stream>>>(a.cells[d], pk[d], F, H, a.variant);
+      A3GC_LAUNCH_CHECK("pack_lstm_kernel");
+    }
+    if (a.num_dirs == 1) pk[1] = pk[0];
+    if (att) {
+      A3GC_CUDA_TRY(cudaFuncSetAttribute(lstm_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      lstm_layer_kernel<true><<<grid, kThreads, smem, stream>>>(pk[0], pk[1], dp[0], dp[1], g);
+    } else {
+      A3GC_CUDA_TRY(cudaFuncSetAttribute(lstm_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      lstm_layer_kernel<false><<<grid, kThreads, smem, stream>>>(pk[0], pk[1], dp[0], dp[1], g);
+    }
+    A3GC_LAUNCH_CHECK("lstm_layer_kernel");
+  }
+  return A3GC_OK;
+}
+
+int simt_gc_forward(const a3gc_gc_params* p, const float* x, float* y, int64_t frames, int f_in,
+                    int f_out, int act, cudaStream_t stream) {
+  if (frames == 0) return A3GC_OK;
+  const int smem_max = max_optin_smem();
+  if (smem_max <= 0) { set_error("no CUDA device"); return A3GC_ERR_NO_DEVICE; }
+  int FR = 8;
+  auto bytes = [&](int fr) { return (256 + (size_t)2 * fr * kNodes * f_in) * sizeof(float); };
+  while (FR > 1 && bytes(FR) > (size_t)96 * 1024) --FR;
+  if (bytes(FR) > (size_t)smem_max) { set_error("gc_forward: f_in=%d too large", f_in); return A3GC_ERR_UNSUPPORTED; }
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  int64_t blocks = (frames + FR - 1) / FR;
+  if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+  A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(FR)));
+  gc_kernel<<<(unsigned)blocks, kThreads, bytes(FR), stream>>>(*p, x, y, frames, f_in, f_out, act, FR);
+  A3GC_LAUNCH_CHECK("gc_kernel");
+  return A3GC_OK;
+}
+
+int simt_prepare_input(const float* acc, const float* ori, const float* acc_mean, const float* acc_std,
+                       const float* ori_mean, const float* ori_std, float* x, int64_t frames, int ld_x,
+                       cudaStream_t stream) {
+  if (frames == 0) return A3GC_OK;
+  int64_t total = frames * kNodes * 12;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  prepare_input_kernel<<<(unsigned)blocks, 256, 0, stream>>>(acc, ori, acc_mean, acc_std, ori_mean, ori_std, x, frames, ld_x);
+  A3GC_LAUNCH_CHECK("prepare_input_kernel");
+  return A3GC_OK;
+}
+
+int simt_concat_stage_input(const float* x, const float* pos, float* dst, int64_t frames, cudaStream_t stream) {
+  if (frames == 0) return A3GC_OK;
+  int64_t rows = frames * kNodes;
+  int64_t blocks = (rows * 15 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  concat_stage_input_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, pos, dst, rows);
+  A3GC_LAUNCH_CHECK("concat_stage_input_kernel");
+  return A3GC_OK;
+}
+
+}  // namespace a3gc

@@ -1,0 +1,93 @@
+"""Three-stage "TP" inference chain of evaluate_a3gc_tp.py:64-94, 164-172 on the device.
+
+    x  = prepare_input(ori, acc)                 # normalise, drop IMU 6, scatter to nodes [3,4,13,14,10]
+    y1 = net1(x)                                 # leaf joint positions   [B,T,15,3]
+    y2 = net2(cat(x, y1))                        # full joint positions   [B,T,15,3]
+    y3 = net3(cat(x, y2))                        # reduced global pose    [B,T,15,9]
+
+The reference runs this at B=1 per recording; here B is arbitrary (independent sequences).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+INPUT_JOINTS = [3, 4, 13, 14, 10]          # evaluate_a3gc_tp.py:65
+NUM_NODES = 15
+
+
+def prepare_input(ori: Tensor, acc: Tensor, stats: Optional[dict] = None, out: Optional[Tensor] = None) -> Tensor:
+    """Device version of ``prepare_input`` (evaluate_a3gc_tp.py:64-94).
+
+    ori [..., 54], acc [..., 18] (CUDA fp32) -> [..., 15, 12].  ``stats`` is the dict of
+    ``data/all*_train_stats.pt`` (``--norm``); None skips the normalisation.
+    """
+    ori = _lib.require_cuda_f32(ori, "ori")
+    acc = _lib.require_cuda_f32(acc, "acc")
+    if ori.shape[-1] != 54 or acc.shape[-1] != 18 or ori.shape[:-1] != acc.shape[:-1]:
+        raise RuntimeError(f"prepare_input expects ori [...,54] and acc [...,18], got {tuple(ori.shape)} / {tuple(acc.shape)}")
+    lead = tuple(ori.shape[:-1])
+    frames = ori.numel() // 54
+    if out is None:
+        out = torch.empty(*lead, NUM_NODES, 12, dtype=torch.float32, device=ori.device)
+    dev = ori.device
+    if stats is not None:
+        am = stats["acc"]["mean_channel"].to(dev, torch.float32).contiguous()
+        asd = stats["acc"]["std_channel"].to(dev, torch.float32).contiguous()
+        om = stats["ori"]["mean_channel"].to(dev, torch.float32).contiguous()
+        osd = stats["ori"]["std_channel"].to(dev, torch.float32).contiguous()
+        ptrs = (am.data_ptr(), asd.data_ptr(), om.data_ptr(), osd.data_ptr())
+    else:
+        ptrs = (None, None, None, None)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().a3gc_prepare_input(acc.data_ptr(), ori.data_ptr(), *ptrs, out.data_ptr(), frames, 12, _lib.stream_ptr(dev))
+    _lib.check(rc, "a3gc_prepare_input")
+    return out
+
+
+def concat_stage_input(x: Tensor, pos: Tensor) -> Tensor:
+    """``torch.cat((x, pos.view(B, T, 15, 3)), dim=-1)`` (evaluate_a3gc_tp.py:168, 170) as one kernel."""
+    x = _lib.require_cuda_f32(x, "x")
+    pos = _lib.require_cuda_f32(pos, "pos")
+    B, T = x.shape[0], x.shape[1]
+    out = torch.empty(B, T, NUM_NODES, 15, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().a3gc_concat_stage_input(x.data_ptr(), pos.data_ptr(), out.data_ptr(), B * T, _lib.stream_ptr(x.device))
+    _lib.check(rc, "a3gc_concat_stage_input")
+    return out
+
+
+class TPPipeline(torch.nn.Module):
+    """net1 (12 -> 3), net2 (15 -> 3), net3 (15 -> 9) chained as evaluate_a3gc_tp.py:164-172."""
+
+    def __init__(self, net1: torch.nn.Module, net2: torch.nn.Module, net3: torch.nn.Module, stats: Optional[dict] = None):
+        super().__init__()
+        self.net1, self.net2, self.net3 = net1, net2, net3
+        self.stats = stats
+
+    @torch.no_grad()
+    def forward(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+        y1, _ = self.net1(x)
+        y2, _ = self.net2(concat_stage_input(x, y1))
+        y3, _ = self.net3(concat_stage_input(x, y2))
+        return y1, y2, y3
+
+    @torch.no_grad()
+    def forward_raw(self, ori: Tensor, acc: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+        return self.forward(prepare_input(ori, acc, self.stats))
+
+    @torch.no_grad()
+    def forward_host(self, x_host: Tensor, out_host: Optional[Tensor] = None, device: Optional[torch.device] = None) -> Tensor:
+        """End-to-end call with HOST buffers: H2D copy of x, three stages, D2H copy of the pose."""
+        device = device or next(self.parameters()).device
+        x = x_host.to(device, non_blocking=True)
+        _, _, y3 = self.forward(x)
+        if out_host is None:
+            return y3.cpu()
+        out_host.copy_(y3, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        return out_host

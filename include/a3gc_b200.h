@@ -1,0 +1,203 @@
+/*
+ * a3gc_b200.h -- C ABI of the B200-native A3GC-IP hot path.
+ *
+ * Drop-in boundary for the recurrent adaptive-graph-convolution path of trikpachu/A3GC-IP
+ * (reference file net_aagc.py:40-695, chained as in evaluate_a3gc_tp.py:164-172).  The reference
+ * is pure PyTorch, so the "FFI" a maintainer binds is a ctypes stub: the
+ * drop-in torch.nn.Modules in a3gc_ip_b200/net_aagc.py hand raw device pointers of their
+ * parameters and activations to these entry points.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a CUDA device pointer to fp32 data unless
+ *     stated otherwise; the caller (torch) owns all memory, including the workspace;
+ *   - the library never allocates persistent device memory and never frees caller memory;
+ *   - every entry point returns 0 on success, a negative a3gc_status on error, and never throws;
+ *     a3gc_last_error() returns a thread-local description of the last failure;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ *   - the graph always has A3GC_NODES = 15 nodes (net_aagc.py:142,233,319 assert it).
+ */
+#ifndef A3GC_B200_H_
+#define A3GC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define A3GC_ABI_VERSION 1
+#define A3GC_NODES 15
+
+/* Cell family.  Values are part of the ABI. */
+typedef enum a3gc_variant {
+  A3GC_VARIANT_AAGC = 0, /* AAGC_LSTM_cell  net_aagc.py:68-126  (4 learnable adjacencies, no attention) */
+  A3GC_VARIANT_A3GC = 1, /* A3GC_LSTM_cell  net_aagc.py:128-217 (4 learnable adjacencies + joint attention) */
+  A3GC_VARIANT_AGC = 2,  /* AGC_LSTM_cell   net_aagc.py:219-303 (1 frozen adjacency, applied transposed, + attention) */
+  A3GC_VARIANT_GGRU = 3  /* G_GRU_cell      net_aagc.py:305-368 */
+} a3gc_variant;
+
+typedef enum a3gc_activation {
+  A3GC_ACT_LINEAR = 0, /* 'linear' (net_aagc.py:46) */
+  A3GC_ACT_TANH = 1,   /* 'tanh'   (net_aagc.py:48) */
+  A3GC_ACT_RELU = 2    /* the torch.relu the nets apply after linear_in (net_aagc.py:641) */
+} a3gc_activation;
+
+/* Arithmetic of the gate / attention contractions. */
+typedef enum a3gc_precision {
+  A3GC_PREC_FP32 = 0, /* fp32-accurate (parity bar 1e-4 rel vs the reference's CPU fp32 forward) */
+  A3GC_PREC_BF16 = 1  /* bf16 operands, fp32 accumulate and state (stated looser bound) */
+} a3gc_precision;
+
+/* Which kernels run the recurrent layers. */
+typedef enum a3gc_engine {
+  A3GC_ENGINE_AUTO = 0, /* tensor-core engine when the shape allows it, else SIMT */
+  A3GC_ENGINE_SIMT = 1, /* fp32 CUDA-core kernels, any shape */
+  A3GC_ENGINE_TC = 2    /* tcgen05 / TMEM kernels (hidden size multiple of 64); error if unsupported */
+} a3gc_engine;
+
+typedef enum a3gc_status {
+  A3GC_OK = 0,
+  A3GC_ERR_INVALID_ARG = -1,
+  A3GC_ERR_UNSUPPORTED = -2,
+  A3GC_ERR_WORKSPACE = -3,
+  A3GC_ERR_NO_DEVICE = -4,
+  A3GC_ERR_CUDA = -5
+} a3gc_status;
+
+/* Parameters of one AAGC graph convolution (class AAGC, net_aagc.py:55-57). */
+typedef struct a3gc_gc_params {
+  const float* gcn_kernel; /* [f_out, f_in] */
+  const float* adj;        /* [15, 15], used as adj @ x (net_aagc.py:63) */
+  const float* gcn_bias;   /* [f_out] */
+} a3gc_gc_params;
+
+/*
+ * Parameters of one recurrent cell, exactly the tensors of the reference's state_dict, in the
+ * reference's storage layout (no repacking by the caller).  Gate order is i, f, c, o.
+ *   LSTM family (AAGC / A3GC / AGC): gcn_kernel[g] [H, F+H] (columns: x features first, then h --
+ *   the cat order of net_aagc.py:182), gcn_bias[g] [H], adjacency[g] [15,15].
+ *   AGC stores ONE frozen `adjacency` (net_aagc.py:238): pass it in adjacency[0]; [1..3] are ignored.
+ *   attention_* (A3GC / AGC only, NULL for AAGC): w, wq, wh [H,H]; u [1,H]; bs [H]; bu [15].
+ *   G-GRU: g_gcn_kernel [H,H], g_adjacency [15,15] (used transposed, net_aagc.py:348),
+ *   dense_in_w[r,u,c] [H,F], dense_in_b[r,u,c] [H], dense_hid_w[r,u,c] [H,H].  The frozen,
+ *   unused `a` buffer of G_GRU_cell (net_aagc.py:324) never crosses the ABI.
+ */
+typedef struct a3gc_cell_params {
+  const float* gcn_kernel[4];
+  const float* adjacency[4];
+  const float* gcn_bias[4];
+  const float* attention_w;
+  const float* attention_wq;
+  const float* attention_wh;
+  const float* attention_u;
+  const float* attention_bs;
+  const float* attention_bu;
+  const float* g_gcn_kernel;
+  const float* g_adjacency;
+  const float* dense_in_w[3];
+  const float* dense_in_b[3];
+  const float* dense_hid_w[3];
+} a3gc_cell_params;
+
+/* One whole net: linear_in -> relu -> rnn1 (2 directions) -> rnn2 (2 directions) -> linear_out
+ * (A3GC_net & co., net_aagc.py:595-695).  rnn[layer][direction]; direction 1 is the reverse layer. */
+typedef struct a3gc_net_params {
+  a3gc_gc_params linear_in;
+  a3gc_cell_params rnn[2][2];
+  a3gc_gc_params linear_out;
+} a3gc_net_params;
+
+/* Version of this ABI (A3GC_ABI_VERSION of the library that was built). */
+int a3gc_abi_version(void);
+
+/* Thread-local text of the last error returned on this thread ("" if none). */
+const char* a3gc_last_error(void);
+
+/* Number of CUDA devices visible to the library; negative a3gc_status if the runtime fails. */
+int a3gc_device_count(void);
+
+/*
+ * AAGC.forward (net_aagc.py:61-66):  y = act((adj @ x) @ W^T + b), eval mode.
+ *   x [frames, 15, f_in] contiguous, y [frames, 15, f_out] contiguous; frames = B*T.
+ */
+int a3gc_gc_forward(const a3gc_gc_params* p, const float* x, float* y, int64_t frames, int f_in,
+                    int f_out, int act, void* stream);
+
+/* Bytes of caller-provided workspace a3gc_layer_forward needs (0 is possible). */
+size_t a3gc_layer_workspace_bytes(int variant, int64_t batch, int64_t steps, int f_in, int hidden,
+                                  int num_dirs, int precision, int engine);
+
+/*
+ * Time loop of num_dirs (1 or 2) recurrent layer directions over the same input, run concurrently:
+ * A3GC_LSTM / ReverseA3GC_LSTM / BiA3GC_LSTM .forward (net_aagc.py:435-441, :449-456, :469-480) and
+ * their AAGC / AGC / G_GRU twins.
+ *   cells[d], reverse[d]   parameters and walking order of direction d (reverse: t = T-1 .. 0,
+ *                          outputs stored at their own t, final state = state after t = 0);
+ *   x      element (b, t, n, k) at x[b*x_stride_b + t*x_stride_t + n*f_in + k]   (any of [B,T,..] / [T,B,..]);
+ *   h0[d], c0[d]           initial state [B, 15, H] contiguous, NULL = zeros (c0 ignored for G-GRU);
+ *   y      element (b, t, n, j) of direction d at y[b*y_stride_b + t*y_stride_t + n*y_ld + d*H + j];
+ *          holds out_act(h') for the LSTM family, h' for G-GRU (its activation_fn is unused, :368);
+ *   hT[d], cT[d]           final state [B, 15, H] contiguous (may be NULL to skip; cT ignored for G-GRU).
+ */
+int a3gc_layer_forward(int variant, int num_dirs, const a3gc_cell_params* cells, const int* reverse,
+                       const float* x, int64_t x_stride_b, int64_t x_stride_t,
+                       const float* const* h0, const float* const* c0,
+                       float* y, int64_t y_stride_b, int64_t y_stride_t, int64_t y_ld,
+                       float* const* hT, float* const* cT,
+                       int64_t batch, int64_t steps, int f_in, int hidden, int out_act,
+                       int precision, int engine, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Bytes of workspace a3gc_net_forward needs for this shape. */
+size_t a3gc_net_workspace_bytes(int variant, int64_t batch, int64_t steps, int f0, int hidden,
+                                int f_out, int precision, int engine);
+
+/*
+ * {AAGC,A3GC,AGC,G_GRU}_net.forward (net_aagc.py:607-619, :633-645, :659-671, :685-695), eval mode:
+ * linear_in -> relu -> rnn1 -> rnn2 (seeded with rnn1's final state) -> linear_out.
+ *   x [B, T, 15, f0] contiguous;  y [B, T, 15, f_out] contiguous;
+ *   h0[d], c0[d]  initial state of rnn1 direction d ([B,15,H]; NULL = zeros; c0 unused for G-GRU);
+ *   hT[d], cT[d]  final state of rnn2 direction d (may be NULL).
+ */
+int a3gc_net_forward(int variant, const a3gc_net_params* net, const float* x,
+                     const float* const* h0, const float* const* c0, float* y,
+                     float* const* hT, float* const* cT,
+                     int64_t batch, int64_t steps, int f0, int hidden, int f_out,
+                     int precision, int engine, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * prepare_input (evaluate_a3gc_tp.py:64-94) on the device: per frame normalise the raw 18-d
+ * acceleration and 54-d orientation channels ((v - mean) / std; pass NULL mean/std to skip, i.e.
+ * --norm off), drop the 6th IMU and scatter (acc_i, ori_i) of IMU i onto node {3,4,13,14,10}[i].
+ *   acc [frames, 18], ori [frames, 54] -> x [frames, 15, ld_x] (columns 0..11 written; other nodes' 0..11 zeroed).
+ */
+int a3gc_prepare_input(const float* acc, const float* ori, const float* acc_mean, const float* acc_std,
+                       const float* ori_mean, const float* ori_std, float* x, int64_t frames, int ld_x,
+                       void* stream);
+
+/*
+ * Stage chaining of evaluate_a3gc_tp.py:168,170:  dst[f, n, 0..12) = x[f, n, 0..12),
+ * dst[f, n, 12..15) = pos[f, n, 0..3)   (torch.cat((x, pos), dim=-1)).
+ */
+int a3gc_concat_stage_input(const float* x, const float* pos, float* dst, int64_t frames, void* stream);
+
+/*
+ * Optional per-launch timing of the recurrent-layer kernels (used by bench.py for the roofline):
+ * while enabled, every layer launch is bracketed by CUDA events on the launching stream.
+ * a3gc_profile_get must be called after the stream has been synchronised; it returns the launch's
+ * duration in ms, its algorithmic dense FLOPs (2*M*N*K of the gate + attention contractions, the
+ * SURVEY.md 8d convention), and a short label "<engine>:<variant>:F<f_in>:H<hidden>".
+ */
+int a3gc_profile_enable(int on);            /* on != 0: start a fresh recording; 0: stop */
+int a3gc_profile_count(void);
+int a3gc_profile_get(int index, char* label, int label_bytes, float* ms, double* flops);
+
+/* Number of kernels this library has launched on the calling thread since the last reset. */
+int64_t a3gc_launch_count(void);
+void a3gc_reset_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* A3GC_B200_H_ */

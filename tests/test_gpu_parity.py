@@ -1,0 +1,182 @@
+"""Parity of the CUDA path (through the C ABI) with the reference's golden outputs and the CPU oracle.
+
+Tolerances (SURVEY.md section 8d / BASELINE.json north_star):
+  fp32 path: rel-L2 <= 1e-4 and max|err|/max|ref| <= 1e-4 against the reference's CPU fp32 forward;
+  index / topology handling (prepare_input, stage concat): bit-exact.
+"""
+import os
+
+import pytest
+import torch
+
+import a3gc_ip_b200 as A
+from conftest import load_golden, rel_l2, max_rel
+from oracle import net_oracle as O
+from util import build_net, build_tp, case_sd, unflatten_h, flatten_h, CELL_CLS_NAMES, tp_state_dicts
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+NET_CASES = load_golden("net_cases.pt")
+CELL_CASES = load_golden("cell_cases.pt")
+
+
+def engines_for(variant, f_in, hidden):
+    """Every engine that claims support for this shape; SIMT always."""
+    L = A.lib()
+    out = ["simt"]
+    if L.a3gc_layer_workspace_bytes(A._lib.VARIANT[variant], 8, 8, f_in, hidden, 2, 0, 2) > 0:
+        out.append("tc")
+    return out
+
+
+def assert_close(got, want, tol=TOL, what=""):
+    assert got.shape == want.shape, what
+    assert torch.isfinite(got).all(), what
+    r, m = rel_l2(got.cpu(), want), max_rel(got.cpu(), want)
+    assert r <= tol and m <= tol, f"{what}: rel_l2={r:.3e} max_rel={m:.3e} (tol {tol})"
+
+
+@pytest.mark.parametrize("case", NET_CASES, ids=[c["name"] for c in NET_CASES])
+def test_net_matches_reference_golden(case, nira):
+    sd = case_sd(case, nira)
+    v, H = case["variant"], case["hidden"]
+    engines = sorted(set(engines_for(v, H, H)) & set(engines_for(v, 2 * H, H))) or ["simt"]
+    for eng in engines:
+        net = build_net(v, case["f0"], case["out"], H, sd, nira, engine=eng)
+        y, h = net(case["x"].cuda(), unflatten_h(v, case["h0"], "cuda"))
+        assert_close(y, case["y"], what=f"{case['name']}[{eng}] y")
+        for i, (a, b) in enumerate(zip(flatten_h(h), case["h_out"])):
+            assert_close(a, b, what=f"{case['name']}[{eng}] state{i}")
+
+
+@pytest.mark.parametrize("case", CELL_CASES, ids=[f'{c["variant"]}_{c["f_in"]}_{c["hidden"]}' for c in CELL_CASES])
+def test_cell_matches_reference_golden(case, nira):
+    v = case["variant"]
+    cell = getattr(A, CELL_CLS_NAMES[v])(case["f_in"], case["hidden"], nira.float(), activation_fn="tanh")
+    cell.load_state_dict(case["sd"], strict=True)
+    cell = cell.cuda().eval().set_engine("simt")
+    x, h, c = case["x"].cuda(), case["h"].cuda(), case["c"].cuda()
+    if v == "GGRU":
+        o, hn = cell(x, h)
+        outs = [o, hn]
+    else:
+        o, (hn, cn) = cell(x, (h, c))
+        outs = [o, hn, cn]
+    for a, b in zip(outs, case["outs"]):
+        assert_close(a, b, what=v)
+
+
+@pytest.mark.parametrize("variant", O.VARIANTS)
+def test_time_major_layers_match_oracle(variant, nira):
+    """A3GC_LSTM / ReverseA3GC_LSTM style layers: time-major input, single direction."""
+    H, F, T, B = 12, 20, 9, 5
+    names = {"AAGC": ("AAGC_LSTM", "ReverseAAGC_LSTM"), "A3GC": ("A3GC_LSTM", "ReverseA3GC_LSTM"),
+             "AGC": ("AGC_LSTM", "ReverseAGC_LSTM"), "GGRU": ("G_GRU", "ReverseG_GRU")}[variant]
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(T, B, 15, F, generator=g)
+    h0, c0 = 0.3 * torch.randn(B, 15, H, generator=g), 0.3 * torch.randn(B, 15, H, generator=g)
+    for rev, name in enumerate(names):
+        layer = getattr(A, name)(F, H, nira.float(), activation_fn="tanh")
+        for p_name, shape in O.cell_param_shapes(variant, F, H):
+            obj = layer.cell
+            for part in p_name.split("."):
+                obj = getattr(obj, part)
+            obj.data = 0.2 * torch.randn(shape, generator=g) + (nira.float().t() if shape == (15, 15) else 0)
+        sd = {"l." + k: v for k, v in layer.state_dict().items()}
+        state = h0 if variant == "GGRU" else (h0, c0)
+        with torch.no_grad():
+            want_y, want_s = O.layer_forward(variant, x, state, sd, "l.", reverse=bool(rev))
+        layer = layer.cuda().eval().set_engine("simt")
+        st = h0.cuda() if variant == "GGRU" else (h0.cuda(), c0.cuda())
+        y, s = layer(x.cuda(), st)
+        assert_close(y, want_y, what=name)
+        for a, b in zip(flatten_h([s]), flatten_h([want_s])):
+            assert_close(a, b, what=name + " state")
+
+
+def test_aagc_graph_conv_matches_oracle(nira):
+    g = torch.Generator().manual_seed(4)
+    for f_in, f_out, act in ((12, 32, "linear"), (64, 9, "tanh"), (15, 256, "linear"), (512, 3, "linear")):
+        m = A.AAGC(f_in, f_out, nira.float(), activation_fn=act)
+        m.gcn_bias.data = torch.randn(f_out, generator=g)
+        m.adj.data += 0.1 * torch.randn(15, 15, generator=g)
+        x = torch.randn(3, 5, 15, f_in, generator=g)
+        sd = {"m." + k: v.clone() for k, v in m.state_dict().items()}
+        want = O.aagc_forward(x, sd, "m.", act)
+        assert_close(m.cuda().eval()(x.cuda()), want, what=f"AAGC {f_in}->{f_out}")
+
+
+def test_prepare_input_and_concat_bit_exact():
+    g = load_golden("prepare_input.pt")
+    for tag, stats_name in (("nonorm", None), ("norm", "all_train_stats.pt"), ("norm_cda", "all_sym_train_stats.pt")):
+        stats = None if stats_name is None else load_golden(stats_name)
+        for ori, acc, want in zip(g["oris"], g["accs"], g["outs"][tag]):
+            got = A.prepare_input(ori.cuda(), acc.cuda(), stats).unsqueeze(0).cpu()
+            assert torch.equal(got, want), tag
+    x = torch.randn(2, 3, 15, 12).cuda()
+    p = torch.randn(2, 3, 15, 3).cuda()
+    assert torch.equal(A.concat_stage_input(x, p), torch.cat((x, p), dim=-1))
+
+
+@pytest.mark.parametrize("variant", ["A3GC", "GGRU"])
+def test_tp_chain_cfg1_golden(variant, nira):
+    """BASELINE cfg 1 (B=1, T=300, three stages) against the reference's own output."""
+    g = load_golden("tp_cfg1.pt")[variant]
+    pipe, _ = build_tp(variant, nira)
+    x = O.synthetic_input(1, 300, seed=g["x_seed"]).cuda()
+    y1, y2, y3 = pipe(x)
+    for a, b, nm in ((y1, g["y1"], "y1"), (y2, g["y2"], "y2"), (y3, g["y3"], "y3")):
+        assert_close(a, b, what=f"{variant} {nm}")
+
+
+@pytest.mark.parametrize("variant", O.VARIANTS)
+def test_edge_shapes(variant, nira):
+    """Ragged and degenerate shapes: B not a multiple of the batch tile, T=1, B=1, empty batch."""
+    sd = O.random_state_dict(variant, 12, 3, 24, nira, seed=9)
+    net = build_net(variant, 12, 3, 24, sd, nira, engine="simt")
+    for B, T in ((1, 1), (13, 3), (1, 17), (0, 4)):
+        x = torch.randn(B, T, 15, 12, generator=torch.Generator().manual_seed(B * 100 + T))
+        y, h = net(x.cuda())
+        assert y.shape == (B, T, 15, 3)
+        if B == 0:
+            continue
+        with torch.no_grad():
+            want, want_h = O.net_forward(variant, x, sd)
+        assert_close(y, want, what=f"{variant} B={B} T={T}")
+        for a, b in zip(flatten_h(h), flatten_h(want_h)):
+            assert_close(a, b, what=f"{variant} B={B} T={T} state")
+
+
+def test_batch_independence_and_full_size_subset(nira):
+    """BASELINE cfg 2 shape (B=1024, T=300 is run by bench.py; here B=256, T=300 keeps the test short):
+    sequences are independent, so a strided subset run alone must reproduce the big-batch rows, and
+    those rows must match the CPU oracle."""
+    pipe, sds = build_tp("A3GC", nira)
+    B, T = 256, 300
+    x = O.synthetic_input(B, T, seed=1234)
+    y3 = pipe(x.cuda())[2]
+    idx = torch.arange(0, B, 37)
+    y3_sub = pipe(x[idx].cuda())[2]
+    assert_close(y3[idx.cuda()], y3_sub.cpu(), tol=2e-6, what="batch independence")
+    with torch.no_grad():
+        want = O.tp_forward("A3GC", x[idx[:3]], sds)[2]
+    assert_close(y3[idx[:3].cuda()], want, what="big-batch rows vs oracle")
+
+
+def test_linearity_of_graph_conv(nira):
+    """Size-independent property at a large frame count: AAGC is affine in x."""
+    m = A.AAGC(12, 64, nira.float()).cuda().eval()
+    x1, x2 = torch.randn(64, 300, 15, 12).cuda(), torch.randn(64, 300, 15, 12).cuda()
+    zero = m(torch.zeros_like(x1))
+    lhs = m(x1 + 2 * x2) - zero
+    rhs = (m(x1) - zero) + 2 * (m(x2) - zero)
+    assert rel_l2(lhs.cpu(), rhs.cpu()) < 1e-5
+
+
+def test_launch_counter_counts_kernels(nira):
+    sd = O.random_state_dict("A3GC", 12, 3, 8, nira, seed=1)
+    net = build_net("A3GC", 12, 3, 8, sd, nira, engine="simt")
+    L = A.lib()
+    L.a3gc_reset_launch_count()
+    net(torch.zeros(2, 3, 15, 12).cuda())
+    assert L.a3gc_launch_count() == 8      # in-GC, 2x(2 packs + layer), out-GC

@@ -1,0 +1,127 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU needed)."""
+import os
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import a3gc_ip_b200 as A
+from conftest import load_golden
+from oracle import net_oracle as O
+from util import NET_CLS_NAMES, CELL_CLS_NAMES, trained_sd
+
+
+@pytest.mark.parametrize("variant", O.VARIANTS)
+@pytest.mark.parametrize("shape", [(12, 3, 256), (15, 3, 64), (15, 9, 128), (12, 3, 8)])
+def test_state_dict_keys_shapes_order(variant, shape, nira):
+    f0, out, hidden = shape
+    net = getattr(A, NET_CLS_NAMES[variant])(f0, out, hidden, nira.float())
+    got = [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
+    assert got == O.net_param_shapes(variant, f0, out, hidden)
+    frozen = {k for k, p in net.named_parameters() if not p.requires_grad}
+    if variant == "AGC":
+        assert frozen == {f"rnn{l}.directions.{d}.cell.adjacency" for l in (1, 2) for d in (0, 1)}
+    elif variant == "GGRU":
+        assert frozen == {f"rnn{l}.directions.{d}.cell.a" for l in (1, 2) for d in (0, 1)}
+    else:
+        assert not frozen
+
+
+@pytest.mark.parametrize("name,cls,args", [("A3GC_model2", "PoseNet3", (15, 3, 64)), ("A3GC_model3", "PoseNet3", (15, 9, 128)),
+                                           ("GGRU_model2", "PoseNet_GGRU", (15, 3, 64)), ("GGRU_model3", "PoseNet_GGRU", (15, 9, 128))])
+def test_shipped_checkpoints_load_strict(name, cls, args, nira):
+    ck = load_golden(os.path.join("weights", name + ".pt"))
+    f0, rot, hidden = args
+    net = getattr(A, cls)(input_size=f0, rotsize=rot, adjacency=nira.float(), n_hidden=hidden)
+    res = net.load_state_dict(ck["state_dict"], strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in ck["state_dict"].items():
+        assert torch.equal(net.state_dict()[k], v)
+
+
+def test_parameters_never_alias(nira):
+    tmpl = nira.float()
+    before = tmpl.clone()
+    for variant in O.VARIANTS:
+        net = getattr(A, NET_CLS_NAMES[variant])(12, 3, 8, tmpl)
+        ptrs = [p.data_ptr() for p in net.parameters()]
+        assert len(set(ptrs)) == len(ptrs)
+        assert tmpl.data_ptr() not in ptrs
+    assert torch.equal(tmpl, before)        # the reference's G_GRU_cell ctor mutates the caller's template; ours must not
+
+
+def test_init_matches_reference_scheme(nira):
+    net = A.A3GC_net(12, 3, 16, nira.float())
+    c = net.rnn1.directions[0].cell
+    assert torch.equal(c.adjacency_i.data, nira.float().t())
+    assert torch.count_nonzero(c.gcn_bias_i) == 0 and torch.count_nonzero(c.attention_bs) == 0
+    bound = (6.0 / (16 + 32)) ** 0.5
+    assert c.gcn_kernel_i.abs().max() <= bound and c.gcn_kernel_i.abs().max() > 0.5 * bound
+
+
+def test_error_behaviour(nira):
+    with pytest.raises(ValueError):
+        A.A3GC_LSTM_cell(8, 8, nira.float(), activation_fn="relu")
+    with pytest.raises(ValueError):
+        A.AAGC(8, 8, nira.float(), activation_fn="sigmoid")
+    with pytest.raises(AssertionError):
+        A.A3GC_LSTM_cell(8, 8, torch.eye(14))
+    with pytest.raises(AssertionError):
+        A.G_GRU_cell(8, 8, torch.eye(24))
+    net = A.A3GC_net(12, 3, 8, nira.float())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net.eval()(torch.zeros(1, 2, 15, 12))
+    if torch.cuda.is_available():
+        return
+    with pytest.raises(ValueError):
+        net.set_engine("cpu")
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from a3gc_ip_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/liba3gc_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU or eager fallback"):
+        _lib.lib()
+
+
+def test_pose_loss():
+    g = load_golden("pose_loss.pt")
+    assert torch.equal(A.pose_loss()(g["pred"], g["targ"]), g["loss"])
+
+
+def test_shard_range_properties():
+    for batch in (0, 1, 7, 8, 1024, 8191):
+        for world in (1, 2, 3, 8):
+            spans = [A.shard_range(batch, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == batch
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        A.shard_range(4, 2, 2)
+
+
+def _gloo_worker(rank, world, port, batch, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x = torch.arange(batch * 3, dtype=torch.float32).view(batch, 3)
+        run = A.ShardedRunner()
+        y_local = run.run(lambda t: t * 2 + 1, x)
+        y = run.gather(y_local, batch)
+        ret[rank] = bool(torch.equal(y, x * 2 + 1)) and y_local.shape[0] == A.shard_range(batch, world, rank)[1] - A.shard_range(batch, world, rank)[0]
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [5, 8])
+def test_sharded_runner_gloo_world2(batch):
+    """N>1 path on CPU: two gloo ranks shard a ragged batch, compute independently, gather equals unsharded."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gloo_worker, args=(2, port, batch, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
