@@ -1,0 +1,85 @@
+// Self-test of the tcgen05 building blocks the tensor-core engine relies on: 1-D bulk copies onto an
+// mbarrier, UMMA shared-memory / instruction descriptors for the no-swizzle K-major layout, the
+// TMEM accumulator layout read back with tcgen05.ld.  D[128, N] = A[128, K] * B[N, K]^T in fp16/bf16
+// with fp32 accumulation, one CTA.  Exposed as a3gc_tc_selftest (include/a3gc_b200.h) and checked
+// against a CPU product in tests/test_gpu_tc.py.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace a3gc {
+namespace {
+
+// operand image: [K/8 chunks][rows][8 elements] 16-bit
+__global__ void __launch_bounds__(128, 1)
+tc_selftest_kernel(const uint16_t* __restrict__ a_img, const uint16_t* __restrict__ b_img, float* __restrict__ d,
+                   int K, int N, int bf16, int swap_lbo_sbo) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_full, bar_mma;
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x / 32;
+  uint8_t* sa = smem;                                  // [K/8][128][16 B]
+  uint8_t* sb = smem + (size_t)K * 128 * 2;            // [K/8][N][16 B]
+  const uint32_t bytes_a = (uint32_t)K * 128 * 2, bytes_b = (uint32_t)K * N * 2;
+
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bar_full, 1);
+    ptx::mbar_init(&bar_mma, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) ptx::tmem_alloc(&tmem_base_slot, 256);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+
+  if (threadIdx.x == 0) {
+    ptx::mbar_arrive_expect_tx(&bar_full, bytes_a + bytes_b);
+    ptx::bulk_g2s(sa, a_img, bytes_a, &bar_full);
+    ptx::bulk_g2s(sb, b_img, bytes_b, &bar_full);
+    ptx::mbar_wait(&bar_full, 0);
+    ptx::tc_fence_after();
+    const uint32_t idesc = ptx::make_idesc_f16(128, N, bf16 != 0);
+    for (int kk = 0; kk < K / 16; ++kk) {
+      // K-chunk stride (LBO) = rows * 16 B; 8-row group stride (SBO) = 128 B
+      uint32_t a_lbo = 128 * 16, a_sbo = 128, b_lbo = (uint32_t)N * 16, b_sbo = 128;
+      if (swap_lbo_sbo) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
+      const uint64_t ad = ptx::make_smem_desc(ptx::smem_u32(sa) + (uint32_t)kk * 2 * 128 * 16, a_lbo, a_sbo);
+      const uint64_t bd = ptx::make_smem_desc(ptx::smem_u32(sb) + (uint32_t)kk * 2 * N * 16, b_lbo, b_sbo);
+      ptx::umma_f16(tmem, ad, bd, idesc, kk > 0 ? 1u : 0u);
+    }
+    ptx::umma_commit(&bar_mma);
+  }
+  __syncwarp();
+  ptx::mbar_wait(&bar_mma, 0);
+  ptx::tc_fence_after();
+  // each warp reads its 32 TMEM lanes (= rows 32*warp .. +31)
+  const int row = warp * 32 + (threadIdx.x & 31);
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float v[32];
+    ptx::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) d[(size_t)row * N + c0 + i] = v[i];
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+}
+
+}  // namespace
+}  // namespace a3gc
+
+extern "C" int a3gc_tc_selftest(const void* a_img, const void* b_img, float* d, int k, int n, int flags, void* stream) {
+  using namespace a3gc;
+  if (!a_img || !b_img || !d || k <= 0 || k % 16 != 0 || n < 16 || n > 256 || n % 16 != 0) {
+    set_error("a3gc_tc_selftest: need K %% 16 == 0 and 16 <= N <= 256, N %% 16 == 0");
+    return A3GC_ERR_INVALID_ARG;
+  }
+  // always the same large allocation, so that a wrong descriptor reads wrong data instead of faulting
+  const size_t smem = 200 * 1024;
+  if ((size_t)k * (128 + n) * 2 > smem) { set_error("a3gc_tc_selftest: K too large"); return A3GC_ERR_INVALID_ARG; }
+  A3GC_CUDA_TRY(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_selftest_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(a_img), static_cast<const uint16_t*>(b_img), d, k, n, flags & 1, (flags >> 1) & 1);
+  A3GC_LAUNCH_CHECK("tc_selftest_kernel");
+  return A3GC_OK;
+}

@@ -193,6 +193,14 @@ int a3gc_profile_enable(int on);            /* on != 0: start a fresh recording;
 int a3gc_profile_count(void);
 int a3gc_profile_get(int index, char* label, int label_bytes, float* ms, double* flops);
 
+/*
+ * Self-test of the tcgen05 building blocks (bulk copy + mbarrier, UMMA descriptors, TMEM read-back):
+ * D[128, n] (fp32) = A[128, k] * B[n, k]^T with 16-bit operands given as K-major no-swizzle images
+ * [k/8][rows][8].  flags bit 0: operands are bf16 (else fp16); bit 1: swap the LBO / SBO descriptor
+ * fields (diagnostic).  One CTA; k %% 16 == 0, 16 <= n <= 256, n %% 16 == 0.
+ */
+int a3gc_tc_selftest(const void* a_img, const void* b_img, float* d, int k, int n, int flags, void* stream);
+
 /* Number of kernels this library has launched on the calling thread since the last reset. */
 int64_t a3gc_launch_count(void);
 void a3gc_reset_launch_count(void);
