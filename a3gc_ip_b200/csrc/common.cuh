@@ -43,6 +43,9 @@ __device__ __forceinline__ float tanhf_(float x) {
   float r = (1.0f - e) / (1.0f + e);
   return copysignf(r, x);
 }
+// fast variants for the tensor-core epilogue: MUFU.EX2 + MUFU.RCP (|err| ~ 2e-7 absolute)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.0f, __fdividef(1.0f, 1.0f + __expf(-2.0f * x)), -1.0f); }
 __device__ __forceinline__ float apply_act(float v, int act) {
   return act == A3GC_ACT_TANH ? tanhf_(v) : (act == A3GC_ACT_RELU ? fmaxf(v, 0.0f) : v);
 }

@@ -25,6 +25,7 @@
 // vs the CPU reference ~1e-6.  A3GC_PREC_BF16: one bf16 pass.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include <cstdlib>
 
 namespace a3gc {
 namespace {
@@ -33,18 +34,24 @@ constexpr int kRows = 128;             // 8 sequences x 16 node slots
 constexpr int kSeqTile = 8;
 constexpr int kUnits = 64;             // hidden units per CTA
 constexpr int kSub = 32;               // staged accumulator columns per sub-chunk (8 units x 4 gates)
-constexpr int kPitch = 132;            // floats per staged column
+constexpr int kPitch = 136;            // floats per staged column (136 = 8 mod 32: conflict-free fragment loads)
 constexpr int kEpiThreads = 256;       // warps 2..9
 constexpr int kThreadsTC = 64 + kEpiThreads;
 constexpr int kMaxStages = 4;
 
+// optional per-phase timeline of CTA (0,0) (A3GC_TC_TRACE=1): [role 0 = epilogue, 1 = mma][step < 16][slot < 16] clock64
+__device__ unsigned long long g_tc_trace[2][16][16];
+#define TC_TRACE(role, slot)                                                                 \
+  do {                                                                                       \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t < 16) g_tc_trace[role][t][slot] = clock64(); \
+  } while (0)
+
 struct TcDir {
-  const uint16_t* wg_img;   // [C][(F+H)/16][NP][2][256][8]   gate weights, rows = 4*unit + gate
-  const uint16_t* wh_img;   // [C][H/16][NP][2][64][8]        attention_wh rows of this chunk
+  const uint16_t* wg_img;   // [C][(F+H)/16][NP][2][256][8]   gate weights, rows = 64*gate + unit
+  const uint16_t* a1_img;   // [C][H/16][NP][2][128][8]       rows 0..63 attention_wh, 64..127 attention_w of this chunk
+  const uint16_t* a2_img;   // [C][H/16][NP][2][64][8]        attention_wq rows of this chunk
   const float* P;           // [4][16][16]  zero padded mixing matrices  z = P_g u
   const float* bias4;       // [H][4]
-  const float* wa_t;        // [H][H]  attention_w  transposed (k-major)
-  const float* wq_t;        // [H][H]  attention_wq transposed
   const float* bs;          // [H]
   const float* u;           // [H]
   const float* bu;          // [16]
@@ -55,32 +62,36 @@ struct TcLayerParams {
   TcDir d[2];
   const uint16_t* x_img;    // [tiles][T][F/16][NP][2][128][8]
   float* y; int64_t syb, syt, yld;
-  int B, T, F, H, out_act, C, S;
+  int B, T, F, H, out_act, C, S, trace;
 };
 
 // barrier slots in shared memory
-enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_ACC_FULL = 2 * kMaxStages, BAR_ATT_FULL = BAR_ACC_FULL + 2,
-       BAR_ACC_EMPTY, BAR_H = BAR_ACC_EMPTY + 2, BAR_HHAT, BAR_Q, BAR_A, BAR_HFREE, BAR_COUNT };
+enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_ACC_FULL = 2 * kMaxStages, BAR_ATT_FULL = BAR_ACC_FULL + 2, BAR_ATT2_FULL,
+       BAR_ACC_EMPTY, BAR_H = BAR_ACC_EMPTY + 2, BAR_HHAT, BAR_Q, BAR_A, BAR_HFREE, BAR_A1FREE, BAR_COUNT };
 
 __host__ __device__ inline size_t tc_fixed_smem_bytes(int C) {
   return (size_t)kSub * kPitch * 4      // staging
-         + (size_t)C * 512 * 4 * 2      // sbuf, qbuf
          + (size_t)C * 128 * 4          // apart
-         + 512 * 4 + 256 * 4            // wqbuf, ahalf
+         + 256 * 4                      // ahalf
          + 256 * 4 + 64 * 4 * 2 + 16 * 4  // bias4, bs, u, bu
+         + 1024 * 4 + 256 * 4           // Pfrag, biasg
          + 32 * 8 + 16;                 // barriers, tmem slot
 }
 
-__device__ __forceinline__ void split_store(uint8_t* hbuf, int H, bool split, int k, int row, float v) {
-  // element (row, k) of the operand image [part][K/8][128][8]
-  const size_t off = ((size_t)(k >> 3) * kRows + row) * 16 + (size_t)(k & 7) * 2;
-  if (split) {
-    const __half hi = __float2half_rn(v);
-    const __half lo = __float2half_rn(v - __half2float(hi));
-    *reinterpret_cast<__half*>(hbuf + off) = hi;
-    *reinterpret_cast<__half*>(hbuf + (size_t)H * 256 + off) = lo;
+// byte offset of element (row, k) inside one part of an operand image [K/8][128][8]
+__device__ __forceinline__ uint32_t img_off(int k, int row) {
+  return (uint32_t)(((k >> 3) * kRows + row) * 16 + (k & 7) * 2);
+}
+
+template <bool SPLIT>
+__device__ __forceinline__ void split_bits(float v, uint16_t& hi, uint16_t& lo) {
+  if (SPLIT) {
+    const __half h = __float2half_rn(v);
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(__float2half_rn(v - __half2float(h)));
   } else {
-    *reinterpret_cast<__nv_bfloat16*>(hbuf + off) = __float2bfloat16_rn(v);
+    hi = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    lo = 0;
   }
 }
 
@@ -91,6 +102,8 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
   constexpr uint32_t kBBytes = NP * 2 * 256 * 16;     // one K=16 block of gate weights (all parts)
   constexpr uint32_t kABytes = NP * 2 * 128 * 16;     // one K=16 block of x rows
   constexpr uint32_t kStageBytes = kBBytes + kABytes;
+  constexpr uint32_t kA1Block = NP * 2 * 128 * 16;    // one K=16 block of [Wh ; Wa] rows
+  constexpr uint32_t kA2Block = NP * 2 * 64 * 16;     // one K=16 block of Wq rows
   constexpr uint32_t kHBlock = 8 * kRows * 16;         // this CTA's 64 units of one operand part: 8 K-chunks
   extern __shared__ __align__(1024) uint8_t smem[];
 
@@ -104,21 +117,20 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
   uint8_t* hbuf = smem;
   uint8_t* ring = hbuf + (size_t)NP * H * 256;
   float* staging = reinterpret_cast<float*>(ring + (size_t)S * kStageBytes);
-  float* sbuf = staging + kSub * kPitch;     // [C][8][64]
-  float* qbuf = sbuf + C * 512;              // [C][8][64]
-  float* apart = qbuf + C * 512;             // [C][128]
-  float* wqbuf = apart + C * 128;            // [8][64]
-  float* ahalf = wqbuf + 512;                // [2][128]
+  float* apart = staging + kSub * kPitch;    // [C][128]
+  float* ahalf = apart + C * 128;            // [2][128]
   float* bias4s = ahalf + 256;               // [64][4]
   float* bss = bias4s + 256;                 // [64]
   float* us = bss + 64;                      // [64]
   float* bus = us + 64;                      // [16]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bus + 16);
+  uint32_t* Pfrag = reinterpret_cast<uint32_t*>(bus + 16);   // [4 gates][hi, lo][4 regs][32 lanes] A fragments of P_g
+  float* biasg = reinterpret_cast<float*>(Pfrag + 1024);     // [4 gates][64 units]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(biasg + 256);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
   // ------------------------------------------------------------------ setup
   if (threadIdx.x == 0) {
-    for (int i = 0; i < BAR_COUNT; ++i) ptx::mbar_init(&bars[i], i == BAR_HFREE ? (uint32_t)C : 1u);
+    for (int i = 0; i < BAR_COUNT; ++i) ptx::mbar_init(&bars[i], (i == BAR_HFREE || i == BAR_A1FREE || i == BAR_Q) ? (uint32_t)C : 1u);
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
@@ -127,6 +139,16 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
     const int n16 = NP * H * 16;
     for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < 256; i += blockDim.x) bias4s[i] = d.bias4[(size_t)c * 256 + i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) biasg[i] = d.bias4[(size_t)c * 256 + (i & 63) * 4 + (i >> 6)];
+    // A fragments (mma.m16n8k16, row-major A = P_g): reg i of lane l holds P_g[l/4 + 8*(i&1)][2*(l%4) + 8*(i>>1) + {0,1}]
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+      const int l = i & 31, r = (i >> 5) & 3, g = i >> 7;
+      const int mm = (l >> 2) + 8 * (r & 1), nn = 2 * (l & 3) + 8 * (r >> 1);
+      uint32_t hi, lo;
+      ptx::split_pair_f16(d.P[(g * 16 + mm) * 16 + nn], d.P[(g * 16 + mm) * 16 + nn + 1], hi, lo);
+      Pfrag[((g * 2 + 0) * 4 + r) * 32 + l] = hi;
+      Pfrag[((g * 2 + 1) * 4 + r) * 32 + l] = lo;
+    }
     if (ATT) {
       for (int i = threadIdx.x; i < 64; i += blockDim.x) { bss[i] = d.bs[c * 64 + i]; us[i] = d.u[c * 64 + i]; }
       if (threadIdx.x < 16) bus[threadIdx.x] = d.bu[threadIdx.x];
@@ -153,7 +175,8 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         ++it;
       };
       const uint8_t* wg = reinterpret_cast<const uint8_t*>(d.wg_img) + (size_t)c * (KF + KH) * kBBytes;
-      const uint8_t* wh = reinterpret_cast<const uint8_t*>(d.wh_img) + (size_t)c * KH * (NP * 2 * 64 * 16);
+      const uint8_t* a1 = reinterpret_cast<const uint8_t*>(d.a1_img) + (size_t)c * KH * kA1Block;
+      const uint8_t* a2 = reinterpret_cast<const uint8_t*>(d.a2_img) + (size_t)c * KH * kA2Block;
       const uint8_t* xi = reinterpret_cast<const uint8_t*>(p.x_img);
       auto xpart = [&](int t) {
         const int ta = d.reverse ? T - 1 - t : t;
@@ -164,19 +187,22 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       for (int t = 0; t < T; ++t) {
         for (int kb = 0; kb < KH; ++kb) load_stage(wg + (size_t)(KF + kb) * kBBytes, kBBytes, nullptr, 0);
         if (t + 1 < T) xpart(t + 1);
-        if (ATT)
-          for (int s4 = 0; s4 < KH / 4; ++s4) load_stage(wh + (size_t)s4 * 4 * (NP * 2 * 64 * 16), 4 * NP * 2 * 64 * 16, nullptr, 0);
+        if (ATT) {
+          for (int s2 = 0; s2 < KH / 2; ++s2) load_stage(a1 + (size_t)s2 * 2 * kA1Block, 2 * kA1Block, nullptr, 0);
+          for (int s4 = 0; s4 < KH / 4; ++s4) load_stage(a2 + (size_t)s4 * 4 * kA2Block, 4 * kA2Block, nullptr, 0);
+        }
       }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (one thread)
     if ((threadIdx.x & 31) == 0) {
       const uint32_t idesc256 = ptx::make_idesc_f16(128, 256, !SPLIT);
+      const uint32_t idesc128 = ptx::make_idesc_f16(128, 128, !SPLIT);
       const uint32_t idesc64 = ptx::make_idesc_f16(128, 64, !SPLIT);
       const uint32_t hbase = ptx::smem_u32(hbuf);
       const uint32_t hpart = (uint32_t)H * 256;
       uint32_t it = 0;
-      uint32_t empty_k[2] = {0, 0};     // completions of BAR_ACC_EMPTY[b] consumed so far
+      uint32_t empty_k[2] = {0, 0};     // completions of BAR_ACC_EMPTY[b] consumed so far (no-attention variant)
       auto wait_stage = [&]() -> uint32_t {
         const uint32_t st = it % S, ph = (it / S) & 1u;
         ptx::mbar_wait(&bars[BAR_FULL + st], ph);
@@ -184,22 +210,23 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         return ptx::smem_u32(ring + (size_t)st * kStageBytes);
       };
       auto release_stage = [&]() { ptx::umma_commit(&bars[BAR_EMPTY + it % S]); ++it; };
-      // one K=16 block of the gate GEMM: A (parts at a0, a0+astride), B parts at b0, b0 + kBBytes/NP
-      auto gate_block = [&](uint32_t dcol, uint32_t a0, uint32_t astride, uint32_t b0, bool first) {
+      // one K=16 block: D[:, dcol..dcol+N) (+)= A * B^T with the split passes hi*hi + lo*hi + hi*lo
+      auto block_mma = [&](uint32_t dcol, uint32_t a0, uint32_t astride, uint32_t b0, uint32_t bstride, uint32_t nrows_b,
+                           uint32_t idesc, bool first) {
         const uint64_t ah = ptx::make_smem_desc(a0, kRows * 16, 128);
-        const uint64_t bh = ptx::make_smem_desc(b0, 256 * 16, 128);
-        ptx::umma_f16(tmem + dcol, ah, bh, idesc256, first ? 0u : 1u);
+        const uint64_t bh = ptx::make_smem_desc(b0, nrows_b * 16, 128);
+        ptx::umma_f16(tmem + dcol, ah, bh, idesc, first ? 0u : 1u);
         if (SPLIT) {
           const uint64_t al = ptx::make_smem_desc(a0 + astride, kRows * 16, 128);
-          const uint64_t bl = ptx::make_smem_desc(b0 + kBBytes / 2, 256 * 16, 128);
-          ptx::umma_f16(tmem + dcol, al, bh, idesc256, 1u);
-          ptx::umma_f16(tmem + dcol, ah, bl, idesc256, 1u);
+          const uint64_t bl = ptx::make_smem_desc(b0 + bstride, nrows_b * 16, 128);
+          ptx::umma_f16(tmem + dcol, al, bh, idesc, 1u);
+          ptx::umma_f16(tmem + dcol, ah, bl, idesc, 1u);
         }
       };
       auto xpart = [&](uint32_t dcol) {
         for (int kb = 0; kb < KF; ++kb) {
           const uint32_t st = wait_stage();
-          gate_block(dcol, st + kBBytes, kABytes / NP, st, kb == 0);
+          block_mma(dcol, st + kBBytes, kABytes / NP, st, kBBytes / NP, 256, idesc256, kb == 0);
           release_stage();
         }
       };
@@ -207,50 +234,65 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       for (int t = 0; t < T; ++t) {
         const uint32_t b = t & 1, dcol = b * 256;
         // h-part of step t (needs h'_{t-1} of every chunk in local shared memory)
-        ptx::mbar_wait_cluster(&bars[BAR_H], t & 1);
+        TC_TRACE(1, 0);
+        ptx::mbar_wait(&bars[BAR_H], t & 1);
         ptx::tc_fence_after();
+        TC_TRACE(1, 1);
         for (int kb = 0; kb < KH; ++kb) {
           const uint32_t st = wait_stage();
-          gate_block(dcol, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, st, false);
+          block_mma(dcol, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, st, kBBytes / NP, 256, idesc256, false);
           release_stage();
         }
         ptx::umma_commit(&bars[BAR_ACC_FULL + b]);
         if (C > 1) ptx::umma_commit_multicast(&bars[BAR_HFREE], cta_mask); else ptx::umma_commit(&bars[BAR_HFREE]);
+        TC_TRACE(1, 2);
         // x-part of step t+1 into the other buffer (free once the epilogue of step t-1 has drained it)
         if (t + 1 < T) {
           if (t >= 1) {
             const uint32_t bo = b ^ 1u;
-            if (ATT) { ptx::mbar_wait(&bars[BAR_ACC_EMPTY + bo], 1u); empty_k[bo] += 1; }
+            if (ATT) ptx::mbar_wait(&bars[BAR_ACC_EMPTY + bo], 1u);
             else { ptx::mbar_wait(&bars[BAR_ACC_EMPTY + bo], empty_k[bo] & 1u); empty_k[bo] += 1; }
             ptx::tc_fence_after();
           }
           xpart((b ^ 1u) * 256);
         }
+        TC_TRACE(1, 3);
         if (ATT) {
-          // attention GEMM  E[128,64] = hy[128,H] * Wh_c[64,H]^T into columns [0,64) of the drained buffer
-          ptx::mbar_wait_cluster(&bars[BAR_HHAT], t & 1);
+          // A1: [Wh hy | Wa (hy, node-sum in row 15)] -> columns [0,128) of the drained buffer
+          ptx::mbar_wait(&bars[BAR_HHAT], t & 1);
           ptx::mbar_wait(&bars[BAR_ACC_EMPTY + b], 0u);
           ptx::tc_fence_after();
+          TC_TRACE(1, 4);
+          for (int s2 = 0; s2 < KH / 2; ++s2) {
+            const uint32_t st = wait_stage();
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int kb = s2 * 2 + j;
+              block_mma(dcol, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, st + (uint32_t)j * kA1Block, kA1Block / NP, 128, idesc128,
+                        (s2 | j) == 0);
+            }
+            release_stage();
+          }
+          ptx::umma_commit(&bars[BAR_ATT_FULL]);
+          if (C > 1) ptx::umma_commit_multicast(&bars[BAR_A1FREE], cta_mask); else ptx::umma_commit(&bars[BAR_A1FREE]);
+          TC_TRACE(1, 5);
+          // A2: Wq q (q sits in row 15 of every sequence) -> columns [128,192)
+          ptx::mbar_wait_cluster(&bars[BAR_Q], t & 1);
+          ptx::fence_proxy_async();
+          ptx::tc_fence_after();
+          TC_TRACE(1, 6);
           for (int s4 = 0; s4 < KH / 4; ++s4) {
             const uint32_t st = wait_stage();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int kb = s4 * 4 + j;
-              const uint32_t a0 = hbase + (uint32_t)kb * 2 * kRows * 16;
-              const uint32_t b0 = st + (uint32_t)j * (NP * 2 * 64 * 16);
-              const uint64_t ah = ptx::make_smem_desc(a0, kRows * 16, 128);
-              const uint64_t bh = ptx::make_smem_desc(b0, 64 * 16, 128);
-              ptx::umma_f16(tmem + dcol, ah, bh, idesc64, (s4 | j) ? 1u : 0u);
-              if (SPLIT) {
-                const uint64_t al = ptx::make_smem_desc(a0 + hpart, kRows * 16, 128);
-                const uint64_t bl = ptx::make_smem_desc(b0 + 2 * 64 * 16, 64 * 16, 128);
-                ptx::umma_f16(tmem + dcol, al, bh, idesc64, 1u);
-                ptx::umma_f16(tmem + dcol, ah, bl, idesc64, 1u);
-              }
+              block_mma(dcol + 128, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, st + (uint32_t)j * kA2Block, kA2Block / NP, 64, idesc64,
+                        (s4 | j) == 0);
             }
             release_stage();
           }
-          ptx::umma_commit(&bars[BAR_ATT_FULL]);
+          ptx::umma_commit(&bars[BAR_ATT2_FULL]);
+          TC_TRACE(1, 7);
         }
       }
     }
@@ -260,40 +302,52 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
     const int ew = et >> 5, lane = et & 31;
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
     const int chalf = ew >> 2;                    // which half of the columns this warp stages
-    const int g = lane & 3, hf = (lane >> 2) & 3, uh = lane >> 4;
-    const int m = 4 * hf + g;                     // node owned for the pointwise update
-    const int s = ew;                             // sequence within the tile
+    const int s = ew;                             // sequence of the tile this warp owns in the pointwise phase
     const int bseq = tile * kSeqTile + s;
-    const bool valid = bseq < p.B && m < kNodes;
-    const int row = 16 * s + m;
+    const bool valid = bseq < p.B;
     const int ycol = blockIdx.y * H + (int)c * 64;
+    // pointwise ownership follows the C fragment of mma.m16n8k16: lane (tq = lane/4, tr = lane%4) of warp s owns,
+    // in every 8-unit block, nodes {tq, tq+8} x units {2tr, 2tr+1}; node 15 (tq == 7, upper half) is the pad slot
+    const int tq = lane >> 2, tr = lane & 3;
+    const bool pad_hi = tq == 7;
 
-    // mixing rows held in registers: Pr[j][n] = P_g[4*hf + j][n]
-    float Pr[4][15];
+    float creg[2][16], hreg[2][16];               // [half of the 64 units][unit block ub (4) x element j (4)]
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int n = 0; n < 15; ++n) Pr[j][n] = d.P[(g * 16 + 4 * hf + j) * 16 + n];
+      for (int e = 0; e < 16; ++e) {
+        const int node = tq + ((e & 2) ? 8 : 0), unit = 32 * h + 8 * (e >> 2) + 2 * tr + (e & 1);
+        const bool ok = valid && node < kNodes;
+        const size_t gi = ((size_t)bseq * kNodes + node) * H + c * 64 + unit;
+        creg[h][e] = (ok && d.c0 != nullptr) ? d.c0[gi] : 0.f;
+        hreg[h][e] = (ok && d.h0 != nullptr) ? d.h0[gi] : 0.f;
+      }
 
-    float creg[32], hreg[32];                     // index q*4+i  <->  unit 8q + 4uh + i
+    // write the 16 values of half h (4 unit blocks x {node tq, tq+8} x 2 units) into the local operand image
+    auto store_half = [&](int h, const float (&v)[16]) {
 #pragma unroll
-    for (int qi = 0; qi < 32; ++qi) {
-      const int ul = 8 * (qi >> 2) + 4 * uh + (qi & 3);
-      const size_t gi = ((size_t)bseq * kNodes + m) * H + c * 64 + ul;
-      creg[qi] = (valid && d.c0 != nullptr) ? d.c0[gi] : 0.f;
-      hreg[qi] = (valid && d.h0 != nullptr) ? d.h0[gi] : 0.f;
-    }
-
-    // write this thread's 32 state values into the local operand image, then send this CTA's 64-unit
-    // block to every peer; `bar` completes in each CTA when all C blocks have landed
-    auto publish_h = [&](int bar, const float* extra, uint32_t extra_bytes) {
-      if (m < kNodes) {
+      for (int ub = 0; ub < 4; ++ub) {
+        const int k = (int)c * 64 + 32 * h + 8 * ub + 2 * tr;
 #pragma unroll
-        for (int qi = 0; qi < 32; ++qi) {
-          const int ul = 8 * (qi >> 2) + 4 * uh + (qi & 3);
-          split_store(hbuf, H, SPLIT, (int)c * 64 + ul, row, hreg[qi]);
+        for (int up = 0; up < 2; ++up) {
+          uint32_t hi, lo;
+          if (SPLIT) {
+            ptx::split_pair_f16(v[ub * 4 + 2 * up], v[ub * 4 + 2 * up + 1], hi, lo);
+          } else {
+            const __nv_bfloat162 bb = __floats2bfloat162_rn(v[ub * 4 + 2 * up], v[ub * 4 + 2 * up + 1]);
+            hi = *reinterpret_cast<const uint32_t*>(&bb);
+            lo = 0;
+          }
+          const uint32_t off = img_off(k, 16 * s + tq + 8 * up);
+          *reinterpret_cast<uint32_t*>(hbuf + off) = hi;
+          if (SPLIT) *reinterpret_cast<uint32_t*>(hbuf + (size_t)H * 256 + off) = lo;
         }
       }
+    };
+    // all 256 epilogue threads have written their part of the local operand image: make it visible to the
+    // async proxy, then send this CTA's 64-unit block to every peer; `bar` completes in each CTA when all C
+    // blocks have landed
+    auto publish_block = [&](int bar) {
       ptx::fence_proxy_async();
       ptx::named_bar_sync(1, kEpiThreads);
       if (et == 0) {
@@ -301,170 +355,248 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
           if (peer == c) continue;
           for (int part = 0; part < NP; ++part)
             ptx::bulk_s2remote(hbuf + (size_t)part * H * 256 + (size_t)c * kHBlock, kHBlock, &bars[bar], peer);
-          if (extra_bytes) ptx::bulk_s2remote(const_cast<float*>(extra), extra_bytes, &bars[bar], peer);
         }
-        ptx::mbar_arrive_expect_tx(&bars[bar], (uint32_t)(C - 1) * (NP * kHBlock + extra_bytes));
+        ptx::mbar_arrive_expect_tx(&bars[bar], (uint32_t)(C - 1) * NP * kHBlock);
       }
     };
-    auto publish_small = [&](int bar, float* buf, uint32_t bytes) {
-      ptx::fence_proxy_async();
-      ptx::named_bar_sync(1, kEpiThreads);
-      if (et == 0) {
-        for (uint32_t peer = 0; peer < (uint32_t)C; ++peer)
-          if (peer != c) ptx::bulk_s2remote(buf, bytes, &bars[bar], peer);
-        ptx::mbar_arrive_expect_tx(&bars[bar], (uint32_t)(C - 1) * bytes);
-      }
+    // y_t and, on the last step, the final hidden state
+    auto emit = [&](int t, int ta, int h, const float (&v)[16]) {
+      if (!valid) return;
+      const bool th = p.out_act == A3GC_ACT_TANH;
+#pragma unroll
+      for (int ub = 0; ub < 4; ++ub)
+#pragma unroll
+        for (int up = 0; up < 2; ++up) {
+          const int node = tq + 8 * up;
+          if (node >= kNodes) continue;
+          const float a0 = v[ub * 4 + 2 * up], a1 = v[ub * 4 + 2 * up + 1];
+          const int col = 32 * h + 8 * ub + 2 * tr;
+          float* yp = p.y + (size_t)bseq * p.syb + (size_t)ta * p.syt + (size_t)node * p.yld + ycol + col;
+          *reinterpret_cast<float2*>(yp) = th ? make_float2(fast_tanh(a0), fast_tanh(a1)) : make_float2(a0, a1);
+          if (t == T - 1 && d.hT != nullptr)
+            *reinterpret_cast<float2*>(d.hT + ((size_t)bseq * kNodes + node) * H + c * 64 + col) = make_float2(a0, a1);
+        }
     };
 
-    publish_h(BAR_H, nullptr, 0);                 // completion #0 of BAR_H: h_{-1} = h0
+    store_half(0, hreg[0]);                       // h_{-1} = h0  (completion #0 of BAR_H)
+    store_half(1, hreg[1]);
+    publish_block(BAR_H);
 
     for (int t = 0; t < T; ++t) {
       const uint32_t b = t & 1;
       const int ta = d.reverse ? T - 1 - t : t;
       // ---------------------------------------------------------------- gates -> c', hy
+      if (et == 0) TC_TRACE(0, 0);
       ptx::mbar_wait(&bars[BAR_ACC_FULL + b], (t >> 1) & 1);
+      // every CTA of the cluster has finished reading h'_{t-1}: the operand images may be overwritten
+      ptx::mbar_wait(&bars[BAR_HFREE], t & 1);
       ptx::tc_fence_after();
+      if (et == 0) TC_TRACE(0, 1);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        {   // phase a: TMEM -> staging[col][row]
-          float v[16];
-          ptx::tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + b * 256 + q * kSub + chalf * 16, v);
-          float* dst = staging + (chalf * 16) * kPitch + quarter * 32 + lane;
+      for (int h = 0; h < 2; ++h) {
+        float e1[16], e2[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dst[i * kPitch] = v[i];
+        for (int g = 0; g < 4; ++g) {
+          {   // phase a: 32 accumulator columns (gate g, units 32h..32h+31) TMEM -> staging[col][row]
+            float v[16];
+            ptx::tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + b * 256 + g * 64 + h * 32 + chalf * 16, v);
+            float* dst = staging + (chalf * 16) * kPitch + quarter * 32 + lane;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dst[i * kPitch] = v[i];
+          }
+          ptx::named_bar_sync(1, kEpiThreads);
+          // phase b: z[16 nodes x 8 units] = P_g (16x16) . U (16 nodes x 8 units) per unit block on the warp-level
+          // tensor path, fp16 hi/lo split (3 passes) so the mix stays fp32-accurate
+          uint32_t ah[4], al[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            ah[i] = Pfrag[((g * 2 + 0) * 4 + i) * 32 + lane];
+            al[i] = Pfrag[((g * 2 + 1) * 4 + i) * 32 + lane];
+          }
+#pragma unroll
+          for (int ub = 0; ub < 4; ++ub) {
+            const float* sp = staging + (8 * ub + tq) * kPitch + 16 * s + 2 * tr;
+            const float2 u0 = *reinterpret_cast<const float2*>(sp);        // nodes 2tr, 2tr+1 of unit column tq
+            const float2 u1 = *reinterpret_cast<const float2*>(sp + 8);    // nodes 2tr+8, 2tr+9
+            uint32_t bh0, bl0, bh1, bl1;
+            ptx::split_pair_f16(u0.x, u0.y, bh0, bl0);
+            ptx::split_pair_f16(u1.x, u1.y, bh1, bl1);
+            const float2 bias = *reinterpret_cast<const float2*>(biasg + g * 64 + 32 * h + 8 * ub + 2 * tr);
+            float z[4] = {bias.x, bias.y, bias.x, bias.y};
+            ptx::mma_16816_f16(z, ah, bh0, bh1);
+            ptx::mma_16816_f16(z, al, bh0, bh1);
+            ptx::mma_16816_f16(z, ah, bl0, bl1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int e = ub * 4 + j;
+              const bool ok = valid && !(pad_hi && j >= 2);
+              // c' = sig(zf) c + sig(zi) tanh(zc), hy = sig(zo) tanh(c'); the clamps only bound the exponentials
+              if (g == 0) {
+                e1[e] = 1.0f + __expf(-fminf(fmaxf(z[j], -28.f), 28.f));                    // 1 + e^-zi
+              } else if (g == 1) {
+                e2[e] = 1.0f + __expf(-fminf(fmaxf(z[j], -28.f), 28.f));                    // 1 + e^-zf
+              } else if (g == 2) {
+                const float eb = __expf(-2.0f * fminf(fmaxf(z[j], -14.f), 14.f));
+                const float dab = e1[e] * (1.0f + eb);
+                float cn = __fdividef(fmaf(creg[h][e], dab, (1.0f - eb) * e2[e]), e2[e] * dab);
+                cn = ok ? cn : 0.f;
+                creg[h][e] = cn;
+                const float ec = __expf(-2.0f * fminf(fmaxf(cn, -14.f), 14.f));
+                e1[e] = __fdividef(1.0f - ec, 1.0f + ec);                                   // tanh(c')
+              } else {
+                const float eo = __expf(-fminf(fmaxf(z[j], -28.f), 28.f));
+                hreg[h][e] = ok ? __fdividef(e1[e], 1.0f + eo) : 0.f;
+              }
+            }
+          }
+          if (g == 3) {
+            if (ATT) {
+              // node sum of hy (q_t = relu((sum_n hy_n) W_a^T), net_aagc.py:200) goes to row 15 of the sequence,
+              // which the attention GEMM reads as a 16th "node": the lanes owning the pad slot store it there
+#pragma unroll
+              for (int ub = 0; ub < 4; ++ub)
+#pragma unroll
+                for (int u2 = 0; u2 < 2; ++u2) {
+                  float sum = hreg[h][ub * 4 + u2] + hreg[h][ub * 4 + 2 + u2];
+                  sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+                  sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+                  sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+                  if (pad_hi) hreg[h][ub * 4 + 2 + u2] = sum;
+                }
+              store_half(h, hreg[h]);
+              if (pad_hi) {
+#pragma unroll
+                for (int ub = 0; ub < 4; ++ub) { hreg[h][ub * 4 + 2] = 0.f; hreg[h][ub * 4 + 3] = 0.f; }
+              }
+            } else {
+              store_half(h, hreg[h]);
+              emit(t, ta, h, hreg[h]);
+            }
+          }
+          if (h == 1 && g == 3) ptx::tc_fence_before();
+          ptx::named_bar_sync(1, kEpiThreads);
         }
-        ptx::named_bar_sync(1, kEpiThreads);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int ul8 = 4 * uh + i;                       // unit within the sub-chunk
-          const float4* sp = reinterpret_cast<const float4*>(staging + (4 * ul8 + g) * kPitch + 16 * s);
-          float un[16];
-#pragma unroll
-          for (int r4 = 0; r4 < 4; ++r4) {
-            const float4 v4 = sp[r4];
-            un[4 * r4] = v4.x; un[4 * r4 + 1] = v4.y; un[4 * r4 + 2] = v4.z; un[4 * r4 + 3] = v4.w;
-          }
-          float z[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float a = 0.f;
-#pragma unroll
-            for (int n = 0; n < 15; ++n) a = fmaf(Pr[j][n], un[n], a);
-            z[j] = a;
-          }
-          // 4x4 transpose over the lanes of one gate group: afterwards zz[gate] is for node m = 4hf + g
-          float zz[4];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const int jsend = (g - r) & 3;
-            const float send = jsend == 0 ? z[0] : (jsend == 1 ? z[1] : (jsend == 2 ? z[2] : z[3]));
-            const float got = __shfl_sync(0xffffffffu, send, (lane & ~3) | ((g + r) & 3));
-            const int gate = (g + r) & 3;
-            if (gate == 0) zz[0] = got; else if (gate == 1) zz[1] = got; else if (gate == 2) zz[2] = got; else zz[3] = got;
-          }
-          const float4 bias = reinterpret_cast<const float4*>(bias4s)[8 * q + ul8];
-          const float ig = sigmoidf_(zz[0] + bias.x);
-          const float fg = sigmoidf_(zz[1] + bias.y);
-          const float cg = tanhf_(zz[2] + bias.z);
-          const float og = sigmoidf_(zz[3] + bias.w);
-          const float cn = valid ? fmaf(fg, creg[q * 4 + i], ig * cg) : 0.f;
-          creg[q * 4 + i] = cn;
-          hreg[q * 4 + i] = valid ? og * tanhf_(cn) : 0.f;
-        }
-        if (q == 7) ptx::tc_fence_before();
-        ptx::named_bar_sync(1, kEpiThreads);
       }
       if (et == 0) ptx::mbar_arrive(&bars[BAR_ACC_EMPTY + b]);
-      // every CTA of the cluster has finished reading h'_{t-1}: the operand images may be overwritten
-      ptx::mbar_wait_cluster(&bars[BAR_HFREE], t & 1);
+      if (et == 0) TC_TRACE(0, 2);
 
-      if (ATT) {
-        // node sums of hy for the attention query (net_aagc.py:200)
-#pragma unroll
-        for (int qi = 0; qi < 32; ++qi) {
-          float v = hreg[qi];
-          v += __shfl_xor_sync(0xffffffffu, v, 1);
-          v += __shfl_xor_sync(0xffffffffu, v, 2);
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          v += __shfl_xor_sync(0xffffffffu, v, 8);
-          if ((lane & 15) == 0) sbuf[c * 512 + s * 64 + 8 * (qi >> 2) + 4 * uh + (qi & 3)] = v;
-        }
-        publish_h(BAR_HHAT, sbuf + c * 512, 2048);
-        ptx::mbar_wait_cluster(&bars[BAR_HHAT], t & 1);
-        // q = relu(sum_n(hy) W_a^T)   this CTA's 64 units, two per thread
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int ul = lane + 32 * r;
-          const float* wcol = d.wa_t + c * 64 + ul;
-          float a0 = 0.f, a1 = 0.f;
-          for (int k = 0; k < H; k += 2) {
-            a0 = fmaf(sbuf[(k >> 6) * 512 + s * 64 + (k & 63)], __ldg(wcol + (size_t)k * H), a0);
-            a1 = fmaf(sbuf[((k + 1) >> 6) * 512 + s * 64 + ((k + 1) & 63)], __ldg(wcol + (size_t)(k + 1) * H), a1);
-          }
-          qbuf[c * 512 + s * 64 + ul] = fmaxf(a0 + a1, 0.f);
-        }
-        publish_small(BAR_Q, qbuf + c * 512, 2048);
-        ptx::mbar_wait_cluster(&bars[BAR_Q], t & 1);
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int ul = lane + 32 * r;
-          const float* wcol = d.wq_t + c * 64 + ul;
-          float a0 = bss[ul], a1 = 0.f;
-          for (int k = 0; k < H; k += 2) {
-            a0 = fmaf(qbuf[(k >> 6) * 512 + s * 64 + (k & 63)], __ldg(wcol + (size_t)k * H), a0);
-            a1 = fmaf(qbuf[((k + 1) >> 6) * 512 + s * 64 + ((k + 1) & 63)], __ldg(wcol + (size_t)(k + 1) * H), a1);
-          }
-          wqbuf[s * 64 + ul] = a0 + a1;
-        }
-        ptx::named_bar_sync(1, kEpiThreads);
-        // e = tanh(Wh hy + Wq q + bs),  partial a = e . u over this CTA's 64 units (lane = row)
-        ptx::mbar_wait(&bars[BAR_ATT_FULL], t & 1);
-        ptx::tc_fence_after();
-        {
-          float v[32];
-          ptx::tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + b * 256 + chalf * 32, v);
-          const int r_ = quarter * 32 + lane;
-          const float* wq = wqbuf + (r_ >> 4) * 64 + chalf * 32;
-          float part = 0.f;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) part = fmaf(tanhf_(v[i] + wq[i]), us[chalf * 32 + i], part);
-          ahalf[chalf * 128 + r_] = part;
-        }
-        ptx::tc_fence_before();
-        ptx::named_bar_sync(1, kEpiThreads);
-        if (et == 0) ptx::mbar_arrive(&bars[BAR_ACC_EMPTY + b]);
-        if (et < 128) apart[c * 128 + et] = ahalf[et] + ahalf[128 + et];
-        publish_small(BAR_A, apart + c * 128, 512);
-        ptx::mbar_wait_cluster(&bars[BAR_A], t & 1);
-        float a = 0.f;
-        if (m < kNodes) {
-          a = bus[m];
-          for (int src = 0; src < C; ++src) a += apart[src * 128 + row];
-          a = 1.0f + sigmoidf_(a);                          // hy + hy * a_t  (net_aagc.py:212-213)
-        }
-#pragma unroll
-        for (int qi = 0; qi < 32; ++qi) hreg[qi] *= a;
+      if (!ATT) {
+        publish_block(BAR_H);
+        if (et == 0) TC_TRACE(0, 11);
+        continue;
       }
-      // ---------------------------------------------------------------- outputs and next-step operand
-      if (valid) {
-        float* yp = p.y + (size_t)bseq * p.syb + (size_t)ta * p.syt + (size_t)m * p.yld + ycol;
+      publish_block(BAR_HHAT);
+      if (et == 0) TC_TRACE(0, 4);
+      // ---- q = relu(Wa . sum_n hy): rows 15 of the A1 accumulator, columns [64,128)
+      ptx::mbar_wait(&bars[BAR_ATT_FULL], t & 1);
+      // rows 15 are about to be overwritten with q in EVERY CTA: all A1 GEMMs of the cluster must have read them
+      ptx::mbar_wait(&bars[BAR_A1FREE], t & 1);
+      ptx::tc_fence_after();
+      if (et == 0) TC_TRACE(0, 5);
 #pragma unroll
-        for (int qi = 0; qi < 32; ++qi)
-          yp[8 * (qi >> 2) + 4 * uh + (qi & 3)] = apply_act(hreg[qi], p.out_act);
+      for (int h16 = 0; h16 < 2; ++h16) {
+        float v[16];
+        ptx::tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + b * 256 + 64 + chalf * 32 + h16 * 16, v);
+        if ((lane & 15) == 15) {
+          const int qrow = quarter * 32 + lane;             // = 16*seq + 15
+#pragma unroll
+          for (int g8 = 0; g8 < 2; ++g8) {                  // 8 consecutive units = one 16-byte K chunk of the row
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint16_t h0, l0, h1, l1;
+              split_bits<SPLIT>(fmaxf(v[g8 * 8 + 2 * j], 0.f), h0, l0);
+              split_bits<SPLIT>(fmaxf(v[g8 * 8 + 2 * j + 1], 0.f), h1, l1);
+              hw[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+              lw[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            }
+            const uint4 hq = make_uint4(hw[0], hw[1], hw[2], hw[3]), lq = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            const uint32_t off = img_off((int)c * 64 + chalf * 32 + h16 * 16 + g8 * 8, qrow);
+            *reinterpret_cast<uint4*>(hbuf + off) = hq;
+            if (SPLIT) *reinterpret_cast<uint4*>(hbuf + (size_t)H * 256 + off) = lq;
+#pragma unroll 1
+            for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) {
+              if (peer == c) continue;
+              ptx::st_remote_v4(hbuf + off, peer, hq);
+              if (SPLIT) ptx::st_remote_v4(hbuf + (size_t)H * 256 + off, peer, lq);
+            }
+          }
+        }
       }
-      publish_h(BAR_H, nullptr, 0);
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      ptx::named_bar_sync(1, kEpiThreads);
+      if (et == 0) {
+        for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) ptx::mbar_arrive_remote(&bars[BAR_Q], peer);
+        TC_TRACE(0, 6);
+      }
+      // ---- e = tanh(Wh hy + Wq q + bs),  partial a = e . u over this CTA's 64 units (lane = row)
+      ptx::mbar_wait(&bars[BAR_ATT2_FULL], t & 1);
+      ptx::tc_fence_after();
+      if (et == 0) TC_TRACE(0, 7);
+      {
+        float part = 0.f;
+#pragma unroll
+        for (int h16 = 0; h16 < 2; ++h16) {
+          float vh[16], vq[16];
+          const int c0 = chalf * 32 + h16 * 16;
+          ptx::tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + b * 256 + c0, vh);
+          ptx::tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + b * 256 + 128 + c0, vq);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float wq = __shfl_sync(0xffffffffu, vq[i], (lane & 16) | 15);
+            part = fmaf(fast_tanh(vh[i] + wq + bss[c0 + i]), us[c0 + i], part);
+          }
+        }
+        ahalf[chalf * 128 + quarter * 32 + lane] = part;
+      }
+      ptx::tc_fence_before();
+      ptx::named_bar_sync(1, kEpiThreads);
+      if (et == 0) ptx::mbar_arrive(&bars[BAR_ACC_EMPTY + b]);
+      if (et < 128) apart[c * 128 + et] = ahalf[et] + ahalf[128 + et];
+      ptx::fence_proxy_async();
+      ptx::named_bar_sync(1, kEpiThreads);
+      if (et == 0) {
+        for (uint32_t peer = 0; peer < (uint32_t)C; ++peer)
+          if (peer != c) ptx::bulk_s2remote(apart + c * 128, 512, &bars[BAR_A], peer);
+        ptx::mbar_arrive_expect_tx(&bars[BAR_A], (uint32_t)(C - 1) * 512);
+      }
+      if (et == 0) TC_TRACE(0, 8);
+      ptx::mbar_wait(&bars[BAR_A], t & 1);
+      if (et == 0) TC_TRACE(0, 9);
+      // a[row] = 1 + sigmoid(sum over chunks + bu[node])   (hy + hy * a_t, net_aagc.py:212-213); one thread per row
+      if (et < 128) {
+        float a = bus[et & 15];
+        for (int src = 0; src < C; ++src) a += apart[src * 128 + et];
+        ahalf[et] = 1.0f + fast_sigmoid(a);
+      }
+      ptx::named_bar_sync(1, kEpiThreads);
+      // ---- h' = hy (1 + a): next step's operand and y_t = act(h')
+      {
+        const float alo = ahalf[16 * s + tq], ahi = pad_hi ? 0.f : ahalf[16 * s + tq + 8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) hreg[h][e] *= (e & 2) ? ahi : alo;
+          store_half(h, hreg[h]);
+          emit(t, ta, h, hreg[h]);
+        }
+      }
+      if (et == 0) TC_TRACE(0, 10);
+      publish_block(BAR_H);
+      if (et == 0) TC_TRACE(0, 11);
     }
-    if (valid) {
+    if (valid && d.cT != nullptr) {
 #pragma unroll
-      for (int qi = 0; qi < 32; ++qi) {
-        const int ul = 8 * (qi >> 2) + 4 * uh + (qi & 3);
-        const size_t gi = ((size_t)bseq * kNodes + m) * H + c * 64 + ul;
-        if (d.hT != nullptr) d.hT[gi] = hreg[qi];
-        if (d.cT != nullptr) d.cT[gi] = creg[qi];
-      }
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int node = tq + ((e & 2) ? 8 : 0), unit = 32 * h + 8 * (e >> 2) + 2 * tr + (e & 1);
+          if (node < kNodes) d.cT[((size_t)bseq * kNodes + node) * H + c * 64 + unit] = creg[h][e];
+        }
     }
     // the last publish must have landed everywhere before any CTA may exit
-    ptx::mbar_wait_cluster(&bars[BAR_H], T & 1);
+    ptx::mbar_wait(&bars[BAR_H], T & 1);
   }
 
   // ------------------------------------------------------------------ teardown
@@ -485,8 +617,8 @@ __device__ __forceinline__ uint16_t part_bits(float v, int part, bool split) {
 }
 
 struct TcPacked {
-  uint16_t* wg_img; uint16_t* wh_img;
-  float* P; float* bias4; float* wa_t; float* wq_t; float* bs; float* u; float* bu;
+  uint16_t* wg_img; uint16_t* a1_img; uint16_t* a2_img;
+  float* P; float* bias4; float* bs; float* u; float* bu;
 };
 
 __global__ void tc_pack_weights_kernel(a3gc_cell_params cp, TcPacked out, int F, int H, int variant, int split) {
@@ -501,7 +633,7 @@ __global__ void tc_pack_weights_kernel(a3gc_cell_params cp, TcPacked out, int F,
     int64_t rest = i >> 12;
     const int part = (int)(rest % NP); rest /= NP;
     const int kb = (int)(rest % KB); const int c = (int)(rest / KB);
-    const int gate = r & 3, j = c * 64 + (r >> 2), k = kb * 16 + kc * 8 + e;
+    const int gate = r >> 6, j = c * 64 + (r & 63), k = kb * 16 + kc * 8 + e;
     out.wg_img[i] = part_bits(cp.gcn_kernel[gate][(size_t)j * K + k], part, split);
   }
   for (int64_t i = tid; i < (int64_t)H * 4; i += stride) out.bias4[i] = cp.gcn_bias[i & 3][i >> 2];
@@ -513,19 +645,24 @@ __global__ void tc_pack_weights_kernel(a3gc_cell_params cp, TcPacked out, int F,
     out.P[i] = v;
   }
   if (cp.attention_w != nullptr) {
-    // attention_wh: index = ((((c*KH + kb)*NP + part)*2 + kc)*64 + ul)*8 + e
-    const int64_t n_wh = (int64_t)C * KH * NP * 2 * 64 * 8;
-    for (int64_t i = tid; i < n_wh; i += stride) {
+    // A1 image: index = ((((c*KH + kb)*NP + part)*2 + kc)*128 + r)*8 + e ; r < 64: attention_wh row, else attention_w row
+    const int64_t n_a1 = (int64_t)C * KH * NP * 2 * 128 * 8;
+    for (int64_t i = tid; i < n_a1; i += stride) {
+      const int e = (int)(i & 7), r = (int)((i >> 3) & 127), kc = (int)((i >> 10) & 1);
+      int64_t rest = i >> 11;
+      const int part = (int)(rest % NP); rest /= NP;
+      const int kb = (int)(rest % KH); const int c = (int)(rest / KH);
+      const float* w = r < 64 ? cp.attention_wh : cp.attention_w;
+      out.a1_img[i] = part_bits(w[(size_t)(c * 64 + (r & 63)) * H + kb * 16 + kc * 8 + e], part, split);
+    }
+    // A2 image (attention_wq): index = ((((c*KH + kb)*NP + part)*2 + kc)*64 + ul)*8 + e
+    const int64_t n_a2 = (int64_t)C * KH * NP * 2 * 64 * 8;
+    for (int64_t i = tid; i < n_a2; i += stride) {
       const int e = (int)(i & 7), ul = (int)((i >> 3) & 63), kc = (int)((i >> 9) & 1);
       int64_t rest = i >> 10;
       const int part = (int)(rest % NP); rest /= NP;
       const int kb = (int)(rest % KH); const int c = (int)(rest / KH);
-      out.wh_img[i] = part_bits(cp.attention_wh[(size_t)(c * 64 + ul) * H + kb * 16 + kc * 8 + e], part, split);
-    }
-    for (int64_t i = tid; i < (int64_t)H * H; i += stride) {
-      const int k = (int)(i / H), j = (int)(i % H);
-      out.wa_t[i] = cp.attention_w[(size_t)j * H + k];
-      out.wq_t[i] = cp.attention_wq[(size_t)j * H + k];
+      out.a2_img[i] = part_bits(cp.attention_wq[(size_t)(c * 64 + ul) * H + kb * 16 + kc * 8 + e], part, split);
     }
     for (int64_t i = tid; i < H; i += stride) { out.bs[i] = cp.attention_bs[i]; out.u[i] = cp.attention_u[i]; }
     for (int64_t i = tid; i < 16; i += stride) out.bu[i] = i < kNodes ? cp.attention_bu[i] : 0.f;
@@ -553,20 +690,20 @@ __global__ void tc_pack_x_kernel(const float* __restrict__ x, int64_t sxb, int64
 size_t tc_dir_bytes(int F, int H, int NP) {
   size_t b = 0;
   b += align_up((size_t)(F + H) * 4 * H * NP * 2, 256);     // wg_img
-  b += align_up((size_t)H * H * NP * 2, 256);                // wh_img
-  b += align_up((size_t)(1024 + 4 * H + 2 * (size_t)H * H + 2 * H + 16) * 4, 256);
+  b += align_up((size_t)2 * H * H * NP * 2, 256);            // a1_img
+  b += align_up((size_t)H * H * NP * 2, 256);                // a2_img
+  b += align_up((size_t)(1024 + 4 * H + 2 * H + 16) * 4, 256);
   return b;
 }
 
 TcPacked tc_carve(char* base, int F, int H, int NP) {
   TcPacked p;
   p.wg_img = reinterpret_cast<uint16_t*>(base); base += align_up((size_t)(F + H) * 4 * H * NP * 2, 256);
-  p.wh_img = reinterpret_cast<uint16_t*>(base); base += align_up((size_t)H * H * NP * 2, 256);
+  p.a1_img = reinterpret_cast<uint16_t*>(base); base += align_up((size_t)2 * H * H * NP * 2, 256);
+  p.a2_img = reinterpret_cast<uint16_t*>(base); base += align_up((size_t)H * H * NP * 2, 256);
   float* f = reinterpret_cast<float*>(base);
   p.P = f; f += 1024;
   p.bias4 = f; f += 4 * H;
-  p.wa_t = f; f += (size_t)H * H;
-  p.wq_t = f; f += (size_t)H * H;
   p.bs = f; f += H;
   p.u = f; f += H;
   p.bu = f;
@@ -613,7 +750,7 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
     tc_pack_weights_kernel<<<148, 256, 0, stream>>>(a.cells[d], pk, F, H, a.variant, split ? 1 : 0);
     A3GC_LAUNCH_CHECK("tc_pack_weights_kernel");
     TcDir& td = p.d[d];
-    td.wg_img = pk.wg_img; td.wh_img = pk.wh_img; td.P = pk.P; td.bias4 = pk.bias4; td.wa_t = pk.wa_t; td.wq_t = pk.wq_t;
+    td.wg_img = pk.wg_img; td.a1_img = pk.a1_img; td.a2_img = pk.a2_img; td.P = pk.P; td.bias4 = pk.bias4;
     td.bs = pk.bs; td.u = pk.u; td.bu = pk.bu;
     td.h0 = a.h0[d]; td.c0 = a.c0[d]; td.hT = a.hT[d]; td.cT = a.cT[d]; td.reverse = a.reverse[d];
   }
@@ -628,12 +765,13 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
   p.x_img = x_img;
   p.y = a.y; p.syb = a.y_stride_b; p.syt = a.y_stride_t; p.yld = a.y_ld;
   p.B = (int)a.batch; p.T = (int)a.steps; p.F = F; p.H = H; p.out_act = a.out_act; p.C = C;
+  p.trace = getenv("A3GC_TC_TRACE") != nullptr ? 1 : 0;
 
   int dev = 0, smem_max = 0;
   A3GC_CUDA_TRY(cudaGetDevice(&dev));
   A3GC_CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const size_t stage_bytes = (size_t)NP * (2 * 256 * 16 + 2 * 128 * 16);
-  const size_t fixed = (size_t)NP * H * 256 + tc_fixed_smem_bytes(C) + 1024;
+  const size_t fixed = (size_t)NP * H * 256 + tc_fixed_smem_bytes(C);
   int S = kMaxStages;
   while (S > 1 && fixed + (size_t)S * stage_bytes > (size_t)smem_max) --S;
   if (fixed + (size_t)S * stage_bytes > (size_t)smem_max || S < 2) {
@@ -666,3 +804,11 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
 }
 
 }  // namespace a3gc
+
+// debug: copy the per-phase clock64 timeline of CTA (0,0) of the last traced launch (2*16*16 uint64)
+extern "C" int a3gc_debug_read_tc_trace(unsigned long long* host_out) {
+  using namespace a3gc;
+  if (!host_out) return A3GC_ERR_INVALID_ARG;
+  A3GC_CUDA_TRY(cudaMemcpyFromSymbol(host_out, g_tc_trace, sizeof(unsigned long long) * 2 * 16 * 16));
+  return A3GC_OK;
+}

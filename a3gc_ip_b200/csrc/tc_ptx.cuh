@@ -95,6 +95,36 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// 16-bit store into the shared memory of CTA `cta` of the cluster (same offset as `local_ptr`)
+__device__ __forceinline__ void st_remote_u16(void* local_ptr, uint32_t cta, uint16_t v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_ptr)), "r"(cta));
+  asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(remote), "h"(v) : "memory");
+}
+
+// 16-byte store into the shared memory of CTA `cta` of the cluster
+__device__ __forceinline__ void st_remote_v4(void* local_ptr, uint32_t cta, uint4 v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_ptr)), "r"(cta));
+  asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---------------------------------------------------------------- warp-level MMA (legacy tensor path, used for the 16x16 adjacency mix)
+// D[16x8] += A[16x16] * B[16x8], fp16 operands, fp32 accumulate (fragment layouts of mma.m16n8k16)
+__device__ __forceinline__ void mma_16816_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (x, y) -> packed fp16 hi pair and fp16 lo (residual) pair; low 16 bits hold x
+__device__ __forceinline__ void split_pair_f16(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x, y);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // ---------------------------------------------------------------- tensor memory
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {   // one full warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");

@@ -58,7 +58,7 @@ tc_selftest_kernel(const uint16_t* __restrict__ a_img, const uint16_t* __restric
     float v[32];
     ptx::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) d[(size_t)row * N + c0 + i] = v[i];
+    for (int i = 0; i < 32; ++i) if (c0 + i < N) d[(size_t)row * N + c0 + i] = v[i];
   }
   ptx::tc_fence_before();
   __syncthreads();

@@ -201,6 +201,10 @@ int a3gc_profile_get(int index, char* label, int label_bytes, float* ms, double*
  */
 int a3gc_tc_selftest(const void* a_img, const void* b_img, float* d, int k, int n, int flags, void* stream);
 
+/* Debug: per-phase clock64 timeline of CTA (0,0) of the last tensor-core layer launch made with the
+ * environment variable A3GC_TC_TRACE set; host_out receives [2 roles][16 steps][16 slots] uint64. */
+int a3gc_debug_read_tc_trace(unsigned long long* host_out);
+
 /* Number of kernels this library has launched on the calling thread since the last reset. */
 int64_t a3gc_launch_count(void);
 void a3gc_reset_launch_count(void);
