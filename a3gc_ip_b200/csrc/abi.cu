@@ -2,6 +2,7 @@
 // engine dispatch and the orchestration of one whole net (linear_in -> relu -> rnn1 -> rnn2 -> linear_out).
 #include "common.cuh"
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 #include <string>
 
@@ -97,9 +98,10 @@ int run_layer(int eng, const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream
 }
 
 struct NetPlan {
-  size_t a0, a1, a2, st, lws, total;   // byte offsets
+  size_t a0, a1, a2, st, lws, img1, img2, total;   // byte offsets
   size_t lws_bytes;
   int eng1, eng2;
+  bool use_img1, use_img2;   // linear_in -> rnn1 and rnn1 -> rnn2 hand-off as operand images (tensor-core engine)
 };
 
 int plan_net(int variant, int64_t B, int64_t T, int f0, int H, int precision, int engine, NetPlan* p) {
@@ -108,10 +110,16 @@ int plan_net(int variant, int64_t B, int64_t T, int f0, int H, int precision, in
   p->eng2 = pick_engine(engine, variant, 2 * H, H, precision);
   if (p->eng2 < 0) return p->eng2;
   const size_t frames = (size_t)B * T;
+  const int img_mode = getenv("A3GC_TC_IMG") ? atoi(getenv("A3GC_TC_IMG")) : 3;   // debug: bit0 = fused linear_in image, bit1 = rnn1->rnn2 image
+  p->use_img1 = p->eng1 == A3GC_ENGINE_TC && (img_mode & 1);
+  p->use_img2 = p->eng1 == A3GC_ENGINE_TC && p->eng2 == A3GC_ENGINE_TC && (img_mode & 2);
   size_t off = 0;
-  p->a0 = off; off += align_up(frames * kNodes * H * sizeof(float), 256);
-  p->a1 = off; off += align_up(frames * kNodes * 2 * H * sizeof(float), 256);
+  // fp32 activations are only materialised where a consumer needs them; tensor-core layers exchange operand images
+  p->a0 = off; off += p->use_img1 ? 0 : align_up(frames * kNodes * H * sizeof(float), 256);
+  p->a1 = off; off += p->use_img2 ? 0 : align_up(frames * kNodes * 2 * H * sizeof(float), 256);
   p->a2 = off; off += align_up(frames * kNodes * 2 * H * sizeof(float), 256);
+  p->img1 = off; off += p->use_img1 ? tc_image_bytes(B, T, H, precision) : 0;
+  p->img2 = off; off += p->use_img2 ? tc_image_bytes(B, T, 2 * H, precision) : 0;
   p->st = off; off += align_up((size_t)4 * B * kNodes * H * sizeof(float), 256);   // rnn1 final (h,c) x 2 directions
   const size_t l1 = layer_ws(p->eng1, variant, B, T, H, H, 2, precision);
   const size_t l2 = layer_ws(p->eng2, variant, B, T, 2 * H, H, 2, precision);
@@ -259,8 +267,12 @@ int a3gc_net_forward(int variant, const a3gc_net_params* net, const float* x,
   const int64_t frames = batch * steps;
   const size_t state_elems = (size_t)batch * kNodes * H;
 
-  // linear_in + relu  (net_aagc.py:640-641)
-  rc = simt_gc_forward(&net->linear_in, x, a0, frames, f0, H, A3GC_ACT_RELU, s);
+  const bool tc1 = p.use_img1;
+  uint16_t* img1 = p.use_img1 ? reinterpret_cast<uint16_t*>(ws + p.img1) : nullptr;
+  uint16_t* img2 = p.use_img2 ? reinterpret_cast<uint16_t*>(ws + p.img2) : nullptr;
+  // linear_in + relu  (net_aagc.py:640-641); on the tensor-core path written straight into rnn1's operand image
+  if (tc1) rc = gc_forward_image(&net->linear_in, x, img1, batch, steps, f0, H, A3GC_ACT_RELU, precision == A3GC_PREC_FP32 ? 1 : 0, s);
+  else rc = simt_gc_forward(&net->linear_in, x, a0, frames, f0, H, A3GC_ACT_RELU, s);
   if (rc) return rc;
 
   const int rev[2] = {0, 1};
@@ -278,8 +290,10 @@ int a3gc_net_forward(int variant, const a3gc_net_params* net, const float* x,
     a.hT[d] = h1[d];
     a.cT[d] = gru ? nullptr : c1[d];
   }
-  a.x = a0; a.x_stride_b = (int64_t)steps * kNodes * H; a.x_stride_t = (int64_t)kNodes * H;
-  a.y = a1; a.y_stride_b = (int64_t)steps * kNodes * 2 * H; a.y_stride_t = (int64_t)kNodes * 2 * H; a.y_ld = 2 * H;
+  a.x = tc1 ? nullptr : a0; a.x_stride_b = (int64_t)steps * kNodes * H; a.x_stride_t = (int64_t)kNodes * H;
+  a.x_img = img1;
+  a.y = img2 ? nullptr : a1; a.y_stride_b = (int64_t)steps * kNodes * 2 * H; a.y_stride_t = (int64_t)kNodes * 2 * H; a.y_ld = 2 * H;
+  a.y_img = img2; a.y_img_f = 2 * H;
   a.batch = batch; a.steps = steps; a.f_in = H; a.hidden = H;
   a.out_act = A3GC_ACT_TANH;   // activation_fn='tanh' for both recurrent layers (net_aagc.py:629-630)
   a.precision = precision;
@@ -294,8 +308,9 @@ int a3gc_net_forward(int variant, const a3gc_net_params* net, const float* x,
     a.hT[d] = hT ? hT[d] : nullptr;
     a.cT[d] = (cT && !gru) ? cT[d] : nullptr;
   }
-  a.x = a1; a.x_stride_b = (int64_t)steps * kNodes * 2 * H; a.x_stride_t = (int64_t)kNodes * 2 * H;
-  a.y = a2;
+  a.x = img2 ? nullptr : a1; a.x_stride_b = (int64_t)steps * kNodes * 2 * H; a.x_stride_t = (int64_t)kNodes * 2 * H;
+  a.x_img = img2;
+  a.y = a2; a.y_img = nullptr; a.y_img_f = 0;
   a.f_in = 2 * H;
   rc = run_layer(p.eng2, a, ws + p.lws, p.lws_bytes, s);
   if (rc) return rc;

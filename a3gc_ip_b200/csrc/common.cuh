@@ -67,12 +67,21 @@ struct LayerArgs {
   int64_t batch, steps;
   int f_in, hidden, out_act;
   int precision;
+  // tensor-core engine only: operand images handed between kernels instead of fp32 activations
+  const uint16_t* x_img;   // if non-null: the layer input already packed as [tiles][T][F/16][NP][2][128][8] (x may be null)
+  uint16_t* y_img;         // if non-null: also write act(h') into the next layer's input image ...
+  int y_img_f;             // ... which has this many features (direction d writes columns d*H .. d*H+H-1)
 };
 
 size_t simt_layer_workspace_bytes(int variant, int f_in, int hidden, int num_dirs);
 int simt_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t stream);
 int simt_gc_forward(const a3gc_gc_params* p, const float* x, float* y, int64_t frames, int f_in,
                     int f_out, int act, cudaStream_t stream);
+// gc_kernels.cu: HBM-bound implementations of the AAGC graph convolution for the shapes the nets use
+int gc_forward_fast(const a3gc_gc_params* p, const float* x, float* y, int64_t frames, int f_in, int f_out, int act,
+                    cudaStream_t stream, int* handled);
+int gc_forward_image(const a3gc_gc_params* p, const float* x, uint16_t* img, int64_t batch, int64_t steps, int f_in,
+                     int f_out, int act, int split, cudaStream_t stream);
 int simt_prepare_input(const float* acc, const float* ori, const float* acc_mean, const float* acc_std,
                        const float* ori_mean, const float* ori_std, float* x, int64_t frames, int ld_x,
                        cudaStream_t stream);
@@ -81,6 +90,7 @@ int simt_concat_stage_input(const float* x, const float* pos, float* dst, int64_
 // ---- tensor-core (tcgen05) engine: tc_kernels.cu ----------------------------------------
 bool tc_layer_supported(int variant, int f_in, int hidden, int precision);
 size_t tc_layer_workspace_bytes(int variant, int64_t batch, int64_t steps, int f_in, int hidden, int num_dirs, int precision);
+size_t tc_image_bytes(int64_t batch, int64_t steps, int features, int precision);
 int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 }  // namespace a3gc

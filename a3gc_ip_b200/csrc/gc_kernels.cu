@@ -1,0 +1,268 @@
+// AAGC graph convolution y = act((adj @ x) @ W^T + b)  (net_aagc.py:61-66), the non-recurrent layers
+// around the recurrent ones (linear_in: 12/15 -> H, linear_out: 2H -> 3/9).  Both are HBM-bound:
+//   gc_in   small f_in (<= 32): one CTA per 8 frames; writes either fp32 [frames,15,O] (coalesced float4)
+//           or directly the UMMA operand image of the first recurrent layer (fp16 hi/lo or bf16), so the
+//           activation never makes an fp32 round trip through HBM on the tensor-core path;
+//   gc_out  large f_in, f_out <= 16: 8 rows per warp, K split over the lanes with 128-bit coalesced loads,
+//           W read from shared memory once per 8 rows, shuffle reduction, then the 15x15 mix per frame.
+#include "common.cuh"
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+namespace a3gc {
+namespace {
+
+constexpr int kGcThreads = 256;
+
+__device__ __forceinline__ void split16(float v, bool split, uint16_t& hi, uint16_t& lo) {
+  if (split) {
+    const __half h = __float2half_rn(v);
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+  } else {
+    hi = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    lo = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// gc_in: f_in <= 32.  Block = 8 frames.  IMG = false: frames f0..f0+7 -> y fp32.
+// IMG = true: the 8 frames are (tile, t): sequences 8*tile..8*tile+7 at time t -> operand image
+// [tiles][T][O/16][NP][2][128][8] (row = 16*seq + node, row 15 of every sequence zero).
+// ------------------------------------------------------------------------------------------
+template <bool IMG>
+__global__ void __launch_bounds__(kGcThreads)
+gc_in_kernel(a3gc_gc_params p, const float* __restrict__ x, float* __restrict__ y, uint16_t* __restrict__ img,
+             int64_t frames, int B, int T, int K, int O, int act, int split) {
+  extern __shared__ __align__(16) float smem[];
+  float* adj = smem;                 // [16][16]
+  float* wt = adj + 256;             // [K][O]   W transposed
+  float* bias = wt + (size_t)K * O;  // [O]
+  float* xs = bias + O;              // [8][15][K]
+  float* xm = xs + 8 * kNodes * K;   // [128][K]  (adj @ x), row 15 of each frame zero
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    const int m = i >> 4, n = i & 15;
+    adj[i] = (m < kNodes && n < kNodes) ? p.adj[m * kNodes + n] : 0.f;
+  }
+  for (int i = threadIdx.x; i < K * O; i += blockDim.x) { const int k = i / O, o = i % O; wt[i] = p.gcn_kernel[(size_t)o * K + k]; }
+  for (int i = threadIdx.x; i < O; i += blockDim.x) bias[i] = p.gcn_bias[i];
+  const int per_frame = kNodes * K;
+  const int NP = split ? 2 : 1;
+  const int64_t groups = IMG ? (int64_t)((B + 7) / 8) * T : (frames + 7) / 8;
+  for (int64_t grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    __syncthreads();
+    // ---- load the 8 frames of this group
+    int64_t tile = 0; int t = 0;
+    if (IMG) { tile = grp / T; t = (int)(grp % T); }
+    for (int i = threadIdx.x; i < 8 * per_frame; i += blockDim.x) {
+      const int fr = i / per_frame, r = i % per_frame;
+      float v = 0.f;
+      if (IMG) {
+        const int64_t b = tile * 8 + fr;
+        if (b < B) v = __ldg(x + ((size_t)b * T + t) * per_frame + r);
+      } else {
+        const int64_t f = grp * 8 + fr;
+        if (f < frames) v = __ldg(x + (size_t)f * per_frame + r);
+      }
+      xs[i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 128 * K; i += blockDim.x) {
+      const int k = i % K, row = i / K, fr = row >> 4, m = row & 15;
+      float s = 0.f;
+      if (m < kNodes) {
+        const float* col = xs + (size_t)fr * per_frame + k;
+#pragma unroll
+        for (int n = 0; n < kNodes; ++n) s = fmaf(adj[m * 16 + n], col[n * K], s);
+      }
+      xm[i] = s;
+    }
+    __syncthreads();
+    if (IMG) {
+      // item = (8 consecutive outputs, row): one 16-byte chunk of the image per part
+      const int chunks = O / 8;
+      uint8_t* base = reinterpret_cast<uint8_t*>(img) + ((size_t)tile * T + t) * (size_t)O * 128 * NP * 2;
+      for (int i = threadIdx.x; i < chunks * 128; i += blockDim.x) {
+        const int row = i & 127, ch = i >> 7;
+        const float* a = xm + (size_t)row * K;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = bias[ch * 8 + j];
+        for (int k = 0; k < K; ++k) {
+          const float av = a[k];
+          const float4 w0 = *reinterpret_cast<const float4*>(wt + (size_t)k * O + ch * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(wt + (size_t)k * O + ch * 8 + 4);
+          acc[0] = fmaf(av, w0.x, acc[0]); acc[1] = fmaf(av, w0.y, acc[1]); acc[2] = fmaf(av, w0.z, acc[2]); acc[3] = fmaf(av, w0.w, acc[3]);
+          acc[4] = fmaf(av, w1.x, acc[4]); acc[5] = fmaf(av, w1.y, acc[5]); acc[6] = fmaf(av, w1.z, acc[6]); acc[7] = fmaf(av, w1.w, acc[7]);
+        }
+        uint16_t hi[8], lo[8];
+        const bool live = (row & 15) < kNodes;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split16(live ? apply_act(acc[j], act) : 0.f, split != 0, hi[j], lo[j]);
+        // image offset: [kb = ch/2][part][kc = ch%2][row][8]
+        const size_t off = ((((size_t)(ch >> 1) * NP + 0) * 2 + (ch & 1)) * 128 + row) * 16;
+        *reinterpret_cast<uint4*>(base + off) = make_uint4((uint32_t)hi[0] | ((uint32_t)hi[1] << 16), (uint32_t)hi[2] | ((uint32_t)hi[3] << 16), (uint32_t)hi[4] | ((uint32_t)hi[5] << 16), (uint32_t)hi[6] | ((uint32_t)hi[7] << 16));
+        if (split)
+          *reinterpret_cast<uint4*>(base + off + (size_t)2 * 128 * 16) =
+              make_uint4((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16), (uint32_t)lo[4] | ((uint32_t)lo[5] << 16), (uint32_t)lo[6] | ((uint32_t)lo[7] << 16));
+      }
+    } else {
+      // item = (4 consecutive outputs, frame-row): float4 stores, consecutive threads -> consecutive addresses
+      const int quads = (O + 3) / 4;
+      const int nrows = 8 * kNodes;
+      for (int i = threadIdx.x; i < quads * nrows; i += blockDim.x) {
+        const int qd = i % quads, r = i / quads, fr = r / kNodes, m = r % kNodes;
+        const int64_t f = grp * 8 + fr;
+        if (f >= frames) continue;
+        const float* a = xm + (size_t)(fr * 16 + m) * K;
+        float acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = (qd * 4 + j < O) ? bias[qd * 4 + j] : 0.f;
+        for (int k = 0; k < K; ++k) {
+          const float av = a[k];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (qd * 4 + j < O) acc[j] = fmaf(av, wt[(size_t)k * O + qd * 4 + j], acc[j]);
+        }
+        float* yp = y + ((size_t)f * kNodes + m) * O + qd * 4;
+        if ((O & 3) == 0) {
+          *reinterpret_cast<float4*>(yp) = make_float4(apply_act(acc[0], act), apply_act(acc[1], act), apply_act(acc[2], act), apply_act(acc[3], act));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (qd * 4 + j < O) yp[j] = apply_act(acc[j], act);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// gc_out: f_in % 128 == 0, f_out <= 16.  Block = 16 frames (240 rows); each warp takes 8 rows at a time.
+// ------------------------------------------------------------------------------------------
+template <int OMAX>
+__global__ void __launch_bounds__(kGcThreads)
+gc_out_kernel(a3gc_gc_params p, const float* __restrict__ x, float* __restrict__ y, int64_t frames, int K, int O, int act) {
+  extern __shared__ __align__(16) float smem[];
+  float* adj = smem;                         // [16][16]
+  float* ws = adj + 256;                     // [O][K]
+  float* v = ws + (size_t)O * K;             // [16 frames][15][OMAX]
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    const int m = i >> 4, n = i & 15;
+    adj[i] = (m < kNodes && n < kNodes) ? p.adj[m * kNodes + n] : 0.f;
+  }
+  for (int i = threadIdx.x; i < O * K; i += blockDim.x) ws[i] = p.gcn_kernel[i];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t groups = (frames + 15) / 16;
+  for (int64_t grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const int64_t row0 = grp * 16 * kNodes;
+    const int64_t nrows = ((frames - grp * 16) < 16 ? (frames - grp * 16) : 16) * kNodes;
+    __syncthreads();
+    for (int r8 = warp * 8; r8 < nrows; r8 += 8 * (kGcThreads / 32)) {
+      float acc[8][OMAX];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int o = 0; o < OMAX; ++o) acc[r][o] = 0.f;
+      for (int k0 = lane * 4; k0 < K; k0 += 128) {
+        float4 xv[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          xv[r] = (r8 + r < nrows) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)(row0 + r8 + r) * K + k0)) : make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int o = 0; o < OMAX; ++o) {
+          if (o < O) {
+            const float4 w = *reinterpret_cast<const float4*>(ws + (size_t)o * K + k0);
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+              acc[r][o] = fmaf(xv[r].x, w.x, fmaf(xv[r].y, w.y, fmaf(xv[r].z, w.z, fmaf(xv[r].w, w.w, acc[r][o]))));
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int o = 0; o < OMAX; ++o) {
+          float s = acc[r][o];
+          s += __shfl_xor_sync(0xffffffffu, s, 16);
+          s += __shfl_xor_sync(0xffffffffu, s, 8);
+          s += __shfl_xor_sync(0xffffffffu, s, 4);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          if (lane == 0 && r8 + r < nrows) v[(size_t)(r8 + r) * OMAX + o] = s;
+        }
+    }
+    __syncthreads();
+    // y[f][m][o] = sum_n adj[m][n] v[f][n][o] + b[o]
+    const int outs = (int)(nrows / kNodes) * kNodes * O;
+    for (int i = threadIdx.x; i < outs; i += blockDim.x) {
+      const int o = i % O, m = (i / O) % kNodes, fr = i / (O * kNodes);
+      float s = p.gcn_bias[o];
+      const float* vf = v + (size_t)fr * kNodes * OMAX + o;
+#pragma unroll
+      for (int n = 0; n < kNodes; ++n) s = fmaf(adj[m * 16 + n], vf[n * OMAX], s);
+      y[(size_t)(grp * 16) * kNodes * O + i] = apply_act(s, act);
+    }
+  }
+}
+
+int sm_count() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+}  // namespace
+
+// 0 = handled here, 1 = shape not covered (caller falls back to the generic kernel)
+int gc_forward_fast(const a3gc_gc_params* p, const float* x, float* y, int64_t frames, int f_in, int f_out, int act,
+                    cudaStream_t stream, int* handled) {
+  *handled = 0;
+  if (frames == 0) { *handled = 1; return A3GC_OK; }
+  const int sms = sm_count();
+  if (f_in <= 32) {
+    const size_t smem = (256 + (size_t)f_in * f_out + f_out + 8 * kNodes * f_in + 128 * f_in) * sizeof(float);
+    if (smem > 160 * 1024) return A3GC_OK;
+    int64_t groups = (frames + 7) / 8;
+    int64_t blocks = groups < (int64_t)sms * 8 ? groups : (int64_t)sms * 8;
+    A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_in_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gc_in_kernel<false><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, x, y, nullptr, frames, 0, 0, f_in, f_out, act, 0);
+    A3GC_LAUNCH_CHECK("gc_in_kernel");
+    *handled = 1;
+  } else if (f_out <= 16 && f_in % 128 == 0) {
+    const size_t smem = (256 + (size_t)f_out * f_in + 16 * kNodes * 16) * sizeof(float);
+    if (smem > 200 * 1024) return A3GC_OK;
+    int64_t groups = (frames + 15) / 16;
+    int64_t blocks = groups < (int64_t)sms * 4 ? groups : (int64_t)sms * 4;
+    if (f_out <= 4) {
+      A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_out_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      gc_out_kernel<4><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, x, y, frames, f_in, f_out, act);
+    } else if (f_out <= 9) {
+      A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_out_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      gc_out_kernel<9><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, x, y, frames, f_in, f_out, act);
+    } else {
+      A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_out_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      gc_out_kernel<16><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, x, y, frames, f_in, f_out, act);
+    }
+    A3GC_LAUNCH_CHECK("gc_out_kernel");
+    *handled = 1;
+  }
+  return A3GC_OK;
+}
+
+// linear_in fused with the operand-image packing of the first recurrent layer (tensor-core engine)
+int gc_forward_image(const a3gc_gc_params* p, const float* x, uint16_t* img, int64_t batch, int64_t steps, int f_in,
+                     int f_out, int act, int split, cudaStream_t stream) {
+  if (batch == 0 || steps == 0) return A3GC_OK;
+  if (f_in > 32 || f_out % 16 != 0) { set_error("gc_forward_image: unsupported shape"); return A3GC_ERR_UNSUPPORTED; }
+  const size_t smem = (256 + (size_t)f_in * f_out + f_out + 8 * kNodes * f_in + 128 * f_in) * sizeof(float);
+  const int64_t groups = ((batch + 7) / 8) * steps;
+  const int sms = sm_count();
+  int64_t blocks = groups < (int64_t)sms * 8 ? groups : (int64_t)sms * 8;
+  A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_in_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gc_in_kernel<true><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, x, nullptr, img, batch * steps, (int)batch, (int)steps, f_in, f_out, act, split);
+  A3GC_LAUNCH_CHECK("gc_in_kernel<img>");
+  return A3GC_OK;
+}
+
+}  // namespace a3gc

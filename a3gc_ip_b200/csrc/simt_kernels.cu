@@ -624,6 +624,11 @@ int simt_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream
 int simt_gc_forward(const a3gc_gc_params* p, const float* x, float* y, int64_t frames, int f_in,
                     int f_out, int act, cudaStream_t stream) {
   if (frames == 0) return A3GC_OK;
+  {
+    int handled = 0;
+    int rc = gc_forward_fast(p, x, y, frames, f_in, f_out, act, stream, &handled);
+    if (rc != A3GC_OK || handled) return rc;
+  }
   const int smem_max = max_optin_smem();
   if (smem_max <= 0) { set_error("no CUDA device"); return A3GC_ERR_NO_DEVICE; }
   int FR = 8;

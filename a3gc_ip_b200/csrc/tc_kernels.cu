@@ -61,7 +61,8 @@ struct TcDir {
 struct TcLayerParams {
   TcDir d[2];
   const uint16_t* x_img;    // [tiles][T][F/16][NP][2][128][8]
-  float* y; int64_t syb, syt, yld;
+  float* y; int64_t syb, syt, yld;   // fp32 output (may be null)
+  uint16_t* y_img; int y_kf;         // next layer's operand image (may be null) and its K/16
   int B, T, F, H, out_act, C, S, trace;
 };
 
@@ -361,19 +362,39 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
     };
     // y_t and, on the last step, the final hidden state
     auto emit = [&](int t, int ta, int h, const float (&v)[16]) {
-      if (!valid) return;
       const bool th = p.out_act == A3GC_ACT_TANH;
 #pragma unroll
       for (int ub = 0; ub < 4; ++ub)
 #pragma unroll
         for (int up = 0; up < 2; ++up) {
           const int node = tq + 8 * up;
-          if (node >= kNodes) continue;
+          const bool live = valid && node < kNodes;
           const float a0 = v[ub * 4 + 2 * up], a1 = v[ub * 4 + 2 * up + 1];
+          const float o0 = th ? fast_tanh(a0) : a0, o1 = th ? fast_tanh(a1) : a1;
           const int col = 32 * h + 8 * ub + 2 * tr;
-          float* yp = p.y + (size_t)bseq * p.syb + (size_t)ta * p.syt + (size_t)node * p.yld + ycol + col;
-          *reinterpret_cast<float2*>(yp) = th ? make_float2(fast_tanh(a0), fast_tanh(a1)) : make_float2(a0, a1);
-          if (t == T - 1 && d.hT != nullptr)
+          if (live && p.y != nullptr) {
+            float* yp = p.y + (size_t)bseq * p.syb + (size_t)ta * p.syt + (size_t)node * p.yld + ycol + col;
+            *reinterpret_cast<float2*>(yp) = make_float2(o0, o1);
+          }
+          if (p.y_img != nullptr) {
+            // element (row 16s+node, feature k) of image [tile][ta][k/16][part][(k/8)%2][128][8]; the pad rows
+            // (node 15, sequences beyond the batch) are written as zeros: the next layer multiplies them by 0
+            const int k = ycol + col;
+            uint32_t hi = 0, lo = 0;
+            if (live) {
+              if (SPLIT) {
+                ptx::split_pair_f16(o0, o1, hi, lo);
+              } else {
+                const __nv_bfloat162 bb = __floats2bfloat162_rn(o0, o1);
+                hi = *reinterpret_cast<const uint32_t*>(&bb);
+              }
+            }
+            uint8_t* ip = reinterpret_cast<uint8_t*>(p.y_img) +
+                          ((((((size_t)tile * T + ta) * p.y_kf + (k >> 4)) * NP) * 2 + ((k >> 3) & 1)) * 128 + 16 * s + node) * 16 + (k & 7) * 2;
+            *reinterpret_cast<uint32_t*>(ip) = hi;
+            if (SPLIT) *reinterpret_cast<uint32_t*>(ip + 2 * 128 * 16) = lo;
+          }
+          if (live && t == T - 1 && d.hT != nullptr)
             *reinterpret_cast<float2*>(d.hT + ((size_t)bseq * kNodes + node) * H + c * 64 + col) = make_float2(a0, a1);
         }
     };
@@ -719,12 +740,17 @@ bool tc_layer_supported(int variant, int f_in, int hidden, int precision) {
   return precision == A3GC_PREC_FP32 || precision == A3GC_PREC_BF16;
 }
 
+size_t tc_image_bytes(int64_t batch, int64_t steps, int features, int precision) {
+  const int NP = precision == A3GC_PREC_FP32 ? 2 : 1;
+  const int64_t tiles = (batch + kSeqTile - 1) / kSeqTile;
+  return align_up((size_t)tiles * steps * features * kRows * NP * 2, 256);
+}
+
 size_t tc_layer_workspace_bytes(int variant, int64_t batch, int64_t steps, int f_in, int hidden, int num_dirs, int precision) {
   (void)variant;
   const int NP = precision == A3GC_PREC_FP32 ? 2 : 1;
-  const int64_t tiles = (batch + kSeqTile - 1) / kSeqTile;
   size_t b = (size_t)num_dirs * tc_dir_bytes(f_in, hidden, NP);
-  b += align_up((size_t)tiles * steps * f_in * kRows * NP * 2, 256);   // x image
+  b += tc_image_bytes(batch, steps, f_in, precision);   // x image (unused when the caller hands one in)
   return b + 256;
 }
 
@@ -754,16 +780,19 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
     td.bs = pk.bs; td.u = pk.u; td.bu = pk.bu;
     td.h0 = a.h0[d]; td.c0 = a.c0[d]; td.hT = a.hT[d]; td.cT = a.cT[d]; td.reverse = a.reverse[d];
   }
-  uint16_t* x_img = reinterpret_cast<uint16_t*>(base + a.num_dirs * dir_bytes);
-  {
+  const uint16_t* x_img = a.x_img;
+  if (x_img == nullptr) {
+    uint16_t* own = reinterpret_cast<uint16_t*>(base + a.num_dirs * dir_bytes);
+    x_img = own;
     const int64_t total = tiles * a.steps * (F / 16) * NP * 2 * kRows * 8;
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    tc_pack_x_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.x, a.x_stride_b, a.x_stride_t, x_img, (int)a.batch, (int)a.steps, F, split ? 1 : 0, total);
+    tc_pack_x_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.x, a.x_stride_b, a.x_stride_t, own, (int)a.batch, (int)a.steps, F, split ? 1 : 0, total);
     A3GC_LAUNCH_CHECK("tc_pack_x_kernel");
   }
   p.x_img = x_img;
   p.y = a.y; p.syb = a.y_stride_b; p.syt = a.y_stride_t; p.yld = a.y_ld;
+  p.y_img = a.y_img; p.y_kf = a.y_img_f / 16;
   p.B = (int)a.batch; p.T = (int)a.steps; p.F = F; p.H = H; p.out_act = a.out_act; p.C = C;
   p.trace = getenv("A3GC_TC_TRACE") != nullptr ? 1 : 0;
 
