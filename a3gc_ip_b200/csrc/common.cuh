@@ -43,9 +43,17 @@ __device__ __forceinline__ float tanhf_(float x) {
   float r = (1.0f - e) / (1.0f + e);
   return copysignf(r, x);
 }
-// fast variants for the tensor-core epilogue: MUFU.EX2 + MUFU.RCP (|err| ~ 2e-7 absolute)
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.0f, __fdividef(1.0f, 1.0f + __expf(-2.0f * x)), -1.0f); }
+// fast variants for the tensor-core epilogue: one MUFU.EX2 + one MUFU.RCP each, flush-to-zero forms (no denormal
+// fix-up code around the MUFU), |err| ~ 2e-7 absolute
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kExpCap = 1.0995116e12f;   // 2^40: products of three capped terms stay finite in fp32
+// 1 + e^-x and e^-2x, capped from above (the cap only matters where the activation is saturated to < 1e-12)
+__device__ __forceinline__ float one_plus_exp_neg(float x) { return 1.0f + fminf(ex2_ftz(x * -kLog2e), kExpCap); }
+__device__ __forceinline__ float exp_neg2(float x) { return fminf(ex2_ftz(x * (-2.0f * kLog2e)), kExpCap); }
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_ftz(one_plus_exp_neg(x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.0f, rcp_ftz(1.0f + exp_neg2(x)), -1.0f); }
 __device__ __forceinline__ float apply_act(float v, int act) {
   return act == A3GC_ACT_TANH ? tanhf_(v) : (act == A3GC_ACT_RELU ? fmaxf(v, 0.0f) : v);
 }

@@ -33,11 +33,11 @@ namespace {
 constexpr int kRows = 128;             // 8 sequences x 16 node slots
 constexpr int kSeqTile = 8;
 constexpr int kUnits = 64;             // hidden units per CTA
-constexpr int kSub = 32;               // staged accumulator columns per sub-chunk (8 units x 4 gates)
-constexpr int kPitch = 136;            // floats per staged column (136 = 8 mod 32: conflict-free fragment loads)
-constexpr int kEpiThreads = 256;       // warps 2..9
+constexpr int kEpiWarps = 16;          // warps 2..17: warp (qd = warp%4, ug = (warp-2)/4) owns rows 32qd..32qd+31 x units 16ug..16ug+15
+constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kThreadsTC = 64 + kEpiThreads;
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 8;
+constexpr int kWstFloats = 8 * 32;     // warp-private transposition buffer: 8 accumulator columns x 32 rows
 
 // optional per-phase timeline of CTA (0,0) (A3GC_TC_TRACE=1): [role 0 = epilogue, 1 = mma][step < 16][slot < 16] clock64
 __device__ unsigned long long g_tc_trace[2][16][16];
@@ -64,6 +64,7 @@ struct TcLayerParams {
   float* y; int64_t syb, syt, yld;   // fp32 output (may be null)
   uint16_t* y_img; int y_kf;         // next layer's operand image (may be null) and its K/16
   int B, T, F, H, out_act, C, S, trace;
+  int n1, n2;                        // x-part blocks of step t+1 issued before A1 / between A1 and A2 of step t (rest after A2)
 };
 
 // barrier slots in shared memory
@@ -71,12 +72,12 @@ enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_ACC_FULL = 2 * kMaxStages, BAR_
        BAR_ACC_EMPTY, BAR_H = BAR_ACC_EMPTY + 2, BAR_HHAT, BAR_Q, BAR_A, BAR_HFREE, BAR_A1FREE, BAR_COUNT };
 
 __host__ __device__ inline size_t tc_fixed_smem_bytes(int C) {
-  return (size_t)kSub * kPitch * 4      // staging
-         + (size_t)C * 128 * 4          // apart
-         + 256 * 4                      // ahalf
-         + 256 * 4 + 64 * 4 * 2 + 16 * 4  // bias4, bs, u, bu
-         + 1024 * 4 + 256 * 4           // Pfrag, biasg
-         + 32 * 8 + 16;                 // barriers, tmem slot
+  return (size_t)kEpiWarps * kWstFloats * 4   // wst
+         + (size_t)C * 128 * 4                // apart
+         + 4 * 128 * 4                        // ahalf
+         + 256 * 4 + 64 * 4 * 2 + 16 * 4      // biasg, bs, u, bu
+         + 1024 * 4                           // Pfrag
+         + 32 * 8 + 16;                       // barriers, tmem slot
 }
 
 // byte offset of element (row, k) inside one part of an operand image [K/8][128][8]
@@ -114,19 +115,19 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
   const TcDir& d = p.d[blockIdx.y];
   const int KF = F / 16, KH = H / 16;
   const int warp = threadIdx.x >> 5;
+  const int n1 = p.n1, n2 = p.n2;
 
   uint8_t* hbuf = smem;
   uint8_t* ring = hbuf + (size_t)NP * H * 256;
-  float* staging = reinterpret_cast<float*>(ring + (size_t)S * kStageBytes);
-  float* apart = staging + kSub * kPitch;    // [C][128]
-  float* ahalf = apart + C * 128;            // [2][128]
-  float* bias4s = ahalf + 256;               // [64][4]
-  float* bss = bias4s + 256;                 // [64]
+  float* staging = reinterpret_cast<float*>(ring + (size_t)S * kStageBytes);   // [16 warps][8][32]
+  float* apart = staging + kEpiWarps * kWstFloats;   // [C][128]
+  float* ahalf = apart + C * 128;            // [4][128]
+  float* biasg = ahalf + 4 * 128;            // [4 gates][64 units]
+  float* bss = biasg + 256;                  // [64]
   float* us = bss + 64;                      // [64]
   float* bus = us + 64;                      // [16]
-  uint32_t* Pfrag = reinterpret_cast<uint32_t*>(bus + 16);   // [4 gates][hi, lo][4 regs][32 lanes] A fragments of P_g
-  float* biasg = reinterpret_cast<float*>(Pfrag + 1024);     // [4 gates][64 units]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(biasg + 256);
+  uint32_t* Pfrag = reinterpret_cast<uint32_t*>(bus + 16);   // [4 gates][hi, lo][32 lanes][4 regs] A fragments of P_g
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Pfrag + 1024);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
   // ------------------------------------------------------------------ setup
@@ -139,16 +140,15 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
     uint4* z = reinterpret_cast<uint4*>(hbuf);
     const int n16 = NP * H * 16;
     for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) bias4s[i] = d.bias4[(size_t)c * 256 + i];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) biasg[i] = d.bias4[(size_t)c * 256 + (i & 63) * 4 + (i >> 6)];
-    // A fragments (mma.m16n8k16, row-major A = P_g): reg i of lane l holds P_g[l/4 + 8*(i&1)][2*(l%4) + 8*(i>>1) + {0,1}]
+    // A fragments (mma.m16n8k16, row-major A = P_g): reg r of lane l holds P_g[l/4 + 8*(r&1)][2*(l%4) + 8*(r>>1) + {0,1}]
     for (int i = threadIdx.x; i < 512; i += blockDim.x) {
-      const int l = i & 31, r = (i >> 5) & 3, g = i >> 7;
+      const int r = i & 3, l = (i >> 2) & 31, g = i >> 7;
       const int mm = (l >> 2) + 8 * (r & 1), nn = 2 * (l & 3) + 8 * (r >> 1);
       uint32_t hi, lo;
       ptx::split_pair_f16(d.P[(g * 16 + mm) * 16 + nn], d.P[(g * 16 + mm) * 16 + nn + 1], hi, lo);
-      Pfrag[((g * 2 + 0) * 4 + r) * 32 + l] = hi;
-      Pfrag[((g * 2 + 1) * 4 + r) * 32 + l] = lo;
+      Pfrag[((g * 2 + 0) * 32 + l) * 4 + r] = hi;
+      Pfrag[((g * 2 + 1) * 32 + l) * 4 + r] = lo;
     }
     if (ATT) {
       for (int i = threadIdx.x; i < 64; i += blockDim.x) { bss[i] = d.bs[c * 64 + i]; us[i] = d.u[c * 64 + i]; }
@@ -164,34 +164,41 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
 
   if (warp == 0) {
     // ================================================================ producer: weights / x -> ring
+    // The order of the stages is the static issue order of the MMA warp: h-part of step t, then the x-part of step
+    // t+1 cut into three segments placed around the two attention GEMMs of step t, so that the tensor pipe has work
+    // while the epilogue warps are busy and the attention GEMMs are never queued behind a long x-part.
     if ((threadIdx.x & 31) == 0) {
-      uint32_t it = 0;
+      uint32_t st = 0, ph = 0;            // ring slot and the parity of its current fill (no div / mod in the loop)
       auto load_stage = [&](const void* bsrc, uint32_t bbytes, const void* asrc, uint32_t abytes) {
-        const uint32_t st = it % S, ph = (it / S) & 1u;
         ptx::mbar_wait(&bars[BAR_EMPTY + st], ph ^ 1u);
         ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + st], bbytes + abytes);
-        uint8_t* dst = ring + (size_t)st * kStageBytes;
+        uint8_t* dst = ring + st * kStageBytes;
         ptx::bulk_g2s(dst, bsrc, bbytes, &bars[BAR_FULL + st]);
         if (abytes) ptx::bulk_g2s(dst + kBBytes, asrc, abytes, &bars[BAR_FULL + st]);
-        ++it;
+        if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
       };
       const uint8_t* wg = reinterpret_cast<const uint8_t*>(d.wg_img) + (size_t)c * (KF + KH) * kBBytes;
       const uint8_t* a1 = reinterpret_cast<const uint8_t*>(d.a1_img) + (size_t)c * KH * kA1Block;
       const uint8_t* a2 = reinterpret_cast<const uint8_t*>(d.a2_img) + (size_t)c * KH * kA2Block;
       const uint8_t* xi = reinterpret_cast<const uint8_t*>(p.x_img);
-      auto xpart = [&](int t) {
+      auto xblocks = [&](int t, int kb0, int kb1) {
         const int ta = d.reverse ? T - 1 - t : t;
         const uint8_t* xs = xi + ((size_t)tile * T + ta) * KF * kABytes;
-        for (int kb = 0; kb < KF; ++kb) load_stage(wg + (size_t)kb * kBBytes, kBBytes, xs + (size_t)kb * kABytes, kABytes);
+        for (int kb = kb0; kb < kb1; ++kb) load_stage(wg + (size_t)kb * kBBytes, kBBytes, xs + (size_t)kb * kABytes, kABytes);
       };
-      xpart(0);
+      xblocks(0, 0, KF);
       for (int t = 0; t < T; ++t) {
+        const bool nx = t + 1 < T;
         for (int kb = 0; kb < KH; ++kb) load_stage(wg + (size_t)(KF + kb) * kBBytes, kBBytes, nullptr, 0);
-        if (t + 1 < T) xpart(t + 1);
-        if (ATT) {
-          for (int s2 = 0; s2 < KH / 2; ++s2) load_stage(a1 + (size_t)s2 * 2 * kA1Block, 2 * kA1Block, nullptr, 0);
-          for (int s4 = 0; s4 < KH / 4; ++s4) load_stage(a2 + (size_t)s4 * 4 * kA2Block, 4 * kA2Block, nullptr, 0);
+        if (!ATT) {
+          if (nx) xblocks(t + 1, 0, KF);
+          continue;
         }
+        if (nx) xblocks(t + 1, 0, n1);
+        for (int s2 = 0; s2 < KH / 2; ++s2) load_stage(a1 + (size_t)s2 * 2 * kA1Block, 2 * kA1Block, nullptr, 0);
+        if (nx) xblocks(t + 1, n1, n1 + n2);
+        for (int s4 = 0; s4 < KH / 4; ++s4) load_stage(a2 + (size_t)s4 * 4 * kA2Block, 4 * kA2Block, nullptr, 0);
+        if (nx) xblocks(t + 1, n1 + n2, KF);
       }
     }
   } else if (warp == 1) {
@@ -202,156 +209,179 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       const uint32_t idesc64 = ptx::make_idesc_f16(128, 64, !SPLIT);
       const uint32_t hbase = ptx::smem_u32(hbuf);
       const uint32_t hpart = (uint32_t)H * 256;
-      uint32_t it = 0;
+      // The issue loop runs on ONE thread whose dependent-instruction latency bounds the MMA rate, so it is kept
+      // lean: ring slot / parity are counters (no div / mod), descriptors are a constant plus (address >> 4).
+      uint32_t st = 0, ph = 0;
       uint32_t empty_k[2] = {0, 0};     // completions of BAR_ACC_EMPTY[b] consumed so far (no-attention variant)
+      const uint32_t ring_addr = ptx::smem_u32(ring);
       auto wait_stage = [&]() -> uint32_t {
-        const uint32_t st = it % S, ph = (it / S) & 1u;
         ptx::mbar_wait(&bars[BAR_FULL + st], ph);
         ptx::tc_fence_after();
-        return ptx::smem_u32(ring + (size_t)st * kStageBytes);
+        return ring_addr + st * kStageBytes;
       };
-      auto release_stage = [&]() { ptx::umma_commit(&bars[BAR_EMPTY + it % S]); ++it; };
+      auto release_stage = [&]() {
+        ptx::umma_commit(&bars[BAR_EMPTY + st]);
+        if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
+      };
+      const uint64_t dA = ptx::make_smem_desc(0, kRows * 16, 128);
+      const uint64_t dB256 = ptx::make_smem_desc(0, 256 * 16, 128), dB128 = ptx::make_smem_desc(0, 128 * 16, 128),
+                     dB64 = ptx::make_smem_desc(0, 64 * 16, 128);
       // one K=16 block: D[:, dcol..dcol+N) (+)= A * B^T with the split passes hi*hi + lo*hi + hi*lo
-      auto block_mma = [&](uint32_t dcol, uint32_t a0, uint32_t astride, uint32_t b0, uint32_t bstride, uint32_t nrows_b,
+      auto block_mma = [&](uint32_t dcol, uint32_t a0, uint32_t astride, uint32_t b0, uint32_t bstride, uint64_t dB,
                            uint32_t idesc, bool first) {
-        const uint64_t ah = ptx::make_smem_desc(a0, kRows * 16, 128);
-        const uint64_t bh = ptx::make_smem_desc(b0, nrows_b * 16, 128);
+        // (shared-window addresses of non-zero cluster ranks carry the rank above bit 18: keep the 18-bit offset only)
+        const uint64_t ah = dA + ((a0 & 0x3FFFFu) >> 4), bh = dB + ((b0 & 0x3FFFFu) >> 4);
         ptx::umma_f16(tmem + dcol, ah, bh, idesc, first ? 0u : 1u);
         if (SPLIT) {
-          const uint64_t al = ptx::make_smem_desc(a0 + astride, kRows * 16, 128);
-          const uint64_t bl = ptx::make_smem_desc(b0 + bstride, nrows_b * 16, 128);
-          ptx::umma_f16(tmem + dcol, al, bh, idesc, 1u);
-          ptx::umma_f16(tmem + dcol, ah, bl, idesc, 1u);
+          ptx::umma_f16(tmem + dcol, ah + (astride >> 4), bh, idesc, 1u);
+          ptx::umma_f16(tmem + dcol, ah, bh + (bstride >> 4), idesc, 1u);
         }
       };
-      auto xpart = [&](uint32_t dcol) {
-        for (int kb = 0; kb < KF; ++kb) {
-          const uint32_t st = wait_stage();
-          block_mma(dcol, st + kBBytes, kABytes / NP, st, kBBytes / NP, 256, idesc256, kb == 0);
+      auto xblocks = [&](uint32_t dcol, int kb0, int kb1) {
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const uint32_t sa = wait_stage();
+          block_mma(dcol, sa + kBBytes, kABytes / NP, sa, kBBytes / NP, dB256, idesc256, kb == 0);
           release_stage();
         }
       };
-      xpart(0);
+      xblocks(0, 0, KF);
       for (int t = 0; t < T; ++t) {
-        const uint32_t b = t & 1, dcol = b * 256;
+        const uint32_t b = t & 1, bo = b ^ 1u, dcol = b * 256;
+        const bool nx = t + 1 < T;
         // h-part of step t (needs h'_{t-1} of every chunk in local shared memory)
         TC_TRACE(1, 0);
         ptx::mbar_wait(&bars[BAR_H], t & 1);
         ptx::tc_fence_after();
         TC_TRACE(1, 1);
         for (int kb = 0; kb < KH; ++kb) {
-          const uint32_t st = wait_stage();
-          block_mma(dcol, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, st, kBBytes / NP, 256, idesc256, false);
+          const uint32_t sa = wait_stage();
+          block_mma(dcol, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, sa, kBBytes / NP, dB256, idesc256, false);
           release_stage();
         }
         ptx::umma_commit(&bars[BAR_ACC_FULL + b]);
         if (C > 1) ptx::umma_commit_multicast(&bars[BAR_HFREE], cta_mask); else ptx::umma_commit(&bars[BAR_HFREE]);
         TC_TRACE(1, 2);
-        // x-part of step t+1 into the other buffer (free once the epilogue of step t-1 has drained it)
-        if (t + 1 < T) {
-          if (t >= 1) {
-            const uint32_t bo = b ^ 1u;
-            if (ATT) ptx::mbar_wait(&bars[BAR_ACC_EMPTY + bo], 1u);
-            else { ptx::mbar_wait(&bars[BAR_ACC_EMPTY + bo], empty_k[bo] & 1u); empty_k[bo] += 1; }
-            ptx::tc_fence_after();
-          }
-          xpart((b ^ 1u) * 256);
+        // x-part of step t+1 goes into the other buffer (free once the epilogue of step t-1 has drained it)
+        if (nx && t >= 1) {
+          if (ATT) ptx::mbar_wait(&bars[BAR_ACC_EMPTY + bo], 1u);
+          else { ptx::mbar_wait(&bars[BAR_ACC_EMPTY + bo], empty_k[bo] & 1u); empty_k[bo] += 1; }
+          ptx::tc_fence_after();
         }
+        if (!ATT) {
+          if (nx) xblocks(bo * 256, 0, KF);
+          TC_TRACE(1, 3);
+          continue;
+        }
+        if (nx) xblocks(bo * 256, 0, n1);
         TC_TRACE(1, 3);
-        if (ATT) {
-          // A1: [Wh hy | Wa (hy, node-sum in row 15)] -> columns [0,128) of the drained buffer
-          ptx::mbar_wait(&bars[BAR_HHAT], t & 1);
-          ptx::mbar_wait(&bars[BAR_ACC_EMPTY + b], 0u);
-          ptx::tc_fence_after();
-          TC_TRACE(1, 4);
-          for (int s2 = 0; s2 < KH / 2; ++s2) {
-            const uint32_t st = wait_stage();
+        // A1: [Wh hy | Wa (hy, node-sum in row 15)] -> columns [0,128) of the drained buffer
+        ptx::mbar_wait(&bars[BAR_HHAT], t & 1);
+        ptx::mbar_wait(&bars[BAR_ACC_EMPTY + b], 0u);
+        ptx::tc_fence_after();
+        TC_TRACE(1, 4);
+        for (int s2 = 0; s2 < KH / 2; ++s2) {
+          const uint32_t sa = wait_stage();
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int kb = s2 * 2 + j;
-              block_mma(dcol, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, st + (uint32_t)j * kA1Block, kA1Block / NP, 128, idesc128,
-                        (s2 | j) == 0);
-            }
-            release_stage();
+          for (int j = 0; j < 2; ++j) {
+            const int kb = s2 * 2 + j;
+            block_mma(dcol, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, sa + (uint32_t)j * kA1Block, kA1Block / NP, dB128, idesc128,
+                      (s2 | j) == 0);
           }
-          ptx::umma_commit(&bars[BAR_ATT_FULL]);
-          if (C > 1) ptx::umma_commit_multicast(&bars[BAR_A1FREE], cta_mask); else ptx::umma_commit(&bars[BAR_A1FREE]);
-          TC_TRACE(1, 5);
-          // A2: Wq q (q sits in row 15 of every sequence) -> columns [128,192)
-          ptx::mbar_wait_cluster(&bars[BAR_Q], t & 1);
-          ptx::fence_proxy_async();
-          ptx::tc_fence_after();
-          TC_TRACE(1, 6);
-          for (int s4 = 0; s4 < KH / 4; ++s4) {
-            const uint32_t st = wait_stage();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int kb = s4 * 4 + j;
-              block_mma(dcol + 128, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, st + (uint32_t)j * kA2Block, kA2Block / NP, 64, idesc64,
-                        (s4 | j) == 0);
-            }
-            release_stage();
-          }
-          ptx::umma_commit(&bars[BAR_ATT2_FULL]);
-          TC_TRACE(1, 7);
+          release_stage();
         }
+        ptx::umma_commit(&bars[BAR_ATT_FULL]);
+        if (C > 1) ptx::umma_commit_multicast(&bars[BAR_A1FREE], cta_mask); else ptx::umma_commit(&bars[BAR_A1FREE]);
+        TC_TRACE(1, 5);
+        if (nx) xblocks(bo * 256, n1, n1 + n2);
+        // A2: Wq q (q sits in row 15 of every sequence) -> columns [128,192)
+        ptx::mbar_wait_cluster(&bars[BAR_Q], t & 1);
+        ptx::fence_proxy_async();
+        ptx::tc_fence_after();
+        TC_TRACE(1, 6);
+        for (int s4 = 0; s4 < KH / 4; ++s4) {
+          const uint32_t sa = wait_stage();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int kb = s4 * 4 + j;
+            block_mma(dcol + 128, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, sa + (uint32_t)j * kA2Block, kA2Block / NP, dB64, idesc64,
+                      (s4 | j) == 0);
+          }
+          release_stage();
+        }
+        ptx::umma_commit(&bars[BAR_ATT2_FULL]);
+        TC_TRACE(1, 7);
+        if (nx) xblocks(bo * 256, n1 + n2, KF);
+        TC_TRACE(1, 8);
       }
     }
   } else {
-    // ================================================================ epilogue warps (256 threads)
+    // ================================================================ epilogue warps (512 threads)
+    // Warp (qd, ug) owns accumulator rows 32qd..32qd+31 (sequences 2qd, 2qd+1 of the tile; a warp may only read the
+    // TMEM lane quarter warp%4) x hidden units 16ug..16ug+15 of this CTA's 64.  Gate accumulators go TMEM -> registers
+    // (lane = row) -> a WARP-PRIVATE transposition buffer -> B fragments of mma.m16n8k16 (k = node), so the whole
+    // gate phase needs no CTA-wide barrier.  Pointwise ownership follows the C fragment: lane (tq = lane/4,
+    // tr = lane%4) owns, for sequence sq and 8-unit block ub, nodes {tq, tq+8} x units {2tr, 2tr+1};
+    // node 15 (tq == 7, upper half) is the pad slot.
     const int et = threadIdx.x - 64;
     const int ew = et >> 5, lane = et & 31;
-    const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
-    const int chalf = ew >> 2;                    // which half of the columns this warp stages
-    const int s = ew;                             // sequence of the tile this warp owns in the pointwise phase
-    const int bseq = tile * kSeqTile + s;
-    const bool valid = bseq < p.B;
-    const int ycol = blockIdx.y * H + (int)c * 64;
-    // pointwise ownership follows the C fragment of mma.m16n8k16: lane (tq = lane/4, tr = lane%4) of warp s owns,
-    // in every 8-unit block, nodes {tq, tq+8} x units {2tr, 2tr+1}; node 15 (tq == 7, upper half) is the pad slot
+    const int qd = warp & 3;
+    const int ug = ew >> 2;
     const int tq = lane >> 2, tr = lane & 3;
     const bool pad_hi = tq == 7;
+    float* wst = staging + ew * kWstFloats;
+    const uint32_t tmem_row = tmem + ((uint32_t)(qd * 32) << 16);
+    const int ycol = blockIdx.y * H + (int)c * 64;
+    const int ubase = 16 * ug;                       // first unit (within the CTA's 64) of this warp
+    int bseq[2]; bool valid[2];
+#pragma unroll
+    for (int sq = 0; sq < 2; ++sq) { bseq[sq] = tile * kSeqTile + 2 * qd + sq; valid[sq] = bseq[sq] < p.B; }
 
-    float creg[2][16], hreg[2][16];               // [half of the 64 units][unit block ub (4) x element j (4)]
+    float creg[2][2][4], hreg[2][2][4];              // [sequence sq][unit block ub][element j]
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
+    for (int sq = 0; sq < 2; ++sq)
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int node = tq + ((e & 2) ? 8 : 0), unit = 32 * h + 8 * (e >> 2) + 2 * tr + (e & 1);
-        const bool ok = valid && node < kNodes;
-        const size_t gi = ((size_t)bseq * kNodes + node) * H + c * 64 + unit;
-        creg[h][e] = (ok && d.c0 != nullptr) ? d.c0[gi] : 0.f;
-        hreg[h][e] = (ok && d.h0 != nullptr) ? d.h0[gi] : 0.f;
-      }
-
-    // write the 16 values of half h (4 unit blocks x {node tq, tq+8} x 2 units) into the local operand image
-    auto store_half = [&](int h, const float (&v)[16]) {
+      for (int ub = 0; ub < 2; ++ub)
 #pragma unroll
-      for (int ub = 0; ub < 4; ++ub) {
-        const int k = (int)c * 64 + 32 * h + 8 * ub + 2 * tr;
-#pragma unroll
-        for (int up = 0; up < 2; ++up) {
-          uint32_t hi, lo;
-          if (SPLIT) {
-            ptx::split_pair_f16(v[ub * 4 + 2 * up], v[ub * 4 + 2 * up + 1], hi, lo);
-          } else {
-            const __nv_bfloat162 bb = __floats2bfloat162_rn(v[ub * 4 + 2 * up], v[ub * 4 + 2 * up + 1]);
-            hi = *reinterpret_cast<const uint32_t*>(&bb);
-            lo = 0;
-          }
-          const uint32_t off = img_off(k, 16 * s + tq + 8 * up);
-          *reinterpret_cast<uint32_t*>(hbuf + off) = hi;
-          if (SPLIT) *reinterpret_cast<uint32_t*>(hbuf + (size_t)H * 256 + off) = lo;
+        for (int j = 0; j < 4; ++j) {
+          const int node = tq + 8 * (j >> 1), unit = ubase + 8 * ub + 2 * tr + (j & 1);
+          const bool ok = valid[sq] && node < kNodes;
+          const size_t gi = ((size_t)bseq[sq] * kNodes + node) * H + c * 64 + unit;
+          creg[sq][ub][j] = (ok && d.c0 != nullptr) ? d.c0[gi] : 0.f;
+          hreg[sq][ub][j] = (ok && d.h0 != nullptr) ? d.h0[gi] : 0.f;
         }
-      }
+
+    // write this thread's 16 values into the local operand image (rows of sequences 2qd, 2qd+1)
+    auto store_units = [&](const float (&v)[2][2][4]) {
+#pragma unroll
+      for (int sq = 0; sq < 2; ++sq)
+#pragma unroll
+        for (int ub = 0; ub < 2; ++ub) {
+          const int k = (int)c * 64 + ubase + 8 * ub + 2 * tr;
+#pragma unroll
+          for (int up = 0; up < 2; ++up) {
+            uint32_t hi, lo;
+            if (SPLIT) {
+              ptx::split_pair_f16(v[sq][ub][2 * up], v[sq][ub][2 * up + 1], hi, lo);
+            } else {
+              const __nv_bfloat162 bb = __floats2bfloat162_rn(v[sq][ub][2 * up], v[sq][ub][2 * up + 1]);
+              hi = *reinterpret_cast<const uint32_t*>(&bb);
+              lo = 0;
+            }
+            const uint32_t off = img_off(k, 16 * (2 * qd + sq) + tq + 8 * up);
+            *reinterpret_cast<uint32_t*>(hbuf + off) = hi;
+            if (SPLIT) *reinterpret_cast<uint32_t*>(hbuf + (size_t)H * 256 + off) = lo;
+          }
+        }
     };
-    // all 256 epilogue threads have written their part of the local operand image: make it visible to the
-    // async proxy, then send this CTA's 64-unit block to every peer; `bar` completes in each CTA when all C
-    // blocks have landed
-    auto publish_block = [&](int bar) {
+    // all epilogue threads have written their part of the local operand image: make it visible to the async proxy,
+    // then send this CTA's 64-unit block to every peer; `bar` completes in each CTA when all C blocks have landed.
+    // `acc_empty` >= 0: the accumulator buffer has been drained as well (tcgen05 loads fenced before the barrier).
+    auto publish_block = [&](int bar, int acc_empty) {
       ptx::fence_proxy_async();
+      if (acc_empty >= 0) ptx::tc_fence_before();
       ptx::named_bar_sync(1, kEpiThreads);
       if (et == 0) {
+        if (acc_empty >= 0) ptx::mbar_arrive(&bars[BAR_ACC_EMPTY + acc_empty]);
         for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) {
           if (peer == c) continue;
           for (int part = 0; part < NP; ++part)
@@ -360,48 +390,63 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         ptx::mbar_arrive_expect_tx(&bars[bar], (uint32_t)(C - 1) * NP * kHBlock);
       }
     };
-    // y_t and, on the last step, the final hidden state
-    auto emit = [&](int t, int ta, int h, const float (&v)[16]) {
+    // y_t = act(h'_t).  All addressing that does not depend on t is folded into per-thread bases; the values of
+    // pad slots (node 15, sequences beyond the batch) are exact zeros already (masked in the gate phase), so the
+    // operand-image stores need no predicate: the next layer multiplies those rows by zero weights of P.
+    const int col0 = ycol + ubase + 2 * tr;                        // feature of (ub = 0, unit 2tr)
+    const int64_t ybase = (int64_t)bseq[0] * p.syb + (int64_t)tq * p.yld + col0;
+    const int ysq = (int)p.syb, yup = 8 * (int)p.yld;               // element offsets of (sq = 1) and (node + 8)
+    const size_t img_step = (size_t)p.y_kf * NP * 4096;             // bytes of one (tile, t) slab of the output image
+    const size_t img_base = ((size_t)tile * T * p.y_kf + (col0 >> 4)) * NP * 4096 + (size_t)(32 * qd + tq) * 16 + 4 * tr;
+    auto emit = [&](int ta, const float (&v)[2][2][4]) {
       const bool th = p.out_act == A3GC_ACT_TANH;
+      float o[2][2][4];
 #pragma unroll
-      for (int ub = 0; ub < 4; ++ub)
+      for (int sq = 0; sq < 2; ++sq)
 #pragma unroll
-        for (int up = 0; up < 2; ++up) {
-          const int node = tq + 8 * up;
-          const bool live = valid && node < kNodes;
-          const float a0 = v[ub * 4 + 2 * up], a1 = v[ub * 4 + 2 * up + 1];
-          const float o0 = th ? fast_tanh(a0) : a0, o1 = th ? fast_tanh(a1) : a1;
-          const int col = 32 * h + 8 * ub + 2 * tr;
-          if (live && p.y != nullptr) {
-            float* yp = p.y + (size_t)bseq * p.syb + (size_t)ta * p.syt + (size_t)node * p.yld + ycol + col;
-            *reinterpret_cast<float2*>(yp) = make_float2(o0, o1);
+        for (int ub = 0; ub < 2; ++ub)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[sq][ub][j] = th ? fast_tanh(v[sq][ub][j]) : v[sq][ub][j];
+      if (p.y != nullptr) {
+        float* yp = p.y + ybase + (int64_t)ta * p.syt;
+#pragma unroll
+        for (int sq = 0; sq < 2; ++sq)
+#pragma unroll
+          for (int up = 0; up < 2; ++up) {
+            if (!valid[sq] || (up == 1 && pad_hi)) continue;
+#pragma unroll
+            for (int ub = 0; ub < 2; ++ub)
+              *reinterpret_cast<float2*>(yp + sq * ysq + up * yup + 8 * ub) = make_float2(o[sq][ub][2 * up], o[sq][ub][2 * up + 1]);
           }
-          if (p.y_img != nullptr) {
-            // element (row 16s+node, feature k) of image [tile][ta][k/16][part][(k/8)%2][128][8]; the pad rows
-            // (node 15, sequences beyond the batch) are written as zeros: the next layer multiplies them by 0
-            const int k = ycol + col;
-            uint32_t hi = 0, lo = 0;
-            if (live) {
+      }
+      if (p.y_img != nullptr) {
+        // element (row 16s+node, feature k) of image [tile][ta][k/16][part][(k/8)%2][128][8]
+        uint8_t* ip = reinterpret_cast<uint8_t*>(p.y_img) + img_base + (size_t)ta * img_step;
+#pragma unroll
+        for (int sq = 0; sq < 2; ++sq)
+#pragma unroll
+          for (int ub = 0; ub < 2; ++ub)
+#pragma unroll
+            for (int up = 0; up < 2; ++up) {
+              uint32_t hi, lo = 0;
               if (SPLIT) {
-                ptx::split_pair_f16(o0, o1, hi, lo);
+                ptx::split_pair_f16(o[sq][ub][2 * up], o[sq][ub][2 * up + 1], hi, lo);
               } else {
-                const __nv_bfloat162 bb = __floats2bfloat162_rn(o0, o1);
+                const __nv_bfloat162 bb = __floats2bfloat162_rn(o[sq][ub][2 * up], o[sq][ub][2 * up + 1]);
                 hi = *reinterpret_cast<const uint32_t*>(&bb);
               }
+              uint8_t* q = ip + ub * 2048 + sq * 256 + up * 128;
+              *reinterpret_cast<uint32_t*>(q) = hi;
+              if (SPLIT) *reinterpret_cast<uint32_t*>(q + 4096) = lo;
             }
-            uint8_t* ip = reinterpret_cast<uint8_t*>(p.y_img) +
-                          ((((((size_t)tile * T + ta) * p.y_kf + (k >> 4)) * NP) * 2 + ((k >> 3) & 1)) * 128 + 16 * s + node) * 16 + (k & 7) * 2;
-            *reinterpret_cast<uint32_t*>(ip) = hi;
-            if (SPLIT) *reinterpret_cast<uint32_t*>(ip + 2 * 128 * 16) = lo;
-          }
-          if (live && t == T - 1 && d.hT != nullptr)
-            *reinterpret_cast<float2*>(d.hT + ((size_t)bseq * kNodes + node) * H + c * 64 + col) = make_float2(a0, a1);
-        }
+      }
     };
 
-    store_half(0, hreg[0]);                       // h_{-1} = h0  (completion #0 of BAR_H)
-    store_half(1, hreg[1]);
-    publish_block(BAR_H);
+    store_units(hreg);                            // h_{-1} = h0  (completion #0 of BAR_H)
+    publish_block(BAR_H, -1);
+
+    const uint4* Pfrag4 = reinterpret_cast<const uint4*>(Pfrag);
+    const int swz = 8 * (tq & 3);                 // XOR swizzle of the transposition buffer column tq
 
     for (int t = 0; t < T; ++t) {
       const uint32_t b = t & 1;
@@ -414,99 +459,96 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       ptx::tc_fence_after();
       if (et == 0) TC_TRACE(0, 1);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float e1[16], e2[16];
+      for (int ub = 0; ub < 2; ++ub) {
+        float e1[2][4], e2[2][4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          {   // phase a: 32 accumulator columns (gate g, units 32h..32h+31) TMEM -> staging[col][row]
-            float v[16];
-            ptx::tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + b * 256 + g * 64 + h * 32 + chalf * 16, v);
-            float* dst = staging + (chalf * 16) * kPitch + quarter * 32 + lane;
+          {   // 8 accumulator columns (gate g, units ubase+8ub .. +7) TMEM -> wst[col][row ^ swizzle(col)]
+            float v[8];
+            ptx::tmem_ld8(tmem_row + b * 256 + g * 64 + ubase + 8 * ub, v);
+            __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dst[i * kPitch] = v[i];
+            for (int j = 0; j < 8; ++j) wst[j * 32 + (lane ^ (8 * (j & 3)))] = v[j];
+            __syncwarp();
           }
-          ptx::named_bar_sync(1, kEpiThreads);
-          // phase b: z[16 nodes x 8 units] = P_g (16x16) . U (16 nodes x 8 units) per unit block on the warp-level
-          // tensor path, fp16 hi/lo split (3 passes) so the mix stays fp32-accurate
-          uint32_t ah[4], al[4];
+          // z[16 nodes x 8 units] = P_g (16x16) . U (16 nodes x 8 units) per sequence on the warp-level tensor path,
+          // fp16 hi/lo split (3 passes) so the mix stays fp32-accurate
+          const uint4 ah4 = Pfrag4[(g * 2 + 0) * 32 + lane], al4 = Pfrag4[(g * 2 + 1) * 32 + lane];
+          const uint32_t ah[4] = {ah4.x, ah4.y, ah4.z, ah4.w}, al[4] = {al4.x, al4.y, al4.z, al4.w};
+          const float2 bias = *reinterpret_cast<const float2*>(biasg + g * 64 + ubase + 8 * ub + 2 * tr);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            ah[i] = Pfrag[((g * 2 + 0) * 4 + i) * 32 + lane];
-            al[i] = Pfrag[((g * 2 + 1) * 4 + i) * 32 + lane];
-          }
-#pragma unroll
-          for (int ub = 0; ub < 4; ++ub) {
-            const float* sp = staging + (8 * ub + tq) * kPitch + 16 * s + 2 * tr;
-            const float2 u0 = *reinterpret_cast<const float2*>(sp);        // nodes 2tr, 2tr+1 of unit column tq
-            const float2 u1 = *reinterpret_cast<const float2*>(sp + 8);    // nodes 2tr+8, 2tr+9
+          for (int sq = 0; sq < 2; ++sq) {
+            const float* sp = wst + tq * 32;
+            const float2 u0 = *reinterpret_cast<const float2*>(sp + ((16 * sq + 2 * tr) ^ swz));        // nodes 2tr, 2tr+1 of unit column tq
+            const float2 u1 = *reinterpret_cast<const float2*>(sp + ((16 * sq + 2 * tr + 8) ^ swz));    // nodes 2tr+8, 2tr+9
             uint32_t bh0, bl0, bh1, bl1;
             ptx::split_pair_f16(u0.x, u0.y, bh0, bl0);
             ptx::split_pair_f16(u1.x, u1.y, bh1, bl1);
-            const float2 bias = *reinterpret_cast<const float2*>(biasg + g * 64 + 32 * h + 8 * ub + 2 * tr);
             float z[4] = {bias.x, bias.y, bias.x, bias.y};
             ptx::mma_16816_f16(z, ah, bh0, bh1);
             ptx::mma_16816_f16(z, al, bh0, bh1);
             ptx::mma_16816_f16(z, ah, bl0, bl1);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int e = ub * 4 + j;
-              const bool ok = valid && !(pad_hi && j >= 2);
-              // c' = sig(zf) c + sig(zi) tanh(zc), hy = sig(zo) tanh(c'); the clamps only bound the exponentials
+              const bool ok = valid[sq] && !(pad_hi && j >= 2);
+              // c' = sig(zf) c + sig(zi) tanh(zc), hy = sig(zo) tanh(c') with shared reciprocals: 5 ex2 + 2 rcp per element
               if (g == 0) {
-                e1[e] = 1.0f + __expf(-fminf(fmaxf(z[j], -28.f), 28.f));                    // 1 + e^-zi
+                e1[sq][j] = one_plus_exp_neg(z[j]);                                              // 1 + e^-zi
               } else if (g == 1) {
-                e2[e] = 1.0f + __expf(-fminf(fmaxf(z[j], -28.f), 28.f));                    // 1 + e^-zf
+                e2[sq][j] = one_plus_exp_neg(z[j]);                                              // 1 + e^-zf
               } else if (g == 2) {
-                const float eb = __expf(-2.0f * fminf(fmaxf(z[j], -14.f), 14.f));
-                const float dab = e1[e] * (1.0f + eb);
-                float cn = __fdividef(fmaf(creg[h][e], dab, (1.0f - eb) * e2[e]), e2[e] * dab);
+                const float eb = exp_neg2(z[j]);                                                 // tanh(zc) = (1 - eb) / (1 + eb)
+                const float dab = e1[sq][j] * (1.0f + eb);
+                float cn = fmaf(creg[sq][ub][j], dab, (1.0f - eb) * e2[sq][j]) * rcp_ftz(e2[sq][j] * dab);
                 cn = ok ? cn : 0.f;
-                creg[h][e] = cn;
-                const float ec = __expf(-2.0f * fminf(fmaxf(cn, -14.f), 14.f));
-                e1[e] = __fdividef(1.0f - ec, 1.0f + ec);                                   // tanh(c')
+                creg[sq][ub][j] = cn;
+                const float ec = exp_neg2(cn);
+                e1[sq][j] = 1.0f - ec;                                                           // tanh(c') = (1 - ec) / (1 + ec)
+                e2[sq][j] = 1.0f + ec;
               } else {
-                const float eo = __expf(-fminf(fmaxf(z[j], -28.f), 28.f));
-                hreg[h][e] = ok ? __fdividef(e1[e], 1.0f + eo) : 0.f;
+                const float hy = e1[sq][j] * rcp_ftz(e2[sq][j] * one_plus_exp_neg(z[j]));
+                hreg[sq][ub][j] = ok ? hy : 0.f;
               }
             }
           }
-          if (g == 3) {
-            if (ATT) {
-              // node sum of hy (q_t = relu((sum_n hy_n) W_a^T), net_aagc.py:200) goes to row 15 of the sequence,
-              // which the attention GEMM reads as a 16th "node": the lanes owning the pad slot store it there
-#pragma unroll
-              for (int ub = 0; ub < 4; ++ub)
-#pragma unroll
-                for (int u2 = 0; u2 < 2; ++u2) {
-                  float sum = hreg[h][ub * 4 + u2] + hreg[h][ub * 4 + 2 + u2];
-                  sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-                  sum += __shfl_xor_sync(0xffffffffu, sum, 8);
-                  sum += __shfl_xor_sync(0xffffffffu, sum, 16);
-                  if (pad_hi) hreg[h][ub * 4 + 2 + u2] = sum;
-                }
-              store_half(h, hreg[h]);
-              if (pad_hi) {
-#pragma unroll
-                for (int ub = 0; ub < 4; ++ub) { hreg[h][ub * 4 + 2] = 0.f; hreg[h][ub * 4 + 3] = 0.f; }
-              }
-            } else {
-              store_half(h, hreg[h]);
-              emit(t, ta, h, hreg[h]);
-            }
-          }
-          if (h == 1 && g == 3) ptx::tc_fence_before();
-          ptx::named_bar_sync(1, kEpiThreads);
         }
       }
-      if (et == 0) ptx::mbar_arrive(&bars[BAR_ACC_EMPTY + b]);
+      if (ATT) {
+        // node sum of hy (q_t = relu((sum_n hy_n) W_a^T), net_aagc.py:200) goes to row 15 of the sequence, which the
+        // attention GEMM reads as a 16th "node": the lanes owning the pad slot store it there
+        float keep[2][2][2];
+#pragma unroll
+        for (int sq = 0; sq < 2; ++sq)
+#pragma unroll
+          for (int ub = 0; ub < 2; ++ub)
+#pragma unroll
+            for (int u2 = 0; u2 < 2; ++u2) {
+              float sum = hreg[sq][ub][u2] + hreg[sq][ub][2 + u2];
+              sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+              sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+              sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+              keep[sq][ub][u2] = hreg[sq][ub][2 + u2];
+              if (pad_hi) hreg[sq][ub][2 + u2] = sum;
+            }
+        store_units(hreg);
+#pragma unroll
+        for (int sq = 0; sq < 2; ++sq)
+#pragma unroll
+          for (int ub = 0; ub < 2; ++ub)
+#pragma unroll
+            for (int u2 = 0; u2 < 2; ++u2) hreg[sq][ub][2 + u2] = keep[sq][ub][u2];
+      } else {
+        store_units(hreg);
+        emit(ta, hreg);
+      }
       if (et == 0) TC_TRACE(0, 2);
 
       if (!ATT) {
-        publish_block(BAR_H);
+        publish_block(BAR_H, (int)b);
         if (et == 0) TC_TRACE(0, 11);
         continue;
       }
-      publish_block(BAR_HHAT);
+      publish_block(BAR_HHAT, (int)b);
       if (et == 0) TC_TRACE(0, 4);
       // ---- q = relu(Wa . sum_n hy): rows 15 of the A1 accumulator, columns [64,128)
       ptx::mbar_wait(&bars[BAR_ATT_FULL], t & 1);
@@ -514,12 +556,11 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       ptx::mbar_wait(&bars[BAR_A1FREE], t & 1);
       ptx::tc_fence_after();
       if (et == 0) TC_TRACE(0, 5);
-#pragma unroll
-      for (int h16 = 0; h16 < 2; ++h16) {
+      {
         float v[16];
-        ptx::tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + b * 256 + 64 + chalf * 32 + h16 * 16, v);
+        ptx::tmem_ld16(tmem_row + b * 256 + 64 + ubase, v);
         if ((lane & 15) == 15) {
-          const int qrow = quarter * 32 + lane;             // = 16*seq + 15
+          const int qrow = qd * 32 + lane;                  // = 16*seq + 15
 #pragma unroll
           for (int g8 = 0; g8 < 2; ++g8) {                  // 8 consecutive units = one 16-byte K chunk of the row
             uint32_t hw[4], lw[4];
@@ -532,7 +573,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
               lw[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
             }
             const uint4 hq = make_uint4(hw[0], hw[1], hw[2], hw[3]), lq = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-            const uint32_t off = img_off((int)c * 64 + chalf * 32 + h16 * 16 + g8 * 8, qrow);
+            const uint32_t off = img_off((int)c * 64 + ubase + g8 * 8, qrow);
             *reinterpret_cast<uint4*>(hbuf + off) = hq;
             if (SPLIT) *reinterpret_cast<uint4*>(hbuf + (size_t)H * 256 + off) = lq;
 #pragma unroll 1
@@ -551,30 +592,26 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) ptx::mbar_arrive_remote(&bars[BAR_Q], peer);
         TC_TRACE(0, 6);
       }
-      // ---- e = tanh(Wh hy + Wq q + bs),  partial a = e . u over this CTA's 64 units (lane = row)
+      // ---- e = tanh(Wh hy + Wq q + bs),  partial a = e . u over this warp's 16 units (lane = row)
       ptx::mbar_wait(&bars[BAR_ATT2_FULL], t & 1);
       ptx::tc_fence_after();
       if (et == 0) TC_TRACE(0, 7);
       {
         float part = 0.f;
+        float vh[16], vq[16];
+        ptx::tmem_ld16(tmem_row + b * 256 + ubase, vh);
+        ptx::tmem_ld16(tmem_row + b * 256 + 128 + ubase, vq);
 #pragma unroll
-        for (int h16 = 0; h16 < 2; ++h16) {
-          float vh[16], vq[16];
-          const int c0 = chalf * 32 + h16 * 16;
-          ptx::tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + b * 256 + c0, vh);
-          ptx::tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + b * 256 + 128 + c0, vq);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float wq = __shfl_sync(0xffffffffu, vq[i], (lane & 16) | 15);
-            part = fmaf(fast_tanh(vh[i] + wq + bss[c0 + i]), us[c0 + i], part);
-          }
+        for (int i = 0; i < 16; ++i) {
+          const float wq = __shfl_sync(0xffffffffu, vq[i], (lane & 16) | 15);
+          part = fmaf(fast_tanh(vh[i] + wq + bss[ubase + i]), us[ubase + i], part);
         }
-        ahalf[chalf * 128 + quarter * 32 + lane] = part;
+        ahalf[ug * 128 + qd * 32 + lane] = part;
       }
       ptx::tc_fence_before();
       ptx::named_bar_sync(1, kEpiThreads);
       if (et == 0) ptx::mbar_arrive(&bars[BAR_ACC_EMPTY + b]);
-      if (et < 128) apart[c * 128 + et] = ahalf[et] + ahalf[128 + et];
+      if (et < 128) apart[c * 128 + et] = (ahalf[et] + ahalf[128 + et]) + (ahalf[256 + et] + ahalf[384 + et]);
       ptx::fence_proxy_async();
       ptx::named_bar_sync(1, kEpiThreads);
       if (et == 0) {
@@ -593,27 +630,34 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       }
       ptx::named_bar_sync(1, kEpiThreads);
       // ---- h' = hy (1 + a): next step's operand and y_t = act(h')
-      {
-        const float alo = ahalf[16 * s + tq], ahi = pad_hi ? 0.f : ahalf[16 * s + tq + 8];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+      for (int sq = 0; sq < 2; ++sq) {
+        const int r0 = 16 * (2 * qd + sq) + tq;
+        const float alo = ahalf[r0], ahi = pad_hi ? 0.f : ahalf[r0 + 8];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) hreg[h][e] *= (e & 2) ? ahi : alo;
-          store_half(h, hreg[h]);
-          emit(t, ta, h, hreg[h]);
-        }
+        for (int ub = 0; ub < 2; ++ub)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) hreg[sq][ub][j] *= (j & 2) ? ahi : alo;
       }
+      store_units(hreg);
+      emit(ta, hreg);
       if (et == 0) TC_TRACE(0, 10);
-      publish_block(BAR_H);
+      publish_block(BAR_H, -1);
       if (et == 0) TC_TRACE(0, 11);
     }
-    if (valid && d.cT != nullptr) {
+    // final state: h' and c' after the last step (registers)
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
+    for (int sq = 0; sq < 2; ++sq) {
+      if (!valid[sq]) continue;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int node = tq + ((e & 2) ? 8 : 0), unit = 32 * h + 8 * (e >> 2) + 2 * tr + (e & 1);
-          if (node < kNodes) d.cT[((size_t)bseq * kNodes + node) * H + c * 64 + unit] = creg[h][e];
+      for (int ub = 0; ub < 2; ++ub)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int node = tq + 8 * (j >> 1), unit = ubase + 8 * ub + 2 * tr + (j & 1);
+          if (node >= kNodes) continue;
+          const size_t gi = ((size_t)bseq[sq] * kNodes + node) * H + c * 64 + unit;
+          if (d.cT != nullptr) d.cT[gi] = creg[sq][ub][j];
+          if (d.hT != nullptr) d.hT[gi] = hreg[sq][ub][j];
         }
     }
     // the last publish must have landed everywhere before any CTA may exit
@@ -795,6 +839,19 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
   p.y_img = a.y_img; p.y_kf = a.y_img_f / 16;
   p.B = (int)a.batch; p.T = (int)a.steps; p.F = F; p.H = H; p.out_act = a.out_act; p.C = C;
   p.trace = getenv("A3GC_TC_TRACE") != nullptr ? 1 : 0;
+  {
+    // static placement of the x-part of step t+1 around the attention GEMMs of step t: ~45 % of its K blocks while the
+    // epilogue warps run the gate phase, ~20 % during the q hand-off, the rest during e.u / h' / the state exchange
+    const int KF = F / 16;
+    int n1 = (KF * 45 + 99) / 100, n2 = KF / 5;
+    if (const char* e = getenv("A3GC_TC_SPLIT")) {
+      int a = 0, b = 0;
+      if (sscanf(e, "%d,%d", &a, &b) == 2) { n1 = KF * a / 100; n2 = KF * b / 100; }
+    }
+    if (n1 > KF) n1 = KF;
+    if (n1 + n2 > KF) n2 = KF - n1;
+    p.n1 = n1; p.n2 = n2;
+  }
 
   int dev = 0, smem_max = 0;
   A3GC_CUDA_TRY(cudaGetDevice(&dev));
@@ -802,6 +859,7 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
   const size_t stage_bytes = (size_t)NP * (2 * 256 * 16 + 2 * 128 * 16);
   const size_t fixed = (size_t)NP * H * 256 + tc_fixed_smem_bytes(C);
   int S = kMaxStages;
+  if (const char* e = getenv("A3GC_TC_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= kMaxStages) S = v; }
   while (S > 1 && fixed + (size_t)S * stage_bytes > (size_t)smem_max) --S;
   if (fixed + (size_t)S * stage_bytes > (size_t)smem_max || S < 2) {
     set_error("tc engine: shared memory budget exceeded (hidden=%d)", H);

@@ -65,6 +65,52 @@ tc_selftest_kernel(const uint16_t* __restrict__ a_img, const uint16_t* __restric
   if (warp == 0) ptx::tmem_dealloc(tmem, 256);
 }
 
+
+// Micro-benchmark of the UMMA issue rate for a given shared-memory operand layout: `iters` back-to-back
+// tcgen05.mma (M=128, N=n, K=16, fp16) cycling over `nk` K-steps of one resident tile; reports clock64 cycles per
+// MMA of CTA 0.  Operand contents are zeros -- only the addressing pattern matters.
+__global__ void __launch_bounds__(128, 1)
+tc_mma_bench_kernel(int n, int layout_type, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int a_kstep, int b_kstep,
+                    int nk, int iters, float* __restrict__ cycles_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x / 32;
+  for (int i = threadIdx.x; i < 160 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { ptx::mbar_init(&bar_mma, 1); ptx::fence_mbar_init(); }
+  if (warp == 0) ptx::tmem_alloc(&tmem_base_slot, 256);
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = ptx::make_idesc_f16(128, n, false);
+    const uint32_t sa = ptx::smem_u32(smem), sb = sa + 64 * 1024;
+    const uint64_t lt = (uint64_t)layout_type << 61;
+    // descriptors of the (up to) 4 K-steps are built once: the issue loop is the MMA instructions alone
+    uint64_t ad[4], bd[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      ad[kk] = ptx::make_smem_desc(sa + (uint32_t)(kk % nk) * a_kstep, a_lbo, a_sbo) | lt;
+      bd[kk] = ptx::make_smem_desc(sb + (uint32_t)(kk % nk) * b_kstep, b_lbo, b_sbo) | lt;
+    }
+    ptx::umma_f16(tmem, ad[0], bd[0], idesc, 0u);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) ptx::umma_f16(tmem, ad[kk], bd[kk], idesc, 1u);
+    }
+    ptx::umma_commit(&bar_mma);
+    ptx::mbar_wait(&bar_mma, 0);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0) cycles_out[0] = (float)(t1 - t0) / (float)iters;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+}
+
 }  // namespace
 }  // namespace a3gc
 
@@ -81,5 +127,21 @@ extern "C" int a3gc_tc_selftest(const void* a_img, const void* b_img, float* d, 
   tc_selftest_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint16_t*>(a_img), static_cast<const uint16_t*>(b_img), d, k, n, flags & 1, (flags >> 1) & 1);
   A3GC_LAUNCH_CHECK("tc_selftest_kernel");
+  return A3GC_OK;
+}
+
+// debug / tuning: see tc_mma_bench_kernel.  cycles_out is a device pointer to one float.
+extern "C" int a3gc_tc_mma_bench(int n, int layout_type, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int a_kstep, int b_kstep,
+                                 int nk, int iters, int grid, float* cycles_out, void* stream) {
+  using namespace a3gc;
+  if (!cycles_out || n < 16 || n > 256 || n % 16 != 0 || nk < 1 || iters < 1 || grid < 1) {
+    set_error("a3gc_tc_mma_bench: invalid argument");
+    return A3GC_ERR_INVALID_ARG;
+  }
+  const size_t smem = 160 * 1024;
+  A3GC_CUDA_TRY(cudaFuncSetAttribute(tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_mma_bench_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(n, layout_type, a_lbo, a_sbo, b_lbo, b_sbo, a_kstep, b_kstep,
+                                                                              nk, iters, cycles_out);
+  A3GC_LAUNCH_CHECK("tc_mma_bench_kernel");
   return A3GC_OK;
 }

@@ -201,6 +201,12 @@ int a3gc_profile_get(int index, char* label, int label_bytes, float* ms, double*
  */
 int a3gc_tc_selftest(const void* a_img, const void* b_img, float* d, int k, int n, int flags, void* stream);
 
+/* Tuning aid: cycles per tcgen05.mma (M=128, N=n, K=16, fp16) for a shared-memory operand layout given by the
+ * descriptor fields (layout_type 0 = no swizzle, 2 = 128-byte swizzle; LBO / SBO / per-K-step start offsets in
+ * bytes); `iters` back-to-back MMAs cycling over nk K-steps, `grid` CTAs; cycles_out: device pointer to one float. */
+int a3gc_tc_mma_bench(int n, int layout_type, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int a_kstep, int b_kstep,
+                      int nk, int iters, int grid, float* cycles_out, void* stream);
+
 /* Debug: per-phase clock64 timeline of CTA (0,0) of the last tensor-core layer launch made with the
  * environment variable A3GC_TC_TRACE set; host_out receives [2 roles][16 steps][16 slots] uint64. */
 int a3gc_debug_read_tc_trace(unsigned long long* host_out);
