@@ -48,6 +48,14 @@ class CellParams(C.Structure):
     ]
 
 
+class Tape(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("gates", "u", "c", "hh", "e", "hp", "a", "q", "s")]
+
+
+class TapeGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("dzm", "dep", "dqs", "dqp", "dap")]
+
+
 class NetParams(C.Structure):
     _fields_ = [("linear_in", GcParams), ("rnn", (CellParams * 2) * 2), ("linear_out", GcParams)]
 
@@ -73,6 +81,20 @@ SYMBOLS = {
                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                    C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "a3gc_layer_train_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "a3gc_layer_train_forward": (C.c_int, [C.c_int, C.c_int, C.POINTER(CellParams), C.POINTER(C.c_int),
+                                           C.c_void_p, C.c_int64, C.c_int64,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                           C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                           C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                           C.POINTER(Tape), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "a3gc_layer_backward": (C.c_int, [C.c_int, C.c_int, C.POINTER(CellParams), C.POINTER(C.c_int),
+                                      C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                      C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(Tape), C.POINTER(TapeGrads), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "a3gc_prepare_input": (C.c_int, [C.c_void_p] * 7 + [C.c_int64, C.c_int, C.c_void_p]),
     "a3gc_concat_stage_input": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "a3gc_profile_enable": (C.c_int, [C.c_int]),

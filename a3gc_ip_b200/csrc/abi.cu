@@ -319,6 +319,94 @@ int a3gc_net_forward(int variant, const a3gc_net_params* net, const float* x,
   return simt_gc_forward(&net->linear_out, a2, y, frames, 2 * H, f_out, A3GC_ACT_LINEAR, s);
 }
 
+size_t a3gc_layer_train_workspace_bytes(int variant, int f_in, int hidden, int num_dirs) {
+  if (variant < A3GC_VARIANT_AAGC || variant > A3GC_VARIANT_AGC || num_dirs < 1 || num_dirs > 2 || f_in <= 0 || hidden <= 0) return 0;
+  return simt_train_workspace_bytes(variant, f_in, hidden, num_dirs);
+}
+
+static int check_tape(int variant, const a3gc_tape* t, const char* who) {
+  const bool att = variant != A3GC_VARIANT_AAGC;
+  if (!t || !t->gates || !t->c || !t->hh || !t->hp || (att && (!t->e || !t->a || !t->q || !t->s))) {
+    set_error("%s: incomplete tape", who);
+    return A3GC_ERR_INVALID_ARG;
+  }
+  return A3GC_OK;
+}
+
+int a3gc_layer_train_forward(int variant, int num_dirs, const a3gc_cell_params* cells, const int* reverse,
+                             const float* x, int64_t x_stride_b, int64_t x_stride_t,
+                             const float* const* h0, const float* const* c0,
+                             float* y, int64_t y_stride_b, int64_t y_stride_t, int64_t y_ld,
+                             float* const* hT, float* const* cT,
+                             int64_t batch, int64_t steps, int f_in, int hidden, int out_act,
+                             const a3gc_tape* tape, const float* hmask,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  if (variant < A3GC_VARIANT_AAGC || variant > A3GC_VARIANT_AGC) {
+    set_error("a3gc_layer_train_forward: the training path covers the LSTM-family cells (AAGC / A3GC / AGC)");
+    return A3GC_ERR_UNSUPPORTED;
+  }
+  if (num_dirs < 1 || num_dirs > 2 || !cells || !reverse || batch < 0 || steps < 0 || f_in <= 0 || hidden <= 0 ||
+      out_act < A3GC_ACT_LINEAR || out_act > A3GC_ACT_TANH || (batch * steps > 0 && (!x || !y))) {
+    set_error("a3gc_layer_train_forward: invalid argument");
+    return A3GC_ERR_INVALID_ARG;
+  }
+  for (int d = 0; d < num_dirs; ++d) { int rc = check_cell(variant, cells[d], "a3gc_layer_train_forward"); if (rc) return rc; }
+  if (batch == 0 || steps == 0) return A3GC_OK;
+  int rc = check_tape(variant, tape, "a3gc_layer_train_forward");
+  if (rc) return rc;
+  LayerArgs a;
+  memset(&a, 0, sizeof(a));
+  a.variant = variant; a.num_dirs = num_dirs; a.cells = cells;
+  for (int d = 0; d < num_dirs; ++d) {
+    a.reverse[d] = reverse[d];
+    a.h0[d] = h0 ? h0[d] : nullptr; a.c0[d] = c0 ? c0[d] : nullptr;
+    a.hT[d] = hT ? hT[d] : nullptr; a.cT[d] = cT ? cT[d] : nullptr;
+  }
+  a.x = x; a.x_stride_b = x_stride_b; a.x_stride_t = x_stride_t;
+  a.y = y; a.y_stride_b = y_stride_b; a.y_stride_t = y_stride_t; a.y_ld = y_ld;
+  a.batch = batch; a.steps = steps; a.f_in = f_in; a.hidden = hidden; a.out_act = out_act; a.precision = A3GC_PREC_FP32;
+  return simt_train_forward(a, *tape, hmask, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int a3gc_layer_backward(int variant, int num_dirs, const a3gc_cell_params* cells, const int* reverse,
+                        const float* dy, int64_t dy_stride_b, int64_t dy_stride_t, int64_t dy_ld,
+                        const float* const* c0, const float* const* dhT, const float* const* dcT,
+                        float* const* dh0, float* const* dc0,
+                        int64_t batch, int64_t steps, int f_in, int hidden, int out_act,
+                        const a3gc_tape* tape, const a3gc_tape_grads* grads, const float* hmask,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (variant < A3GC_VARIANT_AAGC || variant > A3GC_VARIANT_AGC) {
+    set_error("a3gc_layer_backward: the training path covers the LSTM-family cells (AAGC / A3GC / AGC)");
+    return A3GC_ERR_UNSUPPORTED;
+  }
+  if (num_dirs < 1 || num_dirs > 2 || !cells || !reverse || batch < 0 || steps < 0 || f_in <= 0 || hidden <= 0 ||
+      out_act < A3GC_ACT_LINEAR || out_act > A3GC_ACT_TANH || (batch * steps > 0 && !dy)) {
+    set_error("a3gc_layer_backward: invalid argument");
+    return A3GC_ERR_INVALID_ARG;
+  }
+  for (int d = 0; d < num_dirs; ++d) { int rc = check_cell(variant, cells[d], "a3gc_layer_backward"); if (rc) return rc; }
+  if (batch == 0 || steps == 0) return A3GC_OK;
+  int rc = check_tape(variant, tape, "a3gc_layer_backward");
+  if (rc) return rc;
+  const bool att = variant != A3GC_VARIANT_AAGC;
+  if (!grads || !grads->dzm || (att && (!grads->dep || !grads->dqs || !grads->dqp || !grads->dap))) {
+    set_error("a3gc_layer_backward: incomplete gradient tape");
+    return A3GC_ERR_INVALID_ARG;
+  }
+  TrainBwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.variant = variant; a.num_dirs = num_dirs; a.cells = cells;
+  for (int d = 0; d < num_dirs; ++d) {
+    a.reverse[d] = reverse[d];
+    a.c0[d] = c0 ? c0[d] : nullptr; a.dhT[d] = dhT ? dhT[d] : nullptr; a.dcT[d] = dcT ? dcT[d] : nullptr;
+    a.dh0[d] = dh0 ? dh0[d] : nullptr; a.dc0[d] = dc0 ? dc0[d] : nullptr;
+  }
+  a.dy = dy; a.dy_stride_b = dy_stride_b; a.dy_stride_t = dy_stride_t; a.dy_ld = dy_ld;
+  a.batch = batch; a.steps = steps; a.f_in = f_in; a.hidden = hidden; a.out_act = out_act;
+  a.tape = *tape; a.grads = *grads; a.hmask = hmask;
+  return simt_train_backward(a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 int a3gc_prepare_input(const float* acc, const float* ori, const float* acc_mean, const float* acc_std,
                        const float* ori_mean, const float* ori_std, float* x, int64_t frames, int ld_x,
                        void* stream) {

@@ -95,6 +95,24 @@ int simt_prepare_input(const float* acc, const float* ori, const float* acc_mean
                        cudaStream_t stream);
 int simt_concat_stage_input(const float* x, const float* pos, float* dst, int64_t frames, cudaStream_t stream);
 
+
+// training path (simt_kernels.cu): forward with a tape, reverse-time backward chain
+struct TrainBwdArgs {
+  int variant, num_dirs;
+  const a3gc_cell_params* cells;
+  int reverse[2];
+  const float* dy; int64_t dy_stride_b, dy_stride_t, dy_ld;
+  const float* c0[2]; const float* dhT[2]; const float* dcT[2];
+  float* dh0[2]; float* dc0[2];
+  int64_t batch, steps;
+  int f_in, hidden, out_act;
+  a3gc_tape tape; a3gc_tape_grads grads;
+  const float* hmask;
+};
+size_t simt_train_workspace_bytes(int variant, int f_in, int hidden, int num_dirs);
+int simt_train_forward(const LayerArgs& a, const a3gc_tape& tape, const float* hmask, void* ws, size_t ws_bytes, cudaStream_t stream);
+int simt_train_backward(const TrainBwdArgs& a, void* ws, size_t ws_bytes, cudaStream_t stream);
+
 // ---- tensor-core (tcgen05) engine: tc_kernels.cu ----------------------------------------
 bool tc_layer_supported(int variant, int f_in, int hidden, int precision);
 size_t tc_layer_workspace_bytes(int variant, int64_t batch, int64_t steps, int f_in, int hidden, int num_dirs, int precision);

@@ -388,6 +388,442 @@ lstm_layer_kernel(LstmPacked w0, LstmPacked w1, DirPtrs d0, DirPtrs d1, LayerGeo
 }
 
 // ------------------------------------------------------------------------------------------
+// Training path of the LSTM family (BPTT): forward with a tape, and the reverse-time backward chain.
+//
+// Tape layout (all fp32, allocated by the caller): one record per (direction d, time t, sequence b),
+// idx = (d*T + t)*B + b, unit-major with the node index fastest and padded to 16 -- the shared-memory
+// layout of the kernels, so every record is written / read as contiguous 64-byte rows; node slot 15 is
+// always 0 so that reductions over the padded axis are exact.
+//   gates [idx][4][H][16]  activated i, f, c~, o          (overwritten in place with dz by the backward)
+//   u     [idx][4][H][16]  pre-mix accumulators S W_g^T   (for the adjacency gradients)
+//   c, hh, e [idx][H][16]   c'_t, hy_t (before attention), e_t = tanh(..)
+//   hp    [D][B][T][15][H]  h'_t, node-major like the layer input x, so that [x | h_prev] and the mixed gate
+//                           gradients dzm [D][B][T][15][4H] are the row-major operands of the hoisted GEMMs
+//   a [idx][16] (sigmoid output), q [idx][H], s [idx][H] (node sums)
+// ------------------------------------------------------------------------------------------
+struct TrainGeom {
+  LayerGeom g;
+  a3gc_tape tape;
+  const float* hmask;   // [D][B][T][15][H] multiplicative recurrent-dropout mask (0 or 1/(1-p)); nullptr = none
+};
+
+template <bool ATT>
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_train_fwd_kernel(LstmPacked w0, LstmPacked w1, DirPtrs d0, DirPtrs d1, TrainGeom tg) {
+  extern __shared__ __align__(16) float smem[];
+  const LayerGeom& g = tg.g;
+  const a3gc_tape& tp = tg.tape;
+  const LstmPacked w = blockIdx.y == 0 ? w0 : w1;
+  const DirPtrs d = blockIdx.y == 0 ? d0 : d1;
+  const int H = g.H, F = g.F, BT = g.BT;
+  const int KX = F > H ? F : H;
+  float* hbuf = smem;                                  // [2][BT][H][16]
+  float* cbuf = hbuf + (size_t)2 * BT * H * kNodesPad; // [BT][H][16]
+  float* xbuf = cbuf + (size_t)BT * H * kNodesPad;     // [BT][KX][16]
+  float* qbuf = xbuf + (size_t)BT * KX * kNodesPad;    // [BT][H]
+  float* sbuf = qbuf + (size_t)BT * H;                 // [BT][H]
+  float* abuf = sbuf + (size_t)BT * H;                 // [BT][16]
+  float* Pbuf = abuf + (size_t)BT * kNodesPad;         // [4][16][16]
+  const int b0 = blockIdx.x * BT;
+  const int y_off = blockIdx.y * H;
+  const size_t HN = (size_t)H * kNodesPad;
+
+  load_state(hbuf, d.h0, b0, g);
+  load_state(cbuf, d.c0, b0, g);
+  for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) Pbuf[i] = w.P[i];
+  int cur = 0;
+  const int ntask = BT * H;
+
+  for (int step = 0; step < g.T; ++step) {
+    const int t = d.reverse ? g.T - 1 - step : step;
+    const size_t rec0 = ((size_t)blockIdx.y * g.T + t) * g.B;      // record index of sequence 0 at (d, t)
+    // node-major arrays [D][B][T][15][H]: offset of (d, b = 0, t, n = 0, j = 0); add ((b*T*15) + n) * H + j
+    const size_t nm0 = ((size_t)blockIdx.y * g.B * g.T + t) * kNodes * H;
+    float* hcur = hbuf + (size_t)cur * BT * HN;
+    float* hnxt = hbuf + (size_t)(cur ^ 1) * BT * HN;
+    __syncthreads();
+    load_x(xbuf, b0, t, g);
+    if (tg.hmask != nullptr) {   // recurrent dropout acts on the h that enters the gates only (net_aagc.py:181)
+      for (int i = threadIdx.x; i < BT * kNodes * H; i += blockDim.x) {
+        const int j = i % H, n = (i / H) % kNodes, s = i / (H * kNodes), b = b0 + s;
+        if (b < g.B) hcur[((size_t)s * H + j) * kNodesPad + n] *= tg.hmask[nm0 + ((size_t)b * g.T * kNodes + n) * H + j];
+      }
+    }
+    __syncthreads();
+
+    for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+      const int s = task / H, j = task % H;
+      const int b = b0 + s;
+      const bool live = b < g.B;
+      const size_t rec = rec0 + b;
+      float acc[4][16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int n = 0; n < 16; ++n) acc[q][n] = 0.f;
+      accum4(acc, xbuf + (size_t)s * F * kNodesPad, w.Wg4 + j, F, H);
+      accum4(acc, hcur + (size_t)s * HN, w.Wg4 + (size_t)F * H + j, H, H);
+      const float4 bias = w.bias4[j];
+      const float bb[4] = {bias.x, bias.y, bias.z, bias.w};
+      float gate[4][16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        acc[q][15] = 0.f;
+        if (live && tp.u != nullptr) store16(tp.u + ((rec * 4 + q) * H + j) * kNodesPad, acc[q]);
+        float tmp[16];
+        mix15(acc[q], Pbuf + q * 256, tmp);
+#pragma unroll
+        for (int m = 0; m < kNodes; ++m) gate[q][m] = q == 2 ? tanhf_(tmp[m] + bb[q]) : sigmoidf_(tmp[m] + bb[q]);
+        gate[q][15] = 0.f;
+        if (live) store16(tp.gates + ((rec * 4 + q) * H + j) * kNodesPad, gate[q]);
+      }
+      float cs[16], hy[16];
+      load16(cs, cbuf + ((size_t)s * H + j) * kNodesPad);
+#pragma unroll
+      for (int m = 0; m < kNodes; ++m) {
+        cs[m] = fmaf(gate[1][m], cs[m], gate[0][m] * gate[2][m]);
+        hy[m] = gate[3][m] * tanhf_(cs[m]);
+      }
+      cs[15] = 0.f; hy[15] = 0.f;
+      store16(cbuf + ((size_t)s * H + j) * kNodesPad, cs);
+      store16(hnxt + ((size_t)s * H + j) * kNodesPad, hy);
+      if (live) {
+        store16(tp.c + (rec * H + j) * kNodesPad, cs);
+        store16(tp.hh + (rec * H + j) * kNodesPad, hy);
+        if (!ATT) {
+          float* hpp = tp.hp + nm0 + (size_t)b * g.T * kNodes * H + j;
+          float* yp = g.y + (size_t)b * g.syb + (size_t)t * g.syt + y_off + j;
+#pragma unroll
+          for (int m = 0; m < kNodes; ++m) { hpp[(size_t)m * H] = hy[m]; yp[(size_t)m * g.yld] = apply_act(hy[m], g.out_act); }
+        }
+      }
+    }
+
+    if (ATT) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < ntask; i += blockDim.x) {
+        float v[16];
+        load16(v, hnxt + (size_t)i * kNodesPad);
+        float sum = 0.f;
+#pragma unroll
+        for (int n = 0; n < kNodes; ++n) sum += v[n];
+        sbuf[i] = sum;
+        const int b = b0 + i / H;
+        if (b < g.B) tp.s[(rec0 + b) * H + i % H] = sum;
+      }
+      __syncthreads();
+      for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+        const int s = task / H, j = task % H;
+        float q = 0.f;
+        const float* sv = sbuf + (size_t)s * H;
+        for (int k = 0; k < H; ++k) q = fmaf(sv[k], __ldg(w.Wa_t + (size_t)k * H + j), q);
+        q = fmaxf(q, 0.f);
+        qbuf[task] = q;
+        if (b0 + s < g.B) tp.q[(rec0 + b0 + s) * H + j] = q;
+      }
+      __syncthreads();
+      for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+        const int s = task / H, j = task % H;
+        float e[16];
+#pragma unroll
+        for (int n = 0; n < 16; ++n) e[n] = 0.f;
+        accum1(e, hnxt + (size_t)s * HN, w.Wh_t + j, H, H);
+        float wq = w.bs[j];
+        const float* qv = qbuf + (size_t)s * H;
+        for (int k = 0; k < H; ++k) wq = fmaf(qv[k], __ldg(w.Wq_t + (size_t)k * H + j), wq);
+        const float uj = w.u[j];
+#pragma unroll
+        for (int n = 0; n < kNodes; ++n) e[n] = tanhf_(e[n] + wq);
+        e[15] = 0.f;
+        if (b0 + s < g.B) store16(tp.e + ((rec0 + b0 + s) * H + j) * kNodesPad, e);
+#pragma unroll
+        for (int n = 0; n < kNodes; ++n) e[n] *= uj;
+        store16(xbuf + ((size_t)s * KX + j) * kNodesPad, e);     // scratch [seq][j][16]
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < BT * kNodesPad; i += blockDim.x) {
+        const int s = i / kNodesPad, n = i % kNodesPad;
+        float a = 0.f, sg = 0.f;
+        if (n < kNodes) {
+          const float* ev = xbuf + (size_t)s * KX * kNodesPad + n;
+          for (int j = 0; j < H; ++j) a += ev[(size_t)j * kNodesPad];
+          sg = sigmoidf_(a + w.bu[n]);
+          a = 1.0f + sg;                                           // hy + hy * a_t  (net_aagc.py:212-213)
+        }
+        abuf[i] = a;
+        if (b0 + s < g.B) tp.a[(rec0 + b0 + s) * kNodesPad + n] = sg;
+      }
+      __syncthreads();
+      for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+        const int s = task / H, j = task % H;
+        float hy[16], av[16];
+        load16(hy, hnxt + (size_t)task * kNodesPad);
+        load16(av, abuf + (size_t)s * kNodesPad);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) hy[m] *= av[m];
+        store16(hnxt + (size_t)task * kNodesPad, hy);
+        const int b = b0 + s;
+        if (b < g.B) {
+          float* hpp = tp.hp + nm0 + (size_t)b * g.T * kNodes * H + j;
+          float* yp = g.y + (size_t)b * g.syb + (size_t)t * g.syt + y_off + j;
+#pragma unroll
+          for (int m = 0; m < kNodes; ++m) { hpp[(size_t)m * H] = hy[m]; yp[(size_t)m * g.yld] = apply_act(hy[m], g.out_act); }
+        }
+      }
+    }
+    cur ^= 1;
+  }
+  __syncthreads();
+  store_state(d.hT, hbuf + (size_t)cur * BT * HN, b0, g);
+  store_state(d.cT, cbuf, b0, g);
+}
+
+// Reverse-time chain of one direction.  Consumes dY (gradient of the layer output act(h'_t)), the incoming
+// gradients of the final state, and the tape; produces per step the gate-pre-activation gradients dz (in place
+// of tape.gates), their mixed form dzm = P_g^T dz_g (the operand of the hoisted weight / input gradient GEMMs),
+// the attention gradients dep / dqs / dqp / dap, and finally the gradients of the initial state.
+struct BwdDir {
+  const float* Wg[4];      // gcn_kernel_g [H][F+H]  (reference layout)
+  const float* Wh;         // attention_wh [H][H]
+  const float* Wq;         // attention_wq [H][H]
+  const float* Wa;         // attention_w  [H][H]
+  const float* u;          // attention_u  [H]
+  const float* PT;         // [4][16][16]  PT_g[n][m] = P_g[m][n]  (zero padded)
+  const float* c0;         // [B][15][H] initial cell state (nullptr = zeros)
+  const float* dhT; const float* dcT;   // [B][15][H] gradients of the final state (nullptr = zeros)
+  float* dh0; float* dc0;               // [B][15][H] gradients of the initial state (nullptr = skip)
+  int reverse;
+};
+struct BwdGeom {
+  const float* dy; int64_t syb, syt, yld;   // dY element (b, t, n, d*H + j)
+  a3gc_tape tape;
+  a3gc_tape_grads gr;
+  const float* hmask;
+  int B, T, F, H, out_act, BT;
+};
+
+template <bool ATT>
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_train_bwd_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
+  extern __shared__ __align__(16) float smem[];
+  const BwdDir d = blockIdx.y == 0 ? d0 : d1;
+  const a3gc_tape& tp = g.tape;
+  const a3gc_tape_grads& gr = g.gr;
+  const int H = g.H, F = g.F, BT = g.BT, K = F + H;
+  const size_t HN = (size_t)H * kNodesPad;
+  float* dh = smem;                       // [BT][H][16]  gradient wrt h'_t carried from the later step
+  float* dc = dh + BT * HN;               // [BT][H][16]
+  float* dhh = dc + BT * HN;              // [BT][H][16]  gradient wrt hy_t
+  float* dep = dhh + BT * HN;             // [BT][H][16]  (ATT) gradient wrt the tanh pre-activation; also scratch
+  float* dzm = dep + BT * HN;             // [4][BT][H][16]
+  float* v1 = dzm + 4 * BT * HN;          // [BT][H]   dqs, then ds
+  float* v2 = v1 + BT * H;                // [BT][H]   dqp
+  float* abuf = v2 + BT * H;              // [BT][16]  dap
+  float* al = abuf + BT * kNodesPad;      // [BT][16]  alpha
+  float* PT = al + BT * kNodesPad;        // [4][16][16]
+  const int b0 = blockIdx.x * BT;
+  const int y_off = blockIdx.y * H;
+  const int ntask = BT * H;
+  LayerGeom lg; lg.B = g.B; lg.H = H; lg.BT = BT;
+  load_state(dh, d.dhT, b0, lg);
+  load_state(dc, d.dcT, b0, lg);
+  for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) PT[i] = d.PT[i];
+
+  for (int step = g.T - 1; step >= 0; --step) {
+    const int t = d.reverse ? g.T - 1 - step : step;                 // time of the forward step being undone
+    const int tprev = d.reverse ? t + 1 : t - 1;                       // time whose c' was this step's c input
+    const size_t rec0 = ((size_t)blockIdx.y * g.T + t) * g.B;
+    const size_t recp0 = ((size_t)blockIdx.y * g.T + tprev) * g.B;
+    const size_t nm0 = ((size_t)blockIdx.y * g.B * g.T + t) * kNodes;   // node-major row of (d, b = 0, t, n = 0); add b*T*15 + n
+    __syncthreads();
+    // ---- A: dh' += dY (1 - y^2);  dhy = dh' (1 + alpha);  partial dalpha[n] = sum_j dh' hy
+    if (ATT) {
+      for (int i = threadIdx.x; i < BT * kNodesPad; i += blockDim.x) {
+        const int b = b0 + i / kNodesPad;
+        al[i] = b < g.B ? tp.a[(rec0 + b) * kNodesPad + i % kNodesPad] : 0.f;
+      }
+      __syncthreads();
+    }
+    for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+      const int s = task / H, j = task % H, b = b0 + s;
+      float dv[16];
+      load16(dv, dh + (size_t)task * kNodesPad);
+      if (b < g.B) {
+        const float* hpp = tp.hp + (nm0 + (size_t)b * g.T * kNodes) * H + j;
+        const float* yp = g.dy + (size_t)b * g.syb + (size_t)t * g.syt + y_off + j;
+#pragma unroll
+        for (int n = 0; n < kNodes; ++n) {
+          const float gy = __ldg(yp + (size_t)n * g.yld);
+          if (g.out_act == A3GC_ACT_TANH) { const float y = tanhf(hpp[(size_t)n * H]); dv[n] = fmaf(gy, 1.0f - y * y, dv[n]); }
+          else dv[n] += gy;
+        }
+        dv[15] = 0.f;
+        if (ATT) {
+          float hh[16], pa[16], av[16];
+          load16(hh, tp.hh + ((rec0 + b) * H + j) * kNodesPad);
+          load16(av, al + (size_t)s * kNodesPad);
+#pragma unroll
+          for (int n = 0; n < 16; ++n) { pa[n] = dv[n] * hh[n]; dv[n] *= 1.0f + av[n]; }
+          store16(dep + (size_t)task * kNodesPad, pa);          // scratch: partial dalpha
+        }
+      } else {
+#pragma unroll
+        for (int n = 0; n < 16; ++n) dv[n] = 0.f;
+        if (ATT) store16(dep + (size_t)task * kNodesPad, dv);
+      }
+      store16(dhh + (size_t)task * kNodesPad, dv);
+    }
+    if (ATT) {
+      __syncthreads();
+      // ---- B: dalpha[n] = sum_j partial;  dap = dalpha * a (1 - a)
+      for (int i = threadIdx.x; i < BT * kNodesPad; i += blockDim.x) {
+        const int s = i / kNodesPad, n = i % kNodesPad;
+        float a = 0.f;
+        const float* pv = dep + (size_t)s * HN + n;
+        for (int j = 0; j < H; ++j) a += pv[(size_t)j * kNodesPad];
+        const float sg = al[i];
+        a *= sg * (1.0f - sg);
+        abuf[i] = a;
+        if (b0 + s < g.B) gr.dap[(rec0 + b0 + s) * kNodesPad + n] = a;
+      }
+      __syncthreads();
+      // ---- C: dep[n][j] = dap[n] u_j (1 - e^2);  dqs_j = sum_n dep
+      for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+        const int s = task / H, j = task % H, b = b0 + s;
+        float e[16], av[16], o[16];
+        float sum = 0.f;
+        if (b < g.B) {
+          load16(e, tp.e + ((rec0 + b) * H + j) * kNodesPad);
+          load16(av, abuf + (size_t)s * kNodesPad);
+          const float uj = d.u[j];
+#pragma unroll
+          for (int n = 0; n < 16; ++n) { o[n] = av[n] * uj * (1.0f - e[n] * e[n]); sum += o[n]; }
+          store16(gr.dep + ((rec0 + b) * H + j) * kNodesPad, o);
+          gr.dqs[(rec0 + b) * H + j] = sum;
+        } else {
+#pragma unroll
+          for (int n = 0; n < 16; ++n) o[n] = 0.f;
+        }
+        store16(dep + (size_t)task * kNodesPad, o);
+        v1[task] = sum;
+      }
+      __syncthreads();
+      // ---- D: dq_j = sum_k dqs_k Wq[k][j];  dqp = dq [q > 0]
+      for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+        const int s = task / H, j = task % H, b = b0 + s;
+        float dq = 0.f;
+        const float* sv = v1 + (size_t)s * H;
+        for (int k = 0; k < H; ++k) dq = fmaf(sv[k], __ldg(d.Wq + (size_t)k * H + j), dq);
+        float r = 0.f;
+        if (b < g.B) {
+          r = tp.q[(rec0 + b) * H + j] > 0.f ? dq : 0.f;
+          gr.dqp[(rec0 + b) * H + j] = r;
+        }
+        v2[task] = r;
+      }
+      __syncthreads();
+      // ---- E: ds_j = sum_k dqp_k Wa[k][j];  dhy[n][j] += ds_j + sum_k dep[n][k] Wh[k][j]
+      for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+        const int s = task / H, j = task % H;
+        float ds = 0.f;
+        const float* sv = v2 + (size_t)s * H;
+        for (int k = 0; k < H; ++k) ds = fmaf(sv[k], __ldg(d.Wa + (size_t)k * H + j), ds);
+        float acc[16];
+        load16(acc, dhh + (size_t)task * kNodesPad);
+        accum1(acc, dep + (size_t)s * HN, d.Wh + j, H, H);
+#pragma unroll
+        for (int n = 0; n < kNodes; ++n) acc[n] += ds;
+        acc[15] = 0.f;
+        store16(dhh + (size_t)task * kNodesPad, acc);
+      }
+    }
+    __syncthreads();
+    // ---- F: LSTM pointwise backward, dz (global, in place of the gates) and dzm = P_g^T dz_g
+    for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+      const int s = task / H, j = task % H, b = b0 + s;
+      float dz[4][16];
+      float dcv[16];
+      if (b < g.B) {
+        float gi[16], gf[16], gg[16], go[16], cc[16], cp[16], dv[16];
+        float* gp = tp.gates + ((rec0 + b) * 4 * H + j) * kNodesPad;
+        load16(gi, gp); load16(gf, gp + HN); load16(gg, gp + 2 * HN); load16(go, gp + 3 * HN);
+        load16(cc, tp.c + ((rec0 + b) * H + j) * kNodesPad);
+        if (step > 0) load16(cp, tp.c + ((recp0 + b) * H + j) * kNodesPad);
+        else {
+#pragma unroll
+          for (int n = 0; n < 16; ++n) cp[n] = (d.c0 != nullptr && n < kNodes) ? d.c0[((size_t)b * kNodes + n) * H + j] : 0.f;
+        }
+        load16(dv, dhh + (size_t)task * kNodesPad);
+        load16(dcv, dc + (size_t)task * kNodesPad);
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
+          const float tc = tanhf(cc[n]);
+          const float dcn = fmaf(dv[n] * go[n], 1.0f - tc * tc, dcv[n]);
+          dz[3][n] = dv[n] * tc * go[n] * (1.0f - go[n]);
+          dz[0][n] = dcn * gg[n] * gi[n] * (1.0f - gi[n]);
+          dz[1][n] = dcn * cp[n] * gf[n] * (1.0f - gf[n]);
+          dz[2][n] = dcn * gi[n] * (1.0f - gg[n] * gg[n]);
+          dcv[n] = dcn * gf[n];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { dz[q][15] = 0.f; store16(gp + q * HN, dz[q]); }
+        dcv[15] = 0.f;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int n = 0; n < 16; ++n) dz[q][n] = 0.f;
+#pragma unroll
+        for (int n = 0; n < 16; ++n) dcv[n] = 0.f;
+      }
+      store16(dc + (size_t)task * kNodesPad, dcv);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float m[16];
+        mix15(dz[q], PT + q * 256, m);
+        store16(dzm + ((size_t)q * BT * H + task) * kNodesPad, m);
+        if (b < g.B) {   // [D][B][T][15][4H], column q*H + j: rows match x [B,T,15,F], so dW and dX are plain GEMMs
+          float* zp = gr.dzm + (nm0 + (size_t)b * g.T * kNodes) * 4 * H + (size_t)q * H + j;
+#pragma unroll
+          for (int n = 0; n < kNodes; ++n) zp[(size_t)n * 4 * H] = m[n];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- G: dh'_{prev}[n][k] = sum_g sum_j dzm_g[n][j] W_g[j][F + k]   (then the recurrent-dropout mask of this step)
+    for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+      const int s = task / H, k = task % H, b = b0 + s;
+      float acc[16];
+#pragma unroll
+      for (int n = 0; n < 16; ++n) acc[n] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) accum1(acc, dzm + ((size_t)q * BT + s) * HN, d.Wg[q] + F + k, H, K);
+      acc[15] = 0.f;
+      if (g.hmask != nullptr && b < g.B) {
+        const float* mp = g.hmask + (nm0 + (size_t)b * g.T * kNodes) * H + k;
+#pragma unroll
+        for (int n = 0; n < kNodes; ++n) acc[n] *= mp[(size_t)n * H];
+      }
+      store16(dh + (size_t)task * kNodesPad, acc);
+    }
+  }
+  __syncthreads();
+  store_state(d.dh0, dh, b0, lg);
+  store_state(d.dc0, dc, b0, lg);
+}
+
+__global__ void pack_pt_kernel(a3gc_cell_params cp, float* out, int variant) {
+  // PT_g[n][m] = P_g[m][n] with P as in pack_lstm_kernel
+  for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) {
+    const int g = i / 256, n = (i % 256) / 16, m = i % 16;
+    float v = 0.f;
+    if (m < kNodes && n < kNodes)
+      v = (variant == A3GC_VARIANT_AGC) ? cp.adjacency[0][n * kNodes + m] : cp.adjacency[g][m * kNodes + n];
+    out[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // G-GRU time loop
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1)
@@ -618,6 +1054,122 @@ int simt_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream
     }
     A3GC_LAUNCH_CHECK("lstm_layer_kernel");
   }
+  return A3GC_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// training path: host side
+// ------------------------------------------------------------------------------------------
+size_t simt_train_workspace_bytes(int variant, int f_in, int hidden, int num_dirs) {
+  (void)variant;
+  const size_t per = align_up(lstm_packed_floats(f_in, hidden) * sizeof(float), 256) + 4 * 256 * sizeof(float);
+  return (size_t)num_dirs * per;
+}
+
+int simt_train_forward(const LayerArgs& a, const a3gc_tape& tape, const float* hmask, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  const int F = a.f_in, H = a.hidden;
+  const size_t need = simt_train_workspace_bytes(a.variant, F, H, a.num_dirs);
+  if (ws_bytes < need || ws == nullptr) {
+    set_error("a3gc_layer_train_forward: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+    return A3GC_ERR_WORKSPACE;
+  }
+  const int smem_max = max_optin_smem();
+  if (smem_max <= 0) { set_error("no CUDA device"); return A3GC_ERR_NO_DEVICE; }
+  const bool att = a.variant == A3GC_VARIANT_A3GC || a.variant == A3GC_VARIANT_AGC;
+  const int KX = F > H ? F : H;
+  auto smem_bytes = [&](int bt) -> size_t {
+    return ((size_t)3 * bt * H * 16 + (size_t)bt * KX * 16 + (size_t)2 * bt * H + (size_t)bt * 16 + 1024) * sizeof(float);
+  };
+  int BT = 8;
+  while (BT > 1 && smem_bytes(BT) > (size_t)smem_max) --BT;
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  while (BT > 1 && ((a.batch + BT - 1) / BT) * a.num_dirs < sms) --BT;
+  if (smem_bytes(BT) > (size_t)smem_max) {
+    set_error("training forward: hidden=%d f_in=%d needs %zu bytes of shared memory (> %d)", H, F, smem_bytes(1), smem_max);
+    return A3GC_ERR_UNSUPPORTED;
+  }
+  char* base = static_cast<char*>(ws);
+  const size_t per = need / a.num_dirs;
+  DirPtrs dp[2] = {};
+  LstmPacked pk[2];
+  for (int d = 0; d < a.num_dirs; ++d) {
+    dp[d].h0 = a.h0[d]; dp[d].c0 = a.c0[d]; dp[d].hT = a.hT[d]; dp[d].cT = a.cT[d]; dp[d].reverse = a.reverse[d];
+    pk[d] = carve_lstm(reinterpret_cast<float*>(base + d * per), F, H);
+    pack_lstm_kernel<<<64, 256, 0, stream>>>(a.cells[d], pk[d], F, H, a.variant);
+    A3GC_LAUNCH_CHECK("pack_lstm_kernel");
+  }
+  if (a.num_dirs == 1) pk[1] = pk[0];
+  TrainGeom tg;
+  LayerGeom& g = tg.g;
+  g.x = a.x; g.sxb = a.x_stride_b; g.sxt = a.x_stride_t;
+  g.y = a.y; g.syb = a.y_stride_b; g.syt = a.y_stride_t; g.yld = a.y_ld;
+  g.B = (int)a.batch; g.T = (int)a.steps; g.F = F; g.H = H; g.out_act = a.out_act; g.BT = BT;
+  tg.tape = tape; tg.hmask = hmask;
+  dim3 grid((unsigned)((a.batch + BT - 1) / BT), (unsigned)a.num_dirs);
+  const size_t smem = smem_bytes(BT);
+  if (att) {
+    A3GC_CUDA_TRY(cudaFuncSetAttribute(lstm_train_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lstm_train_fwd_kernel<true><<<grid, kThreads, smem, stream>>>(pk[0], pk[1], dp[0], dp[1], tg);
+  } else {
+    A3GC_CUDA_TRY(cudaFuncSetAttribute(lstm_train_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lstm_train_fwd_kernel<false><<<grid, kThreads, smem, stream>>>(pk[0], pk[1], dp[0], dp[1], tg);
+  }
+  A3GC_LAUNCH_CHECK("lstm_train_fwd_kernel");
+  return A3GC_OK;
+}
+
+int simt_train_backward(const TrainBwdArgs& a, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  const int F = a.f_in, H = a.hidden;
+  const size_t need = simt_train_workspace_bytes(a.variant, F, H, a.num_dirs);
+  if (ws_bytes < need || ws == nullptr) {
+    set_error("a3gc_layer_backward: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+    return A3GC_ERR_WORKSPACE;
+  }
+  const int smem_max = max_optin_smem();
+  if (smem_max <= 0) { set_error("no CUDA device"); return A3GC_ERR_NO_DEVICE; }
+  const bool att = a.variant == A3GC_VARIANT_A3GC || a.variant == A3GC_VARIANT_AGC;
+  auto smem_bytes = [&](int bt) -> size_t {
+    return ((size_t)8 * bt * H * 16 + (size_t)2 * bt * H + (size_t)2 * bt * 16 + 1024) * sizeof(float);
+  };
+  int BT = 8;
+  while (BT > 1 && smem_bytes(BT) > (size_t)smem_max) --BT;
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  while (BT > 1 && ((a.batch + BT - 1) / BT) * a.num_dirs < sms) --BT;
+  if (smem_bytes(BT) > (size_t)smem_max) {
+    set_error("training backward: hidden=%d needs %zu bytes of shared memory (> %d)", H, smem_bytes(1), smem_max);
+    return A3GC_ERR_UNSUPPORTED;
+  }
+  char* base = static_cast<char*>(ws);
+  const size_t per = need / a.num_dirs;
+  BwdDir bd[2] = {};
+  for (int d = 0; d < a.num_dirs; ++d) {
+    float* pt = reinterpret_cast<float*>(base + d * per + align_up(lstm_packed_floats(F, H) * sizeof(float), 256));
+    pack_pt_kernel<<<1, 256, 0, stream>>>(a.cells[d], pt, a.variant);
+    A3GC_LAUNCH_CHECK("pack_pt_kernel");
+    for (int q = 0; q < 4; ++q) bd[d].Wg[q] = a.cells[d].gcn_kernel[q];
+    bd[d].Wh = a.cells[d].attention_wh; bd[d].Wq = a.cells[d].attention_wq; bd[d].Wa = a.cells[d].attention_w;
+    bd[d].u = a.cells[d].attention_u; bd[d].PT = pt;
+    bd[d].c0 = a.c0[d]; bd[d].dhT = a.dhT[d]; bd[d].dcT = a.dcT[d]; bd[d].dh0 = a.dh0[d]; bd[d].dc0 = a.dc0[d];
+    bd[d].reverse = a.reverse[d];
+  }
+  if (a.num_dirs == 1) bd[1] = bd[0];
+  BwdGeom g;
+  g.dy = a.dy; g.syb = a.dy_stride_b; g.syt = a.dy_stride_t; g.yld = a.dy_ld;
+  g.tape = a.tape; g.gr = a.grads; g.hmask = a.hmask;
+  g.B = (int)a.batch; g.T = (int)a.steps; g.F = F; g.H = H; g.out_act = a.out_act; g.BT = BT;
+  dim3 grid((unsigned)((a.batch + BT - 1) / BT), (unsigned)a.num_dirs);
+  const size_t smem = smem_bytes(BT);
+  if (att) {
+    A3GC_CUDA_TRY(cudaFuncSetAttribute(lstm_train_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lstm_train_bwd_kernel<true><<<grid, kThreads, smem, stream>>>(bd[0], bd[1], g);
+  } else {
+    A3GC_CUDA_TRY(cudaFuncSetAttribute(lstm_train_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lstm_train_bwd_kernel<false><<<grid, kThreads, smem, stream>>>(bd[0], bd[1], g);
+  }
+  A3GC_LAUNCH_CHECK("lstm_train_bwd_kernel");
   return A3GC_OK;
 }
 

@@ -9,8 +9,9 @@ Differences from the reference, all deliberate:
   * adjacency parameters are cloned, never aliased to the caller's template (the reference's
     ``Parameter(adjacency_matrix.t())`` shares one buffer between all cells on CPU; SURVEY #3);
   * the forward and reverse directions of a ``Bi*`` layer run concurrently in one launch;
-  * forward is inference-only in this round: in ``.train()`` mode with a non-zero dropout it raises
-    instead of silently skipping dropout; outputs do not carry autograd history.
+  * ``.eval()`` mode is the inference path (tensor-core engine, no autograd history); ``.train()`` mode is the
+    training path of the LSTM-family classes (a3gc_ip_b200/training.py): forward keeps a tape, backward runs
+    the BPTT chain in CUDA, dropout masks are drawn per call.  G-GRU has no training path yet (it raises).
 """
 from __future__ import annotations
 
@@ -23,6 +24,7 @@ from torch import Tensor
 from torch.nn import Parameter
 
 from . import _lib
+from . import training as _tr
 
 NUM_NODES = 15
 
@@ -83,7 +85,8 @@ class AAGC(torch.nn.Module, _EngineMixin):
         return _lib.GcParams(self.gcn_kernel.data_ptr(), self.adj.data_ptr(), self.gcn_bias.data_ptr())
 
     def forward(self, input: Tensor, _act: Optional[str] = None) -> Tensor:
-        _no_training(self, self.p_dropout)
+        if self.training:
+            return _tr.gc_train(self, _lib.require_cuda_f32(input, "input"), _act or self.activation_name, self.p_dropout)
         x = _lib.require_cuda_f32(input, "input")
         if x.dim() != 4 or x.shape[2] != NUM_NODES or x.shape[3] != self.gcn_kernel.shape[1]:
             raise RuntimeError(f"AAGC expects [B, T, 15, {self.gcn_kernel.shape[1]}], got {tuple(x.shape)}")
@@ -227,7 +230,10 @@ class _LSTMCellBase(_CellBase):
 
     def forward(self, input: Tensor, state: Tuple[Tensor, Tensor]) -> Tuple[Tensor, Tuple[Tensor, Tensor]]:
         """One step: input [B,15,F], state (h, c) [B,15,H] -> (act(h'), (h', c'))."""
-        _no_training(self, self.p_dropout, self.p_recurrent_dropout)
+        if self.training:
+            y, st = _tr.run_layer_train(self.variant, [self], [0], input.unsqueeze(1), [state], self.activation_name, self._ws,
+                                        self.p_dropout, self.p_recurrent_dropout)
+            return y[:, 0], st[0]
         y, st = _run_layer(self.variant, [self], [0], input.unsqueeze(0), True, [state], self.activation_name,
                            self._ws, self.engine, self.precision)
         return y[0], st[0]
@@ -311,9 +317,13 @@ class _Layer(torch.nn.Module, _EngineMixin):
 
     def forward(self, input: Tensor, state):
         c = self.cell
-        if c.variant != "GGRU":
-            _no_training(c, c.p_dropout, c.p_recurrent_dropout)
         act = "linear" if c.variant == "GGRU" else c.activation_name
+        if self.training:
+            if c.variant == "GGRU":
+                raise NotImplementedError("G-GRU has no training path yet; call .eval() for inference")
+            y, st = _tr.run_layer_train(c.variant, [c], [self.reverse], input.transpose(0, 1).contiguous(), [state], act, self._ws,
+                                        c.p_dropout, c.p_recurrent_dropout)
+            return y.transpose(0, 1), st[0]
         y, st = _run_layer(c.variant, [c], [self.reverse], input, True, [state], act, self._ws, self.engine, self.precision)
         return y, st[0]
 
@@ -331,9 +341,11 @@ class _BiLayer(torch.nn.Module, _EngineMixin):
     def forward(self, input: Tensor, states: List):
         cells = [d.cell for d in self.directions]
         c = cells[0]
-        if c.variant != "GGRU":
-            _no_training(c, c.p_dropout, c.p_recurrent_dropout)
         act = "linear" if c.variant == "GGRU" else c.activation_name
+        if self.training:
+            if c.variant == "GGRU":
+                raise NotImplementedError("G-GRU has no training path yet; call .eval() for inference")
+            return _tr.run_layer_train(c.variant, cells, [0, 1], input, states, act, self._ws, c.p_dropout, c.p_recurrent_dropout)
         return _run_layer(c.variant, cells, [0, 1], input, False, states, act, self._ws, self.engine, self.precision)
 
 
@@ -424,10 +436,7 @@ class _Net(torch.nn.Module, _EngineMixin):
         """
         gru = self.variant == "GGRU"
         if self.training:
-            _no_training(self, self.linear_in.p_dropout)
-            if not gru:
-                c = self.rnn1.directions[0].cell
-                _no_training(self, c.p_dropout, c.p_recurrent_dropout)
+            return self._forward_train(x, h)
         x = _lib.require_cuda_f32(x, "x")
         f0, H, O = self.linear_in.gcn_kernel.shape[1], self.units_hidden, self.linear_out.gcn_kernel.shape[0]
         if x.dim() != 4 or x.shape[2] != NUM_NODES or x.shape[3] != f0:
@@ -461,6 +470,25 @@ class _Net(torch.nn.Module, _EngineMixin):
         _lib.check(rc, "a3gc_net_forward")
         h_out = [hT[0], hT[1]] if gru else [(hT[0], cT[0]), (hT[1], cT[1])]
         return y, h_out
+
+
+def _net_forward_train(self, x: Tensor, h=None):
+    """Training-mode forward of the nets (net_aagc.py:633-645 under ``model.train()``, train_a3gc_tp.py:74): same
+    chain as the inference path, each stage differentiable; dropout as the reference configures it."""
+    if self.variant == "GGRU":
+        raise NotImplementedError("G-GRU has no training path yet; call .eval() for inference")
+    x = _lib.require_cuda_f32(x, "x")
+    B, H = x.shape[0], self.units_hidden
+    if h is None:
+        z = lambda: torch.zeros(B, NUM_NODES, H, dtype=torch.float32, device=x.device)     # net_aagc.py:634-639
+        h = [(z(), z()), (z(), z())]
+    a = torch.relu(self.linear_in(x))
+    a, h = self.rnn1(a, h)
+    a, h = self.rnn2(a, h)
+    return self.linear_out(a), h
+
+
+_Net._forward_train = _net_forward_train
 
 
 class AAGC_net(_Net):

@@ -1,0 +1,236 @@
+"""Training path (BPTT) of the LSTM-family layers: the autograd glue around ``a3gc_layer_train_forward`` and
+``a3gc_layer_backward`` (include/a3gc_b200.h).
+
+The reference trains by calling ``model.forward(inputs, rnn_state=None)`` in ``train()`` mode and letting
+autograd unroll the TorchScript time loop (train_a3gc_tp.py:74-84).  Here the forward keeps a tape, the
+recurrent gradient chain runs in one CUDA kernel per layer (reverse time, both directions concurrently), and
+what is left after the chain -- the weight / adjacency / input gradients, which are sums over all (t, b) of
+outer products of per-step tensors the chain has stored -- are plain batched GEMMs, issued through torch
+(cuBLAS fp32) on the caller's stream.
+
+Dropout (net_aagc.py:180-181): input dropout is applied to x by the caller of the layer; recurrent dropout is a
+Bernoulli mask drawn here with torch's generator and applied inside both kernels.  The reference's masks come
+from the TorchScript interpreter's RNG calls and cannot be reproduced bit for bit; gradient parity is tested
+with dropout = 0.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+NUM_NODES = 15
+LSTM_PARAM_NAMES = {
+    "AAGC": [f"gcn_kernel_{g}" for g in "ifco"] + [f"adjacency_{g}" for g in "ifco"] + [f"gcn_bias_{g}" for g in "ifco"],
+    "A3GC": [f"gcn_kernel_{g}" for g in "ifco"] + [f"adjacency_{g}" for g in "ifco"] + [f"gcn_bias_{g}" for g in "ifco"]
+            + ["attention_w", "attention_wq", "attention_wh", "attention_u", "attention_bs", "attention_bu"],
+    "AGC": [f"gcn_kernel_{g}" for g in "ifco"] + ["adjacency"] + [f"gcn_bias_{g}" for g in "ifco"]
+           + ["attention_w", "attention_wq", "attention_wh", "attention_u", "attention_bs", "attention_bu"],
+}
+
+
+def _cell_params_struct(variant: str, ps: Sequence[Tensor]) -> _lib.CellParams:
+    names = LSTM_PARAM_NAMES[variant]
+    d = {n: _lib.require_cuda_f32(t, n) for n, t in zip(names, ps)}
+    p = _lib.CellParams()
+    for i, g in enumerate("ifco"):
+        p.gcn_kernel[i] = d[f"gcn_kernel_{g}"].data_ptr()
+        p.gcn_bias[i] = d[f"gcn_bias_{g}"].data_ptr()
+        p.adjacency[i] = (d["adjacency"] if variant == "AGC" else d[f"adjacency_{g}"]).data_ptr()
+    if variant != "AAGC":
+        for n in ("attention_w", "attention_wq", "attention_wh", "attention_u", "attention_bs", "attention_bu"):
+            setattr(p, n, d[n].data_ptr())
+    return p
+
+
+class _LayerTrainFn(torch.autograd.Function):
+    """y, hT_0, cT_0[, hT_1, cT_1] = layer(x, (h0, c0) per direction, params per direction)."""
+
+    @staticmethod
+    def forward(ctx, meta, x, hmask, *flat):
+        variant, nd, reverse, out_act, ws = meta
+        names = LSTM_PARAM_NAMES[variant]
+        npar = len(names)
+        states = flat[:2 * nd]
+        params = [flat[2 * nd + d * npar: 2 * nd + (d + 1) * npar] for d in range(nd)]
+        x = _lib.require_cuda_f32(x, "input")
+        B, T, _, F = x.shape
+        H = params[0][0].shape[0]
+        dev = x.device
+        att = variant != "AAGC"
+        f32 = dict(dtype=torch.float32, device=dev)
+        tape = {
+            "gates": torch.empty(nd, T, B, 4, H, 16, **f32),
+            "u": torch.empty(nd, T, B, 4, H, 16, **f32) if variant != "AGC" else None,
+            "c": torch.empty(nd, T, B, H, 16, **f32),
+            "hh": torch.empty(nd, T, B, H, 16, **f32),
+            "e": torch.empty(nd, T, B, H, 16, **f32) if att else None,
+            "hp": torch.empty(nd, B, T, NUM_NODES, H, **f32),
+            "a": torch.empty(nd, T, B, 16, **f32) if att else None,
+            "q": torch.empty(nd, T, B, H, **f32) if att else None,
+            "s": torch.empty(nd, T, B, H, **f32) if att else None,
+        }
+        y = torch.empty(B, T, NUM_NODES, nd * H, **f32)
+        h0 = [_lib.require_cuda_f32(states[2 * d], "h0") for d in range(nd)]
+        c0 = [_lib.require_cuda_f32(states[2 * d + 1], "c0") for d in range(nd)]
+        hT = [torch.empty(B, NUM_NODES, H, **f32) for _ in range(nd)]
+        cT = [torch.empty(B, NUM_NODES, H, **f32) for _ in range(nd)]
+        cells = (_lib.CellParams * nd)(*[_cell_params_struct(variant, params[d]) for d in range(nd)])
+        rev = (C.c_int * nd)(*[int(r) for r in reverse])
+        tp = _lib.Tape(*[_lib.ptr(tape[k]) for k in ("gates", "u", "c", "hh", "e", "hp", "a", "q", "s")])
+        L = _lib.lib()
+        v = _lib.VARIANT[variant]
+        with torch.cuda.device(dev):
+            wbuf = ws.get(L.a3gc_layer_train_workspace_bytes(v, F, H, nd), dev)
+            rc = L.a3gc_layer_train_forward(
+                v, nd, cells, rev, x.data_ptr(), T * NUM_NODES * F, NUM_NODES * F,
+                _lib.ptr_array(h0, nd), _lib.ptr_array(c0, nd),
+                y.data_ptr(), T * NUM_NODES * nd * H, NUM_NODES * nd * H, nd * H,
+                _lib.ptr_array(hT, nd), _lib.ptr_array(cT, nd),
+                B, T, F, H, _lib.ACT[out_act], C.byref(tp), _lib.ptr(hmask),
+                wbuf.data_ptr(), wbuf.numel(), _lib.stream_ptr(dev))
+        _lib.check(rc, "a3gc_layer_train_forward")
+        ctx.meta, ctx.tape, ctx.shape = meta, tape, (B, T, F, H)
+        ctx.save_for_backward(x, hmask if hmask is not None else x.new_empty(0), *h0, *c0, *[t for ps in params for t in ps])
+        outs = [y]
+        for d in range(nd):
+            outs += [hT[d], cT[d]]
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, dy, *dstates):
+        variant, nd, reverse, out_act, ws = ctx.meta
+        names = LSTM_PARAM_NAMES[variant]
+        npar = len(names)
+        B, T, F, H = ctx.shape
+        saved = ctx.saved_tensors
+        x, hmask = saved[0], (saved[1] if saved[1].numel() else None)
+        h0, c0 = saved[2:2 + nd], saved[2 + nd:2 + 2 * nd]
+        params = [saved[2 + 2 * nd + d * npar: 2 + 2 * nd + (d + 1) * npar] for d in range(nd)]
+        tape = ctx.tape
+        dev = x.device
+        att = variant != "AAGC"
+        f32 = dict(dtype=torch.float32, device=dev)
+        dy = dy.contiguous() if dy is not None else torch.zeros(B, T, NUM_NODES, nd * H, **f32)
+        dhT = [None if dstates[2 * d] is None else dstates[2 * d].contiguous() for d in range(nd)]
+        dcT = [None if dstates[2 * d + 1] is None else dstates[2 * d + 1].contiguous() for d in range(nd)]
+        gr = {
+            "dzm": torch.empty(nd, B, T, NUM_NODES, 4 * H, **f32),
+            "dep": torch.empty(nd, T, B, H, 16, **f32) if att else None,
+            "dqs": torch.empty(nd, T, B, H, **f32) if att else None,
+            "dqp": torch.empty(nd, T, B, H, **f32) if att else None,
+            "dap": torch.empty(nd, T, B, 16, **f32) if att else None,
+        }
+        dh0 = [torch.empty(B, NUM_NODES, H, **f32) for _ in range(nd)]
+        dc0 = [torch.empty(B, NUM_NODES, H, **f32) for _ in range(nd)]
+        cells = (_lib.CellParams * nd)(*[_cell_params_struct(variant, params[d]) for d in range(nd)])
+        rev = (C.c_int * nd)(*[int(r) for r in reverse])
+        tp = _lib.Tape(*[_lib.ptr(tape[k]) for k in ("gates", "u", "c", "hh", "e", "hp", "a", "q", "s")])
+        tg = _lib.TapeGrads(*[_lib.ptr(gr[k]) for k in ("dzm", "dep", "dqs", "dqp", "dap")])
+        L = _lib.lib()
+        v = _lib.VARIANT[variant]
+        with torch.cuda.device(dev):
+            wbuf = ws.get(L.a3gc_layer_train_workspace_bytes(v, F, H, nd), dev)
+            rc = L.a3gc_layer_backward(
+                v, nd, cells, rev, dy.data_ptr(), T * NUM_NODES * nd * H, NUM_NODES * nd * H, nd * H,
+                _lib.ptr_array(c0, nd), _lib.ptr_array(dhT, nd), _lib.ptr_array(dcT, nd),
+                _lib.ptr_array(dh0, nd), _lib.ptr_array(dc0, nd),
+                B, T, F, H, _lib.ACT[out_act], C.byref(tp), C.byref(tg), _lib.ptr(hmask),
+                wbuf.data_ptr(), wbuf.numel(), _lib.stream_ptr(dev))
+        _lib.check(rc, "a3gc_layer_backward")
+
+        # ---- hoisted contractions over all (t, b): plain GEMMs (torch / cuBLAS fp32 on the current stream)
+        R = B * T * NUM_NODES
+        x2d = x.reshape(R, F)
+        dx = torch.zeros(R, F, **f32)
+        grads: List[Optional[Tensor]] = []
+        for d in range(nd):
+            ps = dict(zip(names, params[d]))
+            dzm2d = gr["dzm"][d].reshape(R, 4 * H)
+            # S = [x | h_prev]: h_prev is h' of the previous step of this direction (h0 at its first step), masked
+            hp = tape["hp"][d]                                           # [B, T, 15, H]
+            if reverse[d]:
+                hprev = torch.cat((hp[:, 1:], h0[d].unsqueeze(1)), dim=1)
+            else:
+                hprev = torch.cat((h0[d].unsqueeze(1), hp[:, :-1]), dim=1)
+            if hmask is not None:
+                hprev = hprev * hmask[d]
+            dWx = dzm2d.t() @ x2d                                        # [4H, F]
+            dWh = dzm2d.t() @ hprev.reshape(R, H)                        # [4H, H]
+            Wx = torch.cat([ps[f"gcn_kernel_{g}"][:, :F] for g in "ifco"], dim=0)   # [4H, F]
+            dx.addmm_(dzm2d, Wx)
+            gW = [torch.cat((dWx[i * H:(i + 1) * H], dWh[i * H:(i + 1) * H]), dim=1) for i in range(4)]
+            dz = tape["gates"][d].reshape(T * B, 4, H, 16)               # the backward left dz here
+            gb = dz.sum(dim=(0, 3))                                      # [4, H]
+            out = {f"gcn_kernel_{g}": gW[i] for i, g in enumerate("ifco")}
+            out.update({f"gcn_bias_{g}": gb[i] for i, g in enumerate("ifco")})
+            if variant == "AGC":
+                out["adjacency"] = None                                  # frozen (requires_grad=False, net_aagc.py:238)
+            else:
+                u = tape["u"][d].reshape(T * B, 4, H, 16)
+                for i, g in enumerate("ifco"):
+                    # dP_g[m][n] = sum dz_g[., j, m] u_g[., j, n];  adjacency_g is stored as P_g (used as P_g @ S)
+                    dP = torch.bmm(dz[:, i].transpose(1, 2), u[:, i]).sum(0)
+                    out[f"adjacency_{g}"] = dP[:NUM_NODES, :NUM_NODES].contiguous()
+            if att:
+                dep = gr["dep"][d].reshape(T * B, H, 16)
+                hh = tape["hh"][d].reshape(T * B, H, 16)
+                e = tape["e"][d].reshape(T * B, H, 16)
+                dap = gr["dap"][d].reshape(T * B, 16)
+                out["attention_wh"] = torch.einsum("rkn,rjn->kj", dep, hh)
+                out["attention_bs"] = dep.sum(dim=(0, 2))
+                out["attention_wq"] = gr["dqs"][d].reshape(T * B, H).t() @ tape["q"][d].reshape(T * B, H)
+                out["attention_w"] = gr["dqp"][d].reshape(T * B, H).t() @ tape["s"][d].reshape(T * B, H)
+                out["attention_u"] = torch.einsum("rn,rjn->j", dap, e).unsqueeze(0)
+                out["attention_bu"] = dap.sum(0)[:NUM_NODES].contiguous()
+            grads += [out[n] for n in names]
+        state_grads: List[Optional[Tensor]] = []
+        for d in range(nd):
+            state_grads += [dh0[d], dc0[d]]
+        ctx.tape = None
+        return (None, dx.reshape(B, T, NUM_NODES, F), None, *state_grads, *grads)
+
+
+def run_layer_train(variant: str, cells: Sequence[torch.nn.Module], reverse: Sequence[int], x: Tensor,
+                    states: Sequence[Tuple[Tensor, Tensor]], out_act: str, ws: _lib.Workspace,
+                    p_in: float = 0.0, p_rec: float = 0.0):
+    """Differentiable batch-major forward of one (bi)layer.  x [B,T,15,F] -> (y [B,T,15,nd*H], [(hT, cT)] * nd)."""
+    if variant not in LSTM_PARAM_NAMES:
+        raise NotImplementedError("the training path covers the LSTM-family cells (AAGC / A3GC / AGC); G-GRU training "
+                                  "is not built yet")
+    nd = len(cells)
+    H = cells[0].units_out
+    if p_in > 0:
+        x = torch.nn.functional.dropout(x, p_in, training=True)                  # net_aagc.py:180
+    hmask = None
+    if p_rec > 0:
+        B, T = x.shape[0], x.shape[1]
+        hmask = (torch.rand(nd, B, T, NUM_NODES, H, device=x.device) >= p_rec).to(torch.float32) / (1.0 - p_rec)   # :181
+    flat: List[Tensor] = []
+    for d in range(nd):
+        flat += [states[d][0], states[d][1]]
+    for c in cells:
+        flat += [getattr(c, n) for n in LSTM_PARAM_NAMES[variant]]
+    meta = (variant, nd, tuple(int(r) for r in reverse), out_act, ws)
+    outs = _LayerTrainFn.apply(meta, x, hmask, *flat)
+    y = outs[0]
+    return y, [(outs[1 + 2 * d], outs[2 + 2 * d]) for d in range(nd)]
+
+
+def gc_train(mod: torch.nn.Module, x: Tensor, act: str, p_drop: float) -> Tensor:
+    """AAGC.forward (net_aagc.py:61-66) with autograd history: the non-recurrent graph convolution is <1 % of the
+    step's FLOPs; in the training path it is expressed with torch ops (einsum + matmul) so autograd provides its
+    backward."""
+    if p_drop > 0:
+        x = torch.nn.functional.dropout(x, p_drop, training=True)
+    y = torch.einsum("bsnf,nm->bsmf", x, mod.adj.t())
+    y = torch.matmul(y, mod.gcn_kernel.t()) + mod.gcn_bias
+    if act == "tanh":
+        y = torch.tanh(y)
+    elif act == "relu":
+        y = torch.relu(y)
+    return y

@@ -167,6 +167,61 @@ int a3gc_net_forward(int variant, const a3gc_net_params* net, const float* x,
                      int precision, int engine, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * ---- Training path (BPTT) of the LSTM family: train_*_tp.py:74-84 calls model.forward in train mode, then
+ * loss.backward().  The forward keeps a tape of per-step intermediates; a3gc_layer_backward walks the
+ * recurrence in reverse and leaves, per step, the operands of the weight / input gradient contractions,
+ * which are plain batched GEMMs over all (t, b) the caller forms afterwards.
+ *
+ * All tape arrays are caller-allocated fp32.  Unit-major arrays hold one record per (direction d, time t,
+ * sequence b) at index (d*T + t)*B + b, each unit row = the 15 nodes padded to 16 (slot 15 = 0); node-major
+ * arrays are [D][B][T][15][.] like the layer input.  G-GRU is not supported.
+ */
+typedef struct a3gc_tape {
+  float* gates; /* [D][T][B][4][H][16] activated i, f, c~, o; OVERWRITTEN by the backward with dz (gate pre-activation grads) */
+  float* u;     /* [D][T][B][4][H][16] pre-mix accumulators S W_g^T (operand of the adjacency gradients); may be NULL */
+  float* c;     /* [D][T][B][H][16]    c'_t */
+  float* hh;    /* [D][T][B][H][16]    hy_t before attention */
+  float* e;     /* [D][T][B][H][16]    e_t = tanh(Wh hy + Wq q + bs)        (A3GC / AGC) */
+  float* hp;    /* [D][B][T][15][H]    h'_t (the carried state; y_t = act(h'_t)), node-major like x */
+  float* a;     /* [D][T][B][16]       sigmoid attention weights           (A3GC / AGC) */
+  float* q;     /* [D][T][B][H]        q_t                                  (A3GC / AGC) */
+  float* s;     /* [D][T][B][H]        node sums of hy_t                    (A3GC / AGC) */
+} a3gc_tape;
+
+typedef struct a3gc_tape_grads {
+  float* dzm;   /* [D][B][T][15][4H]   P_g^T dz_g (column g*H + j), rows as in x: dW = dzm^T [x | h_prev], dX = dzm W_x */
+  float* dep;   /* [D][T][B][H][16]    grads of the tanh pre-activation of e_t (dWh, dbs)   (A3GC / AGC) */
+  float* dqs;   /* [D][T][B][H]        node sums of dep (dWq)                                */
+  float* dqp;   /* [D][T][B][H]        grads of the relu pre-activation of q_t (dWa)         */
+  float* dap;   /* [D][T][B][16]       grads of the sigmoid pre-activation of a_t (du, dbu)  */
+} a3gc_tape_grads;
+
+size_t a3gc_layer_train_workspace_bytes(int variant, int f_in, int hidden, int num_dirs);
+
+/* a3gc_layer_forward in training mode (fp32 CUDA-core engine): same arguments plus the tape and an optional
+ * recurrent-dropout mask hmask [D][B][T][15][H] (0 or 1/(1-p), net_aagc.py:181; NULL = no dropout).  Input
+ * dropout (:180) is applied by the caller to x. */
+int a3gc_layer_train_forward(int variant, int num_dirs, const a3gc_cell_params* cells, const int* reverse,
+                             const float* x, int64_t x_stride_b, int64_t x_stride_t,
+                             const float* const* h0, const float* const* c0,
+                             float* y, int64_t y_stride_b, int64_t y_stride_t, int64_t y_ld,
+                             float* const* hT, float* const* cT,
+                             int64_t batch, int64_t steps, int f_in, int hidden, int out_act,
+                             const a3gc_tape* tape, const float* hmask,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* Reverse-time chain.  dy: gradient of y (same addressing as y); c0[d]: the forward's initial cell state;
+ * dhT/dcT[d]: gradients of the final state (NULL = 0); dh0/dc0[d]: receive the gradients of the initial
+ * state (NULL = skip). */
+int a3gc_layer_backward(int variant, int num_dirs, const a3gc_cell_params* cells, const int* reverse,
+                        const float* dy, int64_t dy_stride_b, int64_t dy_stride_t, int64_t dy_ld,
+                        const float* const* c0, const float* const* dhT, const float* const* dcT,
+                        float* const* dh0, float* const* dc0,
+                        int64_t batch, int64_t steps, int f_in, int hidden, int out_act,
+                        const a3gc_tape* tape, const a3gc_tape_grads* grads, const float* hmask,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * prepare_input (evaluate_a3gc_tp.py:64-94) on the device: per frame normalise the raw 18-d
  * acceleration and 54-d orientation channels ((v - mean) / std; pass NULL mean/std to skip, i.e.
  * --norm off), drop the 6th IMU and scatter (acc_i, ori_i) of IMU i onto node {3,4,13,14,10}[i].

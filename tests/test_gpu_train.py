@@ -1,0 +1,103 @@
+"""Training path (BASELINE cfg 5): forward in train() mode + BPTT backward through the C ABI vs autograd through the
+CPU oracle (same weights, same inputs, dropout = 0 -- the reference's masks come from the TorchScript RNG and cannot
+be reproduced).  Tolerance: rel-L2 <= 1e-4 on the loss, the outputs and every parameter / input gradient."""
+import pytest
+import torch
+
+import a3gc_ip_b200 as A
+from conftest import rel_l2
+from oracle import net_oracle as O
+from util import NET_CLS_NAMES, flatten_h
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _oracle_grads(variant, x, sd, target, h=None):
+    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    y, hout = O.net_forward(variant, xr, sd, h)
+    loss = torch.mean(torch.sum(torch.square(target - y.reshape(target.shape)), -1))       # pose_loss, net_aagc.py:1081-1087
+    loss.backward()
+    return loss.detach(), y.detach(), xr.grad, {k: v.grad for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("variant,hidden,B,T", [("A3GC", 24, 5, 7), ("AAGC", 24, 3, 6), ("AGC", 24, 4, 5), ("A3GC", 64, 3, 9),
+                                                ("A3GC", 128, 2, 4)])
+def test_net_train_step_matches_oracle_autograd(variant, hidden, B, T, nira):
+    f0, out = 15, 9
+    sd = O.random_state_dict(variant, f0, out, hidden, nira, seed=21)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, T, 15, f0, generator=g)
+    target = torch.randn(B, T, 15 * out, generator=g)
+    want_loss, want_y, want_dx, want_g = _oracle_grads(variant, x, sd, target)
+
+    net = getattr(A, NET_CLS_NAMES[variant])(f0, out, hidden, nira.float(), linear_dropout=0.0, dropout=0.0, recurrent_dropout=0.0)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().train()
+    xc = x.cuda().requires_grad_(True)
+    y, _ = net(xc)
+    loss = A.pose_loss()(y.view(B, T, 15 * out), target.cuda())
+    loss.backward()
+    assert rel_l2(y.detach().cpu(), want_y) <= TOL
+    assert abs(float(loss) - float(want_loss)) <= TOL * abs(float(want_loss))
+    assert rel_l2(xc.grad.cpu(), want_dx) <= TOL, f"dx {rel_l2(xc.grad.cpu(), want_dx):.3e}"
+    for name, p in net.named_parameters():
+        w = want_g[name]
+        if not p.requires_grad:
+            assert p.grad is None
+            continue
+        assert p.grad is not None, name
+        r = rel_l2(p.grad.cpu(), w)
+        assert r <= TOL, f"{variant} H={hidden} grad {name}: rel_l2={r:.3e}"
+
+
+def test_bilayer_train_with_initial_state_and_state_grads(nira):
+    """A Bi layer on its own: non-zero (h0, c0), gradients flowing in through y AND the final states (as rnn2 -> rnn1 do)."""
+    variant, F, H, B, T = "A3GC", 20, 16, 4, 6
+    g = torch.Generator().manual_seed(9)
+    layer = A.BiA3GC_LSTM(F, H, nira.float(), activation_fn="tanh")
+    for p in layer.parameters():
+        p.data = 0.2 * torch.randn(p.shape, generator=g) + (nira.float().t() if tuple(p.shape) == (15, 15) else 0)
+    sd = {"l." + k: v.detach().clone() for k, v in layer.state_dict().items()}
+    x = torch.randn(B, T, 15, F, generator=g)
+    st = [tuple(0.3 * torch.randn(B, 15, H, generator=g) for _ in range(2)) for _ in range(2)]
+    wy = torch.randn(B, T, 15, 2 * H, generator=g)
+    ws = [tuple(torch.randn(B, 15, H, generator=g) for _ in range(2)) for _ in range(2)]
+
+    def scalar(y, states):
+        tot = (y * wy.to(y.device)).sum()
+        for (h, c), (a, b) in zip(states, ws):
+            tot = tot + (h * a.to(y.device)).sum() + (c * b.to(y.device)).sum()
+        return tot
+
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    str_ = [tuple(t.clone().requires_grad_(True) for t in s) for s in st]
+    y, so = O.bi_layer_forward(variant, xr, str_, sdr, "l.")
+    scalar(y, so).backward()
+
+    layer = layer.cuda().train()
+    xc = x.cuda().requires_grad_(True)
+    stc = [tuple(t.cuda().requires_grad_(True) for t in s) for s in st]
+    yc, soc = layer(xc, stc)
+    scalar(yc, soc).backward()
+    assert rel_l2(yc.detach().cpu(), y.detach()) <= TOL
+    assert rel_l2(xc.grad.cpu(), xr.grad) <= TOL
+    for a, b in zip(flatten_h(stc), flatten_h(str_)):
+        assert rel_l2(a.grad.cpu(), b.grad) <= TOL
+    for name, p in layer.named_parameters():
+        r = rel_l2(p.grad.cpu(), sdr["l." + name].grad)
+        assert r <= TOL, f"grad {name}: rel_l2={r:.3e}"
+
+
+def test_train_mode_dropout_runs_and_is_stochastic(nira):
+    net = A.A3GC_net(12, 3, 16, nira.float()).cuda().train()      # reference defaults: p = 0.2 / 0.3 / 0.3
+    x = O.synthetic_input(3, 5, seed=1).cuda()
+    y1, _ = net(x)
+    y2, _ = net(x)
+    assert torch.isfinite(y1).all() and not torch.equal(y1, y2)
+    y1.square().mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters() if p.requires_grad)
+    with pytest.raises(NotImplementedError):
+        A.G_GRU_net(12, 3, 16, nira.float()).cuda().train()(x)
