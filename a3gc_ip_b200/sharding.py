@@ -53,3 +53,64 @@ class ShardedRunner:
         outs = [torch.empty_like(pad) for _ in range(self.world)]
         self.dist.all_gather(outs, pad)
         return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(outs, sizes)], dim=0)
+
+
+class FlatGradAllReducer:
+    """Data-parallel training glue: one all-reduce(SUM) of a single flat fp32 bucket that
+    holds every parameter gradient, then a division by the world size -- the loss is a batch mean
+    (net_aagc.py:1086), so the mean of the per-rank gradients is the gradient of the global-batch loss.  The
+    largest stage (A3GC, H = 256) has 3.42 M parameters = 13.7 MB: one NCCL call over NVLink per step.
+
+    The bucket is allocated once; `reduce()` copies the grads in (parameters without a gradient contribute
+    zeros), all-reduces, and writes the averaged gradients back in place, so any torch optimizer can follow.
+    """
+
+    def __init__(self, params, process_group=None):
+        import torch.distributed as dist
+        self.dist = dist if dist.is_available() and dist.is_initialized() else None
+        self.group = process_group
+        self.world = self.dist.get_world_size(process_group) if self.dist else 1
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        self.offsets, n = [], 0
+        for p in self.params:
+            self.offsets.append(n)
+            n += p.numel()
+        self.bucket = torch.zeros(n, dtype=dt, device=dev)
+        self.views = [self.bucket[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
+
+    @property
+    def nbytes(self) -> int:
+        return self.bucket.numel() * self.bucket.element_size()
+
+    def reduce(self) -> None:
+        for v, p in zip(self.views, self.params):
+            if p.grad is None:
+                v.zero_()
+            else:
+                v.copy_(p.grad)
+        if self.dist is not None and self.world > 1:
+            self.dist.all_reduce(self.bucket, op=self.dist.ReduceOp.SUM, group=self.group)
+            self.bucket.div_(self.world)
+        for v, p in zip(self.views, self.params):
+            if p.grad is None:
+                p.grad = v.clone()
+            else:
+                p.grad.copy_(v)
+
+
+def train_step(model: torch.nn.Module, criterion, optimizer, inputs: torch.Tensor, target: torch.Tensor,
+               reducer: "FlatGradAllReducer" = None) -> torch.Tensor:
+    """One optimisation step exactly as train_a3gc_tp.py:74-84 does it (forward in train mode with rnn_state=None,
+    pose loss on the prediction viewed as the target, zero_grad / backward / step), plus the gradient all-reduce
+    when data-parallel.  Returns the (local) loss."""
+    prediction, _ = model.forward(inputs, None)
+    loss = criterion.forward(prediction.view(target.shape), target)
+    optimizer.zero_grad()
+    loss.backward()
+    if reducer is not None:
+        reducer.reduce()
+    optimizer.step()
+    return loss.detach()

@@ -135,6 +135,68 @@ def run_reference(args):
     }))
 
 
+def run_train(args):
+    """Secondary workload (BASELINE cfg 5, not the headline line): A3GC-TP training step -- for each of the three
+    stages one optimisation step as train_a3gc_tp.py:74-84 does it (train-mode forward with the reference's dropout,
+    pose loss, BPTT backward, Adam), B=256 x T=200 per GPU, teacher-forced synthetic inputs; data-parallel ranks
+    all-reduce one flat fp32 gradient bucket per stage over NCCL.  frames/s = world * B * T / step time."""
+    import torch.distributed as dist
+    import a3gc_ip_b200 as A
+    world = int(os.environ.get("WORLD_SIZE", 1)); rank = int(os.environ.get("RANK", 0)); local = int(os.environ.get("LOCAL_RANK", 0))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, T = (args.batch if args.batch != B_PER_GPU else 256), 200
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    nira = load_nira().float()
+    torch.manual_seed(0)                                   # identical initial weights on every rank
+    shapes = ((12, 3, 256), (15, 3, 64), (15, 9, 128))
+    nets = [A.A3GC_net(f0, o, h, nira).to(dev).train() for f0, o, h in shapes]
+    opts = [torch.optim.Adam(n.parameters(), lr=1e-3) for n in nets]
+    reds = [A.FlatGradAllReducer(n.parameters()) if world > 1 else None for n in nets]
+    crit = A.pose_loss()
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    xs = [torch.randn(B, T, 15, f0, generator=g, device=dev) for f0, _, _ in shapes]
+    ts = [torch.randn(B, T, 15 * o, generator=g, device=dev) for _, o, _ in shapes]
+
+    def step():
+        return [A.train_step(n, crit, o, x, t, r) for n, o, x, t, r in zip(nets, opts, xs, ts, reds)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(W):
+        step()
+    barrier()
+    L = A.lib(); L.a3gc_reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        losses = step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    barrier()
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        msk = float(ms.item()) / K
+        print(json.dumps({
+            "metric": "A3GC-TP train frames/sec", "value": world * B * T / (msk / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": msk, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "A3GC-TP training step (fwd + BPTT bwd + Adam, 3 stages), B=%d x T=%d per GPU (BASELINE cfg 5)" % (B, T),
+                       "dropout": "reference defaults 0.2 / 0.3 / 0.3", "allreduce_bytes_per_step": sum(r.nbytes for r in reds if r) or 0,
+                       "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30},
+            "gpu_launches": int(L.a3gc_launch_count()), "losses": [float(l) for l in losses],
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -144,9 +206,13 @@ def main():
     ap.add_argument("--engine", default=os.environ.get("A3GC_ENGINE", "auto"))
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="sequences per GPU (default: the BASELINE cfg-2 value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
+                    help="infer = the headline line (BASELINE cfg 2); train = the secondary cfg-5 training-step line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "train":
+        return run_train(args)
 
     import torch.distributed as dist
     import a3gc_ip_b200 as A

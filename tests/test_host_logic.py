@@ -125,3 +125,39 @@ def test_sharded_runner_gloo_world2(batch):
     ret = mgr.dict()
     mp.spawn(_gloo_worker, args=(2, port, batch, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def _gloo_grad_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        lin = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+        frozen = torch.nn.Parameter(torch.ones(4), requires_grad=False)
+        params = list(lin.parameters()) + [frozen]
+        x = torch.arange(8 * 6, dtype=torch.float32).view(8, 6) / 10.0
+        t = torch.ones(8, 3)
+        # every rank: local mean loss on its half of the batch -> all-reduced mean == gradient of the global-batch mean loss
+        lo, hi = A.shard_range(8, world, rank)
+        red = A.FlatGradAllReducer(params)
+        loss = ((lin(x[lo:hi]) - t[lo:hi]) ** 2).sum(-1).mean()
+        loss.backward()
+        red.reduce()
+        got = torch.cat([p.grad.flatten() for p in lin.parameters()])
+        lin.zero_grad()
+        ((lin(x) - t) ** 2).sum(-1).mean().backward()
+        want = torch.cat([p.grad.flatten() for p in lin.parameters()])
+        ret[rank] = bool(torch.allclose(got, want, rtol=1e-5, atol=1e-6)) and red.nbytes == 4 * sum(p.numel() for p in lin.parameters())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_grad_allreduce_gloo_world2():
+    """cfg-5 data parallelism on CPU: the flat-bucket all-reduce over two gloo ranks reproduces the global-batch gradient."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gloo_grad_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
