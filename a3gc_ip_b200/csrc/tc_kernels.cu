@@ -489,10 +489,14 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
             uint32_t bh0, bl0, bh1, bl1;
             ptx::split_pair_f16(u0.x, u0.y, bh0, bl0);
             ptx::split_pair_f16(u1.x, u1.y, bh1, bl1);
-            float z[4] = {bias.x, bias.y, bias.x, bias.y};
+            // three INDEPENDENT accumulators: a warp-level HMMA queues behind the UMMAs that share the tensor pipe, so a
+            // dependent chain of three would pay that latency three times
+            float z[4] = {bias.x, bias.y, bias.x, bias.y}, z2[4] = {0.f, 0.f, 0.f, 0.f}, z3[4] = {0.f, 0.f, 0.f, 0.f};
             ptx::mma_16816_f16(z, ah, bh0, bh1);
-            ptx::mma_16816_f16(z, al, bh0, bh1);
-            ptx::mma_16816_f16(z, ah, bl0, bl1);
+            ptx::mma_16816_f16(z2, al, bh0, bh1);
+            ptx::mma_16816_f16(z3, ah, bl0, bl1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) z[j] += z2[j] + z3[j];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const bool ok = valid[sq] && !(pad_hi && j >= 2);
@@ -544,12 +548,12 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
             for (int u2 = 0; u2 < 2; ++u2) hreg[sq][ub][2 + u2] = keep[sq][ub][u2];
       } else {
         store_units(hreg);
-        emit(ta, hreg);
       }
       if (et == 0) TC_TRACE(0, 2);
 
       if (!ATT) {
         publish_block(BAR_H, (int)b);
+        emit(ta, hreg);                 // global stores of y_t after the hand-off: off the recurrence's critical path
         if (et == 0) TC_TRACE(0, 11);
         continue;
       }
@@ -594,7 +598,9 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       ptx::tc_fence_before();
       ptx::named_bar_sync(1, kEpiThreads);
       if (et == 0) {
-        for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) ptx::mbar_arrive_remote(&bars[BAR_Q], peer);
+        // one cluster-scope release fence, then relaxed arrives (a release arrive per peer costs a MEMBAR.GPU each)
+        if (C > 1) ptx::fence_acq_rel_cluster();
+        for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) ptx::mbar_arrive_remote_relaxed(&bars[BAR_Q], peer);
         TC_TRACE(0, 6);
       }
       // ---- e = tanh(Wh hy + Wq q + bs),  partial a = e . u over this warp's 16 units (lane = row)
@@ -645,9 +651,9 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
           for (int j = 0; j < 4; ++j) hreg[sq][ub][j] *= (j & 2) ? ahi : alo;
       }
       store_units(hreg);
-      emit(ta, hreg);
       if (et == 0) TC_TRACE(0, 10);
       publish_block(BAR_H, -1);
+      emit(ta, hreg);                   // global stores of y_t after the hand-off: off the recurrence's critical path
       if (et == 0) TC_TRACE(0, 11);
     }
     // final state: h' and c' after the last step (registers)
@@ -905,4 +911,25 @@ extern "C" int a3gc_debug_read_tc_trace(unsigned long long* host_out) {
   if (!host_out) return A3GC_ERR_INVALID_ARG;
   A3GC_CUDA_TRY(cudaMemcpyFromSymbol(host_out, g_tc_trace, sizeof(unsigned long long) * 2 * 16 * 16));
   return A3GC_OK;
+}
+
+// debug / tuning: how many clusters of `cluster_size` CTAs of the fp32-split attention kernel (with `smem_bytes` of
+// dynamic shared memory each) the device can hold at once
+extern "C" int a3gc_debug_max_active_clusters(int cluster_size, int smem_bytes) {
+  using namespace a3gc;
+  void (*kern)(const TcLayerParams) = tc_lstm_layer_kernel<true, true>;
+  A3GC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  if (cluster_size > 8) A3GC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(cluster_size * 64), 2, 1);
+  cfg.blockDim = dim3(kThreadsTC, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  A3GC_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+  return n;
 }

@@ -419,6 +419,14 @@ class _Net(torch.nn.Module, _EngineMixin):
         self.linear_out = AAGC(units_hidden * 2, units_out, adjacency_matrix, activation_fn="linear", dropout=0.0)
         self._ws = _lib.Workspace()
 
+    def _workspace(self, slot: int) -> "_lib.Workspace":
+        if slot == 0:
+            return self._ws
+        pool = self.__dict__.setdefault("_ws_pool", {})
+        if slot not in pool:
+            pool[slot] = _lib.Workspace()
+        return pool[slot]
+
     def _net_params(self) -> _lib.NetParams:
         p = _lib.NetParams()
         p.linear_in = self.linear_in._params()
@@ -428,8 +436,11 @@ class _Net(torch.nn.Module, _EngineMixin):
                 p.rnn[l][d] = rnn.directions[d].cell._cell_params()
         return p
 
-    def forward(self, x: Tensor, h=None):
+    def forward(self, x: Tensor, h=None, _slot: int = 0):
         """x [B, T, 15, units_in] -> (y [B, T, 15, units_out], rnn2 final states).
+
+        ``_slot`` (not part of the reference's signature) selects one of the module's workspaces, so that calls on
+        different CUDA streams (batch chunks run concurrently by ``TPPipeline``) do not share scratch memory.
 
         h: None (zero state) or the reference's structure: ``[(h, c), (h, c)]`` ([h, h] for G-GRU),
         each [B, 15, units_hidden]; the returned states have the same structure.
@@ -463,7 +474,7 @@ class _Net(torch.nn.Module, _EngineMixin):
             nbytes = L.a3gc_net_workspace_bytes(v, B, T, f0, H, O, pr, en)
             if nbytes == 0 and B * T > 0:
                 raise RuntimeError("a3gc_net_workspace_bytes: " + L.a3gc_last_error().decode(errors="replace"))
-            wbuf = self._ws.get(nbytes, dev)
+            wbuf = self._workspace(_slot).get(nbytes, dev)
             rc = L.a3gc_net_forward(v, C.byref(p), x.data_ptr(), _lib.ptr_array(h0), _lib.ptr_array(c0), y.data_ptr(),
                                     _lib.ptr_array(hT), _lib.ptr_array(cT), B, T, f0, H, O, pr, en,
                                     wbuf.data_ptr(), wbuf.numel(), _lib.stream_ptr(dev))

@@ -64,17 +64,50 @@ def concat_stage_input(x: Tensor, pos: Tensor) -> Tensor:
 class TPPipeline(torch.nn.Module):
     """net1 (12 -> 3), net2 (15 -> 3), net3 (15 -> 9) chained as evaluate_a3gc_tp.py:164-172."""
 
-    def __init__(self, net1: torch.nn.Module, net2: torch.nn.Module, net3: torch.nn.Module, stats: Optional[dict] = None):
+    def __init__(self, net1: torch.nn.Module, net2: torch.nn.Module, net3: torch.nn.Module, stats: Optional[dict] = None,
+                 streams: int = 1):
         super().__init__()
         self.net1, self.net2, self.net3 = net1, net2, net3
         self.stats = stats
+        self.streams = max(1, int(streams))
+        self._side = {}
+
+    def _chain(self, x: Tensor, slot: int) -> Tuple[Tensor, Tensor, Tensor]:
+        y1, _ = self.net1(x, None, slot)
+        y2, _ = self.net2(concat_stage_input(x, y1), None, slot)
+        y3, _ = self.net3(concat_stage_input(x, y2), None, slot)
+        return y1, y2, y3
 
     @torch.no_grad()
     def forward(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
-        y1, _ = self.net1(x)
-        y2, _ = self.net2(concat_stage_input(x, y1))
-        y3, _ = self.net3(concat_stage_input(x, y2))
-        return y1, y2, y3
+        """Sequences are independent, so with ``streams`` > 1 the batch is cut into that many contiguous chunks whose
+        three-stage chains run concurrently on separate CUDA streams: a chunk's small stages (cluster size 1 / 2) fill
+        the SMs that the 4-CTA clusters of another chunk's H = 256 stage cannot use, and partial last waves overlap."""
+        n = min(self.streams, max(1, x.shape[0] // 8))
+        if n <= 1 or not x.is_cuda:
+            return self._chain(x, 0)
+        dev = x.device
+        main = torch.cuda.current_stream(dev)
+        side = self._side.setdefault(dev, [])
+        while len(side) < n:
+            side.append(torch.cuda.Stream(device=dev))
+        # chunk boundaries on multiples of the 8-sequence batch tile
+        tiles = (x.shape[0] + 7) // 8
+        bounds = [min(x.shape[0], 8 * ((tiles * i) // n)) for i in range(n + 1)]
+        ready = torch.cuda.Event()
+        ready.record(main)
+        outs = []
+        for i in range(n):
+            st = side[i]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                xi = x[bounds[i]:bounds[i + 1]]
+                outs.append(self._chain(xi, i))
+        for i in range(n):
+            main.wait_stream(side[i])
+            for t in outs[i]:
+                t.record_stream(main)
+        return tuple(torch.cat([o[k] for o in outs], dim=0) for k in range(3))
 
     @torch.no_grad()
     def forward_raw(self, ori: Tensor, acc: Tensor) -> Tuple[Tensor, Tensor, Tensor]:

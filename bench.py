@@ -206,6 +206,12 @@ def main():
     ap.add_argument("--engine", default=os.environ.get("A3GC_ENGINE", "auto"))
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="sequences per GPU (default: the BASELINE cfg-2 value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("A3GC_STREAMS", 3)),
+                    help="batch chunks whose three-stage chains run concurrently on separate CUDA streams")
+    ap.add_argument("--variant", default="A3GC", choices=["A3GC", "AAGC", "AGC", "GGRU"],
+                    help="cell family of the three-stage pipeline (headline: A3GC; the others are the cfg 3 / cfg 4 side lines)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"], help="fp32 = parity path (headline); bf16 = cfg-3 path")
+    ap.add_argument("--seq-len", type=int, default=T_STEPS)
     ap.add_argument("--workload", default="infer", choices=["infer", "train"],
                     help="infer = the headline line (BASELINE cfg 2); train = the secondary cfg-5 training-step line")
     args = ap.parse_args()
@@ -230,12 +236,17 @@ def main():
     W, K = max(args.warmup, 3), max(args.steps, 1)
     B = args.batch
     nira = load_nira()
-    pipe, _ = build_tp("A3GC", nira, device=dev, engine=args.engine)
+    T = args.seq_len
+    pipe, _ = build_tp(args.variant, nira, device=dev, engine=args.engine, precision=args.precision)
+    pipe.streams = args.streams
+    mflop = {"A3GC": 115.70, "AGC": 115.70, "AAGC": 103.95, "GGRU": 88.46}[args.variant]
+    headline = args.variant == "A3GC" and args.precision == "fp32" and T == T_STEPS and B == B_PER_GPU
+    workload = WORKLOAD if headline else f"{args.variant}-TP forward {args.precision}, B={B} x T={T} per GPU (side line, not the headline config)"
     L = A.lib()
 
     # synthetic inputs: seed 1234 + rank; x is 221 MB (> 126 MB L2), pose output 166 MB
-    x_host = O.synthetic_input(B, T_STEPS, seed=1234 + rank).pin_memory()
-    y_host = torch.empty(B, T_STEPS, 15, 9, dtype=torch.float32).pin_memory()
+    x_host = O.synthetic_input(B, T, seed=1234 + rank).pin_memory()
+    y_host = torch.empty(B, T, 15, 9, dtype=torch.float32).pin_memory()
     x = x_host.to(dev)
 
     def barrier():
@@ -275,7 +286,9 @@ def main():
 
     # dominant kernel: per-launch CUDA-event times of the recurrent layer launches
     L.a3gc_profile_enable(1)
+    pipe.streams = 1                      # each launch timed alone (no co-running chunk on another stream)
     pipe(x)
+    pipe.streams = args.streams
     torch.cuda.synchronize(dev)
     recs = []
     for i in range(L.a3gc_profile_count()):
@@ -289,7 +302,7 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    frames_per_step = world * B * T_STEPS
+    frames_per_step = world * B * T
     fps = frames_per_step * K / (ms_total / 1e3)
     fps_e2e = frames_per_step * K / (ms_e2e / 1e3)
     peaks, src = measured_peaks()
@@ -300,12 +313,18 @@ def main():
     if dom:
         ach = dom["gflop"] / dom["ms"]            # GFLOP / ms == TFLOP/s
         tc = dom["kernel"].startswith("tc")
-        roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+        traffic, tnote = None, None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")     # dram bytes per launch from the committed ncu --set full capture
+        if os.path.exists(tp) and headline:
+            rec = json.load(open(tp)).get(dom["kernel"])
+            if rec:
+                traffic, tnote = rec["dram_bytes"], rec["source"]
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic, "traffic_source": tnote,
                 "kernel": dom["kernel"], "kernel_ms": dom["ms"], "peak_source": f"bf16_tflops_sustained ({src})",
-                "note": ("algorithmic FLOPs (2MNK of gate+attention GEMMs); the fp32-parity tensor path executes 3 fp16-split passes, "
-                         "so executed tensor FLOPs are 3x" if tc else "SIMT fp32 engine: FFMA pipe, quoted against the tensor peak"),
+                "note": (("algorithmic FLOPs (2MNK of gate+attention GEMMs); the fp32-parity tensor path executes 3 fp16-split passes, "
+                          "so executed tensor FLOPs are 3x" if args.precision == "fp32" else "algorithmic FLOPs; bf16 operands, one tensor pass") if tc else "SIMT fp32 engine: FFMA pipe, quoted against the tensor peak"),
                 "layer_share_of_step": layer_ms / (ms_total / K), "launches": recs,
-                "whole_step_tflops": MFLOP_PER_FRAME * 1e6 * (B * T_STEPS) / (ms_total / K / 1e3) / 1e12}
+                "whole_step_tflops": mflop * 1e6 * (B * T) / (ms_total / K / 1e3) / 1e12}
     cpu = None
     if not args.no_cpu_baseline:
         sb = 16
@@ -314,8 +333,8 @@ def main():
                "sample": f"oracle port of net_aagc.py (torch CPU eager), B={sb} x T={T_STEPS}, 1 warm-up + 2 timed passes"}
     out = {
         "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "seq_len": T_STEPS, "engine": args.engine,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "config": {"workload": workload, "batch_per_gpu": B, "seq_len": T, "engine": args.engine, "streams": args.streams,
                    "l2": "inputs larger than L2 (x 221 MB, activations GBs per step); no explicit flush",
                    "weights": "stage1 random-init seed 0; stages 2-3 trained_models/A3GC"},
         "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world, "d2h_bytes_per_step": y_host.numel() * 4 * world,

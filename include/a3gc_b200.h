@@ -266,6 +266,10 @@ int a3gc_tc_mma_bench(int n, int layout_type, int a_lbo, int a_sbo, int b_lbo, i
  * environment variable A3GC_TC_TRACE set; host_out receives [2 roles][16 steps][16 slots] uint64. */
 int a3gc_debug_read_tc_trace(unsigned long long* host_out);
 
+/* Tuning aid: clusters of `cluster_size` CTAs of the tensor-core layer kernel (smem_bytes dynamic shared memory per CTA)
+ * the device can hold at once (cudaOccupancyMaxActiveClusters); negative a3gc_status on error. */
+int a3gc_debug_max_active_clusters(int cluster_size, int smem_bytes);
+
 /* Number of kernels this library has launched on the calling thread since the last reset. */
 int64_t a3gc_launch_count(void);
 void a3gc_reset_launch_count(void);
