@@ -118,5 +118,8 @@ bool tc_layer_supported(int variant, int f_in, int hidden, int precision);
 size_t tc_layer_workspace_bytes(int variant, int64_t batch, int64_t steps, int f_in, int hidden, int num_dirs, int precision);
 size_t tc_image_bytes(int64_t batch, int64_t steps, int features, int precision);
 int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t stream);
+// tc_gru_kernels.cu: graph-GRU layers on the tensor-core engine
+size_t tc_gru_weights_bytes(int f_in, int hidden, int num_dirs, int precision);
+int tc_gru_layer_launch(const LayerArgs& a, const uint16_t* x_img, char* weights_ws, cudaStream_t stream);
 
 }  // namespace a3gc

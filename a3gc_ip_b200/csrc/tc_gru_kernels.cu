@@ -1,0 +1,537 @@
+// tcgen05 / TMEM engine for the graph-GRU recurrent layers (G_GRU_cell, net_aagc.py:343-368, looped as in :547-568).
+//
+//   msg = P^T-mix (h Wg^T)                      G1: D1[128, 64]  = h[128, H]   * Wg_c[64, H]^T      (tcgen05, N = 64)
+//   r = sig(Wri x + br + Wrh msg)               G2: D2[128, 256] = x[128, F]   * [Wri; Wui; Wci]^T  (N = 192, cols r | u | cx)
+//   u = sig(Wui x + bu + Wuh msg)                               + msg[128, H] * [Wrh; Wuh]^T       (N = 128, cols r | u)
+//   c = tanh(Wci x + bc + r * (Wch msg))                        ,  msg[128, H] * Wch^T             (N = 64,  cols ch)
+//   h' = u h + (1 - u) c                        returns (h', h'): no output activation (:368)
+//
+// Same decomposition as the LSTM-family kernel (tc_kernels.cu): a CTA owns 8 sequences (128 accumulator rows) x 64
+// hidden units of one direction for all T steps, a cluster of C = H/64 CTAs covers the hidden dimension, the state
+// operand image lives in shared memory and is all-gathered through DSMEM -- here twice per step, because the message
+// (needed with full K by G2) and the new state alternate in the SAME buffer: h -> msg -> h' -> ...
+// The x part of step t+1 is issued around the two dependent GEMMs of step t (ping-pong accumulator buffers); G1 of
+// step t writes the 64 columns of the OTHER buffer that no x part touches.  The node mix of G1's output runs on the
+// warp-level tensor path exactly like the gate mix of the LSTM kernel; the gate math needs no mix and runs in the
+// TMEM-native layout (thread = row), so the new state goes back to the operand image with 16-byte stores.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include <cstdlib>
+#include <cstring>
+
+namespace a3gc {
+namespace {
+
+constexpr int kRows = 128;
+constexpr int kSeqTile = 8;
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kThreadsTC = 64 + kEpiThreads;
+constexpr int kMaxStages = 8;
+constexpr int kWstFloats = 8 * 32;
+
+struct GruDir {
+  const uint16_t* wx_img;   // [C][F/16][NP][2][192][8]   rows 64*g + unit of dense_{r,u,c}_in.weight
+  const uint16_t* wm_img;   // [C][H/16][NP][2][192][8]   rows 64*g + unit of dense_{r,u,c}_hid.weight
+  const uint16_t* wg_img;   // [C][H/16][NP][2][64][8]    gcn_kernel rows of this chunk
+  const float* P;           // [16][16] zero padded, msg = P u  (P[n][m] = adjacency[m][n], net_aagc.py:348)
+  const float* bias3;       // [H][4]   (b_r, b_u, b_c, 0)
+  const float* h0; float* hT;
+  int reverse;
+};
+struct GruLayerParams {
+  GruDir d[2];
+  const uint16_t* x_img;    // [tiles][T][F/16][NP][2][128][8]
+  float* y; int64_t syb, syt, yld;
+  uint16_t* y_img; int y_kf;
+  int B, T, F, H, C, S, n1;
+};
+
+enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_ACC_FULL = 2 * kMaxStages, BAR_ACC_EMPTY = BAR_ACC_FULL + 2, BAR_G1_FULL = BAR_ACC_EMPTY + 2,
+       BAR_H, BAR_MSG, BAR_HFREE, BAR_MFREE, BAR_COUNT };
+
+__host__ __device__ inline size_t gru_fixed_smem_bytes() {
+  return (size_t)kEpiWarps * kWstFloats * 4 + 256 * 4 + 256 * 4 + 32 * 8 + 16;   // wst, bias, Pfrag, barriers, tmem slot
+}
+
+__device__ __forceinline__ uint32_t img_off(int k, int row) {
+  return (uint32_t)(((k >> 3) * kRows + row) * 16 + (k & 7) * 2);
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(kThreadsTC, 1)
+tc_gru_layer_kernel(const GruLayerParams p) {
+  constexpr int NP = SPLIT ? 2 : 1;
+  constexpr uint32_t kXB = NP * 2 * 192 * 16;       // one K=16 block of [Wri; Wui; Wci] (all parts)
+  constexpr uint32_t kXA = NP * 2 * 128 * 16;       // one K=16 block of x rows
+  constexpr uint32_t kMB = NP * 2 * 192 * 16;       // one K=16 block of [Wrh; Wuh; Wch]
+  constexpr uint32_t kGB = NP * 2 * 64 * 16;        // one K=16 block of gcn_kernel rows
+  constexpr uint32_t kStageBytes = 2 * kMB;          // ring slot: 2 msg blocks >= 1 x block (B + A) >= 4 G1 blocks
+  constexpr uint32_t kHBlock = 8 * kRows * 16;
+  extern __shared__ __align__(1024) uint8_t smem[];
+
+  const int C = p.C, S = p.S, H = p.H, F = p.F, T = p.T;
+  const uint32_t c = C > 1 ? ptx::cluster_ctarank() : 0u;
+  const int tile = blockIdx.x / C;
+  const GruDir& d = p.d[blockIdx.y];
+  const int KF = F / 16, KH = H / 16;
+  const int warp = threadIdx.x >> 5;
+  const int n1 = p.n1;
+
+  uint8_t* hbuf = smem;                                              // operand image of h / msg: [NP][H/8][128][8]
+  uint8_t* ring = hbuf + (size_t)NP * H * 256;
+  float* staging = reinterpret_cast<float*>(ring + (size_t)S * kStageBytes);
+  float* biasg = staging + kEpiWarps * kWstFloats;                   // [3][64]  (+ 64 pad)
+  uint32_t* Pfrag = reinterpret_cast<uint32_t*>(biasg + 256);        // [hi, lo][32 lanes][4 regs]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Pfrag + 256);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < BAR_COUNT; ++i) ptx::mbar_init(&bars[i], (i == BAR_HFREE || i == BAR_MFREE) ? (uint32_t)C : 1u);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+  {
+    uint4* z = reinterpret_cast<uint4*>(hbuf);
+    const int n16 = NP * H * 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 192; i += blockDim.x) biasg[i] = d.bias3[(size_t)c * 256 + (i & 63) * 4 + (i >> 6)];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+      const int r = i & 3, l = i >> 2;
+      const int mm = (l >> 2) + 8 * (r & 1), nn = 2 * (l & 3) + 8 * (r >> 1);
+      uint32_t hi, lo;
+      ptx::split_pair_f16(d.P[mm * 16 + nn], d.P[mm * 16 + nn + 1], hi, lo);
+      Pfrag[(0 * 32 + l) * 4 + r] = hi;
+      Pfrag[(1 * 32 + l) * 4 + r] = lo;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (C > 1) ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint16_t cta_mask = (uint16_t)((1u << C) - 1u);
+
+  if (warp == 0) {
+    // ================================================================ producer
+    if ((threadIdx.x & 31) == 0) {
+      uint32_t st = 0, ph = 0;
+      auto load_stage = [&](const void* bsrc, uint32_t bbytes, uint32_t aoff, const void* asrc, uint32_t abytes) {
+        ptx::mbar_wait(&bars[BAR_EMPTY + st], ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + st], bbytes + abytes);
+        uint8_t* dst = ring + st * kStageBytes;
+        ptx::bulk_g2s(dst, bsrc, bbytes, &bars[BAR_FULL + st]);
+        if (abytes) ptx::bulk_g2s(dst + aoff, asrc, abytes, &bars[BAR_FULL + st]);
+        if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
+      };
+      const uint8_t* wx = reinterpret_cast<const uint8_t*>(d.wx_img) + (size_t)c * KF * kXB;
+      const uint8_t* wm = reinterpret_cast<const uint8_t*>(d.wm_img) + (size_t)c * KH * kMB;
+      const uint8_t* wg = reinterpret_cast<const uint8_t*>(d.wg_img) + (size_t)c * KH * kGB;
+      const uint8_t* xi = reinterpret_cast<const uint8_t*>(p.x_img);
+      auto xblocks = [&](int t, int kb0, int kb1) {
+        const int ta = d.reverse ? T - 1 - t : t;
+        const uint8_t* xs = xi + ((size_t)tile * T + ta) * KF * kXA;
+        for (int kb = kb0; kb < kb1; ++kb) load_stage(wx + (size_t)kb * kXB, kXB, kXB, xs + (size_t)kb * kXA, kXA);
+      };
+      xblocks(0, 0, KF);
+      for (int t = 0; t < T; ++t) {
+        const bool nx = t + 1 < T;
+        for (int s4 = 0; s4 < KH / 4; ++s4) load_stage(wg + (size_t)s4 * 4 * kGB, 4 * kGB, 0, nullptr, 0);
+        if (nx) xblocks(t + 1, 0, n1);
+        for (int s2 = 0; s2 < KH / 2; ++s2) load_stage(wm + (size_t)s2 * 2 * kMB, 2 * kMB, 0, nullptr, 0);
+        if (nx) xblocks(t + 1, n1, KF);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (one thread)
+    if ((threadIdx.x & 31) == 0) {
+      const uint32_t idesc192 = ptx::make_idesc_f16(128, 192, !SPLIT);
+      const uint32_t idesc128 = ptx::make_idesc_f16(128, 128, !SPLIT);
+      const uint32_t idesc64 = ptx::make_idesc_f16(128, 64, !SPLIT);
+      const uint32_t hbase = ptx::smem_u32(hbuf);
+      const uint32_t hpart = (uint32_t)H * 256;
+      uint32_t st = 0, ph = 0;
+      uint32_t empty_k[2] = {0, 0};
+      const uint32_t ring_addr = ptx::smem_u32(ring);
+      auto wait_stage = [&]() -> uint32_t {
+        ptx::mbar_wait(&bars[BAR_FULL + st], ph);
+        ptx::tc_fence_after();
+        return ring_addr + st * kStageBytes;
+      };
+      auto release_stage = [&]() {
+        ptx::umma_commit(&bars[BAR_EMPTY + st]);
+        if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
+      };
+      const uint64_t dA = ptx::make_smem_desc(0, kRows * 16, 128);
+      const uint64_t dB192 = ptx::make_smem_desc(0, 192 * 16, 128), dB64 = ptx::make_smem_desc(0, 64 * 16, 128);
+      auto block_mma = [&](uint32_t dcol, uint32_t a0, uint32_t astride, uint32_t b0, uint32_t bstride, uint64_t dB, uint32_t idesc, bool first) {
+        const uint64_t ah = dA + ((a0 & 0x3FFFFu) >> 4), bh = dB + ((b0 & 0x3FFFFu) >> 4);
+        ptx::umma_f16(tmem + dcol, ah, bh, idesc, first ? 0u : 1u);
+        if (SPLIT) {
+          ptx::umma_f16(tmem + dcol, ah + (astride >> 4), bh, idesc, 1u);
+          ptx::umma_f16(tmem + dcol, ah, bh + (bstride >> 4), idesc, 1u);
+        }
+      };
+      auto xblocks = [&](uint32_t dcol, int kb0, int kb1) {
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const uint32_t sa = wait_stage();
+          block_mma(dcol, sa + kXB, kXA / NP, sa, kXB / NP, dB192, idesc192, kb == 0);
+          release_stage();
+        }
+      };
+      xblocks(0, 0, KF);
+      for (int t = 0; t < T; ++t) {
+        const uint32_t b = t & 1, bo = b ^ 1u;
+        const bool nx = t + 1 < T;
+        // G1: h Wg^T -> the 64 columns of the other buffer that no x part touches
+        ptx::mbar_wait(&bars[BAR_H], t & 1);
+        ptx::tc_fence_after();
+        for (int s4 = 0; s4 < KH / 4; ++s4) {
+          const uint32_t sa = wait_stage();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int kb = s4 * 4 + j;
+            block_mma(bo * 256 + 192, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, sa + (uint32_t)j * kGB, kGB / NP, dB64, idesc64, (s4 | j) == 0);
+          }
+          release_stage();
+        }
+        ptx::umma_commit(&bars[BAR_G1_FULL]);
+        if (C > 1) ptx::umma_commit_multicast(&bars[BAR_HFREE], cta_mask); else ptx::umma_commit(&bars[BAR_HFREE]);
+        // x part of step t+1 -> columns [0,192) of the other buffer (free once the gate math of step t-1 has drained it)
+        if (nx && t >= 1) {
+          ptx::mbar_wait(&bars[BAR_ACC_EMPTY + bo], empty_k[bo] & 1u);
+          empty_k[bo] += 1;
+          ptx::tc_fence_after();
+        }
+        if (nx) xblocks(bo * 256, 0, n1);
+        // G2, message part: r | u accumulate onto the x part, ch starts fresh in columns [192,256)
+        ptx::mbar_wait(&bars[BAR_MSG], t & 1);
+        ptx::tc_fence_after();
+        for (int s2 = 0; s2 < KH / 2; ++s2) {
+          const uint32_t sa = wait_stage();
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int kb = s2 * 2 + j;
+            const uint32_t a0 = hbase + (uint32_t)kb * 2 * kRows * 16, b0 = sa + (uint32_t)j * kMB;
+            block_mma(b * 256, a0, hpart, b0, kMB / NP, dB192, idesc128, false);
+            block_mma(b * 256 + 192, a0, hpart, b0 + 128 * 16, kMB / NP, dB192, idesc64, (s2 | j) == 0);
+          }
+          release_stage();
+        }
+        ptx::umma_commit(&bars[BAR_ACC_FULL + b]);
+        if (C > 1) ptx::umma_commit_multicast(&bars[BAR_MFREE], cta_mask); else ptx::umma_commit(&bars[BAR_MFREE]);
+        if (nx) xblocks(bo * 256, n1, KF);
+      }
+    }
+  } else {
+    // ================================================================ epilogue warps
+    const int et = threadIdx.x - 64;
+    const int ew = et >> 5, lane = et & 31;
+    const int qd = warp & 3;                         // TMEM lane quarter: rows 32qd .. 32qd+31 (sequences 2qd, 2qd+1)
+    const int ug = ew >> 2;
+    const int ubase = 16 * ug;                       // this warp's 16 units of the CTA's 64
+    const int tq = lane >> 2, tr = lane & 3;
+    float* wst = staging + ew * kWstFloats;
+    const uint32_t tmem_row = tmem + ((uint32_t)(qd * 32) << 16);
+    const int ycol = blockIdx.y * H + (int)c * 64;
+    // gate-math ownership (TMEM-native): this thread = accumulator row `row`, units ubase .. ubase+15
+    const int row = 32 * qd + lane;
+    const int rseq = tile * kSeqTile + (row >> 4), rnode = row & 15;
+    const bool rvalid = rseq < p.B && rnode < kNodes;
+    float hreg[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      hreg[i] = (rvalid && d.h0 != nullptr) ? d.h0[((size_t)rseq * kNodes + rnode) * H + c * 64 + ubase + i] : 0.f;
+
+    // this thread's 16 units of row `row` -> local operand image (two 16-byte K chunks per part)
+    auto store_row = [&](const float (&v)[16]) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (SPLIT) {
+            ptx::split_pair_f16(v[hf * 8 + 2 * j], v[hf * 8 + 2 * j + 1], hw[j], lw[j]);
+          } else {
+            const __nv_bfloat162 bb = __floats2bfloat162_rn(v[hf * 8 + 2 * j], v[hf * 8 + 2 * j + 1]);
+            hw[j] = *reinterpret_cast<const uint32_t*>(&bb);
+            lw[j] = 0;
+          }
+        }
+        const uint32_t off = img_off((int)c * 64 + ubase + 8 * hf, row);
+        *reinterpret_cast<uint4*>(hbuf + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        if (SPLIT) *reinterpret_cast<uint4*>(hbuf + (size_t)H * 256 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+    };
+    auto publish_block = [&](int bar, int acc_empty, bool tmem_read) {
+      ptx::fence_proxy_async();
+      if (tmem_read) ptx::tc_fence_before();
+      ptx::named_bar_sync(1, kEpiThreads);
+      if (et == 0) {
+        if (acc_empty >= 0) ptx::mbar_arrive(&bars[BAR_ACC_EMPTY + acc_empty]);
+        for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) {
+          if (peer == c) continue;
+          for (int part = 0; part < NP; ++part)
+            ptx::bulk_s2remote(hbuf + (size_t)part * H * 256 + (size_t)c * kHBlock, kHBlock, &bars[bar], peer);
+        }
+        ptx::mbar_arrive_expect_tx(&bars[bar], (uint32_t)(C - 1) * NP * kHBlock);
+      }
+    };
+    const size_t img_step = (size_t)p.y_kf * NP * 4096;
+    const size_t img_base = ((size_t)tile * T * p.y_kf + ((ycol + ubase) >> 4)) * NP * 4096 + (size_t)row * 16;
+    auto emit = [&](int ta, const float (&v)[16]) {
+      if (p.y != nullptr && rvalid) {
+        float4* yp = reinterpret_cast<float4*>(p.y + (size_t)rseq * p.syb + (size_t)ta * p.syt + (size_t)rnode * p.yld + ycol + ubase);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      if (p.y_img != nullptr) {
+        uint8_t* ip = reinterpret_cast<uint8_t*>(p.y_img) + img_base + (size_t)ta * img_step;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (SPLIT) {
+              ptx::split_pair_f16(v[hf * 8 + 2 * j], v[hf * 8 + 2 * j + 1], hw[j], lw[j]);
+            } else {
+              const __nv_bfloat162 bb = __floats2bfloat162_rn(v[hf * 8 + 2 * j], v[hf * 8 + 2 * j + 1]);
+              hw[j] = *reinterpret_cast<const uint32_t*>(&bb);
+              lw[j] = 0;
+            }
+          }
+          *reinterpret_cast<uint4*>(ip + hf * 2048) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          if (SPLIT) *reinterpret_cast<uint4*>(ip + hf * 2048 + 4096) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      }
+    };
+
+    store_row(hreg);                                 // h_{-1} = h0
+    publish_block(BAR_H, -1, false);
+
+    const uint4* Pfrag4 = reinterpret_cast<const uint4*>(Pfrag);
+    const int swz = 8 * (tq & 3);
+
+    for (int t = 0; t < T; ++t) {
+      const uint32_t b = t & 1, bo = b ^ 1u;
+      const int ta = d.reverse ? T - 1 - t : t;
+      // ---------------------------------------------------------------- msg = P (h Wg^T): node mix of G1's output
+      ptx::mbar_wait(&bars[BAR_G1_FULL], t & 1);
+      ptx::mbar_wait(&bars[BAR_HFREE], t & 1);       // every CTA has finished reading h: the image may hold msg now
+      ptx::tc_fence_after();
+      {
+        const uint4 ah4 = Pfrag4[0 * 32 + lane], al4 = Pfrag4[1 * 32 + lane];
+        const uint32_t ah[4] = {ah4.x, ah4.y, ah4.z, ah4.w}, al[4] = {al4.x, al4.y, al4.z, al4.w};
+#pragma unroll
+        for (int ub = 0; ub < 2; ++ub) {
+          float v[8];
+          ptx::tmem_ld8(tmem_row + bo * 256 + 192 + ubase + 8 * ub, v);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) wst[j * 32 + (lane ^ (8 * (j & 3)))] = v[j];
+          __syncwarp();
+          const int k = (int)c * 64 + ubase + 8 * ub + 2 * tr;
+#pragma unroll
+          for (int sq = 0; sq < 2; ++sq) {
+            const float* sp = wst + tq * 32;
+            const float2 u0 = *reinterpret_cast<const float2*>(sp + ((16 * sq + 2 * tr) ^ swz));
+            const float2 u1 = *reinterpret_cast<const float2*>(sp + ((16 * sq + 2 * tr + 8) ^ swz));
+            uint32_t bh0, bl0, bh1, bl1;
+            ptx::split_pair_f16(u0.x, u0.y, bh0, bl0);
+            ptx::split_pair_f16(u1.x, u1.y, bh1, bl1);
+            float z[4] = {0.f, 0.f, 0.f, 0.f}, z2[4] = {0.f, 0.f, 0.f, 0.f}, z3[4] = {0.f, 0.f, 0.f, 0.f};
+            ptx::mma_16816_f16(z, ah, bh0, bh1);
+            ptx::mma_16816_f16(z2, al, bh0, bh1);
+            ptx::mma_16816_f16(z3, ah, bl0, bl1);
+#pragma unroll
+            for (int up = 0; up < 2; ++up) {           // C fragment: nodes tq + 8up, units 2tr, 2tr+1 -> operand image
+              const float m0 = z[2 * up] + z2[2 * up] + z3[2 * up], m1 = z[2 * up + 1] + z2[2 * up + 1] + z3[2 * up + 1];
+              uint32_t hi, lo = 0;
+              if (SPLIT) {
+                ptx::split_pair_f16(m0, m1, hi, lo);
+              } else {
+                const __nv_bfloat162 bb = __floats2bfloat162_rn(m0, m1);
+                hi = *reinterpret_cast<const uint32_t*>(&bb);
+              }
+              const uint32_t off = img_off(k, 16 * (2 * qd + sq) + tq + 8 * up);
+              *reinterpret_cast<uint32_t*>(hbuf + off) = hi;
+              if (SPLIT) *reinterpret_cast<uint32_t*>(hbuf + (size_t)H * 256 + off) = lo;
+            }
+          }
+        }
+      }
+      publish_block(BAR_MSG, -1, true);
+      // ---------------------------------------------------------------- gates (TMEM-native layout: thread = row)
+      ptx::mbar_wait(&bars[BAR_ACC_FULL + b], (t >> 1) & 1);
+      ptx::mbar_wait(&bars[BAR_MFREE], t & 1);       // every CTA has finished reading msg: the image may hold h' now
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float zr[8], zu[8], zx[8], zh[8];
+        const uint32_t col = tmem_row + b * 256 + ubase + 8 * hf;
+        ptx::tmem_ld8(col, zr);
+        ptx::tmem_ld8(col + 64, zu);
+        ptx::tmem_ld8(col + 128, zx);
+        ptx::tmem_ld8(col + 192, zh);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int un = ubase + 8 * hf + i;
+          const float r = fast_sigmoid(zr[i] + biasg[un]);
+          const float u = fast_sigmoid(zu[i] + biasg[64 + un]);
+          const float cc = fast_tanh(fmaf(r, zh[i], zx[i] + biasg[128 + un]));
+          const float hn = fmaf(u, hreg[hf * 8 + i] - cc, cc);            // u h + (1 - u) c   (net_aagc.py:364)
+          hreg[hf * 8 + i] = rvalid ? hn : 0.f;
+        }
+      }
+      store_row(hreg);
+      publish_block(BAR_H, (int)b, true);
+      emit(ta, hreg);
+    }
+    if (rvalid && d.hT != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) d.hT[((size_t)rseq * kNodes + rnode) * H + c * 64 + ubase + i] = hreg[i];
+    }
+    ptx::mbar_wait(&bars[BAR_H], T & 1);             // the last publish must have landed everywhere before any CTA exits
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (C > 1) ptx::cluster_sync_all();
+  if (warp == 1) ptx::tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------ packing
+__device__ __forceinline__ uint16_t part_bits(float v, int part, bool split) {
+  if (!split) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  const __half hi = __float2half_rn(v);
+  if (part == 0) return __half_as_ushort(hi);
+  return __half_as_ushort(__float2half_rn(v - __half2float(hi)));
+}
+
+struct GruPackedTc { uint16_t* wx_img; uint16_t* wm_img; uint16_t* wg_img; float* P; float* bias3; };
+
+__global__ void tc_pack_gru_kernel(a3gc_cell_params cp, GruPackedTc out, int F, int H, int split) {
+  const int NP = split ? 2 : 1;
+  const int KF = F / 16, KH = H / 16, C = H / 64;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // 192-row images: index = ((((c*KB + kb)*NP + part)*2 + kc)*192 + r)*8 + e,  r = 64*g + unit
+  for (int which = 0; which < 2; ++which) {
+    const int KB = which == 0 ? KF : KH, K = which == 0 ? F : H;
+    uint16_t* img = which == 0 ? out.wx_img : out.wm_img;
+    const int64_t n = (int64_t)C * KB * NP * 2 * 192 * 8;
+    for (int64_t i = tid; i < n; i += stride) {
+      const int e = (int)(i & 7);
+      int64_t rest = i >> 3;
+      const int r = (int)(rest % 192); rest /= 192;
+      const int kc = (int)(rest & 1); rest >>= 1;
+      const int part = (int)(rest % NP); rest /= NP;
+      const int kb = (int)(rest % KB); const int c = (int)(rest / KB);
+      const int g = r >> 6, j = c * 64 + (r & 63), k = kb * 16 + kc * 8 + e;
+      const float* w = which == 0 ? cp.dense_in_w[g] : cp.dense_hid_w[g];
+      img[i] = part_bits(w[(size_t)j * K + k], part, split);
+    }
+  }
+  const int64_t n_g = (int64_t)C * KH * NP * 2 * 64 * 8;
+  for (int64_t i = tid; i < n_g; i += stride) {
+    const int e = (int)(i & 7), ul = (int)((i >> 3) & 63), kc = (int)((i >> 9) & 1);
+    int64_t rest = i >> 10;
+    const int part = (int)(rest % NP); rest /= NP;
+    const int kb = (int)(rest % KH); const int c = (int)(rest / KH);
+    out.wg_img[i] = part_bits(cp.g_gcn_kernel[(size_t)(c * 64 + ul) * H + kb * 16 + kc * 8 + e], part, split);
+  }
+  for (int64_t i = tid; i < 256; i += stride) {
+    const int n = (int)(i / 16), m = (int)(i % 16);
+    out.P[i] = (m < kNodes && n < kNodes) ? cp.g_adjacency[m * kNodes + n] : 0.f;     // used transposed (net_aagc.py:348)
+  }
+  for (int64_t i = tid; i < (int64_t)H * 4; i += stride) {
+    const int g = (int)(i & 3);
+    out.bias3[i] = g < 3 ? cp.dense_in_b[g][i >> 2] : 0.f;
+  }
+}
+
+size_t gru_dir_bytes(int F, int H, int NP) {
+  size_t b = 0;
+  b += align_up((size_t)F * 192 * (H / 64) * NP * 2, 256);
+  b += align_up((size_t)H * 192 * (H / 64) * NP * 2, 256);
+  b += align_up((size_t)H * H * NP * 2, 256);
+  b += align_up((size_t)(256 + 4 * H) * 4, 256);
+  return b;
+}
+
+GruPackedTc gru_carve(char* base, int F, int H, int NP) {
+  GruPackedTc p;
+  p.wx_img = reinterpret_cast<uint16_t*>(base); base += align_up((size_t)F * 192 * (H / 64) * NP * 2, 256);
+  p.wm_img = reinterpret_cast<uint16_t*>(base); base += align_up((size_t)H * 192 * (H / 64) * NP * 2, 256);
+  p.wg_img = reinterpret_cast<uint16_t*>(base); base += align_up((size_t)H * H * NP * 2, 256);
+  float* f = reinterpret_cast<float*>(base);
+  p.P = f; p.bias3 = f + 256;
+  return p;
+}
+
+}  // namespace
+
+size_t tc_gru_weights_bytes(int f_in, int hidden, int num_dirs, int precision) {
+  return (size_t)num_dirs * gru_dir_bytes(f_in, hidden, precision == A3GC_PREC_FP32 ? 2 : 1);
+}
+
+// G-GRU layer on the tensor-core engine; a.x_img must hold the packed input (tc_layer_forward packs it if needed)
+int tc_gru_layer_launch(const LayerArgs& a, const uint16_t* x_img, char* wbase, cudaStream_t stream) {
+  const int F = a.f_in, H = a.hidden;
+  const bool split = a.precision == A3GC_PREC_FP32;
+  const int NP = split ? 2 : 1;
+  const int C = H / 64;
+  const int64_t tiles = (a.batch + kSeqTile - 1) / kSeqTile;
+  GruLayerParams p;
+  memset(&p, 0, sizeof(p));
+  const size_t dir_bytes = gru_dir_bytes(F, H, NP);
+  for (int d = 0; d < a.num_dirs; ++d) {
+    GruPackedTc pk = gru_carve(wbase + d * dir_bytes, F, H, NP);
+    tc_pack_gru_kernel<<<148, 256, 0, stream>>>(a.cells[d], pk, F, H, split ? 1 : 0);
+    A3GC_LAUNCH_CHECK("tc_pack_gru_kernel");
+    GruDir& g = p.d[d];
+    g.wx_img = pk.wx_img; g.wm_img = pk.wm_img; g.wg_img = pk.wg_img; g.P = pk.P; g.bias3 = pk.bias3;
+    g.h0 = a.h0[d]; g.hT = a.hT[d]; g.reverse = a.reverse[d];
+  }
+  p.x_img = x_img;
+  p.y = a.y; p.syb = a.y_stride_b; p.syt = a.y_stride_t; p.yld = a.y_ld;
+  p.y_img = a.y_img; p.y_kf = a.y_img_f / 16;
+  p.B = (int)a.batch; p.T = (int)a.steps; p.F = F; p.H = H; p.C = C;
+  {
+    const int KF = F / 16;
+    int n1 = (KF + 1) / 2;
+    if (const char* e = getenv("A3GC_TC_SPLIT")) { int x = 0, y = 0; if (sscanf(e, "%d,%d", &x, &y) >= 1) n1 = KF * x / 100; }
+    p.n1 = n1 > KF ? KF : n1;
+  }
+  int dev = 0, smem_max = 0;
+  A3GC_CUDA_TRY(cudaGetDevice(&dev));
+  A3GC_CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const size_t stage_bytes = (size_t)2 * NP * 2 * 192 * 16;
+  const size_t fixed = (size_t)NP * H * 256 + gru_fixed_smem_bytes();
+  int S = kMaxStages;
+  if (const char* e = getenv("A3GC_TC_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= kMaxStages) S = v; }
+  while (S > 1 && fixed + (size_t)S * stage_bytes > (size_t)smem_max) --S;
+  if (fixed + (size_t)S * stage_bytes > (size_t)smem_max || S < 2) {
+    set_error("tc engine (G-GRU): shared memory budget exceeded (hidden=%d)", H);
+    return A3GC_ERR_UNSUPPORTED;
+  }
+  p.S = S;
+  const size_t smem = fixed + (size_t)S * stage_bytes;
+  void (*kern)(const GruLayerParams) = split ? tc_gru_layer_kernel<true> : tc_gru_layer_kernel<false>;
+  A3GC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(tiles * C), (unsigned)a.num_dirs, 1);
+  cfg.blockDim = dim3(kThreadsTC, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  A3GC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
+  A3GC_LAUNCH_CHECK("tc_gru_layer_kernel");
+  return A3GC_OK;
+}
+
+}  // namespace a3gc

@@ -789,7 +789,7 @@ TcPacked tc_carve(char* base, int F, int H, int NP) {
 }  // namespace
 
 bool tc_layer_supported(int variant, int f_in, int hidden, int precision) {
-  if (variant != A3GC_VARIANT_AAGC && variant != A3GC_VARIANT_A3GC && variant != A3GC_VARIANT_AGC) return false;
+  if (variant < A3GC_VARIANT_AAGC || variant > A3GC_VARIANT_GGRU) return false;
   if (hidden != 64 && hidden != 128 && hidden != 256) return false;
   if (f_in <= 0 || f_in % 16 != 0) return false;
   return precision == A3GC_PREC_FP32 || precision == A3GC_PREC_BF16;
@@ -802,9 +802,9 @@ size_t tc_image_bytes(int64_t batch, int64_t steps, int features, int precision)
 }
 
 size_t tc_layer_workspace_bytes(int variant, int64_t batch, int64_t steps, int f_in, int hidden, int num_dirs, int precision) {
-  (void)variant;
   const int NP = precision == A3GC_PREC_FP32 ? 2 : 1;
-  size_t b = (size_t)num_dirs * tc_dir_bytes(f_in, hidden, NP);
+  size_t b = variant == A3GC_VARIANT_GGRU ? tc_gru_weights_bytes(f_in, hidden, num_dirs, precision)
+                                          : (size_t)num_dirs * tc_dir_bytes(f_in, hidden, NP);
   b += tc_image_bytes(batch, steps, f_in, precision);   // x image (unused when the caller hands one in)
   return b + 256;
 }
@@ -819,6 +819,21 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
     return A3GC_ERR_WORKSPACE;
   }
   if (a.steps == 0) return A3GC_OK;
+  if (a.variant == A3GC_VARIANT_GGRU) {
+    char* wb = static_cast<char*>(ws);
+    const uint16_t* ximg = a.x_img;
+    if (ximg == nullptr) {
+      uint16_t* own = reinterpret_cast<uint16_t*>(wb + tc_gru_weights_bytes(F, H, a.num_dirs, a.precision));
+      ximg = own;
+      const int64_t tl = (a.batch + kSeqTile - 1) / kSeqTile;
+      const int64_t total = tl * a.steps * (F / 16) * NP * 2 * kRows * 8;
+      int64_t blocks = (total + 255) / 256;
+      if (blocks > 148 * 32) blocks = 148 * 32;
+      tc_pack_x_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.x, a.x_stride_b, a.x_stride_t, own, (int)a.batch, (int)a.steps, F, split ? 1 : 0, total);
+      A3GC_LAUNCH_CHECK("tc_pack_x_kernel");
+    }
+    return tc_gru_layer_launch(a, ximg, wb, stream);
+  }
   const bool att = a.variant != A3GC_VARIANT_AAGC;
   const int C = H / 64;
   const int64_t tiles = (a.batch + kSeqTile - 1) / kSeqTile;
