@@ -336,7 +336,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
         "config": {"workload": workload, "batch_per_gpu": B, "seq_len": T, "engine": args.engine, "streams": args.streams,
                    "l2": "inputs larger than L2 (x 221 MB, activations GBs per step); no explicit flush",
-                   "weights": "stage1 random-init seed 0; stages 2-3 trained_models/A3GC"},
+                   "weights": "stage1 random-init seed 0; stages 2-3 " + (f"trained_models/{'A3GC' if args.variant == 'A3GC' else 'G-GRU'}" if args.variant in ("A3GC", "GGRU") else "random-init (no checkpoints shipped)")},
         "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world, "d2h_bytes_per_step": y_host.numel() * 4 * world,
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
