@@ -10,7 +10,7 @@ from .net_aagc import (AAGC, AAGC_LSTM_cell, A3GC_LSTM_cell, AGC_LSTM_cell, G_GR
                        AGC_LSTM, ReverseAGC_LSTM, BiAGC_LSTM, G_GRU, ReverseG_GRU, BiG_GRU,
                        AAGC_net, A3GC_net, AGC_net, G_GRU_net,
                        PoseNet, PoseNet3, PoseNet_AGC, PoseNet_GGRU, pose_loss)
-from .pipeline import TPPipeline, prepare_input, concat_stage_input, INPUT_JOINTS
+from .pipeline import TPPipeline, prepare_input, concat_stage_input, reduced_global_to_full_local, INPUT_JOINTS
 from .sharding import shard_range, ShardedRunner, FlatGradAllReducer, train_step
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -418,6 +418,14 @@ int a3gc_prepare_input(const float* acc, const float* ori, const float* acc_mean
   return simt_prepare_input(acc, ori, acc_mean, acc_std, ori_mean, ori_std, x, frames, ld_x, static_cast<cudaStream_t>(stream));
 }
 
+int a3gc_reduced_to_full_local(const float* pose, float* out, int64_t frames, int rotsize, void* stream) {
+  if (frames < 0 || (rotsize != 9 && rotsize != 6) || (frames > 0 && (!pose || !out))) {
+    set_error("a3gc_reduced_to_full_local: invalid argument (rotsize must be 9 or 6)");
+    return A3GC_ERR_INVALID_ARG;
+  }
+  return simt_reduced_to_full_local(pose, out, frames, rotsize, static_cast<cudaStream_t>(stream));
+}
+
 int a3gc_concat_stage_input(const float* x, const float* pos, float* dst, int64_t frames, void* stream) {
   if (frames < 0 || (frames > 0 && (!x || !pos || !dst))) { set_error("a3gc_concat_stage_input: invalid argument"); return A3GC_ERR_INVALID_ARG; }
   return simt_concat_stage_input(x, pos, dst, frames, static_cast<cudaStream_t>(stream));

@@ -94,6 +94,7 @@ int simt_prepare_input(const float* acc, const float* ori, const float* acc_mean
                        const float* ori_mean, const float* ori_std, float* x, int64_t frames, int ld_x,
                        cudaStream_t stream);
 int simt_concat_stage_input(const float* x, const float* pos, float* dst, int64_t frames, cudaStream_t stream);
+int simt_reduced_to_full_local(const float* pose, float* out, int64_t frames, int rotsize, cudaStream_t stream);
 
 
 // training path (simt_kernels.cu): forward with a tape, reverse-time backward chain

@@ -972,6 +972,60 @@ __global__ void concat_stage_input_kernel(const float* __restrict__ x, const flo
   }
 }
 
+// reduced-global -> full-local pose (PoseNet3._reduced_glb_to_full_local_mat, net_aagc.py:788-800): scatter the 15
+// predicted global rotations into the 24 SMPL joints (identity elsewhere), R_local[i] = R_global[parent[i]]^T R_global[i]
+// along the SMPL tree (articulate/math/spatial.py:115-123), identity on the ignored joints.  One thread per (frame, joint).
+__constant__ int c_smpl_parent[24] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21};   // SMPL kintree_table[0]
+__constant__ int c_full_to_reduced[24] = {-1, 0, 1, 2, 3, 4, 5, -1, -1, 6, -1, -1, 7, 8, 9, 10, 11, 12, 13, 14, -1, -1, -1, -1};   // inverse of joint_set.reduced (config.py:29)
+
+__device__ __forceinline__ void load_global_rot(const float* __restrict__ pose, int64_t f, int joint, int rotsize, float (&R)[9]) {
+  const int r = joint < 0 ? -1 : c_full_to_reduced[joint];
+  if (r < 0) {
+    R[0] = 1.f; R[1] = 0.f; R[2] = 0.f; R[3] = 0.f; R[4] = 1.f; R[5] = 0.f; R[6] = 0.f; R[7] = 0.f; R[8] = 1.f;
+    return;
+  }
+  const float* p = pose + ((size_t)f * kNodes + r) * rotsize;
+  if (rotsize == 9) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = p[i];
+    return;
+  }
+  // 6D -> rotation matrix (articulate/math/angular.py:167-182): columns c0, c1, c0 x c1; NaN -> 0
+  float a[3] = {p[0], p[1], p[2]}, b[3] = {p[3], p[4], p[5]};
+  const float na = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+  float c0[3] = {a[0] / na, a[1] / na, a[2] / na};
+  const float dt = c0[0] * b[0] + c0[1] * b[1] + c0[2] * b[2];
+  float v[3] = {b[0] - dt * c0[0], b[1] - dt * c0[1], b[2] - dt * c0[2]};
+  const float nv = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  float c1[3] = {v[0] / nv, v[1] / nv, v[2] / nv};
+  float c2[3] = {c0[1] * c1[2] - c0[2] * c1[1], c0[2] * c1[0] - c0[0] * c1[2], c0[0] * c1[1] - c0[1] * c1[0]};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { R[3 * i] = c0[i]; R[3 * i + 1] = c1[i]; R[3 * i + 2] = c2[i]; }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) if (R[i] != R[i]) R[i] = 0.f;
+}
+
+__global__ void reduced_to_full_local_kernel(const float* __restrict__ pose, float* __restrict__ out, int64_t frames, int rotsize) {
+  const int64_t total = frames * 24;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = i / 24;
+    const int j = (int)(i % 24);
+    float L[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+    if (c_full_to_reduced[j] >= 0) {                      // joints outside joint_set.reduced are exactly joint_set.ignored
+      float G[9], P[9];
+      load_global_rot(pose, f, j, rotsize, G);
+      load_global_rot(pose, f, c_smpl_parent[j], rotsize, P);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) L[3 * r + c] = P[r] * G[c] + P[3 + r] * G[3 + c] + P[6 + r] * G[6 + c];   // (P^T G)[r][c]
+    }
+    float* o = out + (size_t)i * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) o[k] = L[k];
+  }
+}
+
 int max_optin_smem() {
   int dev = 0, v = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -1216,6 +1270,15 @@ int simt_concat_stage_input(const float* x, const float* pos, float* dst, int64_
   if (blocks > 148 * 16) blocks = 148 * 16;
   concat_stage_input_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, pos, dst, rows);
   A3GC_LAUNCH_CHECK("concat_stage_input_kernel");
+  return A3GC_OK;
+}
+
+int simt_reduced_to_full_local(const float* pose, float* out, int64_t frames, int rotsize, cudaStream_t stream) {
+  if (frames == 0) return A3GC_OK;
+  int64_t blocks = (frames * 24 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  reduced_to_full_local_kernel<<<(unsigned)blocks, 256, 0, stream>>>(pose, out, frames, rotsize);
+  A3GC_LAUNCH_CHECK("reduced_to_full_local_kernel");
   return A3GC_OK;
 }
 

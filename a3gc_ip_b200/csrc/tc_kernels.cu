@@ -65,6 +65,7 @@ struct TcLayerParams {
   uint16_t* y_img; int y_kf;         // next layer's operand image (may be null) and its K/16
   int B, T, F, H, out_act, C, S, trace;
   int chunk;                         // bytes per bulk copy of the weight / x stream
+  int xsplit;                        // x part as two N=128 MMAs per K block
   int n1, n2;                        // x-part blocks of step t+1 issued before A1 / between A1 and A2 of step t (rest after A2)
 };
 
@@ -242,10 +243,19 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
           ptx::umma_f16(tmem + dcol, ah, bh + (bstride >> 4), idesc, 1u);
         }
       };
+      // p.xsplit: issue the (off-critical-path) x part as two N = 128 halves instead of one N = 256 MMA.  The warp-level
+      // HMMAs of the gate mix share the tensor pipe with the UMMAs and only get a slot between two of them; shorter
+      // UMMAs halve that wait at the cost of reading the A operand twice.
+      const bool xsplit = p.xsplit != 0;
       auto xblocks = [&](uint32_t dcol, int kb0, int kb1) {
         for (int kb = kb0; kb < kb1; ++kb) {
           const uint32_t sa = wait_stage();
-          block_mma(dcol, sa + kBBytes, kABytes / NP, sa, kBBytes / NP, dB256, idesc256, kb == 0);
+          if (xsplit) {
+            block_mma(dcol, sa + kBBytes, kABytes / NP, sa, kBBytes / NP, dB256, idesc128, kb == 0);
+            block_mma(dcol + 128, sa + kBBytes, kABytes / NP, sa + 128 * 16, kBBytes / NP, dB256, idesc128, kb == 0);
+          } else {
+            block_mma(dcol, sa + kBBytes, kABytes / NP, sa, kBBytes / NP, dB256, idesc256, kb == 0);
+          }
           release_stage();
         }
       };
@@ -877,6 +887,7 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
     if (n1 > KF) n1 = KF;
     if (n1 + n2 > KF) n2 = KF - n1;
     p.n1 = n1; p.n2 = n2;
+    p.xsplit = getenv("A3GC_TC_XSPLIT") ? atoi(getenv("A3GC_TC_XSPLIT")) : 0;
     p.chunk = 1 << 20;   // measured: one bulk copy per operand is fastest (4 KB pieces: -7 %, 2 KB pieces: -30 %)
     if (const char* e = getenv("A3GC_TC_CHUNK")) { const int v = atoi(e); if (v >= 1024 && v % 16 == 0) p.chunk = v; }
   }

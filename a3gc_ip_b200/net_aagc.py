@@ -528,9 +528,9 @@ class G_GRU_net(_Net):
 class _PoseNetBase(torch.nn.Module):
     """Holds ``self.pose_net`` exactly like the reference's PoseNet* wrappers so that checkpoints
     whose keys start with ``pose_net.`` load with ``strict=True``.  The SMPL ParametricModel the
-    reference attaches (a plain object, never in the state_dict; net_aagc.py:777) is out of scope:
-    ``forward`` is identical, ``forward_offline`` returns the network output for ``rotsize == 3``
-    and raises for the IK post-step (rotsize 6 / 9), which needs the SMPL kinematic tree.
+    reference attaches (a plain object, never in the state_dict; net_aagc.py:777) is not needed: the only thing
+    ``forward_offline`` takes from it is the 24-entry parent table of the SMPL kinematic tree, which the
+    reduced-global -> full-local kernel (``a3gc_reduced_to_full_local``) carries as a constant.
     """
     net_cls = None
 
@@ -555,8 +555,8 @@ class _PoseNetBase(torch.nn.Module):
     def forward_offline(self, imu, rnn_state=None):
         global_reduced_pose, _ = self.forward(imu, rnn_state)
         if self.rotsize in (6, 9):
-            raise NotImplementedError("reduced-global -> full-local pose (SMPL inverse kinematics, net_aagc.py:795-800) "
-                                      "is outside the accelerated hot path; use forward() for the network output")
+            from .pipeline import reduced_global_to_full_local
+            return reduced_global_to_full_local(global_reduced_pose, self.rotsize), None      # net_aagc.py:825-828
         return global_reduced_pose, None
 
 

@@ -61,6 +61,22 @@ def concat_stage_input(x: Tensor, pos: Tensor) -> Tensor:
     return out
 
 
+def reduced_global_to_full_local(pose: Tensor, rotsize: int = 9) -> Tensor:
+    """``PoseNet3._reduced_glb_to_full_local_mat`` (net_aagc.py:795-800; ``rotsize=6``: :788-793) on the device:
+    reduced global pose [..., 15, rotsize] (or [..., 15, 3, 3]) -> full local pose [N, 24, 3, 3]."""
+    p = _lib.require_cuda_f32(pose, "pose")
+    if rotsize not in (6, 9):
+        raise ValueError("rotsize must be 6 or 9")
+    frames = p.numel() // (15 * rotsize)
+    if frames * 15 * rotsize != p.numel():
+        raise RuntimeError(f"pose of shape {tuple(pose.shape)} does not hold [N, 15, {rotsize}]")
+    out = torch.empty(frames, 24, 3, 3, dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        rc = _lib.lib().a3gc_reduced_to_full_local(p.data_ptr(), out.data_ptr(), frames, rotsize, _lib.stream_ptr(p.device))
+    _lib.check(rc, "a3gc_reduced_to_full_local")
+    return out
+
+
 class TPPipeline(torch.nn.Module):
     """net1 (12 -> 3), net2 (15 -> 3), net3 (15 -> 9) chained as evaluate_a3gc_tp.py:164-172."""
 

@@ -238,6 +238,18 @@ int a3gc_prepare_input(const float* acc, const float* ori, const float* acc_mean
 int a3gc_concat_stage_input(const float* x, const float* pos, float* dst, int64_t frames, void* stream);
 
 /*
+ * Reduced-global -> full-local pose post-step of forward_offline (PoseNet3._reduced_glb_to_full_local_mat /
+ * _reduced_glb_6d_to_full_local_mat, net_aagc.py:788-800, 825-829): scatter the 15 predicted global joint rotations
+ * into the 24 SMPL joints by joint_set.reduced (config.py:29), identity elsewhere; inverse kinematics along the SMPL
+ * tree, R_local[i] = R_global[parent[i]]^T R_global[i] (articulate/math/spatial.py:115-123, 197-221); identity on
+ * joint_set.ignored (config.py:30).  The parent table is the published SMPL kinematic tree (the reference reads it
+ * from the SMPL model file, articulate/model.py:37, which it does not ship).
+ *   pose [frames, 15, rotsize] (rotsize 9: row-major 3x3; 6: 6D rotation, articulate/math/angular.py:167-182)
+ *   out  [frames, 24, 3, 3]
+ */
+int a3gc_reduced_to_full_local(const float* pose, float* out, int64_t frames, int rotsize, void* stream);
+
+/*
  * Optional per-launch timing of the recurrent-layer kernels (used by bench.py for the roofline):
  * while enabled, every layer launch is bracketed by CUDA events on the launching stream.
  * a3gc_profile_get must be called after the stream has been synchronised; it returns the launch's

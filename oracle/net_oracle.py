@@ -226,6 +226,39 @@ def reduced_to_full(reduced_pose: Tensor) -> Tensor:
     return full
 
 
+# SMPL 24-joint kinematic tree (kintree_table[0] of the SMPL model file, articulate/model.py:37; the file itself is not
+# shipped with the reference -- config.py:23 -- this is the published SMPL topology, also recorded in tests/golden/ik_cases.pt)
+SMPL_PARENT = [-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21]
+
+
+def r6d_to_rotation_matrix(r6d: Tensor) -> Tensor:
+    """``articulate.math.r6d_to_rotation_matrix`` (articulate/math/angular.py:167-182): Gram-Schmidt of two 3-vectors."""
+    r6d = r6d.reshape(-1, 6)
+    nrm = lambda v: v / v.norm(dim=1, keepdim=True)
+    c0 = nrm(r6d[:, 0:3])
+    c1 = nrm(r6d[:, 3:6] - (c0 * r6d[:, 3:6]).sum(dim=1, keepdim=True) * c0)
+    c2 = torch.cross(c0, c1, dim=1)
+    r = torch.stack((c0, c1, c2), dim=-1)
+    r[torch.isnan(r)] = 0
+    return r
+
+
+def reduced_global_to_full_local(glb_reduced_pose: Tensor, rotsize: int = 9) -> Tensor:
+    """``PoseNet3._reduced_glb_to_full_local_mat`` / ``_reduced_glb_6d_to_full_local_mat`` (net_aagc.py:788-800):
+    [N, 15, 3, 3] (or [N, 15, 6]) -> [N, 24, 3, 3]; scatter by joint_set.reduced, inverse kinematics along the SMPL
+    tree (R_local[i] = R_global[parent[i]]^T R_global[i], articulate/math/spatial.py:115-123, 197-221), identity on
+    joint_set.ignored."""
+    if rotsize == 6:
+        glb_reduced_pose = r6d_to_rotation_matrix(glb_reduced_pose).view(-1, NUM_NODES, 3, 3)
+    g = reduced_to_full(glb_reduced_pose.reshape(-1, NUM_NODES, 3, 3))
+    local = [g[:, 0]]
+    for i in range(1, 24):
+        local.append(torch.bmm(g[:, SMPL_PARENT[i]].transpose(1, 2), g[:, i]))
+    pose = torch.stack(local, dim=1)
+    pose[:, JOINT_IGNORED] = torch.eye(3, dtype=pose.dtype)
+    return pose
+
+
 # --------------------------------------------------------------------------------------
 # parameter tables and seeded random weights
 # --------------------------------------------------------------------------------------

@@ -215,3 +215,23 @@ def test_cfg4_ggru_long_sequence(nira):
     with torch.no_grad():
         want = O.tp_forward("GGRU", x[idx], sds)[2]
     assert_close(y3[idx.cuda()], want, what="G-GRU T=600")
+
+
+def test_ik_post_step_matches_reference_golden(nira):
+    """forward_offline's reduced-global -> full-local pose kernel vs the reference's own IK (tests/golden/ik_cases.pt)."""
+    g = load_golden("ik_cases.pt")
+    y9 = A.reduced_global_to_full_local(g["x9"].cuda(), 9).cpu()
+    y6 = A.reduced_global_to_full_local(g["x6"].cuda(), 6).cpu()
+    assert y9.shape == g["y9"].shape and (y9 - g["y9"]).abs().max() <= 1e-6 * max(1.0, float(g["y9"].abs().max()))
+    assert (y6 - g["y6"]).abs().max() <= 2e-6
+    ident = torch.eye(3).expand(y9.shape[0], len(g["ignored"]), 3, 3)
+    assert torch.equal(y9[:, g["ignored"]], ident)                       # index handling bit-exact
+    # through the wrapper the reference's scripts call (evaluate_a3gc_tp.py:171): PoseNet3.forward_offline, rotsize 9
+    net = A.PoseNet3(input_size=15, rotsize=9, adjacency=nira.float(), n_hidden=64).cuda().eval()
+    x = torch.randn(2, 5, 15, 15).cuda()
+    pose, _ = net.forward_offline(x)
+    raw, _ = net.forward(x)
+    want = O.reduced_global_to_full_local(raw.cpu().view(-1, 15, 3, 3), 9)
+    assert pose.shape == (10, 24, 3, 3) and (pose.cpu() - want).abs().max() <= 1e-5
+    with pytest.raises(ValueError):
+        A.reduced_global_to_full_local(g["x9"].cuda(), 3)

@@ -121,3 +121,14 @@ def test_reverse_direction_final_state_is_t0(nira):
         _, st = O.layer_forward("A3GC", x[1:], (z, z), sd, "rnn1.directions.1.", reverse=True)
         o0, (h0, c0) = O.cell_lstm("A3GC", x[0], st, sd, "rnn1.directions.1.cell.")
     assert torch.allclose(h, h0) and torch.allclose(c, c0) and torch.allclose(out[0], o0)
+
+
+def test_oracle_ik_post_step_matches_reference_golden():
+    """Reduced-global -> full-local pose (net_aagc.py:788-800) against the reference's own functions (oracle/gen_golden_ik.py)."""
+    g = load_golden("ik_cases.pt")
+    assert g["parent"] == O.SMPL_PARENT and g["reduced"] == O.JOINT_REDUCED and g["ignored"] == O.JOINT_IGNORED
+    assert sorted(g["reduced"] + g["ignored"]) == list(range(24))
+    y9 = O.reduced_global_to_full_local(g["x9"], 9)
+    y6 = O.reduced_global_to_full_local(g["x6"], 6)
+    assert torch.equal(y9, g["y9"])
+    assert (y6 - g["y6"]).abs().max() <= 1e-6
