@@ -235,3 +235,23 @@ def test_ik_post_step_matches_reference_golden(nira):
     assert pose.shape == (10, 24, 3, 3) and (pose.cpu() - want).abs().max() <= 1e-5
     with pytest.raises(ValueError):
         A.reduced_global_to_full_local(g["x9"].cuda(), 3)
+
+
+@pytest.mark.parametrize("variant", O.VARIANTS)
+def test_tensor_core_engine_ragged_batch_and_given_state(variant, nira):
+    """tcgen05 engine edge cases: batch not a multiple of the 8-sequence tile (13, 1), T = 1, non-zero initial state,
+    hidden 64 (one CTA per tile) and 128 (2-CTA clusters)."""
+    for hidden in (64, 128):
+        sd = O.random_state_dict(variant, 15, 3, hidden, nira, seed=31 + hidden)
+        net = build_net(variant, 15, 3, hidden, sd, nira, engine="tc")
+        for B, T in ((13, 3), (1, 1), (9, 2)):
+            g = torch.Generator().manual_seed(B * 10 + T)
+            x = torch.randn(B, T, 15, 15, generator=g)
+            st = [0.3 * torch.randn(B, 15, hidden, generator=g) for _ in range(2 if variant == "GGRU" else 4)]
+            h0 = unflatten_h(variant, st)
+            y, h = net(x.cuda(), unflatten_h(variant, st, "cuda"))
+            with torch.no_grad():
+                want, want_h = O.net_forward(variant, x, sd, h0)
+            assert_close(y, want, what=f"{variant} H={hidden} B={B} T={T}")
+            for a, b in zip(flatten_h(h), flatten_h(want_h)):
+                assert_close(a, b, what=f"{variant} H={hidden} B={B} T={T} state")
