@@ -12,5 +12,6 @@ from .net_aagc import (AAGC, AAGC_LSTM_cell, A3GC_LSTM_cell, AGC_LSTM_cell, G_GR
                        PoseNet, PoseNet3, PoseNet_AGC, PoseNet_GGRU, pose_loss)
 from .pipeline import TPPipeline, prepare_input, concat_stage_input, reduced_global_to_full_local, INPUT_JOINTS
 from .sharding import shard_range, ShardedRunner, FlatGradAllReducer, train_step
+from .train_loop import stage_inputs, checkpoint_name, latest_checkpoints, validate, fit_stage
 
 __all__ = [n for n in dir() if not n.startswith("_")]

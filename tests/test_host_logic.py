@@ -161,3 +161,51 @@ def test_flat_grad_allreduce_gloo_world2():
     ret = mgr.dict()
     mp.spawn(_gloo_grad_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def test_training_loop_glue_follows_reference_control_flow(tmp_path):
+    """fit_stage / checkpoint naming / resume discovery (train_a3gc_tp.py:164-187, 241-262) on a CPU stand-in model: the
+    control flow is host logic and does not depend on the CUDA kernels."""
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(4, 2)
+
+        def forward(self, x, rnn_state=None):
+            return self.lin(x), None
+
+    torch.manual_seed(0)
+    model, crit = Tiny(), A.pose_loss()
+    xs = [torch.randn(8, 5, 4) for _ in range(3)]
+    data = [(x, x[..., :2] * 2.0) for x in xs]
+    vals = iter([5.0, 4.0, 4.5, 4.6, 4.7, 4.8, 4.9])       # improves twice, then never: stops once the counter exceeds patience = 2
+
+    class FakeCrit:
+        def forward(self, p, t):
+            return crit.forward(p, t)
+
+    import a3gc_ip_b200.train_loop as TL
+    real_validate = TL.validate
+    TL.validate = lambda m, c, b: next(vals)
+    try:
+        out = A.fit_stage(model, FakeCrit(), lambda: data, lambda: data, model_number=2, save_dir=str(tmp_path), lr=1e-2, patience=2,
+                          max_epochs=50, log=lambda s: None)
+    finally:
+        TL.validate = real_validate
+    assert [e for e, _, _ in out["history"]] == [0, 1, 2, 3, 4]            # epochs 2, 3, 4 do not improve: counter 3 > 2
+    assert out["best_loss"] == 4.0 and out["checkpoint"].endswith("checkpoint_model2_pretrain_1.tar")
+    assert abs(out["lr"] - 1e-2 * 0.8 ** 5) < 1e-12                        # ExponentialLR(0.8), one step per epoch
+    ck = torch.load(out["checkpoint"])
+    assert ck["epoch"] == 2 and set(ck["state_dict"]) == {"lin.weight", "lin.bias"}
+    # resume discovery: highest epoch per model, 'pretrain' preferred when both kinds exist
+    for name in ("checkpoint_model1_pretrain_3.tar", "checkpoint_model1_pretrain_12.tar", "checkpoint_model3_pretrain_7.tar",
+                 "checkpoint_model1_finetuning_40.tar"):
+        (tmp_path / name).write_bytes(b"")
+    found = A.latest_checkpoints(str(tmp_path))
+    assert os.path.basename(found[1]) == "checkpoint_model1_pretrain_12.tar"
+    assert os.path.basename(found[2]) == "checkpoint_model2_pretrain_1.tar" and os.path.basename(found[3]) == "checkpoint_model3_pretrain_7.tar"
+    assert A.checkpoint_name(3, 8, finetuning=True) == "checkpoint_model3_finetuning_8.tar"
+    imu, a, b = torch.zeros(2, 3, 15, 12), torch.ones(2, 3, 15, 3), 2 * torch.ones(2, 3, 15, 3)
+    x2, t2 = A.stage_inputs(2, imu, a, b, "leaf", "full", "smpl")
+    assert x2.shape == (2, 3, 15, 15) and t2 == "full" and torch.equal(x2[..., 12:], a)
+    assert torch.equal(A.stage_inputs(3, imu, a, b, "leaf", "full", "smpl")[0][..., 12:], b)
