@@ -103,6 +103,7 @@ SYMBOLS = {
     "a3gc_profile_get": (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
     "a3gc_tc_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "a3gc_tc_mma_bench": (C.c_int, [C.c_int] * 11 + [C.c_void_p, C.c_void_p]),
+    "a3gc_tc_stream_bench": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "a3gc_debug_read_tc_trace": (C.c_int, [C.c_void_p]),
     "a3gc_debug_max_active_clusters": (C.c_int, [C.c_int, C.c_int]),
     "a3gc_launch_count": (C.c_int64, []),

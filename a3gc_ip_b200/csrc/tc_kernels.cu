@@ -66,6 +66,7 @@ struct TcLayerParams {
   int B, T, F, H, out_act, C, S, trace;
   int chunk;                         // bytes per bulk copy of the weight / x stream
   int xsplit;                        // x part as two N=128 MMAs per K block
+  int xdefer;                        // first x segment only after the gate phase of the step
   int n1, n2;                        // x-part blocks of step t+1 issued before A1 / between A1 and A2 of step t (rest after A2)
 };
 
@@ -287,6 +288,10 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
           TC_TRACE(1, 3);
           continue;
         }
+        // p.xdefer (tuning knob, default off): hold the first x segment back until the gate phase of this step is over.  The
+        // warp-level HMMAs of the mix share the tensor pipe with the UMMAs; deferring shortens the gate phase from ~12 k to
+        // ~7 k cycles at H=256 but the x part then delays the attention GEMM by as much: no net gain (measured).
+        if (p.xdefer) { ptx::mbar_wait(&bars[BAR_ACC_EMPTY + b], 0u); ptx::tc_fence_after(); }
         if (nx) xblocks(bo * 256, 0, n1);
         TC_TRACE(1, 3);
         // A1: [Wh hy | Wa (hy, node-sum in row 15)] -> columns [0,128) of the drained buffer
@@ -888,6 +893,7 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
     if (n1 + n2 > KF) n2 = KF - n1;
     p.n1 = n1; p.n2 = n2;
     p.xsplit = getenv("A3GC_TC_XSPLIT") ? atoi(getenv("A3GC_TC_XSPLIT")) : 0;
+    p.xdefer = getenv("A3GC_TC_XDEFER") ? atoi(getenv("A3GC_TC_XDEFER")) : 0;
     p.chunk = 1 << 20;   // measured: one bulk copy per operand is fastest (4 KB pieces: -7 %, 2 KB pieces: -30 %)
     if (const char* e = getenv("A3GC_TC_CHUNK")) { const int v = atoi(e); if (v >= 1024 && v % 16 == 0) p.chunk = v; }
   }

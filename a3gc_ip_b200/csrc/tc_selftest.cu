@@ -5,6 +5,7 @@
 // against a CPU product in tests/test_gpu_tc.py.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include <cstring>
 
 namespace a3gc {
 namespace {
@@ -111,6 +112,67 @@ tc_mma_bench_kernel(int n, int layout_type, int a_lbo, int a_sbo, int b_lbo, int
   if (warp == 0) ptx::tmem_dealloc(tmem, 256);
 }
 
+
+// Micro-benchmark of the L2 -> shared-memory bulk-copy stream: every CTA pulls `iters` chunks of `chunk` bytes from a
+// `span`-byte (L2-resident) buffer through a `depth`-slot ring, no compute.  `nprod` producer threads (one per warp) each
+// own every nprod-th slot, so the per-copy issue / wait overhead of a single thread can be told apart from the link rate.
+// mcast = 1 (nprod must be 1): the CTAs of a 2-CTA cluster each fetch HALF of every chunk and multicast it to both.
+// Reports bytes per cycle per CTA (CTA 0's clock, slowest producer).
+__global__ void __launch_bounds__(256, 1)
+tc_stream_bench_kernel(const uint8_t* __restrict__ src, size_t span, int chunk, int depth, int iters, int mcast, int nprod, float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full[8], empty[8];
+  __shared__ long long tend[8];
+  const uint32_t rank = mcast ? ptx::cluster_ctarank() : 0u;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < depth; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], mcast ? 2 : 1); }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  if (mcast) ptx::cluster_sync_all();
+  const int w = threadIdx.x >> 5;
+  const long long t0 = clock64();
+  if ((threadIdx.x & 31) == 0 && w < nprod) {
+    const size_t base = ((size_t)(blockIdx.x >> (mcast ? 1 : 0)) * 1315423911ull) % (span - (size_t)chunk * 64);
+    const int my_depth = depth / nprod;                     // this producer's private slots: w, w + nprod, ...
+    const int my_iters = iters / nprod;
+    int st = 0, ph = 0, cs = 0, cp = 0;
+    for (int it = 0; it < my_iters; ++it) {
+      const int slot = st * nprod + w;
+      ptx::mbar_wait(&empty[slot], ph ^ 1);
+      ptx::mbar_arrive_expect_tx(&full[slot], (uint32_t)chunk);
+      const uint8_t* g = src + ((base + (size_t)((it * nprod + w) & 63) * chunk) & ~(size_t)127);
+      if (mcast) {
+        const uint32_t half = (uint32_t)chunk / 2;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                     ::"r"(ptx::smem_u32(smem + (size_t)slot * chunk + rank * half)), "l"(g + rank * half), "r"(half),
+                       "r"(ptx::smem_u32(&full[slot])), "h"((uint16_t)3) : "memory");
+      } else {
+        ptx::bulk_g2s(smem + (size_t)slot * chunk, g, (uint32_t)chunk, &full[slot]);
+      }
+      if (++st == my_depth) { st = 0; ph ^= 1; }
+      if (it >= my_depth - 1) {                              // consumer side: wait for the oldest slot and release it
+        const int cslot = cs * nprod + w;
+        ptx::mbar_wait(&full[cslot], cp);
+        if (mcast) { ptx::mbar_arrive_remote(&empty[cslot], 0); ptx::mbar_arrive_remote(&empty[cslot], 1); } else ptx::mbar_arrive(&empty[cslot]);
+        if (++cs == my_depth) { cs = 0; cp ^= 1; }
+      }
+    }
+    for (int r = 0; r < my_depth - 1; ++r) {
+      ptx::mbar_wait(&full[cs * nprod + w], cp);
+      if (++cs == my_depth) { cs = 0; cp ^= 1; }
+    }
+    tend[w] = clock64();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    long long t1 = t0;
+    for (int i = 0; i < nprod; ++i) t1 = tend[i] > t1 ? tend[i] : t1;
+    out[0] = (float)((double)chunk * (iters / nprod) * nprod / (double)(t1 - t0));
+  }
+  if (mcast) ptx::cluster_sync_all();
+}
+
 }  // namespace
 }  // namespace a3gc
 
@@ -143,5 +205,30 @@ extern "C" int a3gc_tc_mma_bench(int n, int layout_type, int a_lbo, int a_sbo, i
   tc_mma_bench_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(n, layout_type, a_lbo, a_sbo, b_lbo, b_sbo, a_kstep, b_kstep,
                                                                               nk, iters, cycles_out);
   A3GC_LAUNCH_CHECK("tc_mma_bench_kernel");
+  return A3GC_OK;
+}
+
+// tuning aid: see tc_stream_bench_kernel.  src: device buffer of `span` bytes; out: device pointer to one float (B/cycle/CTA)
+extern "C" int a3gc_tc_stream_bench(const void* src, size_t span, int chunk, int depth, int iters, int grid, int mcast, int nprod, float* out, void* stream) {
+  using namespace a3gc;
+  if (!src || !out || chunk < 1024 || chunk % 256 || depth < 2 || depth > 8 || iters < depth || grid < 1 || span < (size_t)chunk * 128 ||
+      (size_t)chunk * depth > 200 * 1024 || (mcast && (grid % 2 || nprod != 1)) || nprod < 1 || nprod > 8 || depth % nprod) {
+    set_error("a3gc_tc_stream_bench: invalid argument");
+    return A3GC_ERR_INVALID_ARG;
+  }
+  const size_t smem = (size_t)chunk * depth;
+  A3GC_CUDA_TRY(cudaFuncSetAttribute(tc_stream_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = mcast ? 2u : 1u; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  A3GC_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_stream_bench_kernel, static_cast<const uint8_t*>(src), span, chunk, depth, iters, mcast, nprod, out));
+  A3GC_LAUNCH_CHECK("tc_stream_bench_kernel");
   return A3GC_OK;
 }

@@ -274,6 +274,12 @@ int a3gc_tc_selftest(const void* a_img, const void* b_img, float* d, int k, int 
 int a3gc_tc_mma_bench(int n, int layout_type, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int a_kstep, int b_kstep,
                       int nk, int iters, int grid, float* cycles_out, void* stream);
 
+/* Tuning aid: L2 -> shared-memory bulk-copy stream rate (bytes per cycle per CTA) with `grid` CTAs each pulling `iters`
+ * chunks of `chunk` bytes from a `span`-byte buffer through a `depth`-slot ring; `nprod` producer threads (one per warp,
+ * each owning every nprod-th slot); mcast != 0: 2-CTA clusters, each CTA fetches half of every chunk and multicasts it to
+ * both.  out: device pointer to one float. */
+int a3gc_tc_stream_bench(const void* src, size_t span, int chunk, int depth, int iters, int grid, int mcast, int nprod, float* out, void* stream);
+
 /* Debug: per-phase clock64 timeline of CTA (0,0) of the last tensor-core layer launch made with the
  * environment variable A3GC_TC_TRACE set; host_out receives [2 roles][16 steps][16 slots] uint64. */
 int a3gc_debug_read_tc_trace(unsigned long long* host_out);
