@@ -81,14 +81,14 @@ SYMBOLS = {
                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                    C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
-    "a3gc_layer_train_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "a3gc_layer_train_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int]),
     "a3gc_layer_train_forward": (C.c_int, [C.c_int, C.c_int, C.POINTER(CellParams), C.POINTER(C.c_int),
                                            C.c_void_p, C.c_int64, C.c_int64,
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                            C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                            C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
-                                           C.POINTER(Tape), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+                                           C.POINTER(Tape), C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "a3gc_layer_backward": (C.c_int, [C.c_int, C.c_int, C.POINTER(CellParams), C.POINTER(C.c_int),
                                       C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),

@@ -319,9 +319,14 @@ int a3gc_net_forward(int variant, const a3gc_net_params* net, const float* x,
   return simt_gc_forward(&net->linear_out, a2, y, frames, 2 * H, f_out, A3GC_ACT_LINEAR, s);
 }
 
-size_t a3gc_layer_train_workspace_bytes(int variant, int f_in, int hidden, int num_dirs) {
-  if (variant < A3GC_VARIANT_AAGC || variant > A3GC_VARIANT_AGC || num_dirs < 1 || num_dirs > 2 || f_in <= 0 || hidden <= 0) return 0;
-  return simt_train_workspace_bytes(variant, f_in, hidden, num_dirs);
+size_t a3gc_layer_train_workspace_bytes(int variant, int64_t batch, int64_t steps, int f_in, int hidden, int num_dirs, int engine) {
+  if (variant < A3GC_VARIANT_AAGC || variant > A3GC_VARIANT_AGC || num_dirs < 1 || num_dirs > 2 || f_in <= 0 || hidden <= 0 || batch < 0 || steps < 0) return 0;
+  size_t b = simt_train_workspace_bytes(variant, f_in, hidden, num_dirs);        // backward (and the CUDA-core forward)
+  if (engine != A3GC_ENGINE_SIMT && tc_layer_supported(variant, f_in, hidden, A3GC_PREC_FP32)) {
+    const size_t t = tc_layer_workspace_bytes(variant, batch, steps, f_in, hidden, num_dirs, A3GC_PREC_FP32);
+    if (t > b) b = t;
+  }
+  return b;
 }
 
 static int check_tape(int variant, const a3gc_tape* t, const char* who) {
@@ -339,7 +344,7 @@ int a3gc_layer_train_forward(int variant, int num_dirs, const a3gc_cell_params* 
                              float* y, int64_t y_stride_b, int64_t y_stride_t, int64_t y_ld,
                              float* const* hT, float* const* cT,
                              int64_t batch, int64_t steps, int f_in, int hidden, int out_act,
-                             const a3gc_tape* tape, const float* hmask,
+                             const a3gc_tape* tape, const float* hmask, int engine,
                              void* workspace, size_t workspace_bytes, void* stream) {
   if (variant < A3GC_VARIANT_AAGC || variant > A3GC_VARIANT_AGC) {
     set_error("a3gc_layer_train_forward: the training path covers the LSTM-family cells (AAGC / A3GC / AGC)");
@@ -365,6 +370,16 @@ int a3gc_layer_train_forward(int variant, int num_dirs, const a3gc_cell_params* 
   a.x = x; a.x_stride_b = x_stride_b; a.x_stride_t = x_stride_t;
   a.y = y; a.y_stride_b = y_stride_b; a.y_stride_t = y_stride_t; a.y_ld = y_ld;
   a.batch = batch; a.steps = steps; a.f_in = f_in; a.hidden = hidden; a.out_act = out_act; a.precision = A3GC_PREC_FP32;
+  if (engine < A3GC_ENGINE_AUTO || engine > A3GC_ENGINE_TC) { set_error("a3gc_layer_train_forward: bad engine %d", engine); return A3GC_ERR_INVALID_ARG; }
+  const bool tc_ok = tc_layer_supported(variant, f_in, hidden, A3GC_PREC_FP32) && x_stride_t == (int64_t)kNodes * f_in;
+  if (engine == A3GC_ENGINE_TC && !tc_ok) {
+    set_error("a3gc_layer_train_forward: tensor-core engine does not support variant=%d f_in=%d hidden=%d", variant, f_in, hidden);
+    return A3GC_ERR_UNSUPPORTED;
+  }
+  if (engine != A3GC_ENGINE_SIMT && tc_ok) {
+    a.tape = tape; a.hmask = hmask;                  // tcgen05 engine in training mode (fp32-parity split, tape, masked state image)
+    return run_layer(A3GC_ENGINE_TC, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+  }
   return simt_train_forward(a, *tape, hmask, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 

@@ -79,6 +79,9 @@ struct LayerArgs {
   const uint16_t* x_img;   // if non-null: the layer input already packed as [tiles][T][F/16][NP][2][128][8] (x may be null)
   uint16_t* y_img;         // if non-null: also write act(h') into the next layer's input image ...
   int y_img_f;             // ... which has this many features (direction d writes columns d*H .. d*H+H-1)
+  // training mode of the tensor-core engine (LSTM family, fp32 precision): keep the tape, apply the recurrent-dropout mask
+  const a3gc_tape* tape;   // null = inference
+  const float* hmask;      // [D][B][T][15][H] or null
 };
 
 size_t simt_layer_workspace_bytes(int variant, int f_in, int hidden, int num_dirs);

@@ -68,6 +68,9 @@ struct TcLayerParams {
   int xsplit;                        // x part as two N=128 MMAs per K block
   int xdefer;                        // first x segment only after the gate phase of the step
   int n1, n2;                        // x-part blocks of step t+1 issued before A1 / between A1 and A2 of step t (rest after A2)
+  // training mode (TRAIN): tape of per-step intermediates (include/a3gc_b200.h, a3gc_tape) and optional recurrent-dropout mask
+  a3gc_tape tape;
+  const float* hmask;                // [D][B][T][15][H] or null
 };
 
 // barrier slots in shared memory
@@ -100,7 +103,7 @@ __device__ __forceinline__ void split_bits(float v, uint16_t& hi, uint16_t& lo) 
   }
 }
 
-template <bool SPLIT, bool ATT>
+template <bool SPLIT, bool ATT, bool TRAIN>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 tc_lstm_layer_kernel(const TcLayerParams p) {
   constexpr int NP = SPLIT ? 2 : 1;
@@ -371,7 +374,9 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         }
 
     // write this thread's 16 values into the local operand image (rows of sequences 2qd, 2qd+1)
-    auto store_units = [&](const float (&v)[2][2][4]) {
+    // tm >= 0 (training with recurrent dropout): the image receives v * hmask[., tm, ., .], the mask of the step that will
+    // consume it (net_aagc.py:181 drops the h that enters the gates only; the carried state stays unmasked)
+    auto store_units = [&](const float (&v)[2][2][4], int tm = -1) {
 #pragma unroll
       for (int sq = 0; sq < 2; ++sq)
 #pragma unroll
@@ -380,10 +385,16 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
 #pragma unroll
           for (int up = 0; up < 2; ++up) {
             uint32_t hi, lo;
+            float v0 = v[sq][ub][2 * up], v1 = v[sq][ub][2 * up + 1];
+            if (TRAIN && tm >= 0 && valid[sq] && tq + 8 * up < kNodes) {
+              const float2 mk = *reinterpret_cast<const float2*>(
+                  p.hmask + ((((size_t)blockIdx.y * p.B + bseq[sq]) * T + tm) * kNodes + tq + 8 * up) * H + k);
+              v0 *= mk.x; v1 *= mk.y;
+            }
             if (SPLIT) {
-              ptx::split_pair_f16(v[sq][ub][2 * up], v[sq][ub][2 * up + 1], hi, lo);
+              ptx::split_pair_f16(v0, v1, hi, lo);
             } else {
-              const __nv_bfloat162 bb = __floats2bfloat162_rn(v[sq][ub][2 * up], v[sq][ub][2 * up + 1]);
+              const __nv_bfloat162 bb = __floats2bfloat162_rn(v0, v1);
               hi = *reinterpret_cast<const uint32_t*>(&bb);
               lo = 0;
             }
@@ -462,15 +473,31 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       }
     };
 
-    store_units(hreg);                            // h_{-1} = h0  (completion #0 of BAR_H)
+    store_units(hreg, (TRAIN && p.hmask != nullptr) ? (d.reverse ? T - 1 : 0) : -1);   // h_{-1} = h0  (completion #0 of BAR_H)
     publish_block(BAR_H, -1);
 
+    // tape.hp [D][B][T][15][H] (node-major like x): h'_t of this thread's elements
+    auto tape_hp = [&](int ta) {
+#pragma unroll
+      for (int sq = 0; sq < 2; ++sq) {
+        if (!valid[sq]) continue;
+#pragma unroll
+        for (int up = 0; up < 2; ++up) {
+          if (tq + 8 * up >= kNodes) continue;
+          float* hp = p.tape.hp + ((((size_t)blockIdx.y * p.B + bseq[sq]) * T + ta) * kNodes + tq + 8 * up) * H + (int)c * 64 + ubase + 2 * tr;
+#pragma unroll
+          for (int ub = 0; ub < 2; ++ub) *reinterpret_cast<float2*>(hp + 8 * ub) = make_float2(hreg[sq][ub][2 * up], hreg[sq][ub][2 * up + 1]);
+        }
+      }
+    };
     const uint4* Pfrag4 = reinterpret_cast<const uint4*>(Pfrag);
     const int swz = 8 * (tq & 3);                 // XOR swizzle of the transposition buffer column tq
 
     for (int t = 0; t < T; ++t) {
       const uint32_t b = t & 1;
       const int ta = d.reverse ? T - 1 - t : t;
+      // time of the next step of this direction (the step that consumes h'_t), -1: none / no recurrent dropout
+      const int tnext = (TRAIN && p.hmask != nullptr && t + 1 < T) ? (d.reverse ? ta - 1 : ta + 1) : -1;
       // ---------------------------------------------------------------- gates -> c', hy
       if (et == 0) TC_TRACE(0, 0);
       ptx::mbar_wait(&bars[BAR_ACC_FULL + b], (t >> 1) & 1);
@@ -486,6 +513,15 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
           {   // 8 accumulator columns (gate g, units ubase+8ub .. +7) TMEM -> wst[col][row ^ swizzle(col)]
             float v[8];
             ptx::tmem_ld8(tmem_row + b * 256 + g * 64 + ubase + 8 * ub, v);
+            if (TRAIN) {
+              // tape.u [rec][gate][unit][16]: this lane = accumulator row = (sequence, node); node slot 15 holds an exact 0
+              const int rs = tile * kSeqTile + 2 * qd + (lane >> 4);
+              if (p.tape.u != nullptr && rs < p.B) {
+                float* up = p.tape.u + ((((size_t)blockIdx.y * T + ta) * p.B + rs) * 4 + g) * H * 16 + (size_t)((int)c * 64 + ubase + 8 * ub) * 16 + (lane & 15);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) up[j * 16] = v[j];
+              }
+            }
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j) wst[j * 32 + (lane ^ (8 * (j & 3)))] = v[j];
@@ -516,12 +552,16 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
             for (int j = 0; j < 4; ++j) {
               const bool ok = valid[sq] && !(pad_hi && j >= 2);
               // c' = sig(zf) c + sig(zi) tanh(zc), hy = sig(zo) tanh(c') with shared reciprocals: 5 ex2 + 2 rcp per element
+              float gv = 0.f;                                                                    // activated gate (tape only)
               if (g == 0) {
                 e1[sq][j] = one_plus_exp_neg(z[j]);                                              // 1 + e^-zi
+                if (TRAIN) gv = rcp_ftz(e1[sq][j]);
               } else if (g == 1) {
                 e2[sq][j] = one_plus_exp_neg(z[j]);                                              // 1 + e^-zf
+                if (TRAIN) gv = rcp_ftz(e2[sq][j]);
               } else if (g == 2) {
                 const float eb = exp_neg2(z[j]);                                                 // tanh(zc) = (1 - eb) / (1 + eb)
+                if (TRAIN) gv = (1.0f - eb) * rcp_ftz(1.0f + eb);
                 const float dab = e1[sq][j] * (1.0f + eb);
                 float cn = fmaf(creg[sq][ub][j], dab, (1.0f - eb) * e2[sq][j]) * rcp_ftz(e2[sq][j] * dab);
                 cn = ok ? cn : 0.f;
@@ -530,11 +570,32 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
                 e1[sq][j] = 1.0f - ec;                                                           // tanh(c') = (1 - ec) / (1 + ec)
                 e2[sq][j] = 1.0f + ec;
               } else {
-                const float hy = e1[sq][j] * rcp_ftz(e2[sq][j] * one_plus_exp_neg(z[j]));
+                const float eo = one_plus_exp_neg(z[j]);
+                const float hy = e1[sq][j] * rcp_ftz(e2[sq][j] * eo);
+                if (TRAIN) gv = rcp_ftz(eo);
                 hreg[sq][ub][j] = ok ? hy : 0.f;
+              }
+              if (TRAIN && valid[sq]) {
+                const int unit = (int)c * 64 + ubase + 8 * ub + 2 * tr + (j & 1), node = tq + 8 * (j >> 1);
+                p.tape.gates[((((size_t)blockIdx.y * T + ta) * p.B + bseq[sq]) * 4 + g) * H * 16 + (size_t)unit * 16 + node] = ok ? gv : 0.f;
               }
             }
           }
+        }
+      }
+      if (TRAIN) {
+#pragma unroll
+        for (int sq = 0; sq < 2; ++sq) {
+          if (!valid[sq]) continue;
+          const size_t rec = ((size_t)blockIdx.y * T + ta) * p.B + bseq[sq];
+#pragma unroll
+          for (int ub = 0; ub < 2; ++ub)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const size_t o = (rec * H + (int)c * 64 + ubase + 8 * ub + 2 * tr + (j & 1)) * 16 + tq + 8 * (j >> 1);
+              p.tape.c[o] = creg[sq][ub][j];          // pad slots hold exact zeros
+              p.tape.hh[o] = hreg[sq][ub][j];
+            }
         }
       }
       if (ATT) {
@@ -553,6 +614,8 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
               sum += __shfl_xor_sync(0xffffffffu, sum, 16);
               keep[sq][ub][u2] = hreg[sq][ub][2 + u2];
               if (pad_hi) hreg[sq][ub][2 + u2] = sum;
+              if (TRAIN && pad_hi && valid[sq])
+                p.tape.s[(((size_t)blockIdx.y * T + ta) * p.B + bseq[sq]) * H + (int)c * 64 + ubase + 8 * ub + 2 * tr + u2] = sum;
             }
         store_units(hreg);
 #pragma unroll
@@ -562,7 +625,8 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
 #pragma unroll
             for (int u2 = 0; u2 < 2; ++u2) hreg[sq][ub][2 + u2] = keep[sq][ub][u2];
       } else {
-        store_units(hreg);
+        if (TRAIN) tape_hp(ta);
+        store_units(hreg, tnext);
       }
       if (et == 0) TC_TRACE(0, 2);
 
@@ -585,6 +649,14 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         ptx::tmem_ld16(tmem_row + b * 256 + 64 + ubase, v);
         if ((lane & 15) == 15) {
           const int qrow = qd * 32 + lane;                  // = 16*seq + 15
+          if (TRAIN) {
+            const int rs = tile * kSeqTile + 2 * qd + (lane >> 4);
+            if (rs < p.B) {
+              float* qp = p.tape.q + (((size_t)blockIdx.y * T + ta) * p.B + rs) * H + (int)c * 64 + ubase;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) qp[i] = fmaxf(v[i], 0.f);
+            }
+          }
 #pragma unroll
           for (int g8 = 0; g8 < 2; ++g8) {                  // 8 consecutive units = one 16-byte K chunk of the row
             uint32_t hw[4], lw[4];
@@ -627,10 +699,14 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         float vh[16], vq[16];
         ptx::tmem_ld16(tmem_row + b * 256 + ubase, vh);
         ptx::tmem_ld16(tmem_row + b * 256 + 128 + ubase, vq);
+        const int rs3 = tile * kSeqTile + 2 * qd + (lane >> 4);
+        float* ep = TRAIN ? p.tape.e + ((((size_t)blockIdx.y * T + ta) * p.B + rs3) * H + (int)c * 64 + ubase) * 16 + (lane & 15) : nullptr;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float wq = __shfl_sync(0xffffffffu, vq[i], (lane & 16) | 15);
-          part = fmaf(fast_tanh(vh[i] + wq + bss[ubase + i]), us[ubase + i], part);
+          const float ev = fast_tanh(vh[i] + wq + bss[ubase + i]);
+          if (TRAIN && rs3 < p.B) ep[i * 16] = (lane & 15) < kNodes ? ev : 0.f;
+          part = fmaf(ev, us[ubase + i], part);
         }
         ahalf[ug * 128 + qd * 32 + lane] = part;
       }
@@ -652,7 +728,12 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       if (et < 128) {
         float a = bus[et & 15];
         for (int src = 0; src < C; ++src) a += apart[src * 128 + et];
-        ahalf[et] = 1.0f + fast_sigmoid(a);
+        const float sg = fast_sigmoid(a);
+        ahalf[et] = 1.0f + sg;
+        if (TRAIN && c == 0) {
+          const int rs = tile * kSeqTile + (et >> 4);
+          if (rs < p.B) p.tape.a[(((size_t)blockIdx.y * T + ta) * p.B + rs) * 16 + (et & 15)] = (et & 15) < kNodes ? sg : 0.f;
+        }
       }
       ptx::named_bar_sync(1, kEpiThreads);
       // ---- h' = hy (1 + a): next step's operand and y_t = act(h')
@@ -665,7 +746,8 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) hreg[sq][ub][j] *= (j & 2) ? ahi : alo;
       }
-      store_units(hreg);
+      if (TRAIN) tape_hp(ta);
+      store_units(hreg, tnext);
       if (et == 0) TC_TRACE(0, 10);
       publish_block(BAR_H, -1);
       emit(ta, hreg);                   // global stores of y_t after the hand-off: off the recurrence's critical path
@@ -913,9 +995,12 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
   p.S = S;
   const size_t smem = fixed + (size_t)S * stage_bytes;
 
-  void (*kern)(const TcLayerParams) =
-      split ? (att ? tc_lstm_layer_kernel<true, true> : tc_lstm_layer_kernel<true, false>)
-            : (att ? tc_lstm_layer_kernel<false, true> : tc_lstm_layer_kernel<false, false>);
+  const bool train = a.tape != nullptr;
+  if (train) { p.tape = *a.tape; p.hmask = a.hmask; }
+  void (*kern)(const TcLayerParams);
+  if (train) kern = att ? tc_lstm_layer_kernel<true, true, true> : tc_lstm_layer_kernel<true, false, true>;   // training: fp32-parity path only
+  else kern = split ? (att ? tc_lstm_layer_kernel<true, true, false> : tc_lstm_layer_kernel<true, false, false>)
+                    : (att ? tc_lstm_layer_kernel<false, true, false> : tc_lstm_layer_kernel<false, false, false>);
   A3GC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -949,7 +1034,7 @@ extern "C" int a3gc_debug_read_tc_trace(unsigned long long* host_out) {
 // dynamic shared memory each) the device can hold at once
 extern "C" int a3gc_debug_max_active_clusters(int cluster_size, int smem_bytes) {
   using namespace a3gc;
-  void (*kern)(const TcLayerParams) = tc_lstm_layer_kernel<true, true>;
+  void (*kern)(const TcLayerParams) = tc_lstm_layer_kernel<true, true, false>;
   A3GC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   if (cluster_size > 8) A3GC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg;

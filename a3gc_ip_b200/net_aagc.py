@@ -232,7 +232,7 @@ class _LSTMCellBase(_CellBase):
         """One step: input [B,15,F], state (h, c) [B,15,H] -> (act(h'), (h', c'))."""
         if self.training:
             y, st = _tr.run_layer_train(self.variant, [self], [0], input.unsqueeze(1), [state], self.activation_name, self._ws,
-                                        self.p_dropout, self.p_recurrent_dropout)
+                                        self.p_dropout, self.p_recurrent_dropout, self.engine)
             return y[:, 0], st[0]
         y, st = _run_layer(self.variant, [self], [0], input.unsqueeze(0), True, [state], self.activation_name,
                            self._ws, self.engine, self.precision)
@@ -322,7 +322,7 @@ class _Layer(torch.nn.Module, _EngineMixin):
             if c.variant == "GGRU":
                 raise NotImplementedError("G-GRU has no training path yet; call .eval() for inference")
             y, st = _tr.run_layer_train(c.variant, [c], [self.reverse], input.transpose(0, 1).contiguous(), [state], act, self._ws,
-                                        c.p_dropout, c.p_recurrent_dropout)
+                                        c.p_dropout, c.p_recurrent_dropout, self.engine)
             return y.transpose(0, 1), st[0]
         y, st = _run_layer(c.variant, [c], [self.reverse], input, True, [state], act, self._ws, self.engine, self.precision)
         return y, st[0]
@@ -345,7 +345,8 @@ class _BiLayer(torch.nn.Module, _EngineMixin):
         if self.training:
             if c.variant == "GGRU":
                 raise NotImplementedError("G-GRU has no training path yet; call .eval() for inference")
-            return _tr.run_layer_train(c.variant, cells, [0, 1], input, states, act, self._ws, c.p_dropout, c.p_recurrent_dropout)
+            return _tr.run_layer_train(c.variant, cells, [0, 1], input, states, act, self._ws, c.p_dropout, c.p_recurrent_dropout,
+                                       self.engine)
         return _run_layer(c.variant, cells, [0, 1], input, False, states, act, self._ws, self.engine, self.precision)
 
 

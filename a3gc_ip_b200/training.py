@@ -52,7 +52,7 @@ class _LayerTrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, meta, x, hmask, *flat):
-        variant, nd, reverse, out_act, ws = meta
+        variant, nd, reverse, out_act, ws, engine = meta
         names = LSTM_PARAM_NAMES[variant]
         npar = len(names)
         states = flat[:2 * nd]
@@ -85,13 +85,13 @@ class _LayerTrainFn(torch.autograd.Function):
         L = _lib.lib()
         v = _lib.VARIANT[variant]
         with torch.cuda.device(dev):
-            wbuf = ws.get(L.a3gc_layer_train_workspace_bytes(v, F, H, nd), dev)
+            wbuf = ws.get(L.a3gc_layer_train_workspace_bytes(v, B, T, F, H, nd, _lib.ENGINE[engine]), dev)
             rc = L.a3gc_layer_train_forward(
                 v, nd, cells, rev, x.data_ptr(), T * NUM_NODES * F, NUM_NODES * F,
                 _lib.ptr_array(h0, nd), _lib.ptr_array(c0, nd),
                 y.data_ptr(), T * NUM_NODES * nd * H, NUM_NODES * nd * H, nd * H,
                 _lib.ptr_array(hT, nd), _lib.ptr_array(cT, nd),
-                B, T, F, H, _lib.ACT[out_act], C.byref(tp), _lib.ptr(hmask),
+                B, T, F, H, _lib.ACT[out_act], C.byref(tp), _lib.ptr(hmask), _lib.ENGINE[engine],
                 wbuf.data_ptr(), wbuf.numel(), _lib.stream_ptr(dev))
         _lib.check(rc, "a3gc_layer_train_forward")
         ctx.meta, ctx.tape, ctx.shape = meta, tape, (B, T, F, H)
@@ -103,7 +103,7 @@ class _LayerTrainFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, *dstates):
-        variant, nd, reverse, out_act, ws = ctx.meta
+        variant, nd, reverse, out_act, ws, engine = ctx.meta
         names = LSTM_PARAM_NAMES[variant]
         npar = len(names)
         B, T, F, H = ctx.shape
@@ -134,7 +134,7 @@ class _LayerTrainFn(torch.autograd.Function):
         L = _lib.lib()
         v = _lib.VARIANT[variant]
         with torch.cuda.device(dev):
-            wbuf = ws.get(L.a3gc_layer_train_workspace_bytes(v, F, H, nd), dev)
+            wbuf = ws.get(L.a3gc_layer_train_workspace_bytes(v, B, T, F, H, nd, _lib.ENGINE[engine]), dev)
             rc = L.a3gc_layer_backward(
                 v, nd, cells, rev, dy.data_ptr(), T * NUM_NODES * nd * H, NUM_NODES * nd * H, nd * H,
                 _lib.ptr_array(c0, nd), _lib.ptr_array(dhT, nd), _lib.ptr_array(dcT, nd),
@@ -197,7 +197,7 @@ class _LayerTrainFn(torch.autograd.Function):
 
 def run_layer_train(variant: str, cells: Sequence[torch.nn.Module], reverse: Sequence[int], x: Tensor,
                     states: Sequence[Tuple[Tensor, Tensor]], out_act: str, ws: _lib.Workspace,
-                    p_in: float = 0.0, p_rec: float = 0.0):
+                    p_in: float = 0.0, p_rec: float = 0.0, engine: str = "auto"):
     """Differentiable batch-major forward of one (bi)layer.  x [B,T,15,F] -> (y [B,T,15,nd*H], [(hT, cT)] * nd)."""
     if variant not in LSTM_PARAM_NAMES:
         raise NotImplementedError("the training path covers the LSTM-family cells (AAGC / A3GC / AGC); G-GRU training "
@@ -215,7 +215,7 @@ def run_layer_train(variant: str, cells: Sequence[torch.nn.Module], reverse: Seq
         flat += [states[d][0], states[d][1]]
     for c in cells:
         flat += [getattr(c, n) for n in LSTM_PARAM_NAMES[variant]]
-    meta = (variant, nd, tuple(int(r) for r in reverse), out_act, ws)
+    meta = (variant, nd, tuple(int(r) for r in reverse), out_act, ws, engine)
     outs = _LayerTrainFn.apply(meta, x, hmask, *flat)
     y = outs[0]
     return y, [(outs[1 + 2 * d], outs[2 + 2 * d]) for d in range(nd)]

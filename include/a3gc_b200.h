@@ -196,18 +196,20 @@ typedef struct a3gc_tape_grads {
   float* dap;   /* [D][T][B][16]       grads of the sigmoid pre-activation of a_t (du, dbu)  */
 } a3gc_tape_grads;
 
-size_t a3gc_layer_train_workspace_bytes(int variant, int f_in, int hidden, int num_dirs);
+/* Workspace for a3gc_layer_train_forward AND a3gc_layer_backward of this shape (the larger of the two). */
+size_t a3gc_layer_train_workspace_bytes(int variant, int64_t batch, int64_t steps, int f_in, int hidden, int num_dirs, int engine);
 
-/* a3gc_layer_forward in training mode (fp32 CUDA-core engine): same arguments plus the tape and an optional
- * recurrent-dropout mask hmask [D][B][T][15][H] (0 or 1/(1-p), net_aagc.py:181; NULL = no dropout).  Input
- * dropout (:180) is applied by the caller to x. */
+/* a3gc_layer_forward in training mode: same arguments plus the tape and an optional recurrent-dropout mask hmask
+ * [D][B][T][15][H] (0 or 1/(1-p), net_aagc.py:181; NULL = no dropout).  Input dropout (:180) is applied by the caller
+ * to x.  engine: A3GC_ENGINE_AUTO / TC run the tcgen05 kernel in training mode (fp32-parity operand split; hidden in
+ * {64,128,256}, f_in % 16 == 0, batch-major x), A3GC_ENGINE_SIMT the CUDA-core kernel (any shape). */
 int a3gc_layer_train_forward(int variant, int num_dirs, const a3gc_cell_params* cells, const int* reverse,
                              const float* x, int64_t x_stride_b, int64_t x_stride_t,
                              const float* const* h0, const float* const* c0,
                              float* y, int64_t y_stride_b, int64_t y_stride_t, int64_t y_ld,
                              float* const* hT, float* const* cT,
                              int64_t batch, int64_t steps, int f_in, int hidden, int out_act,
-                             const a3gc_tape* tape, const float* hmask,
+                             const a3gc_tape* tape, const float* hmask, int engine,
                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* Reverse-time chain.  dy: gradient of y (same addressing as y); c0[d]: the forward's initial cell state;

@@ -22,8 +22,9 @@ def _oracle_grads(variant, x, sd, target, h=None):
     return loss.detach(), y.detach(), xr.grad, {k: v.grad for k, v in sd.items()}
 
 
-@pytest.mark.parametrize("variant,hidden,B,T", [("A3GC", 24, 5, 7), ("AAGC", 24, 3, 6), ("AGC", 24, 4, 5), ("A3GC", 64, 3, 9),
-                                                ("A3GC", 128, 2, 4)])
+@pytest.mark.parametrize("variant,hidden,B,T", [("A3GC", 24, 5, 7), ("AAGC", 24, 3, 6), ("AGC", 24, 4, 5),      # CUDA-core forward
+                                                ("A3GC", 64, 3, 9), ("A3GC", 128, 2, 4), ("AAGC", 64, 9, 3),     # tcgen05 forward
+                                                ("AGC", 128, 11, 5), ("A3GC", 256, 2, 3)])
 def test_net_train_step_matches_oracle_autograd(variant, hidden, B, T, nira):
     f0, out = 15, 9
     sd = O.random_state_dict(variant, f0, out, hidden, nira, seed=21)
@@ -91,8 +92,9 @@ def test_bilayer_train_with_initial_state_and_state_grads(nira):
         assert r <= TOL, f"grad {name}: rel_l2={r:.3e}"
 
 
-def test_train_mode_dropout_runs_and_is_stochastic(nira):
-    net = A.A3GC_net(12, 3, 16, nira.float()).cuda().train()      # reference defaults: p = 0.2 / 0.3 / 0.3
+@pytest.mark.parametrize("hidden", [16, 64])
+def test_train_mode_dropout_runs_and_is_stochastic(hidden, nira):
+    net = A.A3GC_net(12, 3, hidden, nira.float()).cuda().train()      # reference defaults: p = 0.2 / 0.3 / 0.3
     x = O.synthetic_input(3, 5, seed=1).cuda()
     y1, _ = net(x)
     y2, _ = net(x)
@@ -101,3 +103,30 @@ def test_train_mode_dropout_runs_and_is_stochastic(nira):
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters() if p.requires_grad)
     with pytest.raises(NotImplementedError):
         A.G_GRU_net(12, 3, 16, nira.float()).cuda().train()(x)
+
+
+def test_recurrent_dropout_mask_semantics_tc_vs_simt(nira):
+    """Same explicit recurrent-dropout mask through the tcgen05 and the CUDA-core training forwards (and backwards):
+    identical outputs and gradients, i.e. both engines apply the mask to the h that enters the gates only."""
+    from a3gc_ip_b200 import training as TR
+    torch.manual_seed(3)
+    F, H, B, T = 32, 64, 5, 6
+    layer = A.BiA3GC_LSTM(F, H, nira.float(), activation_fn="tanh").cuda().train()
+    x = torch.randn(B, T, 15, F, device="cuda")
+    st = [tuple(0.2 * torch.randn(B, 15, H, device="cuda") for _ in range(2)) for _ in range(2)]
+    hmask = (torch.rand(2, B, T, 15, H, device="cuda") >= 0.3).float() / 0.7
+    outs = {}
+    for eng in ("simt", "tc"):
+        flat = []
+        for s_ in st:
+            flat += [s_[0], s_[1]]
+        for d in layer.directions:
+            flat += [getattr(d.cell, n) for n in TR.LSTM_PARAM_NAMES["A3GC"]]
+        for p_ in layer.parameters():
+            p_.grad = None
+        xr = x.clone().requires_grad_(True)
+        res = TR._LayerTrainFn.apply(("A3GC", 2, (0, 1), "tanh", A._lib.Workspace(), eng), xr, hmask, *flat)
+        (res[0].square().sum() + sum(r.sum() for r in res[1:])).backward()
+        outs[eng] = [res[0].detach().cpu(), xr.grad.cpu()] + [p_.grad.detach().cpu().clone() for p_ in layer.parameters()]
+    for a, b in zip(outs["simt"], outs["tc"]):
+        assert rel_l2(b, a) <= TOL
