@@ -326,7 +326,7 @@ def main():
                 "layer_share_of_step": layer_ms / (ms_total / K), "launches": recs,
                 "whole_step_tflops": mflop * 1e6 * (B * T) / (ms_total / K / 1e3) / 1e12}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:       # the CPU baseline is reported at N = 1 only
         sb = 16
         cfps, cores, _ = cpu_reference_fps(nira, sb, 2, 1)
         cpu = {"value": cfps, "unit": UNIT, "cores": cores, "kind": "port",
