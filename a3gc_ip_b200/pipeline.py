@@ -131,12 +131,37 @@ class TPPipeline(torch.nn.Module):
 
     @torch.no_grad()
     def forward_host(self, x_host: Tensor, out_host: Optional[Tensor] = None, device: Optional[torch.device] = None) -> Tensor:
-        """End-to-end call with HOST buffers: H2D copy of x, three stages, D2H copy of the pose."""
+        """End-to-end call with HOST buffers: H2D copy of x, three stages, D2H copy of the pose.  With ``streams`` > 1 every
+        batch chunk does its own H2D -> chain -> D2H on its stream, so the copies of one chunk overlap the kernels of another
+        (pinned host buffers needed for the overlap; pageable ones still work)."""
         device = device or next(self.parameters()).device
-        x = x_host.to(device, non_blocking=True)
-        _, _, y3 = self.forward(x)
+        B = x_host.shape[0]
+        n = min(self.streams, max(1, B // 8))
         if out_host is None:
-            return y3.cpu()
-        out_host.copy_(y3, non_blocking=True)
-        torch.cuda.current_stream(device).synchronize()
+            out_host = torch.empty(B, x_host.shape[1], 15, 9, dtype=torch.float32, pin_memory=True)
+        if n <= 1:
+            x = x_host.to(device, non_blocking=True)
+            _, _, y3 = self._chain(x, 0)
+            out_host.copy_(y3, non_blocking=True)
+            torch.cuda.current_stream(device).synchronize()
+            return out_host
+        main = torch.cuda.current_stream(device)
+        side = self._side.setdefault(device, [])
+        while len(side) < n:
+            side.append(torch.cuda.Stream(device=device))
+        tiles = (B + 7) // 8
+        bounds = [min(B, 8 * ((tiles * i) // n)) for i in range(n + 1)]
+        ready = torch.cuda.Event()
+        ready.record(main)
+        keep = []
+        for i in range(n):
+            st = side[i]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                xi = x_host[bounds[i]:bounds[i + 1]].to(device, non_blocking=True)
+                y3 = self._chain(xi, i)[2]
+                out_host[bounds[i]:bounds[i + 1]].copy_(y3, non_blocking=True)
+                keep.append((xi, y3))
+        for i in range(n):
+            side[i].synchronize()
         return out_host

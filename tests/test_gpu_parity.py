@@ -255,3 +255,19 @@ def test_tensor_core_engine_ragged_batch_and_given_state(variant, nira):
             assert_close(y, want, what=f"{variant} H={hidden} B={B} T={T}")
             for a, b in zip(flatten_h(h), flatten_h(want_h)):
                 assert_close(a, b, what=f"{variant} H={hidden} B={B} T={T} state")
+
+
+def test_concurrent_batch_chunks_and_host_path_match_single_stream(nira):
+    """TPPipeline(streams=3): chunked concurrent execution and the host-buffer path reproduce the single-stream result."""
+    pipe, _ = build_tp("A3GC", nira)
+    x = O.synthetic_input(41, 20, seed=8)                 # ragged: 41 sequences -> chunks of 8-sequence tiles
+    pipe.streams = 1
+    want = [t.cpu() for t in pipe(x.cuda())]
+    pipe.streams = 3
+    got = [t.cpu() for t in pipe(x.cuda())]
+    for a, b in zip(got, want):
+        assert_close(a, b, tol=2e-6, what="chunked vs single stream")
+    y = pipe.forward_host(x.pin_memory(), None, torch.device("cuda", 0))
+    assert_close(y, want[2], tol=2e-6, what="host path (chunked)")
+    pipe.streams = 1
+    assert_close(pipe.forward_host(x, None, torch.device("cuda", 0)), want[2], tol=2e-6, what="host path (single stream)")
