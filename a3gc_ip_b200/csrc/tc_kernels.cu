@@ -74,8 +74,12 @@ struct TcLayerParams {
 };
 
 // barrier slots in shared memory
+// BAR_H / BAR_HHAT / BAR_Q are ARRAYS of 4 barriers, one per source CTA of the cluster: the MMA warp consumes the K range
+// of a chunk as soon as THAT chunk has arrived, its own chunk (available without any DSMEM transfer) first
 enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_ACC_FULL = 2 * kMaxStages, BAR_ATT_FULL = BAR_ACC_FULL + 2, BAR_ATT2_FULL,
-       BAR_ACC_EMPTY, BAR_H = BAR_ACC_EMPTY + 2, BAR_HHAT, BAR_Q, BAR_A, BAR_HFREE, BAR_A1FREE, BAR_COUNT };
+       BAR_ACC_EMPTY, BAR_A = BAR_ACC_EMPTY + 2, BAR_HFREE, BAR_A1FREE, BAR_H, BAR_HHAT = BAR_H + 4, BAR_Q = BAR_HHAT + 4,
+       BAR_COUNT = BAR_Q + 4 };
+constexpr int kBarSlots = 40;
 
 __host__ __device__ inline size_t tc_fixed_smem_bytes(int C) {
   return (size_t)kEpiWarps * kWstFloats * 4   // wst
@@ -83,7 +87,7 @@ __host__ __device__ inline size_t tc_fixed_smem_bytes(int C) {
          + 4 * 128 * 4                        // ahalf
          + 256 * 4 + 64 * 4 * 2 + 16 * 4      // biasg, bs, u, bu
          + 1024 * 4                           // Pfrag
-         + 32 * 8 + 16;                       // barriers, tmem slot
+         + kBarSlots * 8 + 16;                // barriers, tmem slot
 }
 
 // byte offset of element (row, k) inside one part of an operand image [K/8][128][8]
@@ -134,11 +138,11 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
   float* bus = us + 64;                      // [16]
   uint32_t* Pfrag = reinterpret_cast<uint32_t*>(bus + 16);   // [4 gates][hi, lo][32 lanes][4 regs] A fragments of P_g
   uint64_t* bars = reinterpret_cast<uint64_t*>(Pfrag + 1024);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBarSlots);
 
   // ------------------------------------------------------------------ setup
   if (threadIdx.x == 0) {
-    for (int i = 0; i < BAR_COUNT; ++i) ptx::mbar_init(&bars[i], (i == BAR_HFREE || i == BAR_A1FREE || i == BAR_Q) ? (uint32_t)C : 1u);
+    for (int i = 0; i < BAR_COUNT; ++i) ptx::mbar_init(&bars[i], (i == BAR_HFREE || i == BAR_A1FREE) ? (uint32_t)C : 1u);
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
@@ -199,15 +203,25 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       xblocks(0, 0, KF);
       for (int t = 0; t < T; ++t) {
         const bool nx = t + 1 < T;
-        for (int kb = 0; kb < KH; ++kb) load_stage(wg + (size_t)(KF + kb) * kBBytes, kBBytes, nullptr, 0);
+        // the K range of the state operand is walked chunk by chunk starting with this CTA's own chunk (rotated order)
+        for (int i = 0; i < C; ++i) {
+          const int src = ((int)c + i) % C;
+          for (int kb = 4 * src; kb < 4 * src + 4; ++kb) load_stage(wg + (size_t)(KF + kb) * kBBytes, kBBytes, nullptr, 0);
+        }
         if (!ATT) {
           if (nx) xblocks(t + 1, 0, KF);
           continue;
         }
         if (nx) xblocks(t + 1, 0, n1);
-        for (int s2 = 0; s2 < KH / 2; ++s2) load_stage(a1 + (size_t)s2 * 2 * kA1Block, 2 * kA1Block, nullptr, 0);
+        for (int i = 0; i < C; ++i) {
+          const int src = ((int)c + i) % C;
+          for (int s2 = 2 * src; s2 < 2 * src + 2; ++s2) load_stage(a1 + (size_t)s2 * 2 * kA1Block, 2 * kA1Block, nullptr, 0);
+        }
         if (nx) xblocks(t + 1, n1, n1 + n2);
-        for (int s4 = 0; s4 < KH / 4; ++s4) load_stage(a2 + (size_t)s4 * 4 * kA2Block, 4 * kA2Block, nullptr, 0);
+        for (int i = 0; i < C; ++i) {
+          const int src = ((int)c + i) % C;
+          load_stage(a2 + (size_t)src * 4 * kA2Block, 4 * kA2Block, nullptr, 0);
+        }
         if (nx) xblocks(t + 1, n1 + n2, KF);
       }
     }
@@ -269,13 +283,16 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         const bool nx = t + 1 < T;
         // h-part of step t (needs h'_{t-1} of every chunk in local shared memory)
         TC_TRACE(1, 0);
-        ptx::mbar_wait(&bars[BAR_H], t & 1);
-        ptx::tc_fence_after();
-        TC_TRACE(1, 1);
-        for (int kb = 0; kb < KH; ++kb) {
-          const uint32_t sa = wait_stage();
-          block_mma(dcol, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, sa, kBBytes / NP, dB256, idesc256, false);
-          release_stage();
+        for (int i = 0; i < C; ++i) {
+          const int src = ((int)c + i) % C;
+          ptx::mbar_wait(&bars[BAR_H + src], t & 1);
+          ptx::tc_fence_after();
+          if (i == 0) TC_TRACE(1, 1);
+          for (int kb = 4 * src; kb < 4 * src + 4; ++kb) {
+            const uint32_t sa = wait_stage();
+            block_mma(dcol, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, sa, kBBytes / NP, dB256, idesc256, false);
+            release_stage();
+          }
         }
         ptx::umma_commit(&bars[BAR_ACC_FULL + b]);
         if (C > 1) ptx::umma_commit_multicast(&bars[BAR_HFREE], cta_mask); else ptx::umma_commit(&bars[BAR_HFREE]);
@@ -298,36 +315,40 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         if (nx) xblocks(bo * 256, 0, n1);
         TC_TRACE(1, 3);
         // A1: [Wh hy | Wa (hy, node-sum in row 15)] -> columns [0,128) of the drained buffer
-        ptx::mbar_wait(&bars[BAR_HHAT], t & 1);
         ptx::mbar_wait(&bars[BAR_ACC_EMPTY + b], 0u);
-        ptx::tc_fence_after();
-        TC_TRACE(1, 4);
-        for (int s2 = 0; s2 < KH / 2; ++s2) {
-          const uint32_t sa = wait_stage();
+        for (int i = 0; i < C; ++i) {
+          const int src = ((int)c + i) % C;
+          ptx::mbar_wait(&bars[BAR_HHAT + src], t & 1);
+          ptx::tc_fence_after();
+          if (i == 0) TC_TRACE(1, 4);
+          for (int s2 = 2 * src; s2 < 2 * src + 2; ++s2) {
+            const uint32_t sa = wait_stage();
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int kb = s2 * 2 + j;
-            block_mma(dcol, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, sa + (uint32_t)j * kA1Block, kA1Block / NP, dB128, idesc128,
-                      (s2 | j) == 0);
+            for (int j = 0; j < 2; ++j) {
+              const int kb = s2 * 2 + j;
+              block_mma(dcol, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, sa + (uint32_t)j * kA1Block, kA1Block / NP, dB128, idesc128,
+                        i == 0 && s2 == 2 * src && j == 0);
+            }
+            release_stage();
           }
-          release_stage();
         }
         ptx::umma_commit(&bars[BAR_ATT_FULL]);
         if (C > 1) ptx::umma_commit_multicast(&bars[BAR_A1FREE], cta_mask); else ptx::umma_commit(&bars[BAR_A1FREE]);
         TC_TRACE(1, 5);
         if (nx) xblocks(bo * 256, n1, n1 + n2);
         // A2: Wq q (q sits in row 15 of every sequence) -> columns [128,192)
-        ptx::mbar_wait_cluster(&bars[BAR_Q], t & 1);
-        ptx::fence_proxy_async();
-        ptx::tc_fence_after();
-        TC_TRACE(1, 6);
-        for (int s4 = 0; s4 < KH / 4; ++s4) {
+        for (int i = 0; i < C; ++i) {
+          const int src = ((int)c + i) % C;           // q of chunk src sits in row 15 of K blocks 4 src .. 4 src + 3
+          ptx::mbar_wait_cluster(&bars[BAR_Q + src], t & 1);
+          ptx::fence_proxy_async();
+          ptx::tc_fence_after();
+          if (i == 0) TC_TRACE(1, 6);
           const uint32_t sa = wait_stage();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int kb = s4 * 4 + j;
+            const int kb = src * 4 + j;
             block_mma(dcol + 128, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, sa + (uint32_t)j * kA2Block, kA2Block / NP, dB64, idesc64,
-                      (s4 | j) == 0);
+                      i == 0 && j == 0);
           }
           release_stage();
         }
@@ -413,12 +434,13 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       ptx::named_bar_sync(1, kEpiThreads);
       if (et == 0) {
         if (acc_empty >= 0) ptx::mbar_arrive(&bars[BAR_ACC_EMPTY + acc_empty]);
+        ptx::mbar_arrive(&bars[bar + c]);                               // own chunk: usable at once
         for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) {
           if (peer == c) continue;
-          for (int part = 0; part < NP; ++part)
-            ptx::bulk_s2remote(hbuf + (size_t)part * H * 256 + (size_t)c * kHBlock, kHBlock, &bars[bar], peer);
+          for (int part = 0; part < NP; ++part)                           // lands on the peer's barrier of source c
+            ptx::bulk_s2remote(hbuf + (size_t)part * H * 256 + (size_t)c * kHBlock, kHBlock, &bars[bar + c], peer);
+          ptx::mbar_arrive_expect_tx(&bars[bar + peer], (uint32_t)NP * kHBlock);   // arm the barrier of the peer's block
         }
-        ptx::mbar_arrive_expect_tx(&bars[bar], (uint32_t)(C - 1) * NP * kHBlock);
       }
     };
     // y_t = act(h'_t).  All addressing that does not depend on t is folded into per-thread bases; the values of
@@ -687,7 +709,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       if (et == 0) {
         // one cluster-scope release fence, then relaxed arrives (a release arrive per peer costs a MEMBAR.GPU each)
         if (C > 1) ptx::fence_acq_rel_cluster();
-        for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) ptx::mbar_arrive_remote_relaxed(&bars[BAR_Q], peer);
+        for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) ptx::mbar_arrive_remote_relaxed(&bars[BAR_Q + c], peer);
         TC_TRACE(0, 6);
       }
       // ---- e = tanh(Wh hy + Wq q + bs),  partial a = e . u over this warp's 16 units (lane = row)
@@ -769,7 +791,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         }
     }
     // the last publish must have landed everywhere before any CTA may exit
-    ptx::mbar_wait(&bars[BAR_H], T & 1);
+    for (int src = 0; src < C; ++src) ptx::mbar_wait(&bars[BAR_H + src], T & 1);
   }
 
   // ------------------------------------------------------------------ teardown
