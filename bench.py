@@ -206,7 +206,7 @@ def main():
     ap.add_argument("--engine", default=os.environ.get("A3GC_ENGINE", "auto"))
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="sequences per GPU (default: the BASELINE cfg-2 value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("A3GC_STREAMS", 3)),
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("A3GC_STREAMS", 4)),
                     help="batch chunks whose three-stage chains run concurrently on separate CUDA streams")
     ap.add_argument("--variant", default="A3GC", choices=["A3GC", "AAGC", "AGC", "GGRU"],
                     help="cell family of the three-stage pipeline (headline: A3GC; the others are the cfg 3 / cfg 4 side lines)")
