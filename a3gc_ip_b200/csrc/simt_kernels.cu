@@ -156,7 +156,7 @@ __device__ __forceinline__ void accum4(float (&acc)[4][16], const float* __restr
 
 __device__ __forceinline__ void accum1(float (&acc)[16], const float* __restrict__ act,
                                        const float* __restrict__ w, int K, int ldw) {
-#pragma unroll 4
+#pragma unroll 16
   for (int k = 0; k < K; ++k) {
     const float wv = __ldg(w + (size_t)k * ldw);
     const float4* a4 = reinterpret_cast<const float4*>(act + k * kNodesPad);
