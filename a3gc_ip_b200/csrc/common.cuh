@@ -54,6 +54,9 @@ __device__ __forceinline__ float one_plus_exp_neg(float x) { return 1.0f + fminf
 __device__ __forceinline__ float exp_neg2(float x) { return fminf(ex2_ftz(x * (-2.0f * kLog2e)), kExpCap); }
 __device__ __forceinline__ float fast_sigmoid(float x) { return rcp_ftz(one_plus_exp_neg(x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.0f, rcp_ftz(1.0f + exp_neg2(x)), -1.0f); }
+// bf16 path only (stated bound 5e-3): single-MUFU tanh (relative error ~2^-11) and the sigmoid derived from it
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_approx(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 __device__ __forceinline__ float apply_act(float v, int act) {
   return act == A3GC_ACT_TANH ? tanhf_(v) : (act == A3GC_ACT_RELU ? fmaxf(v, 0.0f) : v);
 }

@@ -559,23 +559,42 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
             const float* sp = wst + tq * 32;
             const float2 u0 = *reinterpret_cast<const float2*>(sp + ((16 * sq + 2 * tr) ^ swz));        // nodes 2tr, 2tr+1 of unit column tq
             const float2 u1 = *reinterpret_cast<const float2*>(sp + ((16 * sq + 2 * tr + 8) ^ swz));    // nodes 2tr+8, 2tr+9
-            uint32_t bh0, bl0, bh1, bl1;
-            ptx::split_pair_f16(u0.x, u0.y, bh0, bl0);
-            ptx::split_pair_f16(u1.x, u1.y, bh1, bl1);
-            // three INDEPENDENT accumulators: a warp-level HMMA queues behind the UMMAs that share the tensor pipe, so a
-            // dependent chain of three would pay that latency three times
-            float z[4] = {bias.x, bias.y, bias.x, bias.y}, z2[4] = {0.f, 0.f, 0.f, 0.f}, z3[4] = {0.f, 0.f, 0.f, 0.f};
-            ptx::mma_16816_f16(z, ah, bh0, bh1);
-            ptx::mma_16816_f16(z2, al, bh0, bh1);
-            ptx::mma_16816_f16(z3, ah, bl0, bl1);
+            float z[4] = {bias.x, bias.y, bias.x, bias.y};
+            if (SPLIT) {
+              uint32_t bh0, bl0, bh1, bl1;
+              ptx::split_pair_f16(u0.x, u0.y, bh0, bl0);
+              ptx::split_pair_f16(u1.x, u1.y, bh1, bl1);
+              // three INDEPENDENT accumulators: a warp-level HMMA queues behind the UMMAs that share the tensor pipe, so a
+              // dependent chain of three would pay that latency three times
+              float z2[4] = {0.f, 0.f, 0.f, 0.f}, z3[4] = {0.f, 0.f, 0.f, 0.f};
+              ptx::mma_16816_f16(z, ah, bh0, bh1);
+              ptx::mma_16816_f16(z2, al, bh0, bh1);
+              ptx::mma_16816_f16(z3, ah, bl0, bl1);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) z[j] += z2[j] + z3[j];
+              for (int j = 0; j < 4; ++j) z[j] += z2[j] + z3[j];
+            } else {
+              // bf16 path (stated bound 5e-3): one fp16 pass for the mix (11-bit operands, fp32 accumulate)
+              const __half2 h0 = __floats2half2_rn(u0.x, u0.y), h1 = __floats2half2_rn(u1.x, u1.y);
+              ptx::mma_16816_f16(z, ah, *reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const bool ok = valid[sq] && !(pad_hi && j >= 2);
               // c' = sig(zf) c + sig(zi) tanh(zc), hy = sig(zo) tanh(c') with shared reciprocals: 5 ex2 + 2 rcp per element
               float gv = 0.f;                                                                    // activated gate (tape only)
-              if (g == 0) {
+              if (!SPLIT) {
+                // bf16 path: single-MUFU activations (5 per element)
+                if (g == 0) e1[sq][j] = sigmoid_approx(z[j]);
+                else if (g == 1) e2[sq][j] = sigmoid_approx(z[j]);
+                else if (g == 2) {
+                  float cn = fmaf(e2[sq][j], creg[sq][ub][j], e1[sq][j] * tanh_approx(z[j]));
+                  cn = ok ? cn : 0.f;
+                  creg[sq][ub][j] = cn;
+                  e1[sq][j] = tanh_approx(cn);
+                } else {
+                  hreg[sq][ub][j] = ok ? sigmoid_approx(z[j]) * e1[sq][j] : 0.f;
+                }
+              } else if (g == 0) {
                 e1[sq][j] = one_plus_exp_neg(z[j]);                                              // 1 + e^-zi
                 if (TRAIN) gv = rcp_ftz(e1[sq][j]);
               } else if (g == 1) {
