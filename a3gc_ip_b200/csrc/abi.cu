@@ -320,9 +320,9 @@ int a3gc_net_forward(int variant, const a3gc_net_params* net, const float* x,
 }
 
 size_t a3gc_layer_train_workspace_bytes(int variant, int64_t batch, int64_t steps, int f_in, int hidden, int num_dirs, int engine) {
-  if (variant < A3GC_VARIANT_AAGC || variant > A3GC_VARIANT_AGC || num_dirs < 1 || num_dirs > 2 || f_in <= 0 || hidden <= 0 || batch < 0 || steps < 0) return 0;
+  if (!variant_ok(variant) || num_dirs < 1 || num_dirs > 2 || f_in <= 0 || hidden <= 0 || batch < 0 || steps < 0) return 0;
   size_t b = simt_train_workspace_bytes(variant, f_in, hidden, num_dirs);        // backward (and the CUDA-core forward)
-  if (engine != A3GC_ENGINE_SIMT && tc_layer_supported(variant, f_in, hidden, A3GC_PREC_FP32)) {
+  if (variant != A3GC_VARIANT_GGRU && engine != A3GC_ENGINE_SIMT && tc_layer_supported(variant, f_in, hidden, A3GC_PREC_FP32)) {
     const size_t t = tc_layer_workspace_bytes(variant, batch, steps, f_in, hidden, num_dirs, A3GC_PREC_FP32);
     if (t > b) b = t;
   }
@@ -330,7 +330,7 @@ size_t a3gc_layer_train_workspace_bytes(int variant, int64_t batch, int64_t step
 }
 
 static int check_tape(int variant, const a3gc_tape* t, const char* who) {
-  const bool att = variant != A3GC_VARIANT_AAGC;
+  const bool att = variant == A3GC_VARIANT_A3GC || variant == A3GC_VARIANT_AGC;
   if (!t || !t->gates || !t->c || !t->hh || !t->hp || (att && (!t->e || !t->a || !t->q || !t->s))) {
     set_error("%s: incomplete tape", who);
     return A3GC_ERR_INVALID_ARG;
@@ -346,10 +346,7 @@ int a3gc_layer_train_forward(int variant, int num_dirs, const a3gc_cell_params* 
                              int64_t batch, int64_t steps, int f_in, int hidden, int out_act,
                              const a3gc_tape* tape, const float* hmask, int engine,
                              void* workspace, size_t workspace_bytes, void* stream) {
-  if (variant < A3GC_VARIANT_AAGC || variant > A3GC_VARIANT_AGC) {
-    set_error("a3gc_layer_train_forward: the training path covers the LSTM-family cells (AAGC / A3GC / AGC)");
-    return A3GC_ERR_UNSUPPORTED;
-  }
+  if (!variant_ok(variant)) { set_error("a3gc_layer_train_forward: bad variant %d", variant); return A3GC_ERR_INVALID_ARG; }
   if (num_dirs < 1 || num_dirs > 2 || !cells || !reverse || batch < 0 || steps < 0 || f_in <= 0 || hidden <= 0 ||
       out_act < A3GC_ACT_LINEAR || out_act > A3GC_ACT_TANH || (batch * steps > 0 && (!x || !y))) {
     set_error("a3gc_layer_train_forward: invalid argument");
@@ -371,7 +368,7 @@ int a3gc_layer_train_forward(int variant, int num_dirs, const a3gc_cell_params* 
   a.y = y; a.y_stride_b = y_stride_b; a.y_stride_t = y_stride_t; a.y_ld = y_ld;
   a.batch = batch; a.steps = steps; a.f_in = f_in; a.hidden = hidden; a.out_act = out_act; a.precision = A3GC_PREC_FP32;
   if (engine < A3GC_ENGINE_AUTO || engine > A3GC_ENGINE_TC) { set_error("a3gc_layer_train_forward: bad engine %d", engine); return A3GC_ERR_INVALID_ARG; }
-  const bool tc_ok = tc_layer_supported(variant, f_in, hidden, A3GC_PREC_FP32) && x_stride_t == (int64_t)kNodes * f_in;
+  const bool tc_ok = variant != A3GC_VARIANT_GGRU && tc_layer_supported(variant, f_in, hidden, A3GC_PREC_FP32) && x_stride_t == (int64_t)kNodes * f_in;
   if (engine == A3GC_ENGINE_TC && !tc_ok) {
     set_error("a3gc_layer_train_forward: tensor-core engine does not support variant=%d f_in=%d hidden=%d", variant, f_in, hidden);
     return A3GC_ERR_UNSUPPORTED;
@@ -390,10 +387,7 @@ int a3gc_layer_backward(int variant, int num_dirs, const a3gc_cell_params* cells
                         int64_t batch, int64_t steps, int f_in, int hidden, int out_act,
                         const a3gc_tape* tape, const a3gc_tape_grads* grads, const float* hmask,
                         void* workspace, size_t workspace_bytes, void* stream) {
-  if (variant < A3GC_VARIANT_AAGC || variant > A3GC_VARIANT_AGC) {
-    set_error("a3gc_layer_backward: the training path covers the LSTM-family cells (AAGC / A3GC / AGC)");
-    return A3GC_ERR_UNSUPPORTED;
-  }
+  if (!variant_ok(variant)) { set_error("a3gc_layer_backward: bad variant %d", variant); return A3GC_ERR_INVALID_ARG; }
   if (num_dirs < 1 || num_dirs > 2 || !cells || !reverse || batch < 0 || steps < 0 || f_in <= 0 || hidden <= 0 ||
       out_act < A3GC_ACT_LINEAR || out_act > A3GC_ACT_TANH || (batch * steps > 0 && !dy)) {
     set_error("a3gc_layer_backward: invalid argument");
@@ -403,8 +397,9 @@ int a3gc_layer_backward(int variant, int num_dirs, const a3gc_cell_params* cells
   if (batch == 0 || steps == 0) return A3GC_OK;
   int rc = check_tape(variant, tape, "a3gc_layer_backward");
   if (rc) return rc;
-  const bool att = variant != A3GC_VARIANT_AAGC;
-  if (!grads || !grads->dzm || (att && (!grads->dep || !grads->dqs || !grads->dqp || !grads->dap))) {
+  const bool att = variant == A3GC_VARIANT_A3GC || variant == A3GC_VARIANT_AGC;
+  if (!grads || !grads->dzm || (att && (!grads->dep || !grads->dqs || !grads->dqp || !grads->dap)) ||
+      (variant == A3GC_VARIANT_GGRU && (!grads->dep || !grads->dqs))) {
     set_error("a3gc_layer_backward: incomplete gradient tape");
     return A3GC_ERR_INVALID_ARG;
   }

@@ -812,6 +812,127 @@ lstm_train_bwd_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
   store_state(d.dc0, dc, b0, lg);
 }
 
+// Reverse-time chain of the graph-GRU (net_aagc.py:343-368).  Per step, with dh' = carried gradient + dY_t:
+//   du = dh' (h_prev - c), dc = dh' (1 - u), dzc = dc (1 - c^2), dzr = dzc zch r (1 - r), dzu = du u (1 - u), dzch = dzc r
+//   dmsg = dzr Wrh + dzu Wuh + dzch Wch,  dM = P^T dmsg,  dh_prev = dh' u + dM Wg
+// Stored for the hoisted GEMMs: (dzr, dzu, dzcx = dzc, dzch) node-major [D][B][T][15][4H] (grads.dzm), dmsg unit-major
+// (grads.dep), dM node-major [D][B][T][15][H] (grads.dqs).
+struct GruBwdDir {
+  const float* Whid[3];    // dense_{r,u,c}_hid.weight [H][H]
+  const float* Wg;         // gcn_kernel [H][H]
+  const float* PT;         // [16][16]  PT[m][n] = P[n][m]
+  const float* h0; const float* dhT; float* dh0;
+  int reverse;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+gru_train_bwd_kernel(GruBwdDir d0, GruBwdDir d1, BwdGeom g) {
+  extern __shared__ __align__(16) float smem[];
+  const GruBwdDir d = blockIdx.y == 0 ? d0 : d1;
+  const a3gc_tape& tp = g.tape;
+  const a3gc_tape_grads& gr = g.gr;
+  const int H = g.H, BT = g.BT;
+  const size_t HN = (size_t)H * kNodesPad;
+  float* dh = smem;                        // [BT][H][16]
+  float* dzs = dh + BT * HN;               // [3][BT][H][16]  dzr, dzu, dzch
+  float* dM = dzs + 3 * BT * HN;           // [BT][H][16]
+  float* PT = dM + BT * HN;                // [16][16]
+  const int b0 = blockIdx.x * BT;
+  const int y_off = blockIdx.y * H;
+  const int ntask = BT * H;
+  LayerGeom lg; lg.B = g.B; lg.H = H; lg.BT = BT;
+  load_state(dh, d.dhT, b0, lg);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) PT[i] = d.PT[i];
+
+  for (int step = g.T - 1; step >= 0; --step) {
+    const int t = d.reverse ? g.T - 1 - step : step;
+    const int tprev = d.reverse ? t + 1 : t - 1;
+    const size_t rec0 = ((size_t)blockIdx.y * g.T + t) * g.B;
+    const size_t nm0 = ((size_t)blockIdx.y * g.B * g.T + t) * kNodes;
+    __syncthreads();
+    // ---- A: gate gradients; dh <- dh' u (the direct path to h_prev)
+    for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+      const int s = task / H, j = task % H, b = b0 + s;
+      float dv[16], zr[16], zu[16], zx[16], zh[16];
+      load16(dv, dh + (size_t)task * kNodesPad);
+      if (b < g.B) {
+        float r[16], u[16], c[16], zch[16];
+        const float* gp = tp.gates + (((rec0 + b) * 4) * H + j) * kNodesPad;
+        load16(r, gp); load16(u, gp + HN); load16(c, gp + 2 * HN); load16(zch, gp + 3 * HN);
+        const float* yp = g.dy + (size_t)b * g.syb + (size_t)t * g.syt + y_off + j;
+        const float* hprev = step > 0 ? tp.hp + ((((size_t)blockIdx.y * g.B + b) * g.T + tprev) * kNodes) * H + j : nullptr;
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
+          float hp = 0.f, gy = 0.f;
+          if (n < kNodes) {
+            gy = __ldg(yp + (size_t)n * g.yld);
+            hp = step > 0 ? hprev[(size_t)n * H] : (d.h0 != nullptr ? d.h0[((size_t)b * kNodes + n) * H + j] : 0.f);
+          }
+          const float dhp = dv[n] + gy;
+          const float dzc = dhp * (1.0f - u[n]) * (1.0f - c[n] * c[n]);
+          zr[n] = dzc * zch[n] * r[n] * (1.0f - r[n]);
+          zu[n] = dhp * (hp - c[n]) * u[n] * (1.0f - u[n]);
+          zx[n] = dzc;
+          zh[n] = dzc * r[n];
+          dv[n] = dhp * u[n];
+        }
+        zr[15] = zu[15] = zx[15] = zh[15] = dv[15] = 0.f;
+        float* zp = gr.dzm + (nm0 + (size_t)b * g.T * kNodes) * 4 * H + j;
+#pragma unroll
+        for (int n = 0; n < kNodes; ++n) {
+          zp[(size_t)n * 4 * H] = zr[n]; zp[(size_t)n * 4 * H + H] = zu[n]; zp[(size_t)n * 4 * H + 2 * H] = zx[n]; zp[(size_t)n * 4 * H + 3 * H] = zh[n];
+        }
+      } else {
+#pragma unroll
+        for (int n = 0; n < 16; ++n) { zr[n] = zu[n] = zh[n] = dv[n] = 0.f; }
+      }
+      store16(dh + (size_t)task * kNodesPad, dv);
+      store16(dzs + (size_t)task * kNodesPad, zr);
+      store16(dzs + ((size_t)BT * H + task) * kNodesPad, zu);
+      store16(dzs + ((size_t)2 * BT * H + task) * kNodesPad, zh);
+    }
+    __syncthreads();
+    // ---- B: dmsg[n][k] = sum_g sum_j dz_g[n][j] Whid_g[j][k];  dM = P^T dmsg
+    for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+      const int s = task / H, k = task % H, b = b0 + s;
+      float acc[16], m[16];
+#pragma unroll
+      for (int n = 0; n < 16; ++n) acc[n] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) accum1(acc, dzs + ((size_t)q * BT + s) * HN, d.Whid[q] + k, H, H);
+      acc[15] = 0.f;
+      mix15(acc, PT, m);
+      store16(dM + (size_t)task * kNodesPad, m);
+      if (b < g.B) {
+        store16(gr.dep + ((rec0 + b) * H + k) * kNodesPad, acc);
+        float* mp = gr.dqs + (nm0 + (size_t)b * g.T * kNodes) * H + k;
+#pragma unroll
+        for (int n = 0; n < kNodes; ++n) mp[(size_t)n * H] = m[n];
+      }
+    }
+    __syncthreads();
+    // ---- C: dh_prev[n][k'] = dh' u + sum_j dM[n][j] Wg[j][k']
+    for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+      const int s = task / H, k = task % H;
+      float acc[16];
+      load16(acc, dh + (size_t)task * kNodesPad);
+      accum1(acc, dM + (size_t)s * HN, d.Wg + k, H, H);
+      acc[15] = 0.f;
+      store16(dh + (size_t)task * kNodesPad, acc);
+    }
+  }
+  __syncthreads();
+  store_state(d.dh0, dh, b0, lg);
+}
+
+__global__ void pack_gru_pt_kernel(a3gc_cell_params cp, float* out) {
+  // P[n][m] = g_adjacency[m][n] (pack_gru_kernel)  ->  PT[m][n] = P[n][m] = g_adjacency[m][n]
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    const int m = i / 16, n = i % 16;
+    out[i] = (m < kNodes && n < kNodes) ? cp.g_adjacency[m * kNodes + n] : 0.f;
+  }
+}
+
 __global__ void pack_pt_kernel(a3gc_cell_params cp, float* out, int variant) {
   // PT_g[n][m] = P_g[m][n] with P as in pack_lstm_kernel
   for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) {
@@ -826,8 +947,11 @@ __global__ void pack_pt_kernel(a3gc_cell_params cp, float* out, int variant) {
 // ------------------------------------------------------------------------------------------
 // G-GRU time loop
 // ------------------------------------------------------------------------------------------
+// TRAIN: also keeps the tape of the graph-GRU backward (a3gc_tape fields, G-GRU meaning): gates = (r, u, c, zch = Wch msg),
+// c = M = h Wg^T (before the node mix), hh = msg, hp = h' (node-major)
+template <bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1)
-gru_layer_kernel(GruPacked w0, GruPacked w1, DirPtrs d0, DirPtrs d1, LayerGeom g) {
+gru_layer_kernel(GruPacked w0, GruPacked w1, DirPtrs d0, DirPtrs d1, LayerGeom g, a3gc_tape tp) {
   extern __shared__ __align__(16) float smem[];
   const GruPacked w = blockIdx.y == 0 ? w0 : w1;
   const DirPtrs d = blockIdx.y == 0 ? d0 : d1;
@@ -857,6 +981,12 @@ gru_layer_kernel(GruPacked w0, GruPacked w1, DirPtrs d0, DirPtrs d1, LayerGeom g
       accum1(m, hcur + (size_t)s * H * kNodesPad, w.Wg_t + j, H, H);
       mix15(m, Pbuf, msg);
       store16(mbuf + (size_t)task * kNodesPad, msg);
+      if (TRAIN && b0 + s < g.B) {
+        const size_t rec = ((size_t)blockIdx.y * g.T + t) * g.B + b0 + s;
+        m[15] = 0.f;
+        store16(tp.c + (rec * H + j) * kNodesPad, m);
+        store16(tp.hh + (rec * H + j) * kNodesPad, msg);
+      }
     }
     __syncthreads();
     for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
@@ -870,6 +1000,7 @@ gru_layer_kernel(GruPacked w0, GruPacked w1, DirPtrs d0, DirPtrs d1, LayerGeom g
       accum4(acc, mbuf + (size_t)s * H * kNodesPad, w.Whid4 + j, H, H);      // r, u, -, c_hid
       const float4 bias = w.bias4[j];
       float hold[16], hy[16];
+      float gr_[16], gu_[16], gc_[16];
       load16(hold, hcur + (size_t)task * kNodesPad);
 #pragma unroll
       for (int n = 0; n < kNodes; ++n) {
@@ -877,6 +1008,7 @@ gru_layer_kernel(GruPacked w0, GruPacked w1, DirPtrs d0, DirPtrs d1, LayerGeom g
         const float u = sigmoidf_(acc[1][n] + bias.y);
         const float c = tanhf_(acc[2][n] + bias.z + r * acc[3][n]);
         hy[n] = u * hold[n] + (1.0f - u) * c;                                  // net_aagc.py:364
+        if (TRAIN) { gr_[n] = r; gu_[n] = u; gc_[n] = c; }
       }
       hy[15] = 0.f;
       store16(hnxt + (size_t)task * kNodesPad, hy);
@@ -885,6 +1017,16 @@ gru_layer_kernel(GruPacked w0, GruPacked w1, DirPtrs d0, DirPtrs d1, LayerGeom g
         float* yp = g.y + (size_t)b * g.syb + (size_t)t * g.syt + y_off + j;
 #pragma unroll
         for (int n = 0; n < kNodes; ++n) yp[(size_t)n * g.yld] = hy[n];        // returns (h, h): no activation
+        if (TRAIN) {
+          const size_t rec = ((size_t)blockIdx.y * g.T + t) * g.B + b;
+          float* gp = tp.gates + ((rec * 4) * H + j) * kNodesPad;
+          gr_[15] = 0.f; gu_[15] = 0.f; gc_[15] = 0.f; acc[3][15] = 0.f;
+          store16(gp, gr_); store16(gp + (size_t)H * kNodesPad, gu_); store16(gp + (size_t)2 * H * kNodesPad, gc_);
+          store16(gp + (size_t)3 * H * kNodesPad, acc[3]);
+          float* hpp = tp.hp + ((((size_t)blockIdx.y * g.B + b) * g.T + t) * kNodes) * H + j;
+#pragma unroll
+          for (int n = 0; n < kNodes; ++n) hpp[(size_t)n * H] = hy[n];
+        }
       }
     }
     cur ^= 1;
@@ -1088,8 +1230,8 @@ int simt_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream
       A3GC_LAUNCH_CHECK("pack_gru_kernel");
     }
     if (a.num_dirs == 1) pk[1] = pk[0];
-    A3GC_CUDA_TRY(cudaFuncSetAttribute(gru_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gru_layer_kernel<<<grid, kThreads, smem, stream>>>(pk[0], pk[1], dp[0], dp[1], g);
+    A3GC_CUDA_TRY(cudaFuncSetAttribute(gru_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gru_layer_kernel<false><<<grid, kThreads, smem, stream>>>(pk[0], pk[1], dp[0], dp[1], g, a3gc_tape{});
     A3GC_LAUNCH_CHECK("gru_layer_kernel");
   } else {
     LstmPacked pk[2];
@@ -1116,12 +1258,88 @@ int simt_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream
 // training path: host side
 // ------------------------------------------------------------------------------------------
 size_t simt_train_workspace_bytes(int variant, int f_in, int hidden, int num_dirs) {
-  (void)variant;
-  const size_t per = align_up(lstm_packed_floats(f_in, hidden) * sizeof(float), 256) + 4 * 256 * sizeof(float);
+  const size_t packed = variant == A3GC_VARIANT_GGRU ? gru_packed_floats(f_in, hidden) : lstm_packed_floats(f_in, hidden);
+  const size_t per = align_up(packed * sizeof(float), 256) + 4 * 256 * sizeof(float);
   return (size_t)num_dirs * per;
 }
 
+// graph-GRU training forward: the SIMT layer kernel with the tape
+static int simt_gru_train_forward(const LayerArgs& a, const a3gc_tape& tape, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  const int F = a.f_in, H = a.hidden;
+  const size_t need = simt_train_workspace_bytes(a.variant, F, H, a.num_dirs);
+  if (ws_bytes < need || ws == nullptr) { set_error("a3gc_layer_train_forward: workspace too small (%zu < %zu bytes)", ws_bytes, need); return A3GC_ERR_WORKSPACE; }
+  const int smem_max = max_optin_smem();
+  if (smem_max <= 0) { set_error("no CUDA device"); return A3GC_ERR_NO_DEVICE; }
+  auto smem_bytes = [&](int bt) -> size_t { return ((size_t)3 * bt * H * 16 + (size_t)bt * F * 16 + 256) * sizeof(float); };
+  int BT = 8;
+  while (BT > 1 && smem_bytes(BT) > (size_t)smem_max) --BT;
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  while (BT > 1 && ((a.batch + BT - 1) / BT) * a.num_dirs < sms) --BT;
+  if (smem_bytes(BT) > (size_t)smem_max) { set_error("G-GRU training forward: hidden=%d f_in=%d does not fit in shared memory", H, F); return A3GC_ERR_UNSUPPORTED; }
+  char* base = static_cast<char*>(ws);
+  const size_t per = need / a.num_dirs;
+  DirPtrs dp[2] = {};
+  GruPacked pk[2];
+  for (int d = 0; d < a.num_dirs; ++d) {
+    dp[d].h0 = a.h0[d]; dp[d].hT = a.hT[d]; dp[d].reverse = a.reverse[d];
+    pk[d] = carve_gru(reinterpret_cast<float*>(base + d * per), F, H);
+    pack_gru_kernel<<<64, 256, 0, stream>>>(a.cells[d], pk[d], F, H);
+    A3GC_LAUNCH_CHECK("pack_gru_kernel");
+  }
+  if (a.num_dirs == 1) pk[1] = pk[0];
+  LayerGeom g;
+  g.x = a.x; g.sxb = a.x_stride_b; g.sxt = a.x_stride_t;
+  g.y = a.y; g.syb = a.y_stride_b; g.syt = a.y_stride_t; g.yld = a.y_ld;
+  g.B = (int)a.batch; g.T = (int)a.steps; g.F = F; g.H = H; g.out_act = a.out_act; g.BT = BT;
+  dim3 grid((unsigned)((a.batch + BT - 1) / BT), (unsigned)a.num_dirs);
+  const size_t smem = smem_bytes(BT);
+  A3GC_CUDA_TRY(cudaFuncSetAttribute(gru_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gru_layer_kernel<true><<<grid, kThreads, smem, stream>>>(pk[0], pk[1], dp[0], dp[1], g, tape);
+  A3GC_LAUNCH_CHECK("gru_layer_kernel");
+  return A3GC_OK;
+}
+
+static int simt_gru_train_backward(const TrainBwdArgs& a, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  const int F = a.f_in, H = a.hidden;
+  const size_t need = simt_train_workspace_bytes(a.variant, F, H, a.num_dirs);
+  if (ws_bytes < need || ws == nullptr) { set_error("a3gc_layer_backward: workspace too small (%zu < %zu bytes)", ws_bytes, need); return A3GC_ERR_WORKSPACE; }
+  const int smem_max = max_optin_smem();
+  if (smem_max <= 0) { set_error("no CUDA device"); return A3GC_ERR_NO_DEVICE; }
+  auto smem_bytes = [&](int bt) -> size_t { return ((size_t)5 * bt * H * 16 + 256) * sizeof(float); };
+  int BT = 8;
+  while (BT > 1 && smem_bytes(BT) > (size_t)smem_max) --BT;
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  while (BT > 1 && ((a.batch + BT - 1) / BT) * a.num_dirs < sms) --BT;
+  if (smem_bytes(BT) > (size_t)smem_max) { set_error("G-GRU training backward: hidden=%d does not fit in shared memory", H); return A3GC_ERR_UNSUPPORTED; }
+  char* base = static_cast<char*>(ws);
+  const size_t per = need / a.num_dirs;
+  GruBwdDir bd[2] = {};
+  for (int d = 0; d < a.num_dirs; ++d) {
+    float* pt = reinterpret_cast<float*>(base + d * per + align_up(gru_packed_floats(F, H) * sizeof(float), 256));
+    pack_gru_pt_kernel<<<1, 256, 0, stream>>>(a.cells[d], pt);
+    A3GC_LAUNCH_CHECK("pack_gru_pt_kernel");
+    for (int q = 0; q < 3; ++q) bd[d].Whid[q] = a.cells[d].dense_hid_w[q];
+    bd[d].Wg = a.cells[d].g_gcn_kernel; bd[d].PT = pt;
+    bd[d].h0 = a.c0[d];                               // for G-GRU the caller passes the forward's initial h here
+    bd[d].dhT = a.dhT[d]; bd[d].dh0 = a.dh0[d]; bd[d].reverse = a.reverse[d];
+  }
+  if (a.num_dirs == 1) bd[1] = bd[0];
+  BwdGeom g;
+  g.dy = a.dy; g.syb = a.dy_stride_b; g.syt = a.dy_stride_t; g.yld = a.dy_ld;
+  g.tape = a.tape; g.gr = a.grads; g.hmask = nullptr;
+  g.B = (int)a.batch; g.T = (int)a.steps; g.F = F; g.H = H; g.out_act = a.out_act; g.BT = BT;
+  dim3 grid((unsigned)((a.batch + BT - 1) / BT), (unsigned)a.num_dirs);
+  const size_t smem = smem_bytes(BT);
+  A3GC_CUDA_TRY(cudaFuncSetAttribute(gru_train_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gru_train_bwd_kernel<<<grid, kThreads, smem, stream>>>(bd[0], bd[1], g);
+  A3GC_LAUNCH_CHECK("gru_train_bwd_kernel");
+  return A3GC_OK;
+}
+
 int simt_train_forward(const LayerArgs& a, const a3gc_tape& tape, const float* hmask, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (a.variant == A3GC_VARIANT_GGRU) return simt_gru_train_forward(a, tape, ws, ws_bytes, stream);
   const int F = a.f_in, H = a.hidden;
   const size_t need = simt_train_workspace_bytes(a.variant, F, H, a.num_dirs);
   if (ws_bytes < need || ws == nullptr) {
@@ -1175,6 +1393,7 @@ int simt_train_forward(const LayerArgs& a, const a3gc_tape& tape, const float* h
 }
 
 int simt_train_backward(const TrainBwdArgs& a, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (a.variant == A3GC_VARIANT_GGRU) return simt_gru_train_backward(a, ws, ws_bytes, stream);
   const int F = a.f_in, H = a.hidden;
   const size_t need = simt_train_workspace_bytes(a.variant, F, H, a.num_dirs);
   if (ws_bytes < need || ws == nullptr) {

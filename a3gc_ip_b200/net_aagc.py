@@ -11,7 +11,7 @@ Differences from the reference, all deliberate:
   * the forward and reverse directions of a ``Bi*`` layer run concurrently in one launch;
   * ``.eval()`` mode is the inference path (tensor-core engine, no autograd history); ``.train()`` mode is the
     training path of the LSTM-family classes (a3gc_ip_b200/training.py): forward keeps a tape, backward runs
-    the BPTT chain in CUDA, dropout masks are drawn per call.  G-GRU has no training path yet (it raises).
+    the BPTT chain in CUDA, dropout masks are drawn per call (the graph-GRU cell has no dropout in the reference either).
 """
 from __future__ import annotations
 
@@ -298,6 +298,9 @@ class G_GRU_cell(_CellBase):
         return p
 
     def forward(self, input: Tensor, state: Tensor) -> Tuple[Tensor, Tensor]:
+        if self.training:
+            y, st = _tr.run_gru_layer_train([self], [0], input.unsqueeze(1), [state], self._ws)
+            return st[0], st[0]
         y, st = _run_layer("GGRU", [self], [0], input.unsqueeze(0), True, [state], "linear", self._ws, self.engine, self.precision)
         return st[0], st[0]
 
@@ -320,7 +323,8 @@ class _Layer(torch.nn.Module, _EngineMixin):
         act = "linear" if c.variant == "GGRU" else c.activation_name
         if self.training:
             if c.variant == "GGRU":
-                raise NotImplementedError("G-GRU has no training path yet; call .eval() for inference")
+                y, st = _tr.run_gru_layer_train([c], [self.reverse], input.transpose(0, 1).contiguous(), [state], self._ws)
+                return y.transpose(0, 1), st[0]
             y, st = _tr.run_layer_train(c.variant, [c], [self.reverse], input.transpose(0, 1).contiguous(), [state], act, self._ws,
                                         c.p_dropout, c.p_recurrent_dropout, self.engine)
             return y.transpose(0, 1), st[0]
@@ -344,7 +348,7 @@ class _BiLayer(torch.nn.Module, _EngineMixin):
         act = "linear" if c.variant == "GGRU" else c.activation_name
         if self.training:
             if c.variant == "GGRU":
-                raise NotImplementedError("G-GRU has no training path yet; call .eval() for inference")
+                return _tr.run_gru_layer_train(cells, [0, 1], input, states, self._ws)
             return _tr.run_layer_train(c.variant, cells, [0, 1], input, states, act, self._ws, c.p_dropout, c.p_recurrent_dropout,
                                        self.engine)
         return _run_layer(c.variant, cells, [0, 1], input, False, states, act, self._ws, self.engine, self.precision)
@@ -487,13 +491,11 @@ class _Net(torch.nn.Module, _EngineMixin):
 def _net_forward_train(self, x: Tensor, h=None):
     """Training-mode forward of the nets (net_aagc.py:633-645 under ``model.train()``, train_a3gc_tp.py:74): same
     chain as the inference path, each stage differentiable; dropout as the reference configures it."""
-    if self.variant == "GGRU":
-        raise NotImplementedError("G-GRU has no training path yet; call .eval() for inference")
     x = _lib.require_cuda_f32(x, "x")
     B, H = x.shape[0], self.units_hidden
     if h is None:
-        z = lambda: torch.zeros(B, NUM_NODES, H, dtype=torch.float32, device=x.device)     # net_aagc.py:634-639
-        h = [(z(), z()), (z(), z())]
+        z = lambda: torch.zeros(B, NUM_NODES, H, dtype=torch.float32, device=x.device)     # net_aagc.py:634-639, :686-687
+        h = [z(), z()] if self.variant == "GGRU" else [(z(), z()), (z(), z())]
     a = torch.relu(self.linear_in(x))
     a, h = self.rnn1(a, h)
     a, h = self.rnn2(a, h)

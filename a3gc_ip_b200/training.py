@@ -200,8 +200,7 @@ def run_layer_train(variant: str, cells: Sequence[torch.nn.Module], reverse: Seq
                     p_in: float = 0.0, p_rec: float = 0.0, engine: str = "auto"):
     """Differentiable batch-major forward of one (bi)layer.  x [B,T,15,F] -> (y [B,T,15,nd*H], [(hT, cT)] * nd)."""
     if variant not in LSTM_PARAM_NAMES:
-        raise NotImplementedError("the training path covers the LSTM-family cells (AAGC / A3GC / AGC); G-GRU training "
-                                  "is not built yet")
+        raise ValueError(f"run_layer_train: unknown LSTM-family variant {variant!r} (the graph-GRU uses run_gru_layer_train)")
     nd = len(cells)
     H = cells[0].units_out
     if p_in > 0:
@@ -219,6 +218,131 @@ def run_layer_train(variant: str, cells: Sequence[torch.nn.Module], reverse: Seq
     outs = _LayerTrainFn.apply(meta, x, hmask, *flat)
     y = outs[0]
     return y, [(outs[1 + 2 * d], outs[2 + 2 * d]) for d in range(nd)]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# graph-GRU (G_GRU_cell, net_aagc.py:305-368): same scheme -- tape-keeping forward, reverse-time chain in CUDA, hoisted GEMMs
+# ----------------------------------------------------------------------------------------------------------------------
+GRU_PARAM_NAMES = ["dense_r_in.weight", "dense_r_in.bias", "dense_u_in.weight", "dense_u_in.bias", "dense_c_in.weight", "dense_c_in.bias",
+                   "dense_r_hid.weight", "dense_u_hid.weight", "dense_c_hid.weight", "adjacency", "gcn_kernel"]
+
+
+def _gru_params_struct(ps: Sequence[Tensor]) -> _lib.CellParams:
+    d = {n: _lib.require_cuda_f32(t, n) for n, t in zip(GRU_PARAM_NAMES, ps)}
+    p = _lib.CellParams()
+    p.g_gcn_kernel, p.g_adjacency = d["gcn_kernel"].data_ptr(), d["adjacency"].data_ptr()
+    for i, g in enumerate("ruc"):
+        p.dense_in_w[i] = d[f"dense_{g}_in.weight"].data_ptr()
+        p.dense_in_b[i] = d[f"dense_{g}_in.bias"].data_ptr()
+        p.dense_hid_w[i] = d[f"dense_{g}_hid.weight"].data_ptr()
+    return p
+
+
+class _GruLayerTrainFn(torch.autograd.Function):
+    """y, hT_0[, hT_1] = gru_layer(x, h0 per direction, params per direction)."""
+
+    @staticmethod
+    def forward(ctx, meta, x, *flat):
+        nd, reverse, ws = meta
+        npar = len(GRU_PARAM_NAMES)
+        h0 = [_lib.require_cuda_f32(t, "h0") for t in flat[:nd]]
+        params = [flat[nd + d * npar: nd + (d + 1) * npar] for d in range(nd)]
+        x = _lib.require_cuda_f32(x, "input")
+        B, T, _, F = x.shape
+        H = params[0][-1].shape[0]
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        tape = {"gates": torch.empty(nd, T, B, 4, H, 16, **f32), "c": torch.empty(nd, T, B, H, 16, **f32),
+                "hh": torch.empty(nd, T, B, H, 16, **f32), "hp": torch.empty(nd, B, T, NUM_NODES, H, **f32)}
+        y = torch.empty(B, T, NUM_NODES, nd * H, **f32)
+        hT = [torch.empty(B, NUM_NODES, H, **f32) for _ in range(nd)]
+        cells = (_lib.CellParams * nd)(*[_gru_params_struct(params[d]) for d in range(nd)])
+        rev = (C.c_int * nd)(*[int(r) for r in reverse])
+        tp = _lib.Tape(_lib.ptr(tape["gates"]), None, _lib.ptr(tape["c"]), _lib.ptr(tape["hh"]), None, _lib.ptr(tape["hp"]), None, None, None)
+        L = _lib.lib()
+        v = _lib.VARIANT["GGRU"]
+        with torch.cuda.device(dev):
+            wbuf = ws.get(L.a3gc_layer_train_workspace_bytes(v, B, T, F, H, nd, _lib.ENGINE["simt"]), dev)
+            rc = L.a3gc_layer_train_forward(
+                v, nd, cells, rev, x.data_ptr(), T * NUM_NODES * F, NUM_NODES * F, _lib.ptr_array(h0, nd), _lib.ptr_array(None, nd),
+                y.data_ptr(), T * NUM_NODES * nd * H, NUM_NODES * nd * H, nd * H, _lib.ptr_array(hT, nd), _lib.ptr_array(None, nd),
+                B, T, F, H, _lib.ACT["linear"], C.byref(tp), None, _lib.ENGINE["simt"], wbuf.data_ptr(), wbuf.numel(), _lib.stream_ptr(dev))
+        _lib.check(rc, "a3gc_layer_train_forward")
+        ctx.meta, ctx.tape, ctx.shape = meta, tape, (B, T, F, H)
+        ctx.save_for_backward(x, *h0, *[t for ps in params for t in ps])
+        return (y, *hT)
+
+    @staticmethod
+    def backward(ctx, dy, *dhT):
+        nd, reverse, ws = ctx.meta
+        npar = len(GRU_PARAM_NAMES)
+        B, T, F, H = ctx.shape
+        saved = ctx.saved_tensors
+        x, h0 = saved[0], saved[1:1 + nd]
+        params = [saved[1 + nd + d * npar: 1 + nd + (d + 1) * npar] for d in range(nd)]
+        tape = ctx.tape
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        dy = dy.contiguous() if dy is not None else torch.zeros(B, T, NUM_NODES, nd * H, **f32)
+        dhTc = [None if g is None else g.contiguous() for g in dhT]
+        gr = {"dzm": torch.empty(nd, B, T, NUM_NODES, 4 * H, **f32), "dep": torch.empty(nd, T, B, H, 16, **f32),
+              "dqs": torch.empty(nd, B, T, NUM_NODES, H, **f32)}
+        dh0 = [torch.empty(B, NUM_NODES, H, **f32) for _ in range(nd)]
+        cells = (_lib.CellParams * nd)(*[_gru_params_struct(params[d]) for d in range(nd)])
+        rev = (C.c_int * nd)(*[int(r) for r in reverse])
+        tp = _lib.Tape(_lib.ptr(tape["gates"]), None, _lib.ptr(tape["c"]), _lib.ptr(tape["hh"]), None, _lib.ptr(tape["hp"]), None, None, None)
+        tg = _lib.TapeGrads(_lib.ptr(gr["dzm"]), _lib.ptr(gr["dep"]), _lib.ptr(gr["dqs"]), None, None)
+        L = _lib.lib()
+        v = _lib.VARIANT["GGRU"]
+        with torch.cuda.device(dev):
+            wbuf = ws.get(L.a3gc_layer_train_workspace_bytes(v, B, T, F, H, nd, _lib.ENGINE["simt"]), dev)
+            rc = L.a3gc_layer_backward(
+                v, nd, cells, rev, dy.data_ptr(), T * NUM_NODES * nd * H, NUM_NODES * nd * H, nd * H,
+                _lib.ptr_array(list(h0), nd), _lib.ptr_array(dhTc, nd), _lib.ptr_array(None, nd), _lib.ptr_array(dh0, nd), _lib.ptr_array(None, nd),
+                B, T, F, H, _lib.ACT["linear"], C.byref(tp), C.byref(tg), None, wbuf.data_ptr(), wbuf.numel(), _lib.stream_ptr(dev))
+        _lib.check(rc, "a3gc_layer_backward")
+        R = B * T * NUM_NODES
+        x2d = x.reshape(R, F)
+        dx = torch.zeros(R, F, **f32)
+        grads: List[Optional[Tensor]] = []
+        for d in range(nd):
+            ps = dict(zip(GRU_PARAM_NAMES, params[d]))
+            dzm2d = gr["dzm"][d].reshape(R, 4 * H)                        # (dzr | dzu | dzc | dzc r)
+            dz_in = dzm2d[:, :3 * H]
+            dW_in = dz_in.t() @ x2d                                       # [3H, F]
+            db_in = dz_in.sum(0)
+            dx.addmm_(dz_in, torch.cat([ps[f"dense_{g}_in.weight"] for g in "ruc"], dim=0))
+            msg2d = tape["hh"][d].permute(1, 0, 3, 2)[:, :, :NUM_NODES].reshape(R, H)       # [T,B,H,16] -> [B,T,15,H]
+            dz_hid = torch.cat((dzm2d[:, :2 * H], dzm2d[:, 3 * H:]), dim=1)
+            dW_hid = dz_hid.t() @ msg2d                                   # [3H, H]
+            hp = tape["hp"][d]
+            hprev = torch.cat((hp[:, 1:], h0[d].unsqueeze(1)), dim=1) if reverse[d] else torch.cat((h0[d].unsqueeze(1), hp[:, :-1]), dim=1)
+            dWg = gr["dqs"][d].reshape(R, H).t() @ hprev.reshape(R, H)    # gcn_kernel [j][k']
+            dmsg = gr["dep"][d].reshape(T * B, H, 16)
+            M = tape["c"][d].reshape(T * B, H, 16)
+            dP = torch.bmm(dmsg.transpose(1, 2), M).sum(0)                # dP[n][m]; the parameter is used transposed (net_aagc.py:348)
+            out = {"adjacency": dP.t()[:NUM_NODES, :NUM_NODES].contiguous(), "gcn_kernel": dWg}
+            for i, g in enumerate("ruc"):
+                out[f"dense_{g}_in.weight"] = dW_in[i * H:(i + 1) * H]
+                out[f"dense_{g}_in.bias"] = db_in[i * H:(i + 1) * H]
+                out[f"dense_{g}_hid.weight"] = dW_hid[i * H:(i + 1) * H]
+            grads += [out[n] for n in GRU_PARAM_NAMES]
+        ctx.tape = None
+        return (None, dx.reshape(B, T, NUM_NODES, F), *dh0, *grads)
+
+
+def run_gru_layer_train(cells: Sequence[torch.nn.Module], reverse: Sequence[int], x: Tensor, states: Sequence[Tensor], ws: _lib.Workspace):
+    """Differentiable batch-major forward of one (bi) graph-GRU layer.  The cell's dropout arguments are unused (net_aagc.py:343-368)."""
+    nd = len(cells)
+    flat: List[Tensor] = list(states)
+    for c in cells:
+        for n in GRU_PARAM_NAMES:
+            obj = c
+            for part in n.split("."):
+                obj = getattr(obj, part)
+            flat.append(obj)
+    outs = _GruLayerTrainFn.apply((nd, tuple(int(r) for r in reverse), ws), x, *flat)
+    return outs[0], list(outs[1:])
 
 
 def gc_train(mod: torch.nn.Module, x: Tensor, act: str, p_drop: float) -> Tensor:

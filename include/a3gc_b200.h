@@ -174,7 +174,11 @@ int a3gc_net_forward(int variant, const a3gc_net_params* net, const float* x,
  *
  * All tape arrays are caller-allocated fp32.  Unit-major arrays hold one record per (direction d, time t,
  * sequence b) at index (d*T + t)*B + b, each unit row = the 15 nodes padded to 16 (slot 15 = 0); node-major
- * arrays are [D][B][T][15][.] like the layer input.  G-GRU is not supported.
+ * arrays are [D][B][T][15][.] like the layer input.
+ * G-GRU (net_aagc.py:343-368) reuses the structs with this meaning: tape.gates = (r, u, c, Wch msg), tape.c = h Wg^T before
+ * the node mix, tape.hh = msg, tape.hp = h'; grads.dzm = (dzr, dzu, dzc, dzc r) node-major [D][B][T][15][4H], grads.dep = dmsg
+ * (unit-major [D][T][B][H][16]), grads.dqs = dM = P^T dmsg node-major [D][B][T][15][H]; the other fields are unused, and
+ * a3gc_layer_backward's c0 argument carries the forward's initial h (the G-GRU state is a single tensor).
  */
 typedef struct a3gc_tape {
   float* gates; /* [D][T][B][4][H][16] activated i, f, c~, o; OVERWRITTEN by the backward with dz (gate pre-activation grads) */

@@ -24,7 +24,8 @@ def _oracle_grads(variant, x, sd, target, h=None):
 
 @pytest.mark.parametrize("variant,hidden,B,T", [("A3GC", 24, 5, 7), ("AAGC", 24, 3, 6), ("AGC", 24, 4, 5),      # CUDA-core forward
                                                 ("A3GC", 64, 3, 9), ("A3GC", 128, 2, 4), ("AAGC", 64, 9, 3),     # tcgen05 forward
-                                                ("AGC", 128, 11, 5), ("A3GC", 256, 2, 3)])
+                                                ("AGC", 128, 11, 5), ("A3GC", 256, 2, 3),
+                                                ("GGRU", 24, 5, 6), ("GGRU", 64, 9, 4)])                         # graph-GRU (CUDA-core)
 def test_net_train_step_matches_oracle_autograd(variant, hidden, B, T, nira):
     f0, out = 15, 9
     sd = O.random_state_dict(variant, f0, out, hidden, nira, seed=21)
@@ -101,8 +102,6 @@ def test_train_mode_dropout_runs_and_is_stochastic(hidden, nira):
     assert torch.isfinite(y1).all() and not torch.equal(y1, y2)
     y1.square().mean().backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters() if p.requires_grad)
-    with pytest.raises(NotImplementedError):
-        A.G_GRU_net(12, 3, 16, nira.float()).cuda().train()(x)
 
 
 def test_recurrent_dropout_mask_semantics_tc_vs_simt(nira):
