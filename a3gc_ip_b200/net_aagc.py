@@ -42,13 +42,6 @@ def _adj_param(adjacency_matrix: Tensor, requires_grad: bool = True, transpose: 
     return Parameter(a.detach().to(torch.float32).clone().contiguous(), requires_grad=requires_grad)
 
 
-def _no_training(mod: torch.nn.Module, *ps: float) -> None:
-    if mod.training and any(p > 0 for p in ps):
-        raise NotImplementedError(
-            f"{type(mod).__name__}: forward in train() mode with dropout > 0 is not implemented by the "
-            "B200 kernels yet (inference path only); call .eval() first")
-
-
 class _EngineMixin:
     """Engine / precision selection shared by all modules (not part of the reference's API)."""
     engine: str = os.environ.get("A3GC_ENGINE", "auto")
