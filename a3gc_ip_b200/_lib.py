@@ -121,7 +121,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         srcs.append(os.path.join(os.path.dirname(_HERE), "include", "a3gc_b200.h"))
         if all(os.path.getmtime(s) <= os.path.getmtime(LIB_PATH) for s in srcs):
             return LIB_PATH
-    cmd = ["make", "-C", CSRC_DIR] + (["-B"] if force else [])
+    cmd = ["make", "-C", CSRC_DIR, "-j", str(min(8, os.cpu_count() or 1))] + (["-B"] if force else [])
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout[-8000:])
