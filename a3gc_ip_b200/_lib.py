@@ -98,6 +98,9 @@ SYMBOLS = {
     "a3gc_prepare_input": (C.c_int, [C.c_void_p] * 7 + [C.c_int64, C.c_int, C.c_void_p]),
     "a3gc_concat_stage_input": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "a3gc_reduced_to_full_local": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "a3gc_train_split_tf32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "a3gc_train_hprev_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                         C.c_int, C.c_int, C.c_void_p]),
     "a3gc_profile_enable": (C.c_int, [C.c_int]),
     "a3gc_profile_count": (C.c_int, []),
     "a3gc_profile_get": (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double)]),

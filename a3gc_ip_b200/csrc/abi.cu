@@ -436,6 +436,24 @@ int a3gc_reduced_to_full_local(const float* pose, float* out, int64_t frames, in
   return simt_reduced_to_full_local(pose, out, frames, rotsize, static_cast<cudaStream_t>(stream));
 }
 
+int a3gc_train_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
+  if (n < 0 || (n > 0 && (!x || !hi || !lo))) { set_error("a3gc_train_split_tf32: invalid argument"); return A3GC_ERR_INVALID_ARG; }
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) {
+    set_error("a3gc_train_split_tf32: buffers must be 16-byte aligned");
+    return A3GC_ERR_INVALID_ARG;
+  }
+  return train_split_tf32(x, hi, lo, n, static_cast<cudaStream_t>(stream));
+}
+
+int a3gc_train_hprev_split(const float* hp, const float* h0, const float* mask, float* hi, float* lo, int64_t batch,
+                           int64_t steps, int hidden, int reverse, void* stream) {
+  if (batch < 0 || steps < 0 || hidden <= 0 || hidden % 4 != 0 || (batch * steps > 0 && (!hp || !hi || !lo))) {
+    set_error("a3gc_train_hprev_split: invalid argument (hidden must be a positive multiple of 4)");
+    return A3GC_ERR_INVALID_ARG;
+  }
+  return train_hprev_split(hp, h0, mask, hi, lo, batch, steps, hidden, reverse, static_cast<cudaStream_t>(stream));
+}
+
 int a3gc_concat_stage_input(const float* x, const float* pos, float* dst, int64_t frames, void* stream) {
   if (frames < 0 || (frames > 0 && (!x || !pos || !dst))) { set_error("a3gc_concat_stage_input: invalid argument"); return A3GC_ERR_INVALID_ARG; }
   return simt_concat_stage_input(x, pos, dst, frames, static_cast<cudaStream_t>(stream));

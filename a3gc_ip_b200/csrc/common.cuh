@@ -101,6 +101,9 @@ int simt_prepare_input(const float* acc, const float* ori, const float* acc_mean
                        cudaStream_t stream);
 int simt_concat_stage_input(const float* x, const float* pos, float* dst, int64_t frames, cudaStream_t stream);
 int simt_reduced_to_full_local(const float* pose, float* out, int64_t frames, int rotsize, cudaStream_t stream);
+int train_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream);
+int train_hprev_split(const float* hp, const float* h0, const float* mask, float* hi, float* lo, int64_t batch,
+                      int64_t steps, int hidden, int reverse, cudaStream_t stream);
 
 
 // training path (simt_kernels.cu): forward with a tape, reverse-time backward chain

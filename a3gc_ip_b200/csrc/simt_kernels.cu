@@ -812,6 +812,342 @@ lstm_train_bwd_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
   store_state(d.dc0, dc, b0, lg);
 }
 
+// acc[si][ui][n] += sum_{k0 <= k < k1} act[si][k][n] * w[k * ldw + ui * ustride]   (act: shared [seq][k][16])
+// Register blocking over NS sequences x NU units: one weight load feeds 16 * NS FMAs, one activation float4 4 * NU.
+template <int NS, int NU>
+__device__ __forceinline__ void accum_blk(float (&acc)[NS][NU][16], const float* __restrict__ act, size_t seq_stride,
+                                          const float* __restrict__ w, int ldw, int ustride, int k0, int k1) {
+#pragma unroll 4
+  for (int k = k0; k < k1; ++k) {
+    float wv[NU];
+#pragma unroll
+    for (int ui = 0; ui < NU; ++ui) wv[ui] = __ldg(w + (size_t)k * ldw + ui * ustride);
+#pragma unroll
+    for (int si = 0; si < NS; ++si) {
+      const float4* a4 = reinterpret_cast<const float4*>(act + si * seq_stride + (size_t)k * kNodesPad);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = a4[q];
+#pragma unroll
+        for (int ui = 0; ui < NU; ++ui) {
+          acc[si][ui][4 * q] = fmaf(wv[ui], v.x, acc[si][ui][4 * q]);
+          acc[si][ui][4 * q + 1] = fmaf(wv[ui], v.y, acc[si][ui][4 * q + 1]);
+          acc[si][ui][4 * q + 2] = fmaf(wv[ui], v.z, acc[si][ui][4 * q + 2]);
+          acc[si][ui][4 * q + 3] = fmaf(wv[ui], v.w, acc[si][ui][4 * q + 3]);
+        }
+      }
+    }
+  }
+}
+
+// Same chain as lstm_train_bwd_kernel for H in {64, 128, 256}, arranged around the two weight contractions that
+// dominate it (phase E: dep x Wh, phase G: dzm x W[:, F:]).  BT * H = 512 (or 256): a thread owns 2 sequences x 2
+// units (u, u + H/2) and 1/KS of the contraction range, so the weights cross L2 once per sequence PAIR and every
+// activation float4 read from shared memory feeds 8 FMAs; the KS partial sums meet in shared memory.  dhy overwrites
+// dh' in place and dep lives in dzm[0], which leaves room for two H=256 sequences per CTA.
+template <bool ATT>
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
+  extern __shared__ __align__(16) float smem[];
+  const BwdDir d = blockIdx.y == 0 ? d0 : d1;
+  const a3gc_tape& tp = g.tape;
+  const a3gc_tape_grads& gr = g.gr;
+  const int H = g.H, F = g.F, BT = g.BT, K = F + H;
+  const size_t HN = (size_t)H * kNodesPad;
+  float* dh = smem;                       // [BT][H][16]  gradient wrt h'_t carried from the later step; then dhy_t in place
+  float* dc = dh + BT * HN;               // [BT][H][16]
+  float* dzm = dc + BT * HN;              // [4][BT][H][16]
+  float* dep = dzm;                       // (ATT) [BT][H][16] until phase F; dzm[1] is scratch for the GEMV partial sums
+  float* scr = dzm + BT * HN;
+  float* v1 = dzm + 4 * BT * HN;          // [BT][H]   dqs, then ds
+  float* v2 = v1 + BT * H;                // [BT][H]   dqp
+  float* abuf = v2 + BT * H;              // [BT][16]  dap
+  float* al = abuf + BT * kNodesPad;      // [BT][16]  alpha
+  float* red = al + BT * kNodesPad;       // [256]
+  float* PT = red + 256;                  // [4][16][16]
+  const int b0 = blockIdx.x * BT;
+  const int y_off = blockIdx.y * H;
+  const int ntask = BT * H;
+  // blocked phases: thread -> (kh, sequence pair sp, unit pair u / u + UH)
+  const int UH = H / 2, ntile = UH * (BT / 2), KS = kThreads / ntile;
+  const int u = threadIdx.x % UH, s0 = 2 * ((threadIdx.x / UH) % (BT / 2)), kh = threadIdx.x / ntile;
+  const int kq = H / KS, k0 = kh * kq, k1 = k0 + kq;
+  // GEMV phases: thread -> (kd, unit j), all BT sequences
+  const int KD = kThreads / H, jd = threadIdx.x % H, kd = threadIdx.x / H;
+  const int kdq = H / KD;
+  LayerGeom lg; lg.B = g.B; lg.H = H; lg.BT = BT;
+  load_state(dh, d.dhT, b0, lg);
+  load_state(dc, d.dcT, b0, lg);
+  for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) PT[i] = d.PT[i];
+
+  for (int step = g.T - 1; step >= 0; --step) {
+    const int t = d.reverse ? g.T - 1 - step : step;
+    const int tprev = d.reverse ? t + 1 : t - 1;
+    const size_t rec0 = ((size_t)blockIdx.y * g.T + t) * g.B;
+    const size_t recp0 = ((size_t)blockIdx.y * g.T + tprev) * g.B;
+    const size_t nm0 = ((size_t)blockIdx.y * g.B * g.T + t) * kNodes;
+    __syncthreads();
+    // ---- A: dh' += dY (1 - y^2);  dhy = dh' (1 + alpha) (in place);  partial dalpha[n] = sum_j dh' hy
+    if (ATT) {
+      for (int i = threadIdx.x; i < BT * kNodesPad; i += blockDim.x) {
+        const int b = b0 + i / kNodesPad;
+        al[i] = b < g.B ? tp.a[(rec0 + b) * kNodesPad + i % kNodesPad] : 0.f;
+      }
+      __syncthreads();
+    }
+    for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+      const int s = task / H, j = task % H, b = b0 + s;
+      float dv[16];
+      load16(dv, dh + (size_t)task * kNodesPad);
+      if (b < g.B) {
+        const float* hpp = tp.hp + (nm0 + (size_t)b * g.T * kNodes) * H + j;
+        const float* yp = g.dy + (size_t)b * g.syb + (size_t)t * g.syt + y_off + j;
+#pragma unroll
+        for (int n = 0; n < kNodes; ++n) {
+          const float gy = __ldg(yp + (size_t)n * g.yld);
+          if (g.out_act == A3GC_ACT_TANH) { const float y = tanhf(hpp[(size_t)n * H]); dv[n] = fmaf(gy, 1.0f - y * y, dv[n]); }
+          else dv[n] += gy;
+        }
+        dv[15] = 0.f;
+        if (ATT) {
+          float hh[16], pa[16], av[16];
+          load16(hh, tp.hh + ((rec0 + b) * H + j) * kNodesPad);
+          load16(av, al + (size_t)s * kNodesPad);
+#pragma unroll
+          for (int n = 0; n < 16; ++n) { pa[n] = dv[n] * hh[n]; dv[n] *= 1.0f + av[n]; }
+          store16(dep + (size_t)task * kNodesPad, pa);
+        }
+      } else {
+#pragma unroll
+        for (int n = 0; n < 16; ++n) dv[n] = 0.f;
+        if (ATT) store16(dep + (size_t)task * kNodesPad, dv);
+      }
+      store16(dh + (size_t)task * kNodesPad, dv);
+    }
+    if (ATT) {
+      __syncthreads();
+      // ---- B: dalpha[n] = sum_j partial (all threads, then BT*16 of them);  dap = dalpha * a (1 - a)
+      {
+        const int nI = BT * kNodesPad, parts = kThreads / nI;
+        const int i = threadIdx.x % nI, part = threadIdx.x / nI;
+        const int s = i / kNodesPad, n = i % kNodesPad;
+        const int jq = H / parts;
+        const float* pv = dep + (size_t)s * HN + (size_t)part * jq * kNodesPad + n;
+        float a = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < jq; ++j) a += pv[(size_t)j * kNodesPad];
+        red[threadIdx.x] = a;
+        __syncthreads();
+        if (threadIdx.x < nI) {
+          float tot = 0.f;
+          for (int q = 0; q < parts; ++q) tot += red[q * nI + i];
+          const float sg = al[i];
+          tot *= sg * (1.0f - sg);
+          abuf[i] = tot;
+          if (b0 + s < g.B) gr.dap[(rec0 + b0 + s) * kNodesPad + n] = tot;
+        }
+      }
+      __syncthreads();
+      // ---- C: dep[n][j] = dap[n] u_j (1 - e^2);  dqs_j = sum_n dep
+      for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+        const int s = task / H, j = task % H, b = b0 + s;
+        float e[16], av[16], o[16];
+        float sum = 0.f;
+        if (b < g.B) {
+          load16(e, tp.e + ((rec0 + b) * H + j) * kNodesPad);
+          load16(av, abuf + (size_t)s * kNodesPad);
+          const float uj = d.u[j];
+#pragma unroll
+          for (int n = 0; n < 16; ++n) { o[n] = av[n] * uj * (1.0f - e[n] * e[n]); sum += o[n]; }
+          store16(gr.dep + ((rec0 + b) * H + j) * kNodesPad, o);
+          gr.dqs[(rec0 + b) * H + j] = sum;
+        } else {
+#pragma unroll
+          for (int n = 0; n < 16; ++n) o[n] = 0.f;
+        }
+        store16(dep + (size_t)task * kNodesPad, o);
+        v1[task] = sum;
+      }
+      __syncthreads();
+      // ---- D: dq_j = sum_k dqs_k Wq[k][j] for all BT sequences at once;  dqp = dq [q > 0]
+      {
+        float part[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) part[s] = 0.f;
+#pragma unroll 4
+        for (int k = kd * kdq; k < (kd + 1) * kdq; ++k) {
+          const float wv = __ldg(d.Wq + (size_t)k * H + jd);
+#pragma unroll
+          for (int s = 0; s < 8; ++s) if (s < BT) part[s] = fmaf(v1[s * H + k], wv, part[s]);
+        }
+#pragma unroll
+        for (int s = 0; s < 8; ++s) if (s < BT) scr[(kd * BT + s) * H + jd] = part[s];
+      }
+      __syncthreads();
+      for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+        const int s = task / H, j = task % H, b = b0 + s;
+        float dq = 0.f;
+        for (int q = 0; q < KD; ++q) dq += scr[(q * BT + s) * H + j];
+        float r = 0.f;
+        if (b < g.B) {
+          r = tp.q[(rec0 + b) * H + j] > 0.f ? dq : 0.f;
+          gr.dqp[(rec0 + b) * H + j] = r;
+        }
+        v2[task] = r;
+      }
+      __syncthreads();
+      // ---- D2: ds_j = sum_k dqp_k Wa[k][j]  (-> v1)
+      {
+        float part[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) part[s] = 0.f;
+#pragma unroll 4
+        for (int k = kd * kdq; k < (kd + 1) * kdq; ++k) {
+          const float wv = __ldg(d.Wa + (size_t)k * H + jd);
+#pragma unroll
+          for (int s = 0; s < 8; ++s) if (s < BT) part[s] = fmaf(v2[s * H + k], wv, part[s]);
+        }
+#pragma unroll
+        for (int s = 0; s < 8; ++s) if (s < BT) scr[(kd * BT + s) * H + jd] = part[s];
+      }
+      __syncthreads();
+      for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+        float ds = 0.f;
+        for (int q = 0; q < KD; ++q) ds += scr[(q * BT + task / H) * H + task % H];
+        v1[task] = ds;
+      }
+      // ---- E: dhy[n][j] += ds_j + sum_k dep[n][k] Wh[k][j]
+      {
+        float acc[2][2][16];
+#pragma unroll
+        for (int si = 0; si < 2; ++si)
+#pragma unroll
+          for (int ui = 0; ui < 2; ++ui)
+#pragma unroll
+            for (int n = 0; n < 16; ++n) acc[si][ui][n] = 0.f;
+        accum_blk<2, 2>(acc, dep + (size_t)s0 * HN, HN, d.Wh + u, H, UH, k0, k1);
+        __syncthreads();                                           // v1 = ds complete
+        for (int r = 0; r < KS; ++r) {
+          if (kh == r) {
+#pragma unroll
+            for (int si = 0; si < 2; ++si)
+#pragma unroll
+              for (int ui = 0; ui < 2; ++ui) {
+                const int task = (s0 + si) * H + u + ui * UH;
+                float cur[16];
+                load16(cur, dh + (size_t)task * kNodesPad);
+                const float ds = r == 0 ? v1[task] : 0.f;
+#pragma unroll
+                for (int n = 0; n < kNodes; ++n) cur[n] += acc[si][ui][n] + ds;
+                cur[15] = 0.f;
+                store16(dh + (size_t)task * kNodesPad, cur);
+              }
+          }
+          if (r + 1 < KS) __syncthreads();
+        }
+      }
+    }
+    __syncthreads();
+    // ---- F: LSTM pointwise backward, dz (global, in place of the gates) and dzm = P_g^T dz_g
+    for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+      const int s = task / H, j = task % H, b = b0 + s;
+      float dz[4][16];
+      float dcv[16];
+      if (b < g.B) {
+        float gi[16], gf[16], gg[16], go[16], cc[16], cp[16], dv[16];
+        float* gp = tp.gates + ((rec0 + b) * 4 * H + j) * kNodesPad;
+        load16(gi, gp); load16(gf, gp + HN); load16(gg, gp + 2 * HN); load16(go, gp + 3 * HN);
+        load16(cc, tp.c + ((rec0 + b) * H + j) * kNodesPad);
+        if (step > 0) load16(cp, tp.c + ((recp0 + b) * H + j) * kNodesPad);
+        else {
+#pragma unroll
+          for (int n = 0; n < 16; ++n) cp[n] = (d.c0 != nullptr && n < kNodes) ? d.c0[((size_t)b * kNodes + n) * H + j] : 0.f;
+        }
+        load16(dv, dh + (size_t)task * kNodesPad);
+        load16(dcv, dc + (size_t)task * kNodesPad);
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
+          const float tc = tanhf(cc[n]);
+          const float dcn = fmaf(dv[n] * go[n], 1.0f - tc * tc, dcv[n]);
+          dz[3][n] = dv[n] * tc * go[n] * (1.0f - go[n]);
+          dz[0][n] = dcn * gg[n] * gi[n] * (1.0f - gi[n]);
+          dz[1][n] = dcn * cp[n] * gf[n] * (1.0f - gf[n]);
+          dz[2][n] = dcn * gi[n] * (1.0f - gg[n] * gg[n]);
+          dcv[n] = dcn * gf[n];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { dz[q][15] = 0.f; store16(gp + q * HN, dz[q]); }
+        dcv[15] = 0.f;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int n = 0; n < 16; ++n) dz[q][n] = 0.f;
+#pragma unroll
+        for (int n = 0; n < 16; ++n) dcv[n] = 0.f;
+      }
+      store16(dc + (size_t)task * kNodesPad, dcv);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float m[16];
+        mix15(dz[q], PT + q * 256, m);
+        store16(dzm + ((size_t)q * BT * H + task) * kNodesPad, m);
+        if (b < g.B) {
+          float* zp = gr.dzm + (nm0 + (size_t)b * g.T * kNodes) * 4 * H + (size_t)q * H + j;
+#pragma unroll
+          for (int n = 0; n < kNodes; ++n) zp[(size_t)n * 4 * H] = m[n];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- G: dh'_{prev}[n][k] = sum_g sum_j dzm_g[n][j] W_g[j][F + k]   (then the recurrent-dropout mask of this step)
+    {
+      float acc[2][2][16];
+#pragma unroll
+      for (int si = 0; si < 2; ++si)
+#pragma unroll
+        for (int ui = 0; ui < 2; ++ui)
+#pragma unroll
+          for (int n = 0; n < 16; ++n) acc[si][ui][n] = 0.f;
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) accum_blk<2, 2>(acc, dzm + ((size_t)q * BT + s0) * HN, HN, d.Wg[q] + F + u, K, UH, k0, k1);
+      for (int r = 0; r < KS; ++r) {
+        if (kh == r) {
+#pragma unroll
+          for (int si = 0; si < 2; ++si)
+#pragma unroll
+            for (int ui = 0; ui < 2; ++ui) {
+              const int k = u + ui * UH, b = b0 + s0 + si;
+              const int task = (s0 + si) * H + k;
+              float cur[16];
+              if (r > 0) {
+                load16(cur, dh + (size_t)task * kNodesPad);
+#pragma unroll
+                for (int n = 0; n < 16; ++n) cur[n] += acc[si][ui][n];
+              } else {
+#pragma unroll
+                for (int n = 0; n < 16; ++n) cur[n] = acc[si][ui][n];
+              }
+              if (r == KS - 1) {
+                cur[15] = 0.f;
+                if (g.hmask != nullptr && b < g.B) {
+                  const float* mp = g.hmask + (nm0 + (size_t)b * g.T * kNodes) * H + k;
+#pragma unroll
+                  for (int n = 0; n < kNodes; ++n) cur[n] *= mp[(size_t)n * H];
+                }
+              }
+              store16(dh + (size_t)task * kNodesPad, cur);
+            }
+        }
+        if (r + 1 < KS) __syncthreads();
+      }
+    }
+  }
+  __syncthreads();
+  store_state(d.dh0, dh, b0, lg);
+  store_state(d.dc0, dc, b0, lg);
+}
+
 // Reverse-time chain of the graph-GRU (net_aagc.py:343-368).  Per step, with dh' = carried gradient + dY_t:
 //   du = dh' (h_prev - c), dc = dh' (1 - u), dzc = dc (1 - c^2), dzr = dzc zch r (1 - r), dzu = du u (1 - u), dzch = dzc r
 //   dmsg = dzr Wrh + dzu Wuh + dzch Wch,  dM = P^T dmsg,  dh_prev = dh' u + dM Wg
@@ -1406,14 +1742,30 @@ int simt_train_backward(const TrainBwdArgs& a, void* ws, size_t ws_bytes, cudaSt
   auto smem_bytes = [&](int bt) -> size_t {
     return ((size_t)8 * bt * H * 16 + (size_t)2 * bt * H + (size_t)2 * bt * 16 + 1024) * sizeof(float);
   };
-  int BT = 8;
-  while (BT > 1 && smem_bytes(BT) > (size_t)smem_max) --BT;
   int sms = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  while (BT > 1 && ((a.batch + BT - 1) / BT) * a.num_dirs < sms) --BT;
-  if (smem_bytes(BT) > (size_t)smem_max) {
-    set_error("training backward: hidden=%d needs %zu bytes of shared memory (> %d)", H, smem_bytes(1), smem_max);
-    return A3GC_ERR_UNSUPPORTED;
+  // blocked kernel (H in {64, 128, 256}): BT * H = 512, halved once when that would leave more than half of the SMs idle
+  const char* blk_env = getenv("A3GC_BWD_BLK");
+  const bool blk = (H == 64 || H == 128 || H == 256) && !(blk_env != nullptr && blk_env[0] == '0');
+  auto blk_smem_bytes = [&](int bt) -> size_t {
+    return ((size_t)6 * bt * H * 16 + (size_t)2 * bt * H + (size_t)2 * bt * 16 + 256 + 1024) * sizeof(float);
+  };
+  int BT = 8;
+  if (blk) {
+    BT = 512 / H;
+    if (((a.batch + BT - 1) / BT) * a.num_dirs * 2 <= sms && BT >= 4) BT /= 2;
+    if (const char* e = getenv("A3GC_BWD_BT")) { const int v = atoi(e); if (v == 512 / H || (v == 256 / H && v >= 2)) BT = v; }
+    if (blk_smem_bytes(BT) > (size_t)smem_max) {
+      set_error("training backward: hidden=%d needs %zu bytes of shared memory (> %d)", H, blk_smem_bytes(BT), smem_max);
+      return A3GC_ERR_UNSUPPORTED;
+    }
+  } else {
+    while (BT > 1 && smem_bytes(BT) > (size_t)smem_max) --BT;
+    while (BT > 1 && ((a.batch + BT - 1) / BT) * a.num_dirs < sms) --BT;
+    if (smem_bytes(BT) > (size_t)smem_max) {
+      set_error("training backward: hidden=%d needs %zu bytes of shared memory (> %d)", H, smem_bytes(1), smem_max);
+      return A3GC_ERR_UNSUPPORTED;
+    }
   }
   char* base = static_cast<char*>(ws);
   const size_t per = need / a.num_dirs;
@@ -1434,6 +1786,18 @@ int simt_train_backward(const TrainBwdArgs& a, void* ws, size_t ws_bytes, cudaSt
   g.tape = a.tape; g.gr = a.grads; g.hmask = a.hmask;
   g.B = (int)a.batch; g.T = (int)a.steps; g.F = F; g.H = H; g.out_act = a.out_act; g.BT = BT;
   dim3 grid((unsigned)((a.batch + BT - 1) / BT), (unsigned)a.num_dirs);
+  if (blk) {
+    const size_t bsmem = blk_smem_bytes(BT);
+    if (att) {
+      A3GC_CUDA_TRY(cudaFuncSetAttribute(lstm_train_bwd_blk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+      lstm_train_bwd_blk_kernel<true><<<grid, kThreads, bsmem, stream>>>(bd[0], bd[1], g);
+    } else {
+      A3GC_CUDA_TRY(cudaFuncSetAttribute(lstm_train_bwd_blk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+      lstm_train_bwd_blk_kernel<false><<<grid, kThreads, bsmem, stream>>>(bd[0], bd[1], g);
+    }
+    A3GC_LAUNCH_CHECK("lstm_train_bwd_blk_kernel");
+    return A3GC_OK;
+  }
   const size_t smem = smem_bytes(BT);
   if (att) {
     A3GC_CUDA_TRY(cudaFuncSetAttribute(lstm_train_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,0 +1,89 @@
+// Helpers of the training step that are not part of the recurrent chain: operand preparation for the hoisted
+// weight / input gradient GEMMs (train_a3gc_tp.py:74-84 runs them as autograd mm/bmm nodes in fp32).
+//
+// The hoisted GEMMs run on the tensor cores as three TF32 passes (hi*hi + lo*hi + hi*lo): every fp32 operand is cut
+// into a head that is exactly representable in TF32 (cvt.rna, 11 significand bits) and the fp32 remainder, so the
+// library's TF32 conversion of the head is exact and the dropped lo*lo term is 2^-22 relative.
+#include "common.cuh"
+
+namespace a3gc {
+namespace {
+
+__device__ __forceinline__ float tf32_head(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi,
+                                                         float4* __restrict__ lo, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    float4 h, l;
+    h.x = tf32_head(v.x); h.y = tf32_head(v.y); h.z = tf32_head(v.z); h.w = tf32_head(v.w);
+    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+    hi[i] = h; lo[i] = l;
+  }
+}
+
+__global__ void split_tf32_tail_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
+                                       int64_t first, int64_t n) {
+  const int64_t i = first + threadIdx.x;
+  if (i < n) { const float h = tf32_head(x[i]); hi[i] = h; lo[i] = x[i] - h; }
+}
+
+// S_h operand of dW_h = dzm^T S_h: the state that entered step t of one direction, i.e. h' of the previous step of
+// that direction (h0 at its first step) times the recurrent-dropout mask of step t (net_aagc.py:181-182), split.
+//   hp [B][T][15][H] (tape), h0 [B][15][H] or nullptr (zeros), mask [B][T][15][H] or nullptr
+__global__ void __launch_bounds__(256) hprev_split_kernel(const float4* __restrict__ hp, const float4* __restrict__ h0,
+                                                          const float4* __restrict__ mask, float4* __restrict__ hi,
+                                                          float4* __restrict__ lo, int B, int T, int row4, int reverse) {
+  const int64_t n4 = (int64_t)B * T * row4;                     // row4 = 15*H/4 float4 per (b, t)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bt = i / row4;
+    const int r = (int)(i - bt * row4);
+    const int b = (int)(bt / T), t = (int)(bt - (int64_t)b * T);
+    const int tp = reverse ? t + 1 : t - 1;
+    float4 v;
+    if (tp < 0 || tp >= T) v = h0 != nullptr ? __ldg(h0 + (int64_t)b * row4 + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+    else v = __ldg(hp + ((int64_t)b * T + tp) * row4 + r);
+    if (mask != nullptr) { const float4 m = __ldg(mask + i); v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w; }
+    float4 h, l;
+    h.x = tf32_head(v.x); h.y = tf32_head(v.y); h.z = tf32_head(v.z); h.w = tf32_head(v.w);
+    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+    hi[i] = h; lo[i] = l;
+  }
+}
+
+}  // namespace
+
+int train_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream) {
+  if (n == 0) return A3GC_OK;
+  const int64_t n4 = n / 4;
+  if (n4 > 0) {
+    const int64_t blocks = (n4 + 255) / 256;
+    split_tf32_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo), n4);
+    A3GC_LAUNCH_CHECK("split_tf32_kernel");
+  }
+  if (n4 * 4 < n) {
+    split_tf32_tail_kernel<<<1, 32, 0, stream>>>(x, hi, lo, n4 * 4, n);
+    A3GC_LAUNCH_CHECK("split_tf32_tail_kernel");
+  }
+  return A3GC_OK;
+}
+
+int train_hprev_split(const float* hp, const float* h0, const float* mask, float* hi, float* lo, int64_t batch,
+                      int64_t steps, int hidden, int reverse, cudaStream_t stream) {
+  if (batch == 0 || steps == 0) return A3GC_OK;
+  const int row4 = kNodes * hidden / 4;
+  const int64_t n4 = batch * steps * row4;
+  const int64_t blocks = (n4 + 255) / 256;
+  hprev_split_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(hp), reinterpret_cast<const float4*>(h0), reinterpret_cast<const float4*>(mask),
+      reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo), (int)batch, (int)steps, row4, reverse);
+  A3GC_LAUNCH_CHECK("hprev_split_kernel");
+  return A3GC_OK;
+}
+
+}  // namespace a3gc

@@ -6,7 +6,9 @@ autograd unroll the TorchScript time loop (train_a3gc_tp.py:74-84).  Here the fo
 recurrent gradient chain runs in one CUDA kernel per layer (reverse time, both directions concurrently), and
 what is left after the chain -- the weight / adjacency / input gradients, which are sums over all (t, b) of
 outer products of per-step tensors the chain has stored -- are plain batched GEMMs, issued through torch
-(cuBLAS fp32) on the caller's stream.
+(cuBLAS) on the caller's stream.  The large ones run on the tensor cores as three TF32 passes over operands split
+into an exactly-TF32 head and an fp32 remainder (``a3gc_train_split_tf32``; hi*hi + lo*hi + hi*lo, error 2^-22 per
+product); ``A3GC_TRAIN_GEMM=fp32`` selects plain fp32 SGEMM instead.
 
 Dropout (net_aagc.py:180-181): input dropout is applied to x by the caller of the layer; recurrent dropout is a
 Bernoulli mask drawn here with torch's generator and applied inside both kernels.  The reference's masks come
@@ -16,6 +18,7 @@ with dropout = 0.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -31,6 +34,88 @@ LSTM_PARAM_NAMES = {
     "AGC": [f"gcn_kernel_{g}" for g in "ifco"] + ["adjacency"] + [f"gcn_bias_{g}" for g in "ifco"]
            + ["attention_w", "attention_wq", "attention_wh", "attention_u", "attention_bs", "attention_bu"],
 }
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# hoisted GEMMs: fp32 accuracy from three TF32 tensor-core passes
+# ----------------------------------------------------------------------------------------------------------------------
+def _gemm_mode() -> str:
+    mode = os.environ.get("A3GC_TRAIN_GEMM", "tf32x3")
+    if mode not in ("tf32x3", "fp32"):
+        raise ValueError(f"A3GC_TRAIN_GEMM must be tf32x3 or fp32, got {mode!r}")
+    return mode
+
+
+class _Split:
+    """An fp32 matrix as (hi, lo): hi exactly representable in TF32, lo = x - hi.  In fp32 mode hi = x, lo = None."""
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi: Tensor, lo: Optional[Tensor]):
+        self.hi, self.lo = hi, lo
+
+    def cols(self, a: int, b: int) -> "_Split":
+        return _Split(self.hi[:, a:b], None if self.lo is None else self.lo[:, a:b])
+
+
+def _split(x: Tensor) -> _Split:
+    x = x.contiguous()
+    if _gemm_mode() == "fp32":
+        return _Split(x, None)
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().a3gc_train_split_tf32(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _lib.stream_ptr(x.device))
+    _lib.check(rc, "a3gc_train_split_tf32")
+    return _Split(hi, lo)
+
+
+def _hprev_split(hp: Tensor, h0: Optional[Tensor], mask: Optional[Tensor], reverse: int) -> _Split:
+    """Rows of the h half of S = [x | h_prev] of one direction, [B*T*15, H] (see a3gc_train_hprev_split)."""
+    B, T, _, H = hp.shape
+    if _gemm_mode() == "fp32" or H % 4 != 0:
+        hprev = torch.cat((hp[:, 1:], h0.unsqueeze(1)), dim=1) if reverse else torch.cat((h0.unsqueeze(1), hp[:, :-1]), dim=1)
+        if mask is not None:
+            hprev = hprev * mask
+        return _split(hprev.reshape(B * T * NUM_NODES, H))
+    hi, lo = torch.empty(B * T * NUM_NODES, H, dtype=torch.float32, device=hp.device), torch.empty(B * T * NUM_NODES, H, dtype=torch.float32, device=hp.device)
+    with torch.cuda.device(hp.device):
+        rc = _lib.lib().a3gc_train_hprev_split(hp.data_ptr(), _lib.ptr(h0), _lib.ptr(mask), hi.data_ptr(), lo.data_ptr(),
+                                               B, T, H, int(reverse), _lib.stream_ptr(hp.device))
+    _lib.check(rc, "a3gc_train_hprev_split")
+    return _Split(hi, lo)
+
+
+class _tf32_passes:
+    """Scope in which torch's matmuls may use TF32 tensor-core kernels (operands are pre-split, so nothing is lost)."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.fp32_precision
+        torch.backends.cuda.matmul.fp32_precision = "tf32"
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.fp32_precision = self.prev
+        return False
+
+
+def _mm_tn(a: _Split, b: _Split) -> Tensor:
+    """a^T @ b for row-aligned a [R, M], b [R, N]."""
+    if a.lo is None:
+        return a.hi.t() @ b.hi
+    with _tf32_passes():
+        out = a.lo.t() @ b.hi
+        out.addmm_(a.hi.t(), b.lo)
+        out.addmm_(a.hi.t(), b.hi)
+    return out
+
+
+def _addmm_nn(out: Tensor, a: _Split, b: _Split) -> None:
+    """out += a @ b for a [R, K], b [K, N]."""
+    if a.lo is None:
+        out.addmm_(a.hi, b.hi)
+        return
+    with _tf32_passes():
+        out.addmm_(a.lo, b.hi)
+        out.addmm_(a.hi, b.lo)
+        out.addmm_(a.hi, b.hi)
 
 
 def _cell_params_struct(variant: str, ps: Sequence[Tensor]) -> _lib.CellParams:
@@ -145,24 +230,20 @@ class _LayerTrainFn(torch.autograd.Function):
 
         # ---- hoisted contractions over all (t, b): plain GEMMs (torch / cuBLAS fp32 on the current stream)
         R = B * T * NUM_NODES
-        x2d = x.reshape(R, F)
+        x2d = _split(x.reshape(R, F))
         dx = torch.zeros(R, F, **f32)
         grads: List[Optional[Tensor]] = []
         for d in range(nd):
             ps = dict(zip(names, params[d]))
-            dzm2d = gr["dzm"][d].reshape(R, 4 * H)
+            dzm2d = _split(gr["dzm"][d].reshape(R, 4 * H))
             # S = [x | h_prev]: h_prev is h' of the previous step of this direction (h0 at its first step), masked
-            hp = tape["hp"][d]                                           # [B, T, 15, H]
-            if reverse[d]:
-                hprev = torch.cat((hp[:, 1:], h0[d].unsqueeze(1)), dim=1)
-            else:
-                hprev = torch.cat((h0[d].unsqueeze(1), hp[:, :-1]), dim=1)
-            if hmask is not None:
-                hprev = hprev * hmask[d]
-            dWx = dzm2d.t() @ x2d                                        # [4H, F]
-            dWh = dzm2d.t() @ hprev.reshape(R, H)                        # [4H, H]
+            hprev = _hprev_split(tape["hp"][d], h0[d], None if hmask is None else hmask[d], reverse[d])
+            dWx = _mm_tn(dzm2d, x2d)                                     # [4H, F]
+            dWh = _mm_tn(dzm2d, hprev)                                   # [4H, H]
+            del hprev
             Wx = torch.cat([ps[f"gcn_kernel_{g}"][:, :F] for g in "ifco"], dim=0)   # [4H, F]
-            dx.addmm_(dzm2d, Wx)
+            _addmm_nn(dx, dzm2d, _split(Wx))
+            del dzm2d
             gW = [torch.cat((dWx[i * H:(i + 1) * H], dWh[i * H:(i + 1) * H]), dim=1) for i in range(4)]
             dz = tape["gates"][d].reshape(T * B, 4, H, 16)               # the backward left dz here
             gb = dz.sum(dim=(0, 3))                                      # [4, H]
@@ -302,22 +383,22 @@ class _GruLayerTrainFn(torch.autograd.Function):
                 B, T, F, H, _lib.ACT["linear"], C.byref(tp), C.byref(tg), None, wbuf.data_ptr(), wbuf.numel(), _lib.stream_ptr(dev))
         _lib.check(rc, "a3gc_layer_backward")
         R = B * T * NUM_NODES
-        x2d = x.reshape(R, F)
+        x2d = _split(x.reshape(R, F))
         dx = torch.zeros(R, F, **f32)
         grads: List[Optional[Tensor]] = []
         for d in range(nd):
             ps = dict(zip(GRU_PARAM_NAMES, params[d]))
-            dzm2d = gr["dzm"][d].reshape(R, 4 * H)                        # (dzr | dzu | dzc | dzc r)
-            dz_in = dzm2d[:, :3 * H]
-            dW_in = dz_in.t() @ x2d                                       # [3H, F]
-            db_in = dz_in.sum(0)
-            dx.addmm_(dz_in, torch.cat([ps[f"dense_{g}_in.weight"] for g in "ruc"], dim=0))
-            msg2d = tape["hh"][d].permute(1, 0, 3, 2)[:, :, :NUM_NODES].reshape(R, H)       # [T,B,H,16] -> [B,T,15,H]
-            dz_hid = torch.cat((dzm2d[:, :2 * H], dzm2d[:, 3 * H:]), dim=1)
-            dW_hid = dz_hid.t() @ msg2d                                   # [3H, H]
-            hp = tape["hp"][d]
-            hprev = torch.cat((hp[:, 1:], h0[d].unsqueeze(1)), dim=1) if reverse[d] else torch.cat((h0[d].unsqueeze(1), hp[:, :-1]), dim=1)
-            dWg = gr["dqs"][d].reshape(R, H).t() @ hprev.reshape(R, H)    # gcn_kernel [j][k']
+            db_in = gr["dzm"][d].reshape(R, 4 * H)[:, :3 * H].sum(0)
+            dzm2d = _split(gr["dzm"][d].reshape(R, 4 * H))                # (dzr | dzu | dzc | dzc r)
+            dz_in = dzm2d.cols(0, 3 * H)
+            dW_in = _mm_tn(dz_in, x2d)                                    # [3H, F]
+            _addmm_nn(dx, dz_in, _split(torch.cat([ps[f"dense_{g}_in.weight"] for g in "ruc"], dim=0)))
+            msg2d = _split(tape["hh"][d].permute(1, 0, 3, 2)[:, :, :NUM_NODES].reshape(R, H))   # [T,B,H,16] -> [B,T,15,H]
+            dW_hid = torch.cat((_mm_tn(dzm2d.cols(0, 2 * H), msg2d), _mm_tn(dzm2d.cols(3 * H, 4 * H), msg2d)), dim=0)   # [3H, H]
+            del msg2d, dzm2d, dz_in
+            hprev = _hprev_split(tape["hp"][d], h0[d], None, reverse[d])
+            dWg = _mm_tn(_split(gr["dqs"][d].reshape(R, H)), hprev)       # gcn_kernel [j][k']
+            del hprev
             dmsg = gr["dep"][d].reshape(T * B, H, 16)
             M = tape["c"][d].reshape(T * B, H, 16)
             dP = torch.bmm(dmsg.transpose(1, 2), M).sum(0)                # dP[n][m]; the parameter is used transposed (net_aagc.py:348)
@@ -351,8 +432,11 @@ def gc_train(mod: torch.nn.Module, x: Tensor, act: str, p_drop: float) -> Tensor
     backward."""
     if p_drop > 0:
         x = torch.nn.functional.dropout(x, p_drop, training=True)
-    y = torch.einsum("bsnf,nm->bsmf", x, mod.adj.t())
-    y = torch.matmul(y, mod.gcn_kernel.t()) + mod.gcn_bias
+    # (adj @ x) @ W^T = adj @ (x @ W^T): contract the wide side first, so the node mix touches min(F, O) features
+    if mod.gcn_kernel.shape[0] < mod.gcn_kernel.shape[1]:
+        y = torch.einsum("bsnf,nm->bsmf", torch.matmul(x, mod.gcn_kernel.t()), mod.adj.t()).contiguous() + mod.gcn_bias
+    else:
+        y = torch.matmul(torch.einsum("bsnf,nm->bsmf", x, mod.adj.t()), mod.gcn_kernel.t()) + mod.gcn_bias
     if act == "tanh":
         y = torch.tanh(y)
     elif act == "relu":

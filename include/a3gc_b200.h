@@ -256,6 +256,18 @@ int a3gc_concat_stage_input(const float* x, const float* pos, float* dst, int64_
 int a3gc_reduced_to_full_local(const float* pose, float* out, int64_t frames, int rotsize, void* stream);
 
 /*
+ * Operand preparation of the hoisted weight / input gradient GEMMs of the training step (the autograd mm nodes of
+ * train_a3gc_tp.py:77, loss.backward()).  They run as three TF32 tensor-core passes hi*hi + lo*hi + hi*lo:
+ * a3gc_train_split_tf32 cuts x[n] into hi (exactly representable in TF32, round-to-nearest) and lo = x - hi.
+ * a3gc_train_hprev_split builds the h half of S = [x | h_prev] of one direction directly in split form:
+ * h_prev(b, t) = hp(b, t -/+ 1) (h0, or zeros if null, at the direction's first step) times mask(b, t) if given;
+ * hp, mask, hi, lo are [batch, steps, 15, hidden], h0 is [batch, 15, hidden].  All buffers 16-byte aligned.
+ */
+int a3gc_train_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+int a3gc_train_hprev_split(const float* hp, const float* h0, const float* mask, float* hi, float* lo, int64_t batch,
+                           int64_t steps, int hidden, int reverse, void* stream);
+
+/*
  * Optional per-launch timing of the recurrent-layer kernels (used by bench.py for the roofline):
  * while enabled, every layer launch is bracketed by CUDA events on the launching stream.
  * a3gc_profile_get must be called after the stream has been synchronised; it returns the launch's
