@@ -817,27 +817,82 @@ lstm_train_bwd_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
 template <int NS, int NU>
 __device__ __forceinline__ void accum_blk(float (&acc)[NS][NU][16], const float* __restrict__ act, size_t seq_stride,
                                           const float* __restrict__ w, int ldw, int ustride, int k0, int k1) {
-#pragma unroll 4
-  for (int k = k0; k < k1; ++k) {
-    float wv[NU];
+  // weights of the next group of kG contraction steps are fetched (L2 latency) while the current group is consumed;
+  // k1 - k0 is a multiple of kG for every shape the blocked kernel accepts
+  constexpr int kG = 8;
+  float wn[kG][NU];
 #pragma unroll
-    for (int ui = 0; ui < NU; ++ui) wv[ui] = __ldg(w + (size_t)k * ldw + ui * ustride);
+  for (int i = 0; i < kG; ++i)
 #pragma unroll
-    for (int si = 0; si < NS; ++si) {
-      const float4* a4 = reinterpret_cast<const float4*>(act + si * seq_stride + (size_t)k * kNodesPad);
+    for (int ui = 0; ui < NU; ++ui) wn[i][ui] = __ldg(w + (size_t)(k0 + i) * ldw + ui * ustride);
+#pragma unroll 1
+  for (int k = k0; k < k1; k += kG) {
+    float wc[kG][NU];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 v = a4[q];
+    for (int i = 0; i < kG; ++i)
 #pragma unroll
-        for (int ui = 0; ui < NU; ++ui) {
-          acc[si][ui][4 * q] = fmaf(wv[ui], v.x, acc[si][ui][4 * q]);
-          acc[si][ui][4 * q + 1] = fmaf(wv[ui], v.y, acc[si][ui][4 * q + 1]);
-          acc[si][ui][4 * q + 2] = fmaf(wv[ui], v.z, acc[si][ui][4 * q + 2]);
-          acc[si][ui][4 * q + 3] = fmaf(wv[ui], v.w, acc[si][ui][4 * q + 3]);
+      for (int ui = 0; ui < NU; ++ui) wc[i][ui] = wn[i][ui];
+    if (k + kG < k1) {
+#pragma unroll
+      for (int i = 0; i < kG; ++i)
+#pragma unroll
+        for (int ui = 0; ui < NU; ++ui) wn[i][ui] = __ldg(w + (size_t)(k + kG + i) * ldw + ui * ustride);
+    }
+#pragma unroll
+    for (int i = 0; i < kG; ++i) {
+#pragma unroll
+      for (int si = 0; si < NS; ++si) {
+        const float4* a4 = reinterpret_cast<const float4*>(act + si * seq_stride + (size_t)(k + i) * kNodesPad);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = a4[q];
+#pragma unroll
+          for (int ui = 0; ui < NU; ++ui) {
+            acc[si][ui][4 * q] = fmaf(wc[i][ui], v.x, acc[si][ui][4 * q]);
+            acc[si][ui][4 * q + 1] = fmaf(wc[i][ui], v.y, acc[si][ui][4 * q + 1]);
+            acc[si][ui][4 * q + 2] = fmaf(wc[i][ui], v.z, acc[si][ui][4 * q + 2]);
+            acc[si][ui][4 * q + 3] = fmaf(wc[i][ui], v.w, acc[si][ui][4 * q + 3]);
+          }
         }
       }
     }
   }
+}
+
+// Partial products of a batched GEMV out[s][j] = sum_k vec[s][k] W[k][j] for all BT sequences of the CTA: this thread
+// covers units j4..j4+3 (one 16-byte load per k) and contraction steps [kd*kq, (kd+1)*kq); G loads are in flight
+// per thread (G of 16 bytes) because the loop is bound by L2 latency, not bandwidth.  part -> scr[(kd*BT + s)*H + j]
+template <int G>
+__device__ __forceinline__ void gemv_part(const float* __restrict__ vec, const float* __restrict__ W, float* __restrict__ scr,
+                                          int H, int BT, int j4, int kd, int kq) {
+  float part[8][4];
+#pragma unroll
+  for (int s = 0; s < 8; ++s)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) part[s][i] = 0.f;
+  const float4* wp = reinterpret_cast<const float4*>(W + (size_t)kd * kq * H + j4);
+  const float* vp = vec + kd * kq;
+  const int ld4 = H / 4;
+#pragma unroll 1
+  for (int k = 0; k < kq; k += G) {
+    float4 wv[G];
+#pragma unroll
+    for (int i = 0; i < G; ++i) wv[i] = __ldg(wp + (size_t)(k + i) * ld4);
+#pragma unroll
+    for (int i = 0; i < G; ++i)
+#pragma unroll
+      for (int s = 0; s < 8; ++s)
+        if (s < BT) {
+          const float v = vp[s * H + k + i];
+          part[s][0] = fmaf(v, wv[i].x, part[s][0]);
+          part[s][1] = fmaf(v, wv[i].y, part[s][1]);
+          part[s][2] = fmaf(v, wv[i].z, part[s][2]);
+          part[s][3] = fmaf(v, wv[i].w, part[s][3]);
+        }
+  }
+#pragma unroll
+  for (int s = 0; s < 8; ++s)
+    if (s < BT) *reinterpret_cast<float4*>(scr + ((size_t)kd * BT + s) * H + j4) = make_float4(part[s][0], part[s][1], part[s][2], part[s][3]);
 }
 
 // Same chain as lstm_train_bwd_kernel for H in {64, 128, 256}, arranged around the two weight contractions that
@@ -872,8 +927,8 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
   const int UH = H / 2, ntile = UH * (BT / 2), KS = kThreads / ntile;
   const int u = threadIdx.x % UH, s0 = 2 * ((threadIdx.x / UH) % (BT / 2)), kh = threadIdx.x / ntile;
   const int kq = H / KS, k0 = kh * kq, k1 = k0 + kq;
-  // GEMV phases: thread -> (kd, unit j), all BT sequences
-  const int KD = kThreads / H, jd = threadIdx.x % H, kd = threadIdx.x / H;
+  // GEMV phases: thread -> (kd, 4 consecutive units jd..jd+3), all BT sequences, 1/KD of the contraction range
+  const int KD = 4 * kThreads / H, jd = 4 * (threadIdx.x % (H / 4)), kd = threadIdx.x / (H / 4);
   const int kdq = H / KD;
   LayerGeom lg; lg.B = g.B; lg.H = H; lg.BT = BT;
   load_state(dh, d.dhT, b0, lg);
@@ -905,7 +960,7 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
 #pragma unroll
         for (int n = 0; n < kNodes; ++n) {
           const float gy = __ldg(yp + (size_t)n * g.yld);
-          if (g.out_act == A3GC_ACT_TANH) { const float y = tanhf(hpp[(size_t)n * H]); dv[n] = fmaf(gy, 1.0f - y * y, dv[n]); }
+          if (g.out_act == A3GC_ACT_TANH) { const float y = fast_tanh(hpp[(size_t)n * H]); dv[n] = fmaf(gy, 1.0f - y * y, dv[n]); }
           else dv[n] += gy;
         }
         dv[15] = 0.f;
@@ -970,19 +1025,7 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
       }
       __syncthreads();
       // ---- D: dq_j = sum_k dqs_k Wq[k][j] for all BT sequences at once;  dqp = dq [q > 0]
-      {
-        float part[8];
-#pragma unroll
-        for (int s = 0; s < 8; ++s) part[s] = 0.f;
-#pragma unroll 4
-        for (int k = kd * kdq; k < (kd + 1) * kdq; ++k) {
-          const float wv = __ldg(d.Wq + (size_t)k * H + jd);
-#pragma unroll
-          for (int s = 0; s < 8; ++s) if (s < BT) part[s] = fmaf(v1[s * H + k], wv, part[s]);
-        }
-#pragma unroll
-        for (int s = 0; s < 8; ++s) if (s < BT) scr[(kd * BT + s) * H + jd] = part[s];
-      }
+      if (kdq % 8 == 0) gemv_part<8>(v1, d.Wq, scr, H, BT, jd, kd, kdq); else gemv_part<4>(v1, d.Wq, scr, H, BT, jd, kd, kdq);
       __syncthreads();
       for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
         const int s = task / H, j = task % H, b = b0 + s;
@@ -997,19 +1040,7 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
       }
       __syncthreads();
       // ---- D2: ds_j = sum_k dqp_k Wa[k][j]  (-> v1)
-      {
-        float part[8];
-#pragma unroll
-        for (int s = 0; s < 8; ++s) part[s] = 0.f;
-#pragma unroll 4
-        for (int k = kd * kdq; k < (kd + 1) * kdq; ++k) {
-          const float wv = __ldg(d.Wa + (size_t)k * H + jd);
-#pragma unroll
-          for (int s = 0; s < 8; ++s) if (s < BT) part[s] = fmaf(v2[s * H + k], wv, part[s]);
-        }
-#pragma unroll
-        for (int s = 0; s < 8; ++s) if (s < BT) scr[(kd * BT + s) * H + jd] = part[s];
-      }
+      if (kdq % 8 == 0) gemv_part<8>(v2, d.Wa, scr, H, BT, jd, kd, kdq); else gemv_part<4>(v2, d.Wa, scr, H, BT, jd, kd, kdq);
       __syncthreads();
       for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
         float ds = 0.f;
@@ -1067,7 +1098,7 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
         load16(dcv, dc + (size_t)task * kNodesPad);
 #pragma unroll
         for (int n = 0; n < 16; ++n) {
-          const float tc = tanhf(cc[n]);
+          const float tc = fast_tanh(cc[n]);
           const float dcn = fmaf(dv[n] * go[n], 1.0f - tc * tc, dcv[n]);
           dz[3][n] = dv[n] * tc * go[n] * (1.0f - go[n]);
           dz[0][n] = dcn * gg[n] * gi[n] * (1.0f - gi[n]);

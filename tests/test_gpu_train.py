@@ -129,3 +129,34 @@ def test_recurrent_dropout_mask_semantics_tc_vs_simt(nira):
         outs[eng] = [res[0].detach().cpu(), xr.grad.cpu()] + [p_.grad.detach().cpu().clone() for p_ in layer.parameters()]
     for a, b in zip(outs["simt"], outs["tc"]):
         assert rel_l2(b, a) <= TOL
+
+
+@pytest.mark.parametrize("variant,H,B", [("A3GC", 64, 5), ("AAGC", 128, 3), ("AGC", 256, 3)])
+def test_blocked_and_plain_backward_chains_agree(variant, H, B, nira, monkeypatch):
+    """The register-blocked reverse-time chain (H in {64,128,256}; 2 sequences x 2 units x 1/KS of K per thread) against the
+    one-(sequence, unit)-per-thread chain on the same tape, with a recurrent-dropout mask and a ragged batch."""
+    from a3gc_ip_b200 import training as TR
+    torch.manual_seed(5)
+    F, T = 32, 5
+    layer = getattr(A, f"Bi{variant}_LSTM")(F, H, nira.float(), activation_fn="tanh").cuda().train()
+    x = torch.randn(B, T, 15, F, device="cuda")
+    st = [tuple(0.2 * torch.randn(B, 15, H, device="cuda") for _ in range(2)) for _ in range(2)]
+    hmask = (torch.rand(2, B, T, 15, H, device="cuda") >= 0.3).float() / 0.7
+    outs = {}
+    for blk in ("1", "0"):
+        monkeypatch.setenv("A3GC_BWD_BLK", blk)
+        flat = []
+        for s_ in st:
+            flat += [s_[0].clone().requires_grad_(True), s_[1].clone().requires_grad_(True)]
+        for d in layer.directions:
+            flat += [getattr(d.cell, n) for n in TR.LSTM_PARAM_NAMES[variant]]
+        for p_ in layer.parameters():
+            p_.grad = None
+        xr = x.clone().requires_grad_(True)
+        res = TR._LayerTrainFn.apply((variant, 2, (0, 1), "tanh", A._lib.Workspace(), "tc"), xr, hmask, *flat)
+        (res[0].square().sum() + sum(r.sum() for r in res[1:])).backward()
+        outs[blk] = ([xr.grad.cpu()] + [f.grad.cpu() for f in flat[:4]]
+                     + [p_.grad.detach().cpu().clone() for p_ in layer.parameters() if p_.grad is not None])
+    assert len(outs["1"]) == len(outs["0"]) > 10
+    for a, b in zip(outs["0"], outs["1"]):
+        assert rel_l2(b, a) <= 1e-5
