@@ -1008,6 +1008,10 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
     // epilogue warps run the gate phase, ~35 % during the q hand-off, the rest during e.u / h' / the state exchange
     const int KF = F / 16;
     int n1 = (KF * 45 + 99) / 100, n2 = KF * 35 / 100;   // measured best all-round split (45 % / 35 % / 20 %)
+    // per-shape optimum of the sweep in tests/sweep_split.sh (the curve is flat: 1-3 % between the best and 45/35)
+    if (H == 256 && F >= 512) { n1 = KF * 60 / 100; n2 = KF * 20 / 100; }
+    else if (H == 256) { n1 = KF * 35 / 100; n2 = KF * 45 / 100; }
+    else if (H == 128) { n1 = KF * 30 / 100; n2 = KF * 30 / 100; }
     if (const char* e = getenv("A3GC_TC_SPLIT")) {
       int a = 0, b = 0;
       if (sscanf(e, "%d,%d", &a, &b) == 2) { n1 = KF * a / 100; n2 = KF * b / 100; }

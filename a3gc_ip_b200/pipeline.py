@@ -81,12 +81,21 @@ class TPPipeline(torch.nn.Module):
     """net1 (12 -> 3), net2 (15 -> 3), net3 (15 -> 9) chained as evaluate_a3gc_tp.py:164-172."""
 
     def __init__(self, net1: torch.nn.Module, net2: torch.nn.Module, net3: torch.nn.Module, stats: Optional[dict] = None,
-                 streams: int = 1):
+                 streams: int = 1, max_frames: int = 400_000):
+        """``max_frames`` bounds the frames (sequences x steps) in flight: the per-frame workspace of the three stages is
+        ~150 KB (operand images and inter-layer activations), so a larger call is cut into sequential macro-batches of
+        whole sequences that reuse the same workspaces (the default keeps BASELINE cfg 2, 307 200 frames, in one pass and
+        lets cfg 4, 2.46 M frames, run on one 180 GB GPU)."""
         super().__init__()
         self.net1, self.net2, self.net3 = net1, net2, net3
         self.stats = stats
         self.streams = max(1, int(streams))
+        self.max_frames = int(max_frames)
         self._side = {}
+
+    def _macro_batch(self, B: int, T: int) -> int:
+        """Sequences per macro-batch: a multiple of the 8-sequence batch tile, at least one tile."""
+        return max(8, (self.max_frames // max(T, 1)) // 8 * 8)
 
     def _chain(self, x: Tensor, slot: int) -> Tuple[Tensor, Tensor, Tensor]:
         y1, _ = self.net1(x, None, slot)
@@ -99,6 +108,10 @@ class TPPipeline(torch.nn.Module):
         """Sequences are independent, so with ``streams`` > 1 the batch is cut into that many contiguous chunks whose
         three-stage chains run concurrently on separate CUDA streams: a chunk's small stages (cluster size 1 / 2) fill
         the SMs that the 4-CTA clusters of another chunk's H = 256 stage cannot use, and partial last waves overlap."""
+        per = self._macro_batch(x.shape[0], x.shape[1])
+        if x.shape[0] > per:
+            parts = [self.forward(x[i:i + per]) for i in range(0, x.shape[0], per)]
+            return tuple(torch.cat([o[k] for o in parts], dim=0) for k in range(3))
         n = min(self.streams, max(1, x.shape[0] // 8))
         if n <= 1 or not x.is_cuda:
             return self._chain(x, 0)
@@ -136,9 +149,14 @@ class TPPipeline(torch.nn.Module):
         (pinned host buffers needed for the overlap; pageable ones still work)."""
         device = device or next(self.parameters()).device
         B = x_host.shape[0]
-        n = min(self.streams, max(1, B // 8))
         if out_host is None:
             out_host = torch.empty(B, x_host.shape[1], 15, 9, dtype=torch.float32, pin_memory=True)
+        per = self._macro_batch(B, x_host.shape[1])
+        if B > per:
+            for i in range(0, B, per):
+                self.forward_host(x_host[i:i + per], out_host[i:i + per], device)
+            return out_host
+        n = min(self.streams, max(1, B // 8))
         if n <= 1:
             x = x_host.to(device, non_blocking=True)
             _, _, y3 = self._chain(x, 0)

@@ -246,7 +246,8 @@ class _LayerTrainFn(torch.autograd.Function):
             del dzm2d
             gW = [torch.cat((dWx[i * H:(i + 1) * H], dWh[i * H:(i + 1) * H]), dim=1) for i in range(4)]
             dz = tape["gates"][d].reshape(T * B, 4, H, 16)               # the backward left dz here
-            gb = dz.sum(dim=(0, 3))                                      # [4, H]
+            ones = torch.ones(1, T * B, **f32)
+            gb = (ones @ dz.reshape(T * B, 4 * H * 16)).reshape(4, H, 16).sum(2)     # [4, H]; one bandwidth-bound pass
             out = {f"gcn_kernel_{g}": gW[i] for i, g in enumerate("ifco")}
             out.update({f"gcn_bias_{g}": gb[i] for i, g in enumerate("ifco")})
             if variant == "AGC":
@@ -262,11 +263,12 @@ class _LayerTrainFn(torch.autograd.Function):
                 hh = tape["hh"][d].reshape(T * B, H, 16)
                 e = tape["e"][d].reshape(T * B, H, 16)
                 dap = gr["dap"][d].reshape(T * B, 16)
-                out["attention_wh"] = torch.einsum("rkn,rjn->kj", dep, hh)
-                out["attention_bs"] = dep.sum(dim=(0, 2))
+                # sum over (r, n) of dep[r, k, n] hh[r, j, n]: one [H, R*16] x [R*16, H] GEMM over explicitly permuted copies
+                out["attention_wh"] = dep.permute(1, 0, 2).reshape(H, T * B * 16) @ hh.permute(0, 2, 1).reshape(T * B * 16, H)
+                out["attention_bs"] = (ones @ dep.reshape(T * B, H * 16)).reshape(H, 16).sum(1)
                 out["attention_wq"] = gr["dqs"][d].reshape(T * B, H).t() @ tape["q"][d].reshape(T * B, H)
                 out["attention_w"] = gr["dqp"][d].reshape(T * B, H).t() @ tape["s"][d].reshape(T * B, H)
-                out["attention_u"] = torch.einsum("rn,rjn->j", dap, e).unsqueeze(0)
+                out["attention_u"] = torch.bmm(e, dap.unsqueeze(2)).sum(0).reshape(1, H)      # sum_{r,n} dap[r,n] e[r,j,n]
                 out["attention_bu"] = dap.sum(0)[:NUM_NODES].contiguous()
             grads += [out[n] for n in names]
         state_grads: List[Optional[Tensor]] = []

@@ -18,4 +18,4 @@ for it in range(3):
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     y, _ = net(x); loss = crit(y.view(tgt.shape), tgt); opt.zero_grad(); loss.backward(); opt.step(); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=60))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=int(sys.argv[6]) if len(sys.argv) > 6 else 14, max_name_column_width=60))

@@ -271,3 +271,22 @@ def test_concurrent_batch_chunks_and_host_path_match_single_stream(nira):
     assert_close(y, want[2], tol=2e-6, what="host path (chunked)")
     pipe.streams = 1
     assert_close(pipe.forward_host(x, None, torch.device("cuda", 0)), want[2], tol=2e-6, what="host path (single stream)")
+
+
+def test_sequential_macro_batches_match_single_pass(nira):
+    """TPPipeline(max_frames=...): a call larger than the frame budget runs as sequential macro-batches of whole sequences
+    (device and host-buffer paths); results equal the single-pass ones (sequences are independent)."""
+    pipe, _ = build_tp("A3GC", nira)
+    x = O.synthetic_input(29, 12, seed=9)
+    pipe.streams = 2
+    want = [t.cpu() for t in pipe(x.cuda())]
+    pipe.max_frames = 12 * 16                             # 16 sequences per macro-batch -> 16 + 13
+    assert pipe._macro_batch(29, 12) == 16
+    got = [t.cpu() for t in pipe(x.cuda())]
+    for a, b in zip(got, want):
+        assert a.shape == b.shape
+        assert_close(a, b, tol=2e-6, what="macro-batched vs single pass")
+    assert_close(pipe.forward_host(x.pin_memory(), None, torch.device("cuda", 0)), want[2], tol=2e-6, what="macro-batched host path")
+    pipe.max_frames = 1                                   # never below one 8-sequence tile
+    assert pipe._macro_batch(29, 12) == 8
+    assert_close(pipe(x.cuda())[2].cpu(), want[2], tol=2e-6, what="one tile per macro-batch")
