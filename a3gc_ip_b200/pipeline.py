@@ -138,6 +138,46 @@ class TPPipeline(torch.nn.Module):
                 t.record_stream(main)
         return tuple(torch.cat([o[k] for o in outs], dim=0) for k in range(3))
 
+    @staticmethod
+    def window_plan(total: int, window: int, hop: int):
+        """Sliding windows over a recording of ``total`` frames: window starts (the last one is shifted back so that it ends
+        at the final frame) and, per window, the half-open range [lo, hi) of recording frames whose output is taken from it
+        -- the ``hop`` frames around the window centre, the first / last window also covering the head / tail."""
+        if window <= 0 or hop <= 0 or hop > window:
+            raise ValueError(f"window_plan: need 0 < hop <= window, got window={window} hop={hop}")
+        if total <= window:
+            return [0], [(0, total)]
+        starts = list(range(0, total - window, hop)) + [total - window]
+        keep = []
+        for i, s0 in enumerate(starts):
+            lo = 0 if i == 0 else keep[-1][1]
+            hi = total if i == len(starts) - 1 else min(total, s0 + (window + hop) // 2)
+            keep.append((lo, max(lo, hi)))
+        return starts, keep
+
+    @torch.no_grad()
+    def forward_windowed(self, x: Tensor, window: int, hop: int) -> Tensor:
+        """Windowed (near-online) inference of ONE long recording x [T, 15, 12] -> pose [T, 15, 9].
+
+        The nets are bidirectional, so the reference's online plumbing (PoseNet3.reset / rnn_state, net_aagc.py:802-812) cannot
+        stream; the product form is a sliding window: every window of ``window`` frames is an independent sequence, all
+        windows run as ONE batch through the three stages, and each output frame is taken from the window in which it is
+        most central (``window_plan``).  ``window`` >= T reproduces the offline result exactly; the latency of a live
+        deployment is window/2 + hop frames plus one chain evaluation (31 ms at window = 300 on one B200)."""
+        if x.dim() != 3 or x.shape[1] != NUM_NODES:
+            raise RuntimeError(f"forward_windowed expects one recording [T, 15, F], got {tuple(x.shape)}")
+        x = _lib.require_cuda_f32(x, "x")
+        total = x.shape[0]
+        starts, keep = self.window_plan(total, window, hop)
+        w = min(window, total)
+        idx = torch.tensor(starts, device=x.device).unsqueeze(1) + torch.arange(w, device=x.device).unsqueeze(0)
+        y3 = self.forward(x[idx])[2]                                   # [windows, w, 15, 9]
+        out = torch.empty(total, NUM_NODES, y3.shape[-1], dtype=torch.float32, device=x.device)
+        for i, (s0, (lo, hi)) in enumerate(zip(starts, keep)):
+            if hi > lo:
+                out[lo:hi] = y3[i, lo - s0:hi - s0]
+        return out
+
     @torch.no_grad()
     def forward_raw(self, ori: Tensor, acc: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
         return self.forward(prepare_input(ori, acc, self.stats))

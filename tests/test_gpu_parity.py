@@ -290,3 +290,20 @@ def test_sequential_macro_batches_match_single_pass(nira):
     pipe.max_frames = 1                                   # never below one 8-sequence tile
     assert pipe._macro_batch(29, 12) == 8
     assert_close(pipe(x.cuda())[2].cpu(), want[2], tol=2e-6, what="one tile per macro-batch")
+
+
+def test_windowed_inference_matches_per_window_oracle(nira):
+    """TPPipeline.forward_windowed: all sliding windows as one batch, each frame taken from its most central window.
+    window >= T is the offline result; smaller windows equal the oracle run window by window and stitched by window_plan."""
+    pipe, sds = build_tp("A3GC", nira)
+    rec = O.synthetic_input(1, 44, seed=10)[0]                       # one recording [44, 15, 12]
+    offline = pipe(rec.unsqueeze(0).cuda())[2][0].cpu()
+    assert_close(pipe.forward_windowed(rec.cuda(), 64, 8).cpu(), offline, tol=2e-6, what="window >= T")
+    window, hop = 16, 4
+    starts, keep = pipe.window_plan(44, window, hop)
+    assert len(starts) == 8 and keep[0][0] == 0 and keep[-1][1] == 44
+    got = pipe.forward_windowed(rec.cuda(), window, hop).cpu()
+    with torch.no_grad():
+        for s0, (lo, hi) in zip(starts, keep):
+            want = O.tp_forward("A3GC", rec[s0:s0 + window].unsqueeze(0), sds)[2][0]
+            assert_close(got[lo:hi], want[lo - s0:hi - s0], what=f"window at {s0}")

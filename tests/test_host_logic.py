@@ -209,3 +209,17 @@ def test_training_loop_glue_follows_reference_control_flow(tmp_path):
     x2, t2 = A.stage_inputs(2, imu, a, b, "leaf", "full", "smpl")
     assert x2.shape == (2, 3, 15, 15) and t2 == "full" and torch.equal(x2[..., 12:], a)
     assert torch.equal(A.stage_inputs(3, imu, a, b, "leaf", "full", "smpl")[0][..., 12:], b)
+
+
+@pytest.mark.parametrize("total,window,hop", [(100, 40, 10), (100, 40, 40), (37, 40, 10), (41, 40, 7), (1000, 300, 30), (40, 40, 1)])
+def test_window_plan_covers_every_frame_once(total, window, hop):
+    """Windowed inference plan (TPPipeline.window_plan): the kept ranges tile [0, total) and lie inside their windows."""
+    from a3gc_ip_b200.pipeline import TPPipeline
+    starts, keep = TPPipeline.window_plan(total, window, hop)
+    assert len(starts) == len(keep) and keep[0][0] == 0 and keep[-1][1] == total
+    for (a, b), (c, d) in zip(keep, keep[1:]):
+        assert b == c and a <= b
+    for s0, (lo, hi) in zip(starts, keep):
+        assert 0 <= s0 and s0 + min(window, total) <= total and lo >= s0 and hi <= s0 + window
+    with pytest.raises(ValueError):
+        TPPipeline.window_plan(total, window, window + 1)
