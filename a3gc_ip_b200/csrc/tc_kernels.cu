@@ -67,6 +67,9 @@ struct TcLayerParams {
   int chunk;                         // bytes per bulk copy of the weight / x stream
   int xsplit;                        // x part as two N=128 MMAs per K block
   int xdefer;                        // first x segment only after the gate phase of the step
+  int xprefetch;                     // pull the next step's x operand image into L2 one step ahead
+  int rescale;                       // fp32 inference: peers' h' blocks are rescaled locally instead of a second all-gather
+  int pubbytes;                      // TIMING DIAGNOSTIC ONLY (results are wrong if < kHBlock): bytes per state-exchange copy
   int n1, n2;                        // x-part blocks of step t+1 issued before A1 / between A1 and A2 of step t (rest after A2)
   // training mode (TRAIN): tape of per-step intermediates (include/a3gc_b200.h, a3gc_tape) and optional recurrent-dropout mask
   a3gc_tape tape;
@@ -198,6 +201,13 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       auto xblocks = [&](int t, int kb0, int kb1) {
         const int ta = d.reverse ? T - 1 - t : t;
         const uint8_t* xs = xi + ((size_t)tile * T + ta) * KF * kABytes;
+        // the x operand image is read once, from HBM; with three ring slots at H = 256 the stage latency bounds the
+        // x-part stream, so this CTA's share of the NEXT step's image is pulled into L2 one step ahead
+        if (kb0 == 0 && p.xprefetch && t + 1 < T) {
+          const int tn = d.reverse ? T - 2 - t : t + 1;
+          const uint32_t share = (uint32_t)(KF / C) * kABytes;
+          ptx::bulk_prefetch_l2(xi + ((size_t)tile * T + tn) * KF * kABytes + (size_t)c * share, share);
+        }
         for (int kb = kb0; kb < kb1; ++kb) load_stage(wg + (size_t)kb * kBBytes, kBBytes, xs + (size_t)kb * kABytes, kABytes);
       };
       xblocks(0, 0, KF);
@@ -438,8 +448,8 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) {
           if (peer == c) continue;
           for (int part = 0; part < NP; ++part)                           // lands on the peer's barrier of source c
-            ptx::bulk_s2remote(hbuf + (size_t)part * H * 256 + (size_t)c * kHBlock, kHBlock, &bars[bar + c], peer);
-          ptx::mbar_arrive_expect_tx(&bars[bar + peer], (uint32_t)NP * kHBlock);   // arm the barrier of the peer's block
+            ptx::bulk_s2remote(hbuf + (size_t)part * H * 256 + (size_t)c * kHBlock, (uint32_t)p.pubbytes, &bars[bar + c], peer);
+          ptx::mbar_arrive_expect_tx(&bars[bar + peer], (uint32_t)NP * (uint32_t)p.pubbytes);   // arm the barrier of the peer's block
         }
       }
     };
@@ -790,7 +800,43 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       if (TRAIN) tape_hp(ta);
       store_units(hreg, tnext);
       if (et == 0) TC_TRACE(0, 10);
-      publish_block(BAR_H, -1);
+      if (SPLIT && !TRAIN && C > 1 && p.rescale) {
+        // h' = hy (1 + a) differs from hy by a factor per ROW, and every CTA already holds the hy blocks of its peers (they
+        // were exchanged for the attention GEMM) and a[row]: instead of a second all-gather over DSMEM -- measured 8-10 % of
+        // the step at H = 256, the copies also delay the weight stream queued behind them -- each CTA rescales the peers'
+        // blocks in its own operand image.  (hi + lo) is exact in fp32, so the operand differs from split(hy (1 + a)) by
+        // one fp32 rounding (2^-24).  Blocks become ready in the rotated order the MMA warp walks them.
+        ptx::fence_proxy_async();
+        ptx::named_bar_sync(1, kEpiThreads);
+        if (et == 0) ptx::mbar_arrive(&bars[BAR_H + c]);                // own block (from the fp32 registers): usable at once
+        const int rr = et & 127, cg = et >> 7;                           // row, and which 2 of a block's 8 K-chunks
+        const float ar = ahalf[rr];
+        for (int i = 1; i < C; ++i) {
+          const int src = ((int)c + i) % C;
+          ptx::mbar_wait(&bars[BAR_HHAT + src], t & 1);                  // the block has landed (already consumed by A1)
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            uint8_t* ph = hbuf + (size_t)((src * 8 + cg * 2 + h2) * kRows + rr) * 16;
+            uint8_t* pl = ph + (size_t)H * 256;
+            const uint4 hv = *reinterpret_cast<const uint4*>(ph), lv = *reinterpret_cast<const uint4*>(pl);
+            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+            uint32_t ho[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+              const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
+              ptx::split_pair_f16((hf.x + lf.x) * ar, (hf.y + lf.y) * ar, ho[j], lo[j]);
+            }
+            *reinterpret_cast<uint4*>(ph) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+            *reinterpret_cast<uint4*>(pl) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          ptx::fence_proxy_async();
+          ptx::named_bar_sync(1, kEpiThreads);
+          if (et == 0) ptx::mbar_arrive(&bars[BAR_H + src]);
+        }
+      } else {
+        publish_block(BAR_H, -1);
+      }
       emit(ta, hreg);                   // global stores of y_t after the hand-off: off the recurrence's critical path
       if (et == 0) TC_TRACE(0, 11);
     }
@@ -1021,6 +1067,10 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
     p.n1 = n1; p.n2 = n2;
     p.xsplit = getenv("A3GC_TC_XSPLIT") ? atoi(getenv("A3GC_TC_XSPLIT")) : 0;
     p.xdefer = getenv("A3GC_TC_XDEFER") ? atoi(getenv("A3GC_TC_XDEFER")) : 0;
+    p.xprefetch = getenv("A3GC_TC_XPREFETCH") ? atoi(getenv("A3GC_TC_XPREFETCH")) : 0;   // measured: no effect (+-0.3 %)
+    p.rescale = getenv("A3GC_TC_RESCALE") ? atoi(getenv("A3GC_TC_RESCALE")) : 1;
+    p.pubbytes = 16384;  // = kHBlock; A3GC_TC_PUBBYTES < 16384 is a timing diagnostic (truncated state exchange, wrong results)
+    if (const char* e = getenv("A3GC_TC_PUBBYTES")) { const int v = atoi(e); if (v >= 16 && v <= 16384 && v % 16 == 0) p.pubbytes = v; }
     p.chunk = 1 << 20;   // measured: one bulk copy per operand is fastest (4 KB pieces: -7 %, 2 KB pieces: -30 %)
     if (const char* e = getenv("A3GC_TC_CHUNK")) { const int v = atoi(e); if (v >= 1024 && v % 16 == 0) p.chunk = v; }
   }

@@ -80,6 +80,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// global -> L2 only (no destination, no completion): pulls a contiguous range into L2 ahead of the bulk copies that
+// will stage it, so that their latency is the L2's, not HBM's.  bytes: multiple of 16
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 // this CTA's shared memory -> the same offset in CTA `cta` of the cluster; completion on the REMOTE barrier
 __device__ __forceinline__ void bulk_s2remote(void* smem_ptr, uint32_t bytes, uint64_t* bar, uint32_t cta) {
   uint32_t rdst, rbar;
