@@ -45,6 +45,15 @@ __device__ unsigned long long g_tc_trace[2][16][16];
   do {                                                                                       \
     if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t < 16) g_tc_trace[role][t][slot] = clock64(); \
   } while (0)
+// wall-clock nanoseconds next to the cycle counter: their ratio is the SM clock the kernel actually ran at
+#define TC_TRACE_NS(role, slot)                                                              \
+  do {                                                                                       \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t < 16) {                           \
+      unsigned long long ns_;                                                                \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_));                                \
+      g_tc_trace[role][t][slot] = ns_;                                                       \
+    }                                                                                        \
+  } while (0)
 
 struct TcDir {
   const uint16_t* wg_img;   // [C][(F+H)/16][NP][2][256][8]   gate weights, rows = 64*gate + unit
@@ -537,6 +546,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       ptx::mbar_wait(&bars[BAR_HFREE], t & 1);
       ptx::tc_fence_after();
       if (et == 0) TC_TRACE(0, 1);
+      if (et == 0) TC_TRACE_NS(0, 15);
 #pragma unroll
       for (int ub = 0; ub < 2; ++ub) {
         float e1[2][4], e2[2][4];

@@ -43,3 +43,6 @@ if os.environ.get("A3GC_TC_TRACE"):
         x = [int(v) - t0 - e[0] for v in buf[0, t, 12:15]]
         y = [int(v) - t0 - e[0] for v in buf[1, t, 8:13]]
         print(f"        q-step: stores_done={x[0]} fence_done={x[1]} bar_done={x[2]} | ep1 q=1: ld_done={y[0]} sts_done={y[1]} bar1={y[2]} compute_done={y[3]} bar2={y[4]}")
+    cyc = int(buf[0, 12, 1]) - int(buf[0, 2, 1]); ns = int(buf[0, 12, 15]) - int(buf[0, 2, 15])
+    if ns > 0:
+        print(f"steps 2..12 of CTA (0,0): {cyc} cycles in {ns} ns -> SM clock {cyc / ns * 1e3:.0f} MHz while the kernel runs")
