@@ -77,6 +77,7 @@ struct TcLayerParams {
   int xsplit;                        // x part as two N=128 MMAs per K block
   int xdefer;                        // first x segment only after the gate phase of the step
   int xprefetch;                     // pull the next step's x operand image into L2 one step ahead
+  int puborder;                      // order in which a CTA serves its peers in the state exchange
   int rescale;                       // fp32 inference: peers' h' blocks are rescaled locally instead of a second all-gather
   int pubbytes;                      // TIMING DIAGNOSTIC ONLY (results are wrong if < kHBlock): bytes per state-exchange copy
   int n1, n2;                        // x-part blocks of step t+1 issued before A1 / between A1 and A2 of step t (rest after A2)
@@ -340,6 +341,9 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
           ptx::mbar_wait(&bars[BAR_HHAT + src], t & 1);
           ptx::tc_fence_after();
           if (i == 0) TC_TRACE(1, 4);
+          if (i == 1) TC_TRACE(1, 9);
+          if (i == 2) TC_TRACE(1, 10);
+          if (i == 3) TC_TRACE(1, 11);
           for (int s2 = 2 * src; s2 < 2 * src + 2; ++s2) {
             const uint32_t sa = wait_stage();
 #pragma unroll
@@ -454,12 +458,17 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       if (et == 0) {
         if (acc_empty >= 0) ptx::mbar_arrive(&bars[BAR_ACC_EMPTY + acc_empty]);
         ptx::mbar_arrive(&bars[bar + c]);                               // own chunk: usable at once
-        for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) {
-          if (peer == c) continue;
+        // Send order: CTA c serves c-1 first, then c-2, ...: a receiver walks the sources own, r+1, r+2, ... (rotated K order),
+        // so the block it needs first is the one every sender pushes first (p.puborder 0 = fixed order 0, 1, 2, ...; 2 = c+1 first)
+        for (uint32_t i = 1; i < (uint32_t)C; ++i) {
+          const uint32_t peer = p.puborder == 1 ? (c + (uint32_t)C - i) % (uint32_t)C
+                              : p.puborder == 2 ? (c + i) % (uint32_t)C
+                              : (i - 1 < c ? i - 1 : i);
           for (int part = 0; part < NP; ++part)                           // lands on the peer's barrier of source c
             ptx::bulk_s2remote(hbuf + (size_t)part * H * 256 + (size_t)c * kHBlock, (uint32_t)p.pubbytes, &bars[bar + c], peer);
-          ptx::mbar_arrive_expect_tx(&bars[bar + peer], (uint32_t)NP * (uint32_t)p.pubbytes);   // arm the barrier of the peer's block
         }
+        for (uint32_t peer = 0; peer < (uint32_t)C; ++peer)
+          if (peer != c) ptx::mbar_arrive_expect_tx(&bars[bar + peer], (uint32_t)NP * (uint32_t)p.pubbytes);   // arm the barriers of the peers' blocks
       }
     };
     // y_t = act(h'_t).  All addressing that does not depend on t is folded into per-thread bases; the values of
@@ -1078,6 +1087,7 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
     p.xsplit = getenv("A3GC_TC_XSPLIT") ? atoi(getenv("A3GC_TC_XSPLIT")) : 0;
     p.xdefer = getenv("A3GC_TC_XDEFER") ? atoi(getenv("A3GC_TC_XDEFER")) : 0;
     p.xprefetch = getenv("A3GC_TC_XPREFETCH") ? atoi(getenv("A3GC_TC_XPREFETCH")) : 0;   // measured: no effect (+-0.3 %)
+    p.puborder = getenv("A3GC_TC_PUBORDER") ? atoi(getenv("A3GC_TC_PUBORDER")) : 1;
     p.rescale = getenv("A3GC_TC_RESCALE") ? atoi(getenv("A3GC_TC_RESCALE")) : 1;
     p.pubbytes = 16384;  // = kHBlock; A3GC_TC_PUBBYTES < 16384 is a timing diagnostic (truncated state exchange, wrong results)
     if (const char* e = getenv("A3GC_TC_PUBBYTES")) { const int v = atoi(e); if (v >= 16 && v <= 16384 && v % 16 == 0) p.pubbytes = v; }

@@ -42,6 +42,7 @@ if os.environ.get("A3GC_TC_TRACE"):
         print(f"        mma " + " ".join(f"{n}={v - e[0]}" for n, v in zip(names_m, mm)))
         x = [int(v) - t0 - e[0] for v in buf[0, t, 12:15]]
         y = [int(v) - t0 - e[0] for v in buf[1, t, 8:13]]
+        print(f"        attention GEMM: hy block of peer +1 / +2 / +3 available at {y[1]} / {y[2]} / {y[3]}")
         print(f"        q-step: stores_done={x[0]} fence_done={x[1]} bar_done={x[2]} | ep1 q=1: ld_done={y[0]} sts_done={y[1]} bar1={y[2]} compute_done={y[3]} bar2={y[4]}")
     cyc = int(buf[0, 12, 1]) - int(buf[0, 2, 1]); ns = int(buf[0, 12, 15]) - int(buf[0, 2, 15])
     if ns > 0:
