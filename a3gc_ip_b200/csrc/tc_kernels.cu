@@ -77,6 +77,8 @@ struct TcLayerParams {
   int xsplit;                        // x part as two N=128 MMAs per K block
   int xdefer;                        // first x segment only after the gate phase of the step
   int xprefetch;                     // pull the next step's x operand image into L2 one step ahead
+  int earlypub;                      // 4-CTA clusters: first half of a CTA's block is sent while the second half is computed
+                                     // (measured -2..4 % per step at H = 256, +1 % at H = 128, where it stays off)
   int puborder;                      // order in which a CTA serves its peers in the state exchange
   int rescale;                       // fp32 inference: peers' h' blocks are rescaled locally instead of a second all-gather
   int pubbytes;                      // TIMING DIAGNOSTIC ONLY (results are wrong if < kHBlock): bytes per state-exchange copy
@@ -398,7 +400,11 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
     float* wst = staging + ew * kWstFloats;
     const uint32_t tmem_row = tmem + ((uint32_t)(qd * 32) << 16);
     const int ycol = blockIdx.y * H + (int)c * 64;
-    const int ubase = 16 * ug;                       // first unit (within the CTA's 64) of this warp
+    const int ubase = 16 * ug;                       // attention outputs: first unit (within the CTA's 64) of this warp
+    // gate / state units of this warp: gbase + 32 ub + [0, 8).  Unit block ub = 0 of all warps is the first half of the
+    // CTA's 64 units (K chunks 0..3 of its block of the operand image), so that half can be sent to the peers while the
+    // second unit block is still being computed.
+    const int gbase = 8 * ug;
     int bseq[2]; bool valid[2];
 #pragma unroll
     for (int sq = 0; sq < 2; ++sq) { bseq[sq] = tile * kSeqTile + 2 * qd + sq; valid[sq] = bseq[sq] < p.B; }
@@ -410,7 +416,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       for (int ub = 0; ub < 2; ++ub)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int node = tq + 8 * (j >> 1), unit = ubase + 8 * ub + 2 * tr + (j & 1);
+          const int node = tq + 8 * (j >> 1), unit = gbase + 32 * ub + 2 * tr + (j & 1);
           const bool ok = valid[sq] && node < kNodes;
           const size_t gi = ((size_t)bseq[sq] * kNodes + node) * H + c * 64 + unit;
           creg[sq][ub][j] = (ok && d.c0 != nullptr) ? d.c0[gi] : 0.f;
@@ -420,12 +426,13 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
     // write this thread's 16 values into the local operand image (rows of sequences 2qd, 2qd+1)
     // tm >= 0 (training with recurrent dropout): the image receives v * hmask[., tm, ., .], the mask of the step that will
     // consume it (net_aagc.py:181 drops the h that enters the gates only; the carried state stays unmasked)
-    auto store_units = [&](const float (&v)[2][2][4], int tm = -1) {
+    auto store_units = [&](const float (&v)[2][2][4], int tm = -1, int only_ub = -1) {
 #pragma unroll
       for (int sq = 0; sq < 2; ++sq)
 #pragma unroll
         for (int ub = 0; ub < 2; ++ub) {
-          const int k = (int)c * 64 + ubase + 8 * ub + 2 * tr;
+          if (only_ub >= 0 && ub != only_ub) continue;
+          const int k = (int)c * 64 + gbase + 32 * ub + 2 * tr;
 #pragma unroll
           for (int up = 0; up < 2; ++up) {
             uint32_t hi, lo;
@@ -471,14 +478,37 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
           if (peer != c) ptx::mbar_arrive_expect_tx(&bars[bar + peer], (uint32_t)NP * (uint32_t)p.pubbytes);   // arm the barriers of the peers' blocks
       }
     };
+    // The same hand-off in two halves: half 0 = K chunks 0..3 of this CTA's block (unit block ub = 0 of every warp), sent
+    // while the second unit block is still being computed; half 1 completes the block, arms the barriers and releases the
+    // accumulator buffer.  (A complete_tx that lands before the receiver has armed the phase is fine: the phase cannot
+    // complete before its arming arrive.)
+    auto publish_half = [&](int bar, int half, int acc_empty) {
+      ptx::fence_proxy_async();
+      if (acc_empty >= 0) ptx::tc_fence_before();
+      ptx::named_bar_sync(1, kEpiThreads);
+      if (et == 0) {
+        constexpr uint32_t kHalf = kHBlock / 2;
+        for (uint32_t i = 1; i < (uint32_t)C; ++i) {
+          const uint32_t peer = (c + (uint32_t)C - i) % (uint32_t)C;
+          for (int part = 0; part < NP; ++part)
+            ptx::bulk_s2remote(hbuf + (size_t)part * H * 256 + (size_t)c * kHBlock + (size_t)half * kHalf, kHalf, &bars[bar + c], peer);
+        }
+        if (half == 1) {
+          if (acc_empty >= 0) ptx::mbar_arrive(&bars[BAR_ACC_EMPTY + acc_empty]);
+          ptx::mbar_arrive(&bars[bar + c]);
+          for (uint32_t peer = 0; peer < (uint32_t)C; ++peer)
+            if (peer != c) ptx::mbar_arrive_expect_tx(&bars[bar + peer], (uint32_t)NP * kHBlock);
+        }
+      }
+    };
     // y_t = act(h'_t).  All addressing that does not depend on t is folded into per-thread bases; the values of
     // pad slots (node 15, sequences beyond the batch) are exact zeros already (masked in the gate phase), so the
     // operand-image stores need no predicate: the next layer multiplies those rows by zero weights of P.
-    const int col0 = ycol + ubase + 2 * tr;                        // feature of (ub = 0, unit 2tr)
+    const int col0 = ycol + gbase + 2 * tr;                        // feature of (ub = 0, unit 2tr); ub = 1 is 32 features on
     const int64_t ybase = (int64_t)bseq[0] * p.syb + (int64_t)tq * p.yld + col0;
     const int ysq = (int)p.syb, yup = 8 * (int)p.yld;               // element offsets of (sq = 1) and (node + 8)
     const size_t img_step = (size_t)p.y_kf * NP * 4096;             // bytes of one (tile, t) slab of the output image
-    const size_t img_base = ((size_t)tile * T * p.y_kf + (col0 >> 4)) * NP * 4096 + (size_t)(32 * qd + tq) * 16 + 4 * tr;
+    const size_t img_base = ((size_t)tile * T * p.y_kf + (col0 >> 4)) * NP * 4096 + (size_t)(ug & 1) * 2048 + (size_t)(32 * qd + tq) * 16 + 4 * tr;
     auto emit = [&](int ta, const float (&v)[2][2][4]) {
       const bool th = p.out_act == A3GC_ACT_TANH;
       float o[2][2][4];
@@ -497,7 +527,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
             if (!valid[sq] || (up == 1 && pad_hi)) continue;
 #pragma unroll
             for (int ub = 0; ub < 2; ++ub)
-              *reinterpret_cast<float2*>(yp + sq * ysq + up * yup + 8 * ub) = make_float2(o[sq][ub][2 * up], o[sq][ub][2 * up + 1]);
+              *reinterpret_cast<float2*>(yp + sq * ysq + up * yup + 32 * ub) = make_float2(o[sq][ub][2 * up], o[sq][ub][2 * up + 1]);
           }
       }
       if (p.y_img != nullptr) {
@@ -516,7 +546,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
                 const __nv_bfloat162 bb = __floats2bfloat162_rn(o[sq][ub][2 * up], o[sq][ub][2 * up + 1]);
                 hi = *reinterpret_cast<const uint32_t*>(&bb);
               }
-              uint8_t* q = ip + ub * 2048 + sq * 256 + up * 128;
+              uint8_t* q = ip + (size_t)ub * 2 * NP * 4096 + sq * 256 + up * 128;      // ub = 1: two K blocks (32 features) on
               *reinterpret_cast<uint32_t*>(q) = hi;
               if (SPLIT) *reinterpret_cast<uint32_t*>(q + 4096) = lo;
             }
@@ -534,9 +564,9 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
 #pragma unroll
         for (int up = 0; up < 2; ++up) {
           if (tq + 8 * up >= kNodes) continue;
-          float* hp = p.tape.hp + ((((size_t)blockIdx.y * p.B + bseq[sq]) * T + ta) * kNodes + tq + 8 * up) * H + (int)c * 64 + ubase + 2 * tr;
+          float* hp = p.tape.hp + ((((size_t)blockIdx.y * p.B + bseq[sq]) * T + ta) * kNodes + tq + 8 * up) * H + (int)c * 64 + gbase + 2 * tr;
 #pragma unroll
-          for (int ub = 0; ub < 2; ++ub) *reinterpret_cast<float2*>(hp + 8 * ub) = make_float2(hreg[sq][ub][2 * up], hreg[sq][ub][2 * up + 1]);
+          for (int ub = 0; ub < 2; ++ub) *reinterpret_cast<float2*>(hp + 32 * ub) = make_float2(hreg[sq][ub][2 * up], hreg[sq][ub][2 * up + 1]);
         }
       }
     };
@@ -561,14 +591,14 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         float e1[2][4], e2[2][4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          {   // 8 accumulator columns (gate g, units ubase+8ub .. +7) TMEM -> wst[col][row ^ swizzle(col)]
+          {   // 8 accumulator columns (gate g, units gbase+32ub .. +7) TMEM -> wst[col][row ^ swizzle(col)]
             float v[8];
-            ptx::tmem_ld8(tmem_row + b * 256 + g * 64 + ubase + 8 * ub, v);
+            ptx::tmem_ld8(tmem_row + b * 256 + g * 64 + gbase + 32 * ub, v);
             if (TRAIN) {
               // tape.u [rec][gate][unit][16]: this lane = accumulator row = (sequence, node); node slot 15 holds an exact 0
               const int rs = tile * kSeqTile + 2 * qd + (lane >> 4);
               if (p.tape.u != nullptr && rs < p.B) {
-                float* up = p.tape.u + ((((size_t)blockIdx.y * T + ta) * p.B + rs) * 4 + g) * H * 16 + (size_t)((int)c * 64 + ubase + 8 * ub) * 16 + (lane & 15);
+                float* up = p.tape.u + ((((size_t)blockIdx.y * T + ta) * p.B + rs) * 4 + g) * H * 16 + (size_t)((int)c * 64 + gbase + 32 * ub) * 16 + (lane & 15);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) up[j * 16] = v[j];
               }
@@ -582,7 +612,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
           // fp16 hi/lo split (3 passes) so the mix stays fp32-accurate
           const uint4 ah4 = Pfrag4[(g * 2 + 0) * 32 + lane], al4 = Pfrag4[(g * 2 + 1) * 32 + lane];
           const uint32_t ah[4] = {ah4.x, ah4.y, ah4.z, ah4.w}, al[4] = {al4.x, al4.y, al4.z, al4.w};
-          const float2 bias = *reinterpret_cast<const float2*>(biasg + g * 64 + ubase + 8 * ub + 2 * tr);
+          const float2 bias = *reinterpret_cast<const float2*>(biasg + g * 64 + gbase + 32 * ub + 2 * tr);
 #pragma unroll
           for (int sq = 0; sq < 2; ++sq) {
             const float* sp = wst + tq * 32;
@@ -646,12 +676,40 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
                 hreg[sq][ub][j] = ok ? hy : 0.f;
               }
               if (TRAIN && valid[sq]) {
-                const int unit = (int)c * 64 + ubase + 8 * ub + 2 * tr + (j & 1), node = tq + 8 * (j >> 1);
+                const int unit = (int)c * 64 + gbase + 32 * ub + 2 * tr + (j & 1), node = tq + 8 * (j >> 1);
                 p.tape.gates[((((size_t)blockIdx.y * T + ta) * p.B + bseq[sq]) * 4 + g) * H * 16 + (size_t)unit * 16 + node] = ok ? gv : 0.f;
               }
             }
           }
         }
+        // ---- unit block ub is final: write it into the local operand image (+ the node sums for the attention GEMM) and,
+        // for ub = 0, start sending that half of the block to the peers while the second unit block is computed
+        if (ATT) {
+          // node sum of hy (q_t = relu((sum_n hy_n) W_a^T), net_aagc.py:200) goes to row 15 of the sequence, which the
+          // attention GEMM reads as a 16th "node": the lanes owning the pad slot store it there
+          float keep[2][2];
+#pragma unroll
+          for (int sq = 0; sq < 2; ++sq)
+#pragma unroll
+            for (int u2 = 0; u2 < 2; ++u2) {
+              float sum = hreg[sq][ub][u2] + hreg[sq][ub][2 + u2];
+              sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+              sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+              sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+              keep[sq][u2] = hreg[sq][ub][2 + u2];
+              if (pad_hi) hreg[sq][ub][2 + u2] = sum;
+              if (TRAIN && pad_hi && valid[sq])
+                p.tape.s[(((size_t)blockIdx.y * T + ta) * p.B + bseq[sq]) * H + (int)c * 64 + gbase + 32 * ub + 2 * tr + u2] = sum;
+            }
+          store_units(hreg, -1, ub);
+#pragma unroll
+          for (int sq = 0; sq < 2; ++sq)
+#pragma unroll
+            for (int u2 = 0; u2 < 2; ++u2) hreg[sq][ub][2 + u2] = keep[sq][u2];
+        } else {
+          store_units(hreg, tnext, ub);
+        }
+        if (ub == 0 && C > 2 && p.earlypub) publish_half(ATT ? BAR_HHAT : BAR_H, 0, -1);
       }
       if (TRAIN) {
 #pragma unroll
@@ -662,51 +720,22 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
           for (int ub = 0; ub < 2; ++ub)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const size_t o = (rec * H + (int)c * 64 + ubase + 8 * ub + 2 * tr + (j & 1)) * 16 + tq + 8 * (j >> 1);
+              const size_t o = (rec * H + (int)c * 64 + gbase + 32 * ub + 2 * tr + (j & 1)) * 16 + tq + 8 * (j >> 1);
               p.tape.c[o] = creg[sq][ub][j];          // pad slots hold exact zeros
               p.tape.hh[o] = hreg[sq][ub][j];
             }
         }
       }
-      if (ATT) {
-        // node sum of hy (q_t = relu((sum_n hy_n) W_a^T), net_aagc.py:200) goes to row 15 of the sequence, which the
-        // attention GEMM reads as a 16th "node": the lanes owning the pad slot store it there
-        float keep[2][2][2];
-#pragma unroll
-        for (int sq = 0; sq < 2; ++sq)
-#pragma unroll
-          for (int ub = 0; ub < 2; ++ub)
-#pragma unroll
-            for (int u2 = 0; u2 < 2; ++u2) {
-              float sum = hreg[sq][ub][u2] + hreg[sq][ub][2 + u2];
-              sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-              sum += __shfl_xor_sync(0xffffffffu, sum, 8);
-              sum += __shfl_xor_sync(0xffffffffu, sum, 16);
-              keep[sq][ub][u2] = hreg[sq][ub][2 + u2];
-              if (pad_hi) hreg[sq][ub][2 + u2] = sum;
-              if (TRAIN && pad_hi && valid[sq])
-                p.tape.s[(((size_t)blockIdx.y * T + ta) * p.B + bseq[sq]) * H + (int)c * 64 + ubase + 8 * ub + 2 * tr + u2] = sum;
-            }
-        store_units(hreg);
-#pragma unroll
-        for (int sq = 0; sq < 2; ++sq)
-#pragma unroll
-          for (int ub = 0; ub < 2; ++ub)
-#pragma unroll
-            for (int u2 = 0; u2 < 2; ++u2) hreg[sq][ub][2 + u2] = keep[sq][ub][u2];
-      } else {
-        if (TRAIN) tape_hp(ta);
-        store_units(hreg, tnext);
-      }
+      if (!ATT && TRAIN) tape_hp(ta);
       if (et == 0) TC_TRACE(0, 2);
 
       if (!ATT) {
-        publish_block(BAR_H, (int)b);
+        if (C > 2 && p.earlypub) publish_half(BAR_H, 1, (int)b); else publish_block(BAR_H, (int)b);
         emit(ta, hreg);                 // global stores of y_t after the hand-off: off the recurrence's critical path
         if (et == 0) TC_TRACE(0, 11);
         continue;
       }
-      publish_block(BAR_HHAT, (int)b);
+      if (C > 2 && p.earlypub) publish_half(BAR_HHAT, 1, (int)b); else publish_block(BAR_HHAT, (int)b);
       if (et == 0) TC_TRACE(0, 4);
       // ---- q = relu(Wa . sum_n hy): rows 15 of the A1 accumulator, columns [64,128)
       ptx::mbar_wait(&bars[BAR_ATT_FULL], t & 1);
@@ -867,7 +896,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       for (int ub = 0; ub < 2; ++ub)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int node = tq + 8 * (j >> 1), unit = ubase + 8 * ub + 2 * tr + (j & 1);
+          const int node = tq + 8 * (j >> 1), unit = gbase + 32 * ub + 2 * tr + (j & 1);
           if (node >= kNodes) continue;
           const size_t gi = ((size_t)bseq[sq] * kNodes + node) * H + c * 64 + unit;
           if (d.cT != nullptr) d.cT[gi] = creg[sq][ub][j];
@@ -1087,6 +1116,7 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
     p.xsplit = getenv("A3GC_TC_XSPLIT") ? atoi(getenv("A3GC_TC_XSPLIT")) : 0;
     p.xdefer = getenv("A3GC_TC_XDEFER") ? atoi(getenv("A3GC_TC_XDEFER")) : 0;
     p.xprefetch = getenv("A3GC_TC_XPREFETCH") ? atoi(getenv("A3GC_TC_XPREFETCH")) : 0;   // measured: no effect (+-0.3 %)
+    p.earlypub = getenv("A3GC_TC_EARLYPUB") ? atoi(getenv("A3GC_TC_EARLYPUB")) : 1;
     p.puborder = getenv("A3GC_TC_PUBORDER") ? atoi(getenv("A3GC_TC_PUBORDER")) : 1;
     p.rescale = getenv("A3GC_TC_RESCALE") ? atoi(getenv("A3GC_TC_RESCALE")) : 1;
     p.pubbytes = 16384;  // = kHBlock; A3GC_TC_PUBBYTES < 16384 is a timing diagnostic (truncated state exchange, wrong results)
