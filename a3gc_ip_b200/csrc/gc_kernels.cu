@@ -39,7 +39,8 @@ gc_in_kernel(a3gc_gc_params p, const float* __restrict__ x, float* __restrict__ 
   float* wt = adj + 256;             // [K][O]   W transposed
   float* bias = wt + (size_t)K * O;  // [O]
   float* xs = bias + O;              // [8][15][K]
-  float* xm = xs + 8 * kNodes * K;   // [128][K]  (adj @ x), row 15 of each frame zero
+  const int KP = K | 1;              // odd row stride: consecutive rows of xm fall into different banks
+  float* xm = xs + 8 * kNodes * K;   // [128][KP]  (adj @ x), row 15 of each frame zero
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     const int m = i >> 4, n = i & 15;
     adj[i] = (m < kNodes && n < kNodes) ? p.adj[m * kNodes + n] : 0.f;
@@ -75,7 +76,7 @@ gc_in_kernel(a3gc_gc_params p, const float* __restrict__ x, float* __restrict__ 
 #pragma unroll
         for (int n = 0; n < kNodes; ++n) s = fmaf(adj[m * 16 + n], col[n * K], s);
       }
-      xm[i] = s;
+      xm[(size_t)row * KP + k] = s;
     }
     __syncthreads();
     if (IMG) {
@@ -84,7 +85,7 @@ gc_in_kernel(a3gc_gc_params p, const float* __restrict__ x, float* __restrict__ 
       uint8_t* base = reinterpret_cast<uint8_t*>(img) + ((size_t)tile * T + t) * (size_t)O * 128 * NP * 2;
       for (int i = threadIdx.x; i < chunks * 128; i += blockDim.x) {
         const int row = i & 127, ch = i >> 7;
-        const float* a = xm + (size_t)row * K;
+        const float* a = xm + (size_t)row * KP;
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = bias[ch * 8 + j];
@@ -114,7 +115,7 @@ gc_in_kernel(a3gc_gc_params p, const float* __restrict__ x, float* __restrict__ 
         const int qd = i % quads, r = i / quads, fr = r / kNodes, m = r % kNodes;
         const int64_t f = grp * 8 + fr;
         if (f >= frames) continue;
-        const float* a = xm + (size_t)(fr * 16 + m) * K;
+        const float* a = xm + (size_t)(fr * 16 + m) * KP;
         float acc[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[j] = (qd * 4 + j < O) ? bias[qd * 4 + j] : 0.f;
@@ -221,7 +222,7 @@ int gc_forward_fast(const a3gc_gc_params* p, const float* x, float* y, int64_t f
   if (frames == 0) { *handled = 1; return A3GC_OK; }
   const int sms = sm_count();
   if (f_in <= 32) {
-    const size_t smem = (256 + (size_t)f_in * f_out + f_out + 8 * kNodes * f_in + 128 * f_in) * sizeof(float);
+    const size_t smem = (256 + (size_t)f_in * f_out + f_out + 8 * kNodes * f_in + 128 * (f_in | 1)) * sizeof(float);
     if (smem > 160 * 1024) return A3GC_OK;
     int64_t groups = (frames + 7) / 8;
     int64_t blocks = groups < (int64_t)sms * 8 ? groups : (int64_t)sms * 8;
@@ -255,7 +256,7 @@ int gc_forward_image(const a3gc_gc_params* p, const float* x, uint16_t* img, int
                      int f_out, int act, int split, cudaStream_t stream) {
   if (batch == 0 || steps == 0) return A3GC_OK;
   if (f_in > 32 || f_out % 16 != 0) { set_error("gc_forward_image: unsupported shape"); return A3GC_ERR_UNSUPPORTED; }
-  const size_t smem = (256 + (size_t)f_in * f_out + f_out + 8 * kNodes * f_in + 128 * f_in) * sizeof(float);
+  const size_t smem = (256 + (size_t)f_in * f_out + f_out + 8 * kNodes * f_in + 128 * (f_in | 1)) * sizeof(float);
   const int64_t groups = ((batch + 7) / 8) * steps;
   const int sms = sm_count();
   int64_t blocks = groups < (int64_t)sms * 8 ? groups : (int64_t)sms * 8;
