@@ -404,7 +404,10 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
     // gate / state units of this warp: gbase + 32 ub + [0, 8).  Unit block ub = 0 of all warps is the first half of the
     // CTA's 64 units (K chunks 0..3 of its block of the operand image), so that half can be sent to the peers while the
     // second unit block is still being computed.
-    const int gbase = 8 * ug;
+    // (The training variant keeps the contiguous mapping gbase = 16 ug, unit block stride 8: it sends whole blocks, and
+    // its tape stores are measurably faster with 16 contiguous units per warp: 34 vs 40 ms per stage-1 step.)
+    constexpr int kUbs = TRAIN ? 8 : 32;             // unit distance between the two unit blocks of a warp
+    const int gbase = TRAIN ? 16 * ug : 8 * ug;
     int bseq[2]; bool valid[2];
 #pragma unroll
     for (int sq = 0; sq < 2; ++sq) { bseq[sq] = tile * kSeqTile + 2 * qd + sq; valid[sq] = bseq[sq] < p.B; }
@@ -416,7 +419,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       for (int ub = 0; ub < 2; ++ub)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int node = tq + 8 * (j >> 1), unit = gbase + 32 * ub + 2 * tr + (j & 1);
+          const int node = tq + 8 * (j >> 1), unit = gbase + kUbs * ub + 2 * tr + (j & 1);
           const bool ok = valid[sq] && node < kNodes;
           const size_t gi = ((size_t)bseq[sq] * kNodes + node) * H + c * 64 + unit;
           creg[sq][ub][j] = (ok && d.c0 != nullptr) ? d.c0[gi] : 0.f;
@@ -432,7 +435,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
 #pragma unroll
         for (int ub = 0; ub < 2; ++ub) {
           if (only_ub >= 0 && ub != only_ub) continue;
-          const int k = (int)c * 64 + gbase + 32 * ub + 2 * tr;
+          const int k = (int)c * 64 + gbase + kUbs * ub + 2 * tr;
 #pragma unroll
           for (int up = 0; up < 2; ++up) {
             uint32_t hi, lo;
@@ -508,7 +511,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
     const int64_t ybase = (int64_t)bseq[0] * p.syb + (int64_t)tq * p.yld + col0;
     const int ysq = (int)p.syb, yup = 8 * (int)p.yld;               // element offsets of (sq = 1) and (node + 8)
     const size_t img_step = (size_t)p.y_kf * NP * 4096;             // bytes of one (tile, t) slab of the output image
-    const size_t img_base = ((size_t)tile * T * p.y_kf + (col0 >> 4)) * NP * 4096 + (size_t)(ug & 1) * 2048 + (size_t)(32 * qd + tq) * 16 + 4 * tr;
+    const size_t img_base = ((size_t)tile * T * p.y_kf + (col0 >> 4)) * NP * 4096 + (TRAIN ? (size_t)0 : (size_t)(ug & 1) * 2048) + (size_t)(32 * qd + tq) * 16 + 4 * tr;
     auto emit = [&](int ta, const float (&v)[2][2][4]) {
       const bool th = p.out_act == A3GC_ACT_TANH;
       float o[2][2][4];
@@ -527,7 +530,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
             if (!valid[sq] || (up == 1 && pad_hi)) continue;
 #pragma unroll
             for (int ub = 0; ub < 2; ++ub)
-              *reinterpret_cast<float2*>(yp + sq * ysq + up * yup + 32 * ub) = make_float2(o[sq][ub][2 * up], o[sq][ub][2 * up + 1]);
+              *reinterpret_cast<float2*>(yp + sq * ysq + up * yup + kUbs * ub) = make_float2(o[sq][ub][2 * up], o[sq][ub][2 * up + 1]);
           }
       }
       if (p.y_img != nullptr) {
@@ -546,7 +549,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
                 const __nv_bfloat162 bb = __floats2bfloat162_rn(o[sq][ub][2 * up], o[sq][ub][2 * up + 1]);
                 hi = *reinterpret_cast<const uint32_t*>(&bb);
               }
-              uint8_t* q = ip + (size_t)ub * 2 * NP * 4096 + sq * 256 + up * 128;      // ub = 1: two K blocks (32 features) on
+              uint8_t* q = ip + (TRAIN ? (size_t)ub * 2048 : (size_t)ub * 2 * NP * 4096) + sq * 256 + up * 128;   // ub = 1: 8 / 32 features on
               *reinterpret_cast<uint32_t*>(q) = hi;
               if (SPLIT) *reinterpret_cast<uint32_t*>(q + 4096) = lo;
             }
@@ -566,7 +569,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
           if (tq + 8 * up >= kNodes) continue;
           float* hp = p.tape.hp + ((((size_t)blockIdx.y * p.B + bseq[sq]) * T + ta) * kNodes + tq + 8 * up) * H + (int)c * 64 + gbase + 2 * tr;
 #pragma unroll
-          for (int ub = 0; ub < 2; ++ub) *reinterpret_cast<float2*>(hp + 32 * ub) = make_float2(hreg[sq][ub][2 * up], hreg[sq][ub][2 * up + 1]);
+          for (int ub = 0; ub < 2; ++ub) *reinterpret_cast<float2*>(hp + kUbs * ub) = make_float2(hreg[sq][ub][2 * up], hreg[sq][ub][2 * up + 1]);
         }
       }
     };
@@ -593,12 +596,12 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         for (int g = 0; g < 4; ++g) {
           {   // 8 accumulator columns (gate g, units gbase+32ub .. +7) TMEM -> wst[col][row ^ swizzle(col)]
             float v[8];
-            ptx::tmem_ld8(tmem_row + b * 256 + g * 64 + gbase + 32 * ub, v);
+            ptx::tmem_ld8(tmem_row + b * 256 + g * 64 + gbase + kUbs * ub, v);
             if (TRAIN) {
               // tape.u [rec][gate][unit][16]: this lane = accumulator row = (sequence, node); node slot 15 holds an exact 0
               const int rs = tile * kSeqTile + 2 * qd + (lane >> 4);
               if (p.tape.u != nullptr && rs < p.B) {
-                float* up = p.tape.u + ((((size_t)blockIdx.y * T + ta) * p.B + rs) * 4 + g) * H * 16 + (size_t)((int)c * 64 + gbase + 32 * ub) * 16 + (lane & 15);
+                float* up = p.tape.u + ((((size_t)blockIdx.y * T + ta) * p.B + rs) * 4 + g) * H * 16 + (size_t)((int)c * 64 + gbase + kUbs * ub) * 16 + (lane & 15);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) up[j * 16] = v[j];
               }
@@ -612,7 +615,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
           // fp16 hi/lo split (3 passes) so the mix stays fp32-accurate
           const uint4 ah4 = Pfrag4[(g * 2 + 0) * 32 + lane], al4 = Pfrag4[(g * 2 + 1) * 32 + lane];
           const uint32_t ah[4] = {ah4.x, ah4.y, ah4.z, ah4.w}, al[4] = {al4.x, al4.y, al4.z, al4.w};
-          const float2 bias = *reinterpret_cast<const float2*>(biasg + g * 64 + gbase + 32 * ub + 2 * tr);
+          const float2 bias = *reinterpret_cast<const float2*>(biasg + g * 64 + gbase + kUbs * ub + 2 * tr);
 #pragma unroll
           for (int sq = 0; sq < 2; ++sq) {
             const float* sp = wst + tq * 32;
@@ -676,15 +679,17 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
                 hreg[sq][ub][j] = ok ? hy : 0.f;
               }
               if (TRAIN && valid[sq]) {
-                const int unit = (int)c * 64 + gbase + 32 * ub + 2 * tr + (j & 1), node = tq + 8 * (j >> 1);
+                const int unit = (int)c * 64 + gbase + kUbs * ub + 2 * tr + (j & 1), node = tq + 8 * (j >> 1);
                 p.tape.gates[((((size_t)blockIdx.y * T + ta) * p.B + bseq[sq]) * 4 + g) * H * 16 + (size_t)unit * 16 + node] = ok ? gv : 0.f;
               }
             }
           }
         }
         // ---- unit block ub is final: write it into the local operand image (+ the node sums for the attention GEMM) and,
-        // for ub = 0, start sending that half of the block to the peers while the second unit block is computed
-        if (ATT) {
+        // for ub = 0, start sending that half of the block to the peers while the second unit block is computed.  (The
+        // training variant, already short of registers because of the tape, does this once after both unit blocks.)
+        if (TRAIN) {
+        } else if (ATT) {
           // node sum of hy (q_t = relu((sum_n hy_n) W_a^T), net_aagc.py:200) goes to row 15 of the sequence, which the
           // attention GEMM reads as a 16th "node": the lanes owning the pad slot store it there
           float keep[2][2];
@@ -699,7 +704,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
               keep[sq][u2] = hreg[sq][ub][2 + u2];
               if (pad_hi) hreg[sq][ub][2 + u2] = sum;
               if (TRAIN && pad_hi && valid[sq])
-                p.tape.s[(((size_t)blockIdx.y * T + ta) * p.B + bseq[sq]) * H + (int)c * 64 + gbase + 32 * ub + 2 * tr + u2] = sum;
+                p.tape.s[(((size_t)blockIdx.y * T + ta) * p.B + bseq[sq]) * H + (int)c * 64 + gbase + kUbs * ub + 2 * tr + u2] = sum;
             }
           store_units(hreg, -1, ub);
 #pragma unroll
@@ -709,7 +714,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         } else {
           store_units(hreg, tnext, ub);
         }
-        if (ub == 0 && C > 2 && p.earlypub) publish_half(ATT ? BAR_HHAT : BAR_H, 0, -1);
+        if (!TRAIN && ub == 0 && C > 2 && p.earlypub) publish_half(ATT ? BAR_HHAT : BAR_H, 0, -1);
       }
       if (TRAIN) {
 #pragma unroll
@@ -720,22 +725,49 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
           for (int ub = 0; ub < 2; ++ub)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const size_t o = (rec * H + (int)c * 64 + gbase + 32 * ub + 2 * tr + (j & 1)) * 16 + tq + 8 * (j >> 1);
+              const size_t o = (rec * H + (int)c * 64 + gbase + kUbs * ub + 2 * tr + (j & 1)) * 16 + tq + 8 * (j >> 1);
               p.tape.c[o] = creg[sq][ub][j];          // pad slots hold exact zeros
               p.tape.hh[o] = hreg[sq][ub][j];
             }
         }
       }
-      if (!ATT && TRAIN) tape_hp(ta);
+      if (TRAIN && ATT) {
+        float keep[2][2][2];
+#pragma unroll
+        for (int sq = 0; sq < 2; ++sq)
+#pragma unroll
+          for (int ub = 0; ub < 2; ++ub)
+#pragma unroll
+            for (int u2 = 0; u2 < 2; ++u2) {
+              float sum = hreg[sq][ub][u2] + hreg[sq][ub][2 + u2];
+              sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+              sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+              sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+              keep[sq][ub][u2] = hreg[sq][ub][2 + u2];
+              if (pad_hi) hreg[sq][ub][2 + u2] = sum;
+              if (pad_hi && valid[sq])
+                p.tape.s[(((size_t)blockIdx.y * T + ta) * p.B + bseq[sq]) * H + (int)c * 64 + gbase + kUbs * ub + 2 * tr + u2] = sum;
+            }
+        store_units(hreg);
+#pragma unroll
+        for (int sq = 0; sq < 2; ++sq)
+#pragma unroll
+          for (int ub = 0; ub < 2; ++ub)
+#pragma unroll
+            for (int u2 = 0; u2 < 2; ++u2) hreg[sq][ub][2 + u2] = keep[sq][ub][u2];
+      } else if (TRAIN) {
+        tape_hp(ta);
+        store_units(hreg, tnext);
+      }
       if (et == 0) TC_TRACE(0, 2);
 
       if (!ATT) {
-        if (C > 2 && p.earlypub) publish_half(BAR_H, 1, (int)b); else publish_block(BAR_H, (int)b);
+        if (!TRAIN && C > 2 && p.earlypub) publish_half(BAR_H, 1, (int)b); else publish_block(BAR_H, (int)b);
         emit(ta, hreg);                 // global stores of y_t after the hand-off: off the recurrence's critical path
         if (et == 0) TC_TRACE(0, 11);
         continue;
       }
-      if (C > 2 && p.earlypub) publish_half(BAR_HHAT, 1, (int)b); else publish_block(BAR_HHAT, (int)b);
+      if (!TRAIN && C > 2 && p.earlypub) publish_half(BAR_HHAT, 1, (int)b); else publish_block(BAR_HHAT, (int)b);
       if (et == 0) TC_TRACE(0, 4);
       // ---- q = relu(Wa . sum_n hy): rows 15 of the A1 accumulator, columns [64,128)
       ptx::mbar_wait(&bars[BAR_ATT_FULL], t & 1);
@@ -896,7 +928,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       for (int ub = 0; ub < 2; ++ub)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int node = tq + 8 * (j >> 1), unit = gbase + 32 * ub + 2 * tr + (j & 1);
+          const int node = tq + 8 * (j >> 1), unit = gbase + kUbs * ub + 2 * tr + (j & 1);
           if (node >= kNodes) continue;
           const size_t gi = ((size_t)bseq[sq] * kNodes + node) * H + c * 64 + unit;
           if (d.cT != nullptr) d.cT[gi] = creg[sq][ub][j];
