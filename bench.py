@@ -161,8 +161,27 @@ def run_train(args):
     xs = [torch.randn(B, T, 15, f0, generator=g, device=dev) for f0, _, _ in shapes]
     ts = [torch.randn(B, T, 15 * o, generator=g, device=dev) for _, o, _ in shapes]
 
+    # The three stage models are independent (the reference trains each with its own run of train_a3gc_tp.py), so their
+    # optimisation steps are enqueued on three CUDA streams: the small stages fill the SMs that the H=256 stage's partial
+    # waves (reverse-time chain: 256 CTAs on 148 SMs; tcgen05 forward: 33 clusters of 4) leave idle.  --train-streams 1
+    # runs them one after the other.
+    conc = args.train_streams > 1
+    side = [torch.cuda.Stream(device=dev) for _ in nets] if conc else None
+
     def step():
-        return [A.train_step(n, crit, o, x, t, r) for n, o, x, t, r in zip(nets, opts, xs, ts, reds)]
+        if not conc:
+            return [A.train_step(n, crit, o, x, t, r) for n, o, x, t, r in zip(nets, opts, xs, ts, reds)]
+        main = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        out = []
+        for st, n, o, x, t, r in zip(side, nets, opts, xs, ts, reds):
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                out.append(A.train_step(n, crit, o, x, t, r))
+        for st in side:
+            main.wait_stream(st)
+        return out
 
     def barrier():
         if world > 1:
@@ -189,7 +208,7 @@ def run_train(args):
             "metric": "A3GC-TP train frames/sec", "value": world * B * T / (msk / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": msk, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "A3GC-TP training step (fwd + BPTT bwd + Adam, 3 stages), B=%d x T=%d per GPU (BASELINE cfg 5)" % (B, T),
-                       "dropout": "reference defaults 0.2 / 0.3 / 0.3", "allreduce_bytes_per_step": sum(r.nbytes for r in reds if r) or 0,
+                       "dropout": "reference defaults 0.2 / 0.3 / 0.3", "stage_streams": 3 if conc else 1, "allreduce_bytes_per_step": sum(r.nbytes for r in reds if r) or 0,
                        "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30},
             "gpu_launches": int(L.a3gc_launch_count()), "losses": [float(l) for l in losses],
         }))
@@ -208,6 +227,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=int(os.environ.get("A3GC_STREAMS", 4)),
                     help="batch chunks whose three-stage chains run concurrently on separate CUDA streams")
+    ap.add_argument("--train-streams", type=int, default=3, help="--workload train: 3 = the three independent stage steps on three CUDA streams, 1 = sequential")
     ap.add_argument("--variant", default="A3GC", choices=["A3GC", "AAGC", "AGC", "GGRU"],
                     help="cell family of the three-stage pipeline (headline: A3GC; the others are the cfg 3 / cfg 4 side lines)")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"], help="fp32 = parity path (headline); bf16 = cfg-3 path")
