@@ -269,8 +269,10 @@ tc_gru_layer_kernel(const GruLayerParams p) {
       ptx::named_bar_sync(1, kEpiThreads);
       if (et == 0) {
         if (acc_empty >= 0) ptx::mbar_arrive(&bars[BAR_ACC_EMPTY + acc_empty]);
-        for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) {
-          if (peer == c) continue;
+        // rotated send order (c+1, c+2, ...): every receiver is served by one sender at a time instead of all senders
+        // pushing to CTA 0 first
+        for (uint32_t i = 1; i < (uint32_t)C; ++i) {
+          const uint32_t peer = (c + i) % (uint32_t)C;
           for (int part = 0; part < NP; ++part)
             ptx::bulk_s2remote(hbuf + (size_t)part * H * 256 + (size_t)c * kHBlock, kHBlock, &bars[bar], peer);
         }
