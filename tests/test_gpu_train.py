@@ -160,3 +160,29 @@ def test_blocked_and_plain_backward_chains_agree(variant, H, B, nira, monkeypatc
     assert len(outs["1"]) == len(outs["0"]) > 10
     for a, b in zip(outs["0"], outs["1"]):
         assert rel_l2(b, a) <= 1e-5
+
+
+def test_tf32_split_and_hprev_operand_builders():
+    """a3gc_train_split_tf32: hi is exactly representable in TF32 (13 low significand bits zero), hi + lo == x bit for bit;
+    a3gc_train_hprev_split: the shifted, masked h_prev operand equals the torch construction (net_aagc.py:181-182)."""
+    from a3gc_ip_b200 import training as TR
+    torch.manual_seed(11)
+    x = (torch.randn(1027, 33, device="cuda") * torch.logspace(-20, 6, 33, device="cuda")).contiguous()
+    sp = TR._split(x)
+    assert int((sp.hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    assert torch.equal(sp.hi + sp.lo, x)
+    assert float(((sp.lo.abs() > 0) & (sp.lo.abs() > sp.hi.abs() * 2.0 ** -10)).sum()) == 0      # |lo| <= half an ulp of TF32
+    B, T, H = 5, 7, 64
+    hp = torch.randn(B, T, 15, H, device="cuda")
+    h0 = torch.randn(B, 15, H, device="cuda")
+    mask = (torch.rand(B, T, 15, H, device="cuda") >= 0.3).float() / 0.7
+    for reverse in (0, 1):
+        for m in (None, mask):
+            for z in (h0, None):
+                got = TR._hprev_split(hp, z, m, reverse)
+                first = z if z is not None else torch.zeros_like(h0)
+                want = torch.cat((hp[:, 1:], first.unsqueeze(1)), dim=1) if reverse else torch.cat((first.unsqueeze(1), hp[:, :-1]), dim=1)
+                if m is not None:
+                    want = want * m
+                assert torch.equal((got.hi + got.lo).reshape(B, T, 15, H), want)
+                assert int((got.hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
