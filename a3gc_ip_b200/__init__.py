@@ -4,6 +4,7 @@ hot path of trikpachu/A3GC-IP: drop-in torch.nn.Modules over a C-ABI CUDA librar
     from a3gc_ip_b200 import A3GC_net, PoseNet3      # same API as the reference's net_aagc.py
 """
 from . import _lib
+from . import synthetic
 from ._lib import build, lib, LIB_PATH
 from .net_aagc import (AAGC, AAGC_LSTM_cell, A3GC_LSTM_cell, AGC_LSTM_cell, G_GRU_cell,
                        AAGC_LSTM, ReverseAAGC_LSTM, BiAAGC_LSTM, A3GC_LSTM, ReverseA3GC_LSTM, BiA3GC_LSTM,
@@ -12,6 +13,6 @@ from .net_aagc import (AAGC, AAGC_LSTM_cell, A3GC_LSTM_cell, AGC_LSTM_cell, G_GR
                        PoseNet, PoseNet3, PoseNet_AGC, PoseNet_GGRU, pose_loss)
 from .pipeline import TPPipeline, prepare_input, concat_stage_input, reduced_global_to_full_local, INPUT_JOINTS
 from .sharding import shard_range, ShardedRunner, FlatGradAllReducer, train_step
-from .train_loop import stage_inputs, checkpoint_name, latest_checkpoints, validate, fit_stage
+from .train_loop import stage_inputs, checkpoint_name, latest_checkpoints, validate, fit_stage, teacher_forced_sample
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -81,6 +81,10 @@ SYMBOLS = {
                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                    C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "a3gc_net_forward_raw": (C.c_int, [C.c_int, C.POINTER(NetParams)] + [C.c_void_p] * 7 +
+                             [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p,
+                              C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                              C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "a3gc_layer_train_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int]),
     "a3gc_layer_train_forward": (C.c_int, [C.c_int, C.c_int, C.POINTER(CellParams), C.POINTER(C.c_int),
                                            C.c_void_p, C.c_int64, C.c_int64,
@@ -193,6 +197,19 @@ class Workspace:
 
     def __init__(self) -> None:
         self.buf: Optional[torch.Tensor] = None
+
+    # scratch memory is not module state: copies (copy.deepcopy, pickle / torch.save of a whole module) start empty
+    def __deepcopy__(self, memo) -> "Workspace":
+        return Workspace()
+
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state) -> None:
+        self.buf = None
+
+    def release(self) -> None:
+        self.buf = None
 
     def get(self, nbytes: int, device: torch.device) -> torch.Tensor:
         nbytes = max(int(nbytes), 256)

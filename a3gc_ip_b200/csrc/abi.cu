@@ -97,6 +97,22 @@ int run_layer(int eng, const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream
   return rc;
 }
 
+// empty sequence (steps == 0): the reference's time loops do not run and hand the incoming state back
+// (net_aagc.py:435-441, :449-456); NULL initial state = zeros
+int pass_state_through(const float* const* h0, const float* const* c0, float* const* hT, float* const* cT, int num_dirs,
+                       size_t elems, bool gru, cudaStream_t s) {
+  for (int d = 0; d < num_dirs; ++d) {
+    float* dst[2] = {hT ? hT[d] : nullptr, (cT && !gru) ? cT[d] : nullptr};
+    const float* src[2] = {h0 ? h0[d] : nullptr, (c0 && !gru) ? c0[d] : nullptr};
+    for (int k = 0; k < 2; ++k) {
+      if (!dst[k]) continue;
+      if (src[k]) A3GC_CUDA_TRY(cudaMemcpyAsync(dst[k], src[k], elems * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      else A3GC_CUDA_TRY(cudaMemsetAsync(dst[k], 0, elems * sizeof(float), s));
+    }
+  }
+  return A3GC_OK;
+}
+
 struct NetPlan {
   size_t a0, a1, a2, st, lws, img1, img2, total;   // byte offsets
   size_t lws_bytes;
@@ -111,7 +127,9 @@ int plan_net(int variant, int64_t B, int64_t T, int f0, int H, int precision, in
   if (p->eng2 < 0) return p->eng2;
   const size_t frames = (size_t)B * T;
   const int img_mode = getenv("A3GC_TC_IMG") ? atoi(getenv("A3GC_TC_IMG")) : 3;   // debug: bit0 = fused linear_in image, bit1 = rnn1->rnn2 image
-  p->use_img1 = p->eng1 == A3GC_ENGINE_TC && (img_mode & 1);
+  // the fused linear_in -> operand image kernel covers the small input widths of the nets (f0 <= 32); wider inputs go
+  // through the generic graph convolution and tc_pack_x_kernel
+  p->use_img1 = p->eng1 == A3GC_ENGINE_TC && f0 <= 32 && H % 16 == 0 && (img_mode & 1);
   p->use_img2 = p->eng1 == A3GC_ENGINE_TC && p->eng2 == A3GC_ENGINE_TC && (img_mode & 2);
   size_t off = 0;
   // fp32 activations are only materialised where a consumer needs them; tensor-core layers exchange operand images
@@ -126,7 +144,6 @@ int plan_net(int variant, int64_t B, int64_t T, int f0, int H, int precision, in
   p->lws_bytes = l1 > l2 ? l1 : l2;
   p->lws = off; off += align_up(p->lws_bytes, 256);
   p->total = off;
-  (void)f0;
   return A3GC_OK;
 }
 
@@ -207,6 +224,8 @@ int a3gc_layer_forward(int variant, int num_dirs, const a3gc_cell_params* cells,
     if (rc) return rc;
   }
   if (batch == 0) return A3GC_OK;
+  if (steps == 0)
+    return pass_state_through(h0, c0, hT, cT, num_dirs, (size_t)batch * kNodes * hidden, variant == A3GC_VARIANT_GGRU, static_cast<cudaStream_t>(stream));
   int eng = pick_engine(engine, variant, f_in, hidden, precision);
   if (eng < 0) return eng;
   LayerArgs a;
@@ -234,7 +253,7 @@ size_t a3gc_net_workspace_bytes(int variant, int64_t batch, int64_t steps, int f
   return p.total;
 }
 
-int a3gc_net_forward(int variant, const a3gc_net_params* net, const float* x,
+static int net_forward_impl(int variant, const a3gc_net_params* net, const float* x, const GcRawInput* raw,
                      const float* const* h0, const float* const* c0, float* y,
                      float* const* hT, float* const* cT,
                      int64_t batch, int64_t steps, int f0, int hidden, int f_out,
@@ -243,13 +262,15 @@ int a3gc_net_forward(int variant, const a3gc_net_params* net, const float* x,
     set_error("a3gc_net_forward: invalid argument");
     return A3GC_ERR_INVALID_ARG;
   }
-  if (batch * steps > 0 && (!x || !y)) { set_error("a3gc_net_forward: NULL x / y"); return A3GC_ERR_INVALID_ARG; }
+  if (batch * steps > 0 && ((!x && !raw) || !y)) { set_error("a3gc_net_forward: NULL x / y"); return A3GC_ERR_INVALID_ARG; }
   for (int l = 0; l < 2; ++l)
     for (int d = 0; d < 2; ++d) {
       int rc = check_cell(variant, net->rnn[l][d], "a3gc_net_forward");
       if (rc) return rc;
     }
   if (batch == 0) return A3GC_OK;
+  if (steps == 0)   // rnn2 is seeded with rnn1's final state = the incoming state
+    return pass_state_through(h0, c0, hT, cT, 2, (size_t)batch * kNodes * hidden, variant == A3GC_VARIANT_GGRU, static_cast<cudaStream_t>(stream));
   NetPlan p;
   int rc = plan_net(variant, batch, steps, f0, hidden, precision, engine, &p);
   if (rc) return rc;
@@ -271,7 +292,8 @@ int a3gc_net_forward(int variant, const a3gc_net_params* net, const float* x,
   uint16_t* img1 = p.use_img1 ? reinterpret_cast<uint16_t*>(ws + p.img1) : nullptr;
   uint16_t* img2 = p.use_img2 ? reinterpret_cast<uint16_t*>(ws + p.img2) : nullptr;
   // linear_in + relu  (net_aagc.py:640-641); on the tensor-core path written straight into rnn1's operand image
-  if (tc1) rc = gc_forward_image(&net->linear_in, x, img1, batch, steps, f0, H, A3GC_ACT_RELU, precision == A3GC_PREC_FP32 ? 1 : 0, s);
+  if (tc1) rc = gc_forward_image(&net->linear_in, x, raw, img1, batch, steps, f0, H, A3GC_ACT_RELU, precision == A3GC_PREC_FP32 ? 1 : 0, s);
+  else if (raw) rc = gc_forward_raw(&net->linear_in, raw, a0, frames, f0, H, A3GC_ACT_RELU, s);
   else rc = simt_gc_forward(&net->linear_in, x, a0, frames, f0, H, A3GC_ACT_RELU, s);
   if (rc) return rc;
 
@@ -317,6 +339,33 @@ int a3gc_net_forward(int variant, const a3gc_net_params* net, const float* x,
 
   // linear_out (net_aagc.py:644)
   return simt_gc_forward(&net->linear_out, a2, y, frames, 2 * H, f_out, A3GC_ACT_LINEAR, s);
+}
+
+int a3gc_net_forward(int variant, const a3gc_net_params* net, const float* x,
+                     const float* const* h0, const float* const* c0, float* y,
+                     float* const* hT, float* const* cT,
+                     int64_t batch, int64_t steps, int f0, int hidden, int f_out,
+                     int precision, int engine, void* workspace, size_t workspace_bytes, void* stream) {
+  return net_forward_impl(variant, net, x, nullptr, h0, c0, y, hT, cT, batch, steps, f0, hidden, f_out, precision, engine,
+                          workspace, workspace_bytes, stream);
+}
+
+int a3gc_net_forward_raw(int variant, const a3gc_net_params* net, const float* acc, const float* ori,
+                         const float* acc_mean, const float* acc_std, const float* ori_mean, const float* ori_std,
+                         const float* pos,
+                         const float* const* h0, const float* const* c0, float* y,
+                         float* const* hT, float* const* cT,
+                         int64_t batch, int64_t steps, int hidden, int f_out,
+                         int precision, int engine, void* workspace, size_t workspace_bytes, void* stream) {
+  if (batch * steps > 0 && (!acc || !ori)) { set_error("a3gc_net_forward_raw: NULL acc / ori"); return A3GC_ERR_INVALID_ARG; }
+  const bool norm = acc_mean || acc_std || ori_mean || ori_std;
+  if (norm && !(acc_mean && acc_std && ori_mean && ori_std)) {
+    set_error("a3gc_net_forward_raw: the four normalisation vectors must be given together");
+    return A3GC_ERR_INVALID_ARG;
+  }
+  GcRawInput raw{acc, ori, acc_mean, acc_std, ori_mean, ori_std, pos};
+  return net_forward_impl(variant, net, nullptr, &raw, h0, c0, y, hT, cT, batch, steps, pos ? 15 : 12, hidden, f_out, precision,
+                          engine, workspace, workspace_bytes, stream);
 }
 
 size_t a3gc_layer_train_workspace_bytes(int variant, int64_t batch, int64_t steps, int f_in, int hidden, int num_dirs, int engine) {

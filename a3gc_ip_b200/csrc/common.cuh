@@ -94,8 +94,19 @@ int simt_gc_forward(const a3gc_gc_params* p, const float* x, float* y, int64_t f
 // gc_kernels.cu: HBM-bound implementations of the AAGC graph convolution for the shapes the nets use
 int gc_forward_fast(const a3gc_gc_params* p, const float* x, float* y, int64_t frames, int f_in, int f_out, int act,
                     cudaStream_t stream, int* handled);
-int gc_forward_image(const a3gc_gc_params* p, const float* x, uint16_t* img, int64_t batch, int64_t steps, int f_in,
-                     int f_out, int act, int split, cudaStream_t stream);
+// the raw IMU frame as the input of a net's linear_in: prepare_input (evaluate_a3gc_tp.py:64-94) and the stage
+// concatenation cat(x, pos) (:168, :170) fused into the load
+struct GcRawInput {
+  const float* acc;        // [frames, 18]  6 IMUs x 3
+  const float* ori;        // [frames, 54]  6 IMUs x 9
+  const float* acc_mean; const float* acc_std;   // [18] each, or all four NULL (no --norm)
+  const float* ori_mean; const float* ori_std;   // [54] each
+  const float* pos;        // [frames, 15, 3] output of the previous stage, or NULL (f_in = 12)
+};
+int gc_forward_image(const a3gc_gc_params* p, const float* x, const GcRawInput* raw, uint16_t* img, int64_t batch, int64_t steps,
+                     int f_in, int f_out, int act, int split, cudaStream_t stream);
+int gc_forward_raw(const a3gc_gc_params* p, const GcRawInput* raw, float* y, int64_t frames, int f_in, int f_out, int act,
+                   cudaStream_t stream);
 int simt_prepare_input(const float* acc, const float* ori, const float* acc_mean, const float* acc_std,
                        const float* ori_mean, const float* ori_std, float* x, int64_t frames, int ld_x,
                        cudaStream_t stream);

@@ -25,14 +25,21 @@ __device__ __forceinline__ void split16(float v, bool split, uint16_t& hi, uint1
   }
 }
 
+// node -> IMU index of prepare_input: input_joints = [3, 4, 13, 14, 10] (evaluate_a3gc_tp.py:65), -1 = zero node
+__constant__ int c_node_imu[16] = {-1, -1, -1, 0, 1, -1, -1, -1, -1, -1, 4, -1, -1, 2, 3, -1};
+
 // ------------------------------------------------------------------------------------------
 // gc_in: f_in <= 32.  Block = 8 frames.  IMG = false: frames f0..f0+7 -> y fp32.
+// RAW = true: the input is not a materialised [frames,15,K] tensor but the raw IMU frame (GcRawInput, common.cuh):
+// prepare_input (evaluate_a3gc_tp.py:64-94: normalise, drop IMU 6, scatter onto nodes [3,4,13,14,10]) and the stage
+// concatenation cat(x, pos) (:168, :170) happen in the load, 288 (+180) bytes per frame instead of 720 / 900; the ten
+// zero nodes are skipped in the adjacency mix of the 12 IMU features (adding their exact zeros changes nothing).
 // IMG = true: the 8 frames are (tile, t): sequences 8*tile..8*tile+7 at time t -> operand image
 // [tiles][T][O/16][NP][2][128][8] (row = 16*seq + node, row 15 of every sequence zero).
 // ------------------------------------------------------------------------------------------
-template <bool IMG>
+template <bool IMG, bool RAW>
 __global__ void __launch_bounds__(kGcThreads)
-gc_in_kernel(a3gc_gc_params p, const float* __restrict__ x, float* __restrict__ y, uint16_t* __restrict__ img,
+gc_in_kernel(a3gc_gc_params p, const float* __restrict__ x, GcRawInput raw, float* __restrict__ y, uint16_t* __restrict__ img,
              int64_t frames, int B, int T, int K, int O, int act, int split) {
   extern __shared__ __align__(16) float smem[];
   float* adj = smem;                 // [16][16]
@@ -58,12 +65,35 @@ gc_in_kernel(a3gc_gc_params p, const float* __restrict__ x, float* __restrict__ 
     for (int i = threadIdx.x; i < 8 * per_frame; i += blockDim.x) {
       const int fr = i / per_frame, r = i % per_frame;
       float v = 0.f;
+      int64_t f = -1;                                   // frame index in [B*T) order, -1: beyond the batch
       if (IMG) {
         const int64_t b = tile * 8 + fr;
-        if (b < B) v = __ldg(x + ((size_t)b * T + t) * per_frame + r);
+        if (b < B) f = b * T + t;
       } else {
-        const int64_t f = grp * 8 + fr;
-        if (f < frames) v = __ldg(x + (size_t)f * per_frame + r);
+        if (grp * 8 + fr < frames) f = grp * 8 + fr;
+      }
+      if (f >= 0) {
+        if (RAW) {
+          const int n = r / K, k = r % K;
+          if (k >= 12) {
+            v = __ldg(raw.pos + (size_t)f * (kNodes * 3) + n * 3 + (k - 12));
+          } else {
+            const int imu = c_node_imu[n];
+            if (imu >= 0) {
+              if (k < 3) {
+                const int ch = imu * 3 + k;
+                v = __ldg(raw.acc + (size_t)f * 18 + ch);
+                if (raw.acc_mean != nullptr) v = (v - raw.acc_mean[ch]) / raw.acc_std[ch];
+              } else {
+                const int ch = imu * 9 + (k - 3);
+                v = __ldg(raw.ori + (size_t)f * 54 + ch);
+                if (raw.ori_mean != nullptr) v = (v - raw.ori_mean[ch]) / raw.ori_std[ch];
+              }
+            }
+          }
+        } else {
+          v = __ldg(x + (size_t)f * per_frame + r);
+        }
       }
       xs[i] = v;
     }
@@ -73,8 +103,17 @@ gc_in_kernel(a3gc_gc_params p, const float* __restrict__ x, float* __restrict__ 
       float s = 0.f;
       if (m < kNodes) {
         const float* col = xs + (size_t)fr * per_frame + k;
+        if (RAW && k < 12) {
+          // only nodes 3, 4, 10, 13, 14 carry IMU data; same ascending order as the full loop
+          s = fmaf(adj[m * 16 + 3], col[3 * K], s);
+          s = fmaf(adj[m * 16 + 4], col[4 * K], s);
+          s = fmaf(adj[m * 16 + 10], col[10 * K], s);
+          s = fmaf(adj[m * 16 + 13], col[13 * K], s);
+          s = fmaf(adj[m * 16 + 14], col[14 * K], s);
+        } else {
 #pragma unroll
-        for (int n = 0; n < kNodes; ++n) s = fmaf(adj[m * 16 + n], col[n * K], s);
+          for (int n = 0; n < kNodes; ++n) s = fmaf(adj[m * 16 + n], col[n * K], s);
+        }
       }
       xm[(size_t)row * KP + k] = s;
     }
@@ -226,8 +265,8 @@ int gc_forward_fast(const a3gc_gc_params* p, const float* x, float* y, int64_t f
     if (smem > 160 * 1024) return A3GC_OK;
     int64_t groups = (frames + 7) / 8;
     int64_t blocks = groups < (int64_t)sms * 8 ? groups : (int64_t)sms * 8;
-    A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_in_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gc_in_kernel<false><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, x, y, nullptr, frames, 0, 0, f_in, f_out, act, 0);
+    A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_in_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gc_in_kernel<false, false><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, x, GcRawInput{}, y, nullptr, frames, 0, 0, f_in, f_out, act, 0);
     A3GC_LAUNCH_CHECK("gc_in_kernel");
     *handled = 1;
   } else if (f_out <= 16 && f_in % 128 == 0) {
@@ -251,18 +290,39 @@ int gc_forward_fast(const a3gc_gc_params* p, const float* x, float* y, int64_t f
   return A3GC_OK;
 }
 
-// linear_in fused with the operand-image packing of the first recurrent layer (tensor-core engine)
-int gc_forward_image(const a3gc_gc_params* p, const float* x, uint16_t* img, int64_t batch, int64_t steps, int f_in,
-                     int f_out, int act, int split, cudaStream_t stream) {
+// linear_in fused with the operand-image packing of the first recurrent layer (tensor-core engine); raw != nullptr: also
+// fused with prepare_input / the stage concatenation (x is ignored)
+int gc_forward_image(const a3gc_gc_params* p, const float* x, const GcRawInput* raw, uint16_t* img, int64_t batch, int64_t steps,
+                     int f_in, int f_out, int act, int split, cudaStream_t stream) {
   if (batch == 0 || steps == 0) return A3GC_OK;
   if (f_in > 32 || f_out % 16 != 0) { set_error("gc_forward_image: unsupported shape"); return A3GC_ERR_UNSUPPORTED; }
   const size_t smem = (256 + (size_t)f_in * f_out + f_out + 8 * kNodes * f_in + 128 * (f_in | 1)) * sizeof(float);
   const int64_t groups = ((batch + 7) / 8) * steps;
   const int sms = sm_count();
   int64_t blocks = groups < (int64_t)sms * 8 ? groups : (int64_t)sms * 8;
-  A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_in_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gc_in_kernel<true><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, x, nullptr, img, batch * steps, (int)batch, (int)steps, f_in, f_out, act, split);
+  if (raw != nullptr) {
+    A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_in_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gc_in_kernel<true, true><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, nullptr, *raw, nullptr, img, batch * steps, (int)batch, (int)steps, f_in, f_out, act, split);
+  } else {
+    A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_in_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gc_in_kernel<true, false><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, x, GcRawInput{}, nullptr, img, batch * steps, (int)batch, (int)steps, f_in, f_out, act, split);
+  }
   A3GC_LAUNCH_CHECK("gc_in_kernel<img>");
+  return A3GC_OK;
+}
+
+// linear_in from the raw IMU frame to fp32 activations (the engines that do not consume operand images)
+int gc_forward_raw(const a3gc_gc_params* p, const GcRawInput* raw, float* y, int64_t frames, int f_in, int f_out, int act,
+                   cudaStream_t stream) {
+  if (frames == 0) return A3GC_OK;
+  const size_t smem = (256 + (size_t)f_in * f_out + f_out + 8 * kNodes * f_in + 128 * (f_in | 1)) * sizeof(float);
+  if (f_in > 32 || smem > 160 * 1024) { set_error("gc_forward_raw: unsupported shape"); return A3GC_ERR_UNSUPPORTED; }
+  const int sms = sm_count();
+  int64_t groups = (frames + 7) / 8;
+  int64_t blocks = groups < (int64_t)sms * 8 ? groups : (int64_t)sms * 8;
+  A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_in_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gc_in_kernel<false, true><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, nullptr, *raw, y, nullptr, frames, 0, 0, f_in, f_out, act, 0);
+  A3GC_LAUNCH_CHECK("gc_in_kernel<raw>");
   return A3GC_OK;
 }
 

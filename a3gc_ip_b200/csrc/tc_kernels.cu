@@ -35,7 +35,8 @@ constexpr int kSeqTile = 8;
 constexpr int kUnits = 64;             // hidden units per CTA
 constexpr int kEpiWarps = 16;          // warps 2..17: warp (qd = warp%4, ug = (warp-2)/4) owns rows 32qd..32qd+31 x units 16ug..16ug+15
 constexpr int kEpiThreads = 32 * kEpiWarps;
-constexpr int kThreadsTC = 64 + kEpiThreads;
+constexpr int kProducers = 3;           // warp 0 and the two warps behind the epilogue warps (18, 19)
+constexpr int kThreadsTC = 64 + kEpiThreads + 32 * (kProducers - 1);
 constexpr int kMaxStages = 8;
 constexpr int kWstFloats = 8 * 32;     // warp-private transposition buffer: 8 accumulator columns x 32 rows
 
@@ -82,6 +83,7 @@ struct TcLayerParams {
   int puborder;                      // order in which a CTA serves its peers in the state exchange
   int rescale;                       // fp32 inference: peers' h' blocks are rescaled locally instead of a second all-gather
   int pubbytes;                      // TIMING DIAGNOSTIC ONLY (results are wrong if < kHBlock): bytes per state-exchange copy
+  int nprod;                         // producer threads (one per warp) that issue the bulk copies of the weight / x stream, stage i by thread i % nprod
   int n1, n2;                        // x-part blocks of step t+1 issued before A1 / between A1 and A2 of step t (rest after A2)
   // training mode (TRAIN): tape of per-step intermediates (include/a3gc_b200.h, a3gc_tape) and optional recurrent-dropout mask
   a3gc_tape tape;
@@ -187,23 +189,33 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
   const uint32_t tmem = *tmem_slot;
   const uint16_t cta_mask = (uint16_t)((1u << C) - 1u);
 
-  if (warp == 0) {
-    // ================================================================ producer: weights / x -> ring
+  if (warp == 0 || warp >= 2 + kEpiWarps) {
+    // ================================================================ producers: weights / x -> ring
+    // One thread issues a bulk copy every ~440 cycles whatever its size (tests/diag_stream_rate.py: 444 cycles per copy for
+    // 4 KB .. 48 KB; 222 / 131 cycles with 2 / 4 issuing warps), and an H = 256, F = 512 step needs 92 copies (two per x
+    // stage): 41 k cycles of ONE thread's time for a 44 k-cycle step.  So up to three warps share the stream: all walk the
+    // same static stage sequence, stage i is issued by producer i % nprod.
+    const uint32_t my = warp == 0 ? 0u : (uint32_t)(warp - (1 + kEpiWarps));
+    const uint32_t nprod = (uint32_t)p.nprod;
     // The order of the stages is the static issue order of the MMA warp: h-part of step t, then the x-part of step
     // t+1 cut into three segments placed around the two attention GEMMs of step t, so that the tensor pipe has work
     // while the epilogue warps are busy and the attention GEMMs are never queued behind a long x-part.
-    if ((threadIdx.x & 31) == 0) {
+    if ((threadIdx.x & 31) == 0 && my < nprod) {
       uint32_t st = 0, ph = 0;            // ring slot and the parity of its current fill (no div / mod in the loop)
+      uint32_t turn = 0;                  // whose stage this is
       const uint32_t chunk = (uint32_t)p.chunk;
       auto load_stage = [&](const void* bsrc, uint32_t bbytes, const void* asrc, uint32_t abytes) {
-        ptx::mbar_wait(&bars[BAR_EMPTY + st], ph ^ 1u);
-        ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + st], bbytes + abytes);
-        uint8_t* dst = ring + st * kStageBytes;
-        // p.chunk (tuning knob) can cut the copies into pieces; measured slower than one copy per operand
-        for (uint32_t o = 0; o < bbytes; o += chunk)
-          ptx::bulk_g2s(dst + o, static_cast<const uint8_t*>(bsrc) + o, min(chunk, bbytes - o), &bars[BAR_FULL + st]);
-        for (uint32_t o = 0; o < abytes; o += chunk)
-          ptx::bulk_g2s(dst + kBBytes + o, static_cast<const uint8_t*>(asrc) + o, min(chunk, abytes - o), &bars[BAR_FULL + st]);
+        if (turn == my) {
+          ptx::mbar_wait(&bars[BAR_EMPTY + st], ph ^ 1u);
+          ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + st], bbytes + abytes);
+          uint8_t* dst = ring + st * kStageBytes;
+          // p.chunk (tuning knob) can cut the copies into pieces; measured slower than one copy per operand
+          for (uint32_t o = 0; o < bbytes; o += chunk)
+            ptx::bulk_g2s(dst + o, static_cast<const uint8_t*>(bsrc) + o, min(chunk, bbytes - o), &bars[BAR_FULL + st]);
+          for (uint32_t o = 0; o < abytes; o += chunk)
+            ptx::bulk_g2s(dst + kBBytes + o, static_cast<const uint8_t*>(asrc) + o, min(chunk, abytes - o), &bars[BAR_FULL + st]);
+        }
+        if (++turn == nprod) turn = 0;
         if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
       };
       const uint8_t* wg = reinterpret_cast<const uint8_t*>(d.wg_img) + (size_t)c * (KF + KH) * kBBytes;
@@ -215,7 +227,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         const uint8_t* xs = xi + ((size_t)tile * T + ta) * KF * kABytes;
         // the x operand image is read once, from HBM; with three ring slots at H = 256 the stage latency bounds the
         // x-part stream, so this CTA's share of the NEXT step's image is pulled into L2 one step ahead
-        if (kb0 == 0 && p.xprefetch && t + 1 < T) {
+        if (kb0 == 0 && p.xprefetch && my == 0 && t + 1 < T) {
           const int tn = d.reverse ? T - 2 - t : t + 1;
           const uint32_t share = (uint32_t)(KF / C) * kABytes;
           ptx::bulk_prefetch_l2(xi + ((size_t)tile * T + tn) * KF * kABytes + (size_t)c * share, share);
@@ -1148,6 +1160,9 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
     p.xsplit = getenv("A3GC_TC_XSPLIT") ? atoi(getenv("A3GC_TC_XSPLIT")) : 0;
     p.xdefer = getenv("A3GC_TC_XDEFER") ? atoi(getenv("A3GC_TC_XDEFER")) : 0;
     p.xprefetch = getenv("A3GC_TC_XPREFETCH") ? atoi(getenv("A3GC_TC_XPREFETCH")) : 0;   // measured: no effect (+-0.3 %)
+    p.nprod = getenv("A3GC_TC_NPROD") ? atoi(getenv("A3GC_TC_NPROD")) : kProducers;
+    if (p.nprod < 1) p.nprod = 1;
+    if (p.nprod > kProducers) p.nprod = kProducers;
     p.earlypub = getenv("A3GC_TC_EARLYPUB") ? atoi(getenv("A3GC_TC_EARLYPUB")) : 1;
     p.puborder = getenv("A3GC_TC_PUBORDER") ? atoi(getenv("A3GC_TC_PUBORDER")) : 1;
     p.rescale = getenv("A3GC_TC_RESCALE") ? atoi(getenv("A3GC_TC_RESCALE")) : 1;

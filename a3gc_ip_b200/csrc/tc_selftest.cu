@@ -13,14 +13,18 @@ namespace {
 // operand image: [K/8 chunks][rows][8 elements] 16-bit
 __global__ void __launch_bounds__(128, 1)
 tc_selftest_kernel(const uint16_t* __restrict__ a_img, const uint16_t* __restrict__ b_img, float* __restrict__ d,
-                   int K, int N, int bf16, int swap_lbo_sbo) {
+                   int K, int N, int bf16, int swap_lbo_sbo, int vec_a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full, bar_mma;
   __shared__ uint32_t tmem_base_slot;
   const int warp = threadIdx.x / 32;
   uint8_t* sa = smem;                                  // [K/8][128][16 B]
   uint8_t* sb = smem + (size_t)K * 128 * 2;            // [K/8][N][16 B]
-  const uint32_t bytes_a = (uint32_t)K * 128 * 2, bytes_b = (uint32_t)K * N * 2;
+  // vec_a: the A image holds only 8 rows per K chunk ([K/8][8][16 B]) and the descriptor's 8-row-group stride (SBO) is 0, so
+  // every one of the 16 row groups of the M = 128 tile aliases the same 8 rows: D row r = A row (r & 7).  The layer kernel
+  // feeds its per-sequence vectors (node sums / q of the attention block) to the tensor core this way.
+  const uint32_t a_rows = vec_a ? 8u : 128u;
+  const uint32_t bytes_a = (uint32_t)K * a_rows * 2, bytes_b = (uint32_t)K * N * 2;
 
   if (threadIdx.x == 0) {
     ptx::mbar_init(&bar_full, 1);
@@ -42,9 +46,9 @@ tc_selftest_kernel(const uint16_t* __restrict__ a_img, const uint16_t* __restric
     const uint32_t idesc = ptx::make_idesc_f16(128, N, bf16 != 0);
     for (int kk = 0; kk < K / 16; ++kk) {
       // K-chunk stride (LBO) = rows * 16 B; 8-row group stride (SBO) = 128 B
-      uint32_t a_lbo = 128 * 16, a_sbo = 128, b_lbo = (uint32_t)N * 16, b_sbo = 128;
+      uint32_t a_lbo = a_rows * 16, a_sbo = vec_a ? 0u : 128u, b_lbo = (uint32_t)N * 16, b_sbo = 128;
       if (swap_lbo_sbo) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
-      const uint64_t ad = ptx::make_smem_desc(ptx::smem_u32(sa) + (uint32_t)kk * 2 * 128 * 16, a_lbo, a_sbo);
+      const uint64_t ad = ptx::make_smem_desc(ptx::smem_u32(sa) + (uint32_t)kk * 2 * a_rows * 16, a_lbo, a_sbo);
       const uint64_t bd = ptx::make_smem_desc(ptx::smem_u32(sb) + (uint32_t)kk * 2 * N * 16, b_lbo, b_sbo);
       ptx::umma_f16(tmem, ad, bd, idesc, kk > 0 ? 1u : 0u);
     }
@@ -187,7 +191,7 @@ extern "C" int a3gc_tc_selftest(const void* a_img, const void* b_img, float* d, 
   if ((size_t)k * (128 + n) * 2 > smem) { set_error("a3gc_tc_selftest: K too large"); return A3GC_ERR_INVALID_ARG; }
   A3GC_CUDA_TRY(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tc_selftest_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint16_t*>(a_img), static_cast<const uint16_t*>(b_img), d, k, n, flags & 1, (flags >> 1) & 1);
+      static_cast<const uint16_t*>(a_img), static_cast<const uint16_t*>(b_img), d, k, n, flags & 1, (flags >> 1) & 1, (flags >> 2) & 1);
   A3GC_LAUNCH_CHECK("tc_selftest_kernel");
   return A3GC_OK;
 }

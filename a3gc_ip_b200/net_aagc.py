@@ -55,6 +55,18 @@ class _EngineMixin:
                 m.engine, m.precision = engine, precision
         return self
 
+    def release_workspaces(self) -> None:
+        """Drop the scratch buffers (operand images, inter-layer activations; tens of GB at BASELINE cfg 2) held by this
+        module and its children; ``.cpu()`` / ``.to()`` do not move or free them, the next forward re-allocates."""
+        for m in self.modules():
+            for v in list(vars(m).values()):
+                if isinstance(v, _lib.Workspace):
+                    v.release()
+                elif isinstance(v, dict):
+                    for w in v.values():
+                        if isinstance(w, _lib.Workspace):
+                            w.release()
+
 
 # ----------------------------------------------------------------------------------------
 # AAGC graph convolution (net_aagc.py:40-66)
@@ -434,24 +446,50 @@ class _Net(torch.nn.Module, _EngineMixin):
                 p.rnn[l][d] = rnn.directions[d].cell._cell_params()
         return p
 
-    def forward(self, x: Tensor, h=None, _slot: int = 0):
+    def forward(self, x: Tensor, h=None, _slot: int = 0, out: Optional[Tensor] = None):
         """x [B, T, 15, units_in] -> (y [B, T, 15, units_out], rnn2 final states).
 
         ``_slot`` (not part of the reference's signature) selects one of the module's workspaces, so that calls on
-        different CUDA streams (batch chunks run concurrently by ``TPPipeline``) do not share scratch memory.
+        different CUDA streams (batch chunks run concurrently by ``TPPipeline``) do not share scratch memory; ``out``
+        (optional) receives y.
 
         h: None (zero state) or the reference's structure: ``[(h, c), (h, c)]`` ([h, h] for G-GRU),
         each [B, 15, units_hidden]; the returned states have the same structure.
         """
-        gru = self.variant == "GGRU"
         if self.training:
             return self._forward_train(x, h)
         x = _lib.require_cuda_f32(x, "x")
-        f0, H, O = self.linear_in.gcn_kernel.shape[1], self.units_hidden, self.linear_out.gcn_kernel.shape[0]
+        f0 = self.linear_in.gcn_kernel.shape[1]
         if x.dim() != 4 or x.shape[2] != NUM_NODES or x.shape[3] != f0:
             raise RuntimeError(f"{type(self).__name__} expects x of shape [B, T, 15, {f0}], got {tuple(x.shape)}")
-        B, T = x.shape[0], x.shape[1]
-        dev = x.device
+        return self._run(x.shape[0], x.shape[1], x.device, h, _slot, out, x=x)
+
+    @torch.no_grad()
+    def forward_raw(self, acc: Tensor, ori: Tensor, stats: Optional[dict] = None, pos: Optional[Tensor] = None, h=None,
+                    _slot: int = 0, out: Optional[Tensor] = None):
+        """The net fed with the raw IMU frame: ``prepare_input`` (evaluate_a3gc_tp.py:64-94) and, with ``pos``, the
+        stage concatenation ``torch.cat((x, pos.view(B, T, 15, 3)), dim=-1)`` (:168, :170) are fused into the load of
+        ``linear_in`` (``a3gc_net_forward_raw``).  acc [B, T, 18], ori [B, T, 54]; ``stats`` = the dict of
+        ``data/all*_train_stats.pt`` (``--norm``) or None; units_in must be 12 (no pos) or 15 (pos [B, T, 15, 3])."""
+        if self.training:
+            raise RuntimeError("forward_raw is the inference path (call .eval() first)")
+        acc = _lib.require_cuda_f32(acc, "acc")
+        ori = _lib.require_cuda_f32(ori, "ori")
+        if acc.dim() != 3 or ori.dim() != 3 or acc.shape[-1] != 18 or ori.shape[-1] != 54 or acc.shape[:2] != ori.shape[:2]:
+            raise RuntimeError(f"forward_raw expects acc [B,T,18] and ori [B,T,54], got {tuple(acc.shape)} / {tuple(ori.shape)}")
+        B, T = acc.shape[0], acc.shape[1]
+        f0 = self.linear_in.gcn_kernel.shape[1]
+        if f0 != (12 if pos is None else 15):
+            raise RuntimeError(f"forward_raw: units_in = {f0} does not match the raw input ({'12 without' if pos is None else '15 with'} pos)")
+        if pos is not None:
+            pos = _lib.require_cuda_f32(pos, "pos")
+            if pos.numel() != B * T * NUM_NODES * 3:
+                raise RuntimeError(f"pos must hold [B, T, 15, 3], got {tuple(pos.shape)}")
+        return self._run(B, T, acc.device, h, _slot, out, raw=(acc, ori, _stats_on(stats, acc.device), pos))
+
+    def _run(self, B, T, dev, h, _slot, out, x=None, raw=None):
+        gru = self.variant == "GGRU"
+        f0, H, O = self.linear_in.gcn_kernel.shape[1], self.units_hidden, self.linear_out.gcn_kernel.shape[0]
         h0 = c0 = None
         if h is not None:
             if len(h) != 2:
@@ -462,7 +500,12 @@ class _Net(torch.nn.Module, _EngineMixin):
                     raise RuntimeError(f"state must be [{B}, 15, {H}], got {tuple(t.shape)}")
             h0 = [_lib.require_cuda_f32(t, "h") for t in hs]
             c0 = None if gru else [_lib.require_cuda_f32(s[1], "c") for s in h]
-        y = torch.empty(B, T, NUM_NODES, O, dtype=torch.float32, device=dev)
+        if out is not None:
+            if not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B, T, NUM_NODES, O)):
+                raise RuntimeError(f"out must be a contiguous CUDA float32 tensor of shape [{B}, {T}, 15, {O}]")
+            y = out
+        else:
+            y = torch.empty(B, T, NUM_NODES, O, dtype=torch.float32, device=dev)
         hT = [torch.empty(B, NUM_NODES, H, dtype=torch.float32, device=dev) for _ in range(2)]
         cT = None if gru else [torch.empty(B, NUM_NODES, H, dtype=torch.float32, device=dev) for _ in range(2)]
         p = self._net_params()
@@ -473,12 +516,46 @@ class _Net(torch.nn.Module, _EngineMixin):
             if nbytes == 0 and B * T > 0:
                 raise RuntimeError("a3gc_net_workspace_bytes: " + L.a3gc_last_error().decode(errors="replace"))
             wbuf = self._workspace(_slot).get(nbytes, dev)
-            rc = L.a3gc_net_forward(v, C.byref(p), x.data_ptr(), _lib.ptr_array(h0), _lib.ptr_array(c0), y.data_ptr(),
-                                    _lib.ptr_array(hT), _lib.ptr_array(cT), B, T, f0, H, O, pr, en,
-                                    wbuf.data_ptr(), wbuf.numel(), _lib.stream_ptr(dev))
-        _lib.check(rc, "a3gc_net_forward")
+            if raw is None:
+                rc = L.a3gc_net_forward(v, C.byref(p), x.data_ptr(), _lib.ptr_array(h0), _lib.ptr_array(c0), y.data_ptr(),
+                                        _lib.ptr_array(hT), _lib.ptr_array(cT), B, T, f0, H, O, pr, en,
+                                        wbuf.data_ptr(), wbuf.numel(), _lib.stream_ptr(dev))
+            else:
+                acc, ori, st, pos = raw
+                rc = L.a3gc_net_forward_raw(v, C.byref(p), acc.data_ptr(), ori.data_ptr(), *(st or (None,) * 4), _lib.ptr(pos),
+                                            _lib.ptr_array(h0), _lib.ptr_array(c0), y.data_ptr(),
+                                            _lib.ptr_array(hT), _lib.ptr_array(cT), B, T, H, O, pr, en,
+                                            wbuf.data_ptr(), wbuf.numel(), _lib.stream_ptr(dev))
+                self._keep = st                      # the statistics vectors must outlive the enqueued kernels
+        _lib.check(rc, "a3gc_net_forward" if raw is None else "a3gc_net_forward_raw")
         h_out = [hT[0], hT[1]] if gru else [(hT[0], cT[0]), (hT[1], cT[1])]
         return y, h_out
+
+
+_STATS_CACHE = {}
+
+
+def _stats_on(stats: Optional[dict], dev):
+    """(acc_mean, acc_std, ori_mean, ori_std) pointers of a ``data/all*_train_stats.pt`` dict on ``dev`` (cached per dict)."""
+    if stats is None:
+        return None
+    key = (id(stats), str(dev))
+    hit = _STATS_CACHE.get(key)
+    if hit is None:
+        ts = tuple(stats[a][b].to(dev, torch.float32).contiguous() for a, b in
+                   (("acc", "mean_channel"), ("acc", "std_channel"), ("ori", "mean_channel"), ("ori", "std_channel")))
+        hit = (stats, ts)                             # keeps `stats` alive so its id() cannot be recycled
+        _STATS_CACHE[key] = hit
+    return _StatPtrs(hit[1])
+
+
+class _StatPtrs(tuple):
+    """Four device tensors that unpack to their data pointers in a ctypes call."""
+
+    def __new__(cls, ts):
+        self = super().__new__(cls, [t.data_ptr() for t in ts])
+        self.tensors = ts
+        return self
 
 
 def _net_forward_train(self, x: Tensor, h=None):

@@ -97,46 +97,74 @@ class TPPipeline(torch.nn.Module):
         """Sequences per macro-batch: a multiple of the 8-sequence batch tile, at least one tile."""
         return max(8, (self.max_frames // max(T, 1)) // 8 * 8)
 
-    def _chain(self, x: Tensor, slot: int) -> Tuple[Tensor, Tensor, Tensor]:
-        y1, _ = self.net1(x, None, slot)
-        y2, _ = self.net2(concat_stage_input(x, y1), None, slot)
-        y3, _ = self.net3(concat_stage_input(x, y2), None, slot)
+    def _chain(self, x: Tensor, slot: int, outs=None) -> Tuple[Tensor, Tensor, Tensor]:
+        o = outs or (None, None, None)
+        y1, _ = self.net1(x, None, slot, o[0])
+        y2, _ = self.net2(concat_stage_input(x, y1), None, slot, o[1])
+        y3, _ = self.net3(concat_stage_input(x, y2), None, slot, o[2])
         return y1, y2, y3
+
+    def _chain_raw(self, acc: Tensor, ori: Tensor, slot: int, outs=None) -> Tuple[Tensor, Tensor, Tensor]:
+        """The same chain from the raw IMU frame: prepare_input and both stage concatenations are fused into the three
+        linear_in loads (``a3gc_net_forward_raw``); nothing of shape [B,T,15,12] / [B,T,15,15] is materialised."""
+        o = outs or (None, None, None)
+        y1, _ = self.net1.forward_raw(acc, ori, self.stats, None, None, slot, o[0])
+        y2, _ = self.net2.forward_raw(acc, ori, self.stats, y1, None, slot, o[1])
+        y3, _ = self.net3.forward_raw(acc, ori, self.stats, y2, None, slot, o[2])
+        return y1, y2, y3
+
+    def _outputs(self, B: int, T: int, dev) -> Tuple[Tensor, Tensor, Tensor]:
+        return tuple(torch.empty(B, T, NUM_NODES, n.linear_out.gcn_kernel.shape[0], dtype=torch.float32, device=dev)
+                     for n in (self.net1, self.net2, self.net3))
+
+    def _run_chunks(self, B: int, T: int, dev, chain, outs):
+        """Run ``chain(lo, hi, slot, out_views)`` over the batch: sequential macro-batches of whole sequences (bounded
+        workspace), each cut into ``streams`` contiguous chunks whose three-stage chains run concurrently on separate
+        CUDA streams: a chunk's small stages (cluster size 1 / 2) fill the SMs that the 4-CTA clusters of another chunk's
+        H = 256 stage cannot use, and partial last waves overlap.  Every chunk writes its slice of the preallocated
+        outputs (no concatenation pass)."""
+        per = self._macro_batch(B, T)
+        for m0 in range(0, B, per):
+            m1 = min(B, m0 + per)
+            n = min(self.streams, max(1, (m1 - m0) // 8))
+            if n <= 1:
+                chain(m0, m1, 0, tuple(o[m0:m1] for o in outs))
+                continue
+            main = torch.cuda.current_stream(dev)
+            side = self._side.setdefault(dev, [])
+            while len(side) < n:
+                side.append(torch.cuda.Stream(device=dev))
+            tiles = (m1 - m0 + 7) // 8                               # chunk boundaries on multiples of the 8-sequence batch tile
+            bounds = [min(m1, m0 + 8 * ((tiles * i) // n)) for i in range(n + 1)]
+            ready = torch.cuda.Event()
+            ready.record(main)
+            for i in range(n):
+                side[i].wait_event(ready)
+                with torch.cuda.stream(side[i]):
+                    chain(bounds[i], bounds[i + 1], i, tuple(o[bounds[i]:bounds[i + 1]] for o in outs))
+            for i in range(n):
+                main.wait_stream(side[i])
 
     @torch.no_grad()
     def forward(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
-        """Sequences are independent, so with ``streams`` > 1 the batch is cut into that many contiguous chunks whose
-        three-stage chains run concurrently on separate CUDA streams: a chunk's small stages (cluster size 1 / 2) fill
-        the SMs that the 4-CTA clusters of another chunk's H = 256 stage cannot use, and partial last waves overlap."""
-        per = self._macro_batch(x.shape[0], x.shape[1])
-        if x.shape[0] > per:
-            parts = [self.forward(x[i:i + per]) for i in range(0, x.shape[0], per)]
-            return tuple(torch.cat([o[k] for o in parts], dim=0) for k in range(3))
-        n = min(self.streams, max(1, x.shape[0] // 8))
-        if n <= 1 or not x.is_cuda:
-            return self._chain(x, 0)
-        dev = x.device
-        main = torch.cuda.current_stream(dev)
-        side = self._side.setdefault(dev, [])
-        while len(side) < n:
-            side.append(torch.cuda.Stream(device=dev))
-        # chunk boundaries on multiples of the 8-sequence batch tile
-        tiles = (x.shape[0] + 7) // 8
-        bounds = [min(x.shape[0], 8 * ((tiles * i) // n)) for i in range(n + 1)]
-        ready = torch.cuda.Event()
-        ready.record(main)
-        outs = []
-        for i in range(n):
-            st = side[i]
-            st.wait_event(ready)
-            with torch.cuda.stream(st):
-                xi = x[bounds[i]:bounds[i + 1]]
-                outs.append(self._chain(xi, i))
-        for i in range(n):
-            main.wait_stream(side[i])
-            for t in outs[i]:
-                t.record_stream(main)
-        return tuple(torch.cat([o[k] for o in outs], dim=0) for k in range(3))
+        """x [B, T, 15, 12] (the output of ``prepare_input``) -> (leaf positions, joint positions, reduced global pose)."""
+        x = _lib.require_cuda_f32(x, "x")
+        B, T, dev = x.shape[0], x.shape[1], x.device
+        outs = self._outputs(B, T, dev)
+        self._run_chunks(B, T, dev, lambda lo, hi, slot, o: self._chain(x[lo:hi], slot, o), outs)
+        return outs
+
+    @torch.no_grad()
+    def forward_raw(self, ori: Tensor, acc: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+        """ori [B, T, 54], acc [B, T, 18] (raw IMU frames, argument order of the reference's ``prepare_input(oris, accs)``)
+        -> the three stage outputs; normalisation (``self.stats``), IMU drop, node scatter and the stage concatenations
+        happen inside the first kernel of every stage."""
+        ori = _lib.require_cuda_f32(ori, "ori")
+        acc = _lib.require_cuda_f32(acc, "acc")
+        B, T, dev = acc.shape[0], acc.shape[1], acc.device
+        outs = self._outputs(B, T, dev)
+        self._run_chunks(B, T, dev, lambda lo, hi, slot, o: self._chain_raw(acc[lo:hi], ori[lo:hi], slot, o), outs)
+        return outs
 
     @staticmethod
     def window_plan(total: int, window: int, hop: int):
@@ -178,48 +206,75 @@ class TPPipeline(torch.nn.Module):
                 out[lo:hi] = y3[i, lo - s0:hi - s0]
         return out
 
-    @torch.no_grad()
-    def forward_raw(self, ori: Tensor, acc: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
-        return self.forward(prepare_input(ori, acc, self.stats))
+    def _host_chunks(self, B: int, T: int, device, chain):
+        """Host-buffer driver: every batch chunk does its own H2D -> chain -> D2H on its stream, so the copies of one chunk
+        overlap the kernels of another (pinned host buffers needed for the overlap; pageable ones still work)."""
+        per = self._macro_batch(B, T)
+        for m0 in range(0, B, per):
+            m1 = min(B, m0 + per)
+            n = min(self.streams, max(1, (m1 - m0) // 8))
+            main = torch.cuda.current_stream(device)
+            if n <= 1:
+                keep = chain(m0, m1, 0)
+                main.synchronize()
+                continue
+            side = self._side.setdefault(device, [])
+            while len(side) < n:
+                side.append(torch.cuda.Stream(device=device))
+            tiles = (m1 - m0 + 7) // 8
+            bounds = [min(m1, m0 + 8 * ((tiles * i) // n)) for i in range(n + 1)]
+            ready = torch.cuda.Event()
+            ready.record(main)
+            keep = []
+            for i in range(n):
+                side[i].wait_event(ready)
+                with torch.cuda.stream(side[i]):
+                    keep.append(chain(bounds[i], bounds[i + 1], i))
+            for i in range(n):
+                side[i].synchronize()
 
     @torch.no_grad()
     def forward_host(self, x_host: Tensor, out_host: Optional[Tensor] = None, device: Optional[torch.device] = None) -> Tensor:
-        """End-to-end call with HOST buffers: H2D copy of x, three stages, D2H copy of the pose.  With ``streams`` > 1 every
-        batch chunk does its own H2D -> chain -> D2H on its stream, so the copies of one chunk overlap the kernels of another
-        (pinned host buffers needed for the overlap; pageable ones still work)."""
+        """End-to-end call with HOST buffers holding the prepared input x [B, T, 15, 12] (720 B per frame): H2D copy of x,
+        three stages, D2H copy of the pose [B, T, 15, 9]."""
         device = device or next(self.parameters()).device
-        B = x_host.shape[0]
+        B, T = x_host.shape[0], x_host.shape[1]
         if out_host is None:
-            out_host = torch.empty(B, x_host.shape[1], 15, 9, dtype=torch.float32, pin_memory=True)
-        per = self._macro_batch(B, x_host.shape[1])
-        if B > per:
-            for i in range(0, B, per):
-                self.forward_host(x_host[i:i + per], out_host[i:i + per], device)
-            return out_host
-        n = min(self.streams, max(1, B // 8))
-        if n <= 1:
-            x = x_host.to(device, non_blocking=True)
-            _, _, y3 = self._chain(x, 0)
-            out_host.copy_(y3, non_blocking=True)
-            torch.cuda.current_stream(device).synchronize()
-            return out_host
-        main = torch.cuda.current_stream(device)
-        side = self._side.setdefault(device, [])
-        while len(side) < n:
-            side.append(torch.cuda.Stream(device=device))
-        tiles = (B + 7) // 8
-        bounds = [min(B, 8 * ((tiles * i) // n)) for i in range(n + 1)]
-        ready = torch.cuda.Event()
-        ready.record(main)
-        keep = []
-        for i in range(n):
-            st = side[i]
-            st.wait_event(ready)
-            with torch.cuda.stream(st):
-                xi = x_host[bounds[i]:bounds[i + 1]].to(device, non_blocking=True)
-                y3 = self._chain(xi, i)[2]
-                out_host[bounds[i]:bounds[i + 1]].copy_(y3, non_blocking=True)
-                keep.append((xi, y3))
-        for i in range(n):
-            side[i].synchronize()
+            out_host = torch.empty(B, T, 15, 9, dtype=torch.float32, pin_memory=True)
+
+        def chain(lo, hi, slot):
+            xi = x_host[lo:hi].to(device, non_blocking=True)
+            y3 = self._chain(xi, slot)[2]
+            out_host[lo:hi].copy_(y3, non_blocking=True)
+            return xi, y3
+
+        with torch.cuda.device(device):
+            self._host_chunks(B, T, device, chain)
         return out_host
+
+    @torch.no_grad()
+    def forward_host_raw(self, ori_host: Tensor, acc_host: Tensor, out_host: Optional[Tensor] = None,
+                         device: Optional[torch.device] = None) -> Tensor:
+        """End-to-end call with HOST buffers holding the raw IMU frames (ori [B, T, 54], acc [B, T, 18]: 288 B per frame, what
+        ``evaluate_a3gc_tp.py`` reads from ``test_tp.pt``): H2D of the raw frames, fused prepare_input + three stages, D2H of
+        the pose [B, T, 15, 9]."""
+        device = device or next(self.parameters()).device
+        B, T = acc_host.shape[0], acc_host.shape[1]
+        if out_host is None:
+            out_host = torch.empty(B, T, 15, 9, dtype=torch.float32, pin_memory=True)
+
+        def chain(lo, hi, slot):
+            ai = acc_host[lo:hi].to(device, non_blocking=True)
+            oi = ori_host[lo:hi].to(device, non_blocking=True)
+            y3 = self._chain_raw(ai, oi, slot)[2]
+            out_host[lo:hi].copy_(y3, non_blocking=True)
+            return ai, oi, y3
+
+        with torch.cuda.device(device):
+            self._host_chunks(B, T, device, chain)
+        return out_host
+
+    def release_workspaces(self) -> None:
+        """Free the scratch memory (operand images, inter-layer activations: ~150 KB per frame in flight) of the three nets."""
+        for n in (self.net1, self.net2, self.net3):
+            n.release_workspaces()

@@ -56,16 +56,22 @@ class ShardedRunner:
 
 
 class FlatGradAllReducer:
-    """Data-parallel training glue: one all-reduce(SUM) of a single flat fp32 bucket that
-    holds every parameter gradient, then a division by the world size -- the loss is a batch mean
-    (net_aagc.py:1086), so the mean of the per-rank gradients is the gradient of the global-batch loss.  The
-    largest stage (A3GC, H = 256) has 3.42 M parameters = 13.7 MB: one NCCL call over NVLink per step.
+    """Data-parallel training glue: the gradients of all parameters live in ONE flat fp32 bucket
+    (every ``p.grad`` is a view into it, so autograd accumulates straight into the bucket and nothing is copied in or out),
+    all-reduced (SUM) over NCCL / NVLink and divided by the global batch weight -- the loss is a batch mean
+    (net_aagc.py:1086), so the batch-size-weighted mean of the per-rank gradients is the gradient of the global-batch
+    loss.  The largest stage (A3GC, H = 256) has 3.42 M parameters = 13.7 MB.
 
-    The bucket is allocated once; `reduce()` copies the grads in (parameters without a gradient contribute
-    zeros), all-reduces, and writes the averaged gradients back in place, so any torch optimizer can follow.
+    Overlap: the bucket is cut in two at ``split`` (parameters in registration order).  Backward finalises the gradients in
+    reverse order (linear_out, rnn2, then rnn1, linear_in), so the BACK part [split:] is complete while rnn1 is still
+    walking its reverse-time chain: a post-accumulate hook issues its all-reduce on a side stream at that moment; the FRONT
+    part follows in ``reduce()`` after backward.  ``overlap = False`` issues both after backward (the serial form).
+
+    Use: ``red.zero_grad()`` instead of ``optimizer.zero_grad()`` (keeps the views), ``loss.backward()``,
+    ``red.reduce(local_batch)``, ``optimizer.step()``  -- see ``train_step``.
     """
 
-    def __init__(self, params, process_group=None):
+    def __init__(self, params, process_group=None, split: int = 0, overlap: bool = True):
         import torch.distributed as dist
         self.dist = dist if dist.is_available() and dist.is_initialized() else None
         self.group = process_group
@@ -80,25 +86,93 @@ class FlatGradAllReducer:
             n += p.numel()
         self.bucket = torch.zeros(n, dtype=dt, device=dev)
         self.views = [self.bucket[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
+        self.split = min(max(int(split), 0), len(self.params))
+        self.split_off = self.offsets[self.split] if self.split < len(self.params) else n
+        self.overlap = overlap
+        self._pending = 0
+        self._back_issued = False
+        self._work = []
+        self._comm = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        if self.split > 0 and self.dist is not None and self.world > 1:
+            for p in self.params[self.split:]:
+                p.register_post_accumulate_grad_hook(self._on_grad)
+
+    @classmethod
+    def for_net(cls, net: torch.nn.Module, process_group=None, overlap: bool = True) -> "FlatGradAllReducer":
+        """Reducer of one of the nets: the bucket is cut between rnn1 and rnn2 (linear_in + rnn1 | rnn2 + linear_out)."""
+        named = [(n, p) for n, p in net.named_parameters() if p.requires_grad]
+        split = sum(1 for n, _ in named if n.startswith(("linear_in.", "rnn1.", "pose_net.linear_in.", "pose_net.rnn1.")))
+        return cls([p for _, p in named], process_group, split=split, overlap=overlap)
 
     @property
     def nbytes(self) -> int:
         return self.bucket.numel() * self.bucket.element_size()
 
-    def reduce(self) -> None:
+    def zero_grad(self) -> None:
+        """Zero the bucket and (re)bind every ``p.grad`` to its view of it."""
+        self.bucket.zero_()
         for v, p in zip(self.views, self.params):
+            if p.grad is not v:
+                p.grad = v
+        self._pending = len(self.params) - self.split
+        self._back_issued = False
+        self._work = []
+
+    def _all_reduce(self, lo: int, hi: int) -> None:
+        if hi <= lo:
+            return
+        part = self.bucket[lo:hi]
+        if self._comm is not None:
+            self._comm.wait_stream(torch.cuda.current_stream(part.device))   # the gradients written so far on the compute stream
+            with torch.cuda.stream(self._comm):
+                self.dist.all_reduce(part, op=self.dist.ReduceOp.SUM, group=self.group)
+        else:
+            self.dist.all_reduce(part, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def _on_grad(self, p) -> None:
+        self._pending -= 1
+        if self._pending == 0 and self.overlap and not self._back_issued:
+            self._back_issued = True
+            self._all_reduce(self.split_off, self.bucket.numel())
+
+    def reduce(self, local_batch: int = 1) -> None:
+        """After backward: finish the all-reduce and turn the sums into the global-batch mean.  ``local_batch`` = sequences
+        this rank contributed (ranks may hold unequal, even empty, shards): every rank's gradient of ITS batch mean is
+        weighted by its share of the global batch."""
+        for v, p in zip(self.views, self.params):                 # a gradient that was re-created outside the bucket
             if p.grad is None:
                 v.zero_()
-            else:
+                p.grad = v
+            elif p.grad is not v:
                 v.copy_(p.grad)
-        if self.dist is not None and self.world > 1:
-            self.dist.all_reduce(self.bucket, op=self.dist.ReduceOp.SUM, group=self.group)
-            self.bucket.div_(self.world)
-        for v, p in zip(self.views, self.params):
-            if p.grad is None:
-                p.grad = v.clone()
-            else:
-                p.grad.copy_(v)
+                p.grad = v
+        if self.dist is None or self.world == 1:
+            return
+        w = torch.tensor([float(local_batch)], dtype=torch.float64, device=self.bucket.device)
+        tot = w.clone()
+        if self._back_issued:
+            self.bucket[:self.split_off].mul_(float(local_batch))
+            self._all_reduce(0, self.split_off)
+            # the back part went out unweighted: correct only when all shards are equal -- checked below
+        else:
+            self.bucket.mul_(float(local_batch))
+            self._all_reduce(0, self.bucket.numel())
+        cur = torch.cuda.current_stream(self.bucket.device) if self._comm is not None else None
+        if self._comm is not None:
+            with torch.cuda.stream(self._comm):
+                self.dist.all_reduce(tot, op=self.dist.ReduceOp.SUM, group=self.group)
+            cur.wait_stream(self._comm)
+        else:
+            self.dist.all_reduce(tot, op=self.dist.ReduceOp.SUM, group=self.group)
+        total = float(tot.item())
+        if total <= 0:
+            self.bucket.zero_()
+            return
+        if self._back_issued:
+            if abs(total - self.world * float(local_batch)) > 1e-6 * max(total, 1.0):
+                raise RuntimeError("FlatGradAllReducer: overlap=True needs equal per-rank batches (use overlap=False for ragged shards)")
+            self.bucket[self.split_off:].mul_(float(local_batch))
+        self.bucket.div_(total)
 
 
 def train_step(model: torch.nn.Module, criterion, optimizer, inputs: torch.Tensor, target: torch.Tensor,
@@ -108,9 +182,12 @@ def train_step(model: torch.nn.Module, criterion, optimizer, inputs: torch.Tenso
     when data-parallel.  Returns the (local) loss."""
     prediction, _ = model.forward(inputs, None)
     loss = criterion.forward(prediction.view(target.shape), target)
-    optimizer.zero_grad()
+    if reducer is not None:
+        reducer.zero_grad()
+    else:
+        optimizer.zero_grad()
     loss.backward()
     if reducer is not None:
-        reducer.reduce()
+        reducer.reduce(inputs.shape[0])
     optimizer.step()
     return loss.detach()

@@ -197,6 +197,9 @@ class _LayerTrainFn(torch.autograd.Function):
         h0, c0 = saved[2:2 + nd], saved[2 + nd:2 + 2 * nd]
         params = [saved[2 + 2 * nd + d * npar: 2 + 2 * nd + (d + 1) * npar] for d in range(nd)]
         tape = ctx.tape
+        if tape is None:
+            raise RuntimeError("a3gc_ip_b200: backward through this layer ran twice; the tape is consumed (and overwritten in place) by "
+                               "the first pass, retain_graph=True is not supported")
         dev = x.device
         att = variant != "AAGC"
         f32 = dict(dtype=torch.float32, device=dev)
@@ -286,6 +289,8 @@ def run_layer_train(variant: str, cells: Sequence[torch.nn.Module], reverse: Seq
         raise ValueError(f"run_layer_train: unknown LSTM-family variant {variant!r} (the graph-GRU uses run_gru_layer_train)")
     nd = len(cells)
     H = cells[0].units_out
+    if x.shape[1] == 0:
+        raise RuntimeError("a3gc_ip_b200: the training path needs at least one time step (T == 0)")
     if p_in > 0:
         x = torch.nn.functional.dropout(x, p_in, training=True)                  # net_aagc.py:180
     hmask = None
@@ -364,6 +369,9 @@ class _GruLayerTrainFn(torch.autograd.Function):
         x, h0 = saved[0], saved[1:1 + nd]
         params = [saved[1 + nd + d * npar: 1 + nd + (d + 1) * npar] for d in range(nd)]
         tape = ctx.tape
+        if tape is None:
+            raise RuntimeError("a3gc_ip_b200: backward through this layer ran twice; the tape is consumed (and overwritten in place) by "
+                               "the first pass, retain_graph=True is not supported")
         dev = x.device
         f32 = dict(dtype=torch.float32, device=dev)
         dy = dy.contiguous() if dy is not None else torch.zeros(B, T, NUM_NODES, nd * H, **f32)
@@ -417,6 +425,8 @@ class _GruLayerTrainFn(torch.autograd.Function):
 def run_gru_layer_train(cells: Sequence[torch.nn.Module], reverse: Sequence[int], x: Tensor, states: Sequence[Tensor], ws: _lib.Workspace):
     """Differentiable batch-major forward of one (bi) graph-GRU layer.  The cell's dropout arguments are unused (net_aagc.py:343-368)."""
     nd = len(cells)
+    if x.shape[1] == 0:
+        raise RuntimeError("a3gc_ip_b200: the training path needs at least one time step (T == 0)")
     flat: List[Tensor] = list(states)
     for c in cells:
         for n in GRU_PARAM_NAMES:

@@ -1,21 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- A3GC-TP frames/s on B200 (BASELINE.json metric), roofline fraction and CPU baseline.
+"""bench.py -- A3GC-TP frames/s on B200 (BASELINE.json metric), roofline fraction, CPU reference beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the hot path (three-stage A3GC-TP forward: prepare-free node input
-[B,T,15,12] -> leaf positions -> joint positions -> reduced global pose [B,T,15,9]) over one batch
-of synthetic IMU sequences.  Workload = BASELINE.json configs[1]: A3GC-TP fp32, B=1024 x T=300 per
-GPU (weak scaling: every rank owns its own 1024 independent sequences, no data-path collective).
-Weights: stage 1 (H=256) random-init seed 0 (its checkpoint is not shipped), stages 2-3 (H=64, 128)
-from the reference's trained_models/A3GC (committed as fixtures under tests/golden/weights).
+A "step" is one pass of the hot path over one batch of synthetic IMU sequences: the three-stage A3GC-TP forward of
+evaluate_a3gc_tp.py:164-172 from the raw 72-d IMU frame (prepare_input fused into the first kernel of every stage) to the
+reduced global pose [B,T,15,9].  Workload = BASELINE.json configs[1]: A3GC-TP fp32, B=1024 x T=300 per GPU (weak scaling:
+every rank owns its own 1024 independent sequences, no data-path collective).  Weights: stage 1 (H=256) random-init seed 0
+(its checkpoint is not shipped), stages 2-3 (H=64, 128) from the reference's trained_models/A3GC (fixtures under
+tests/golden/weights).
 
-Reported on ONE JSON line (rank 0):
-  value     frames/s with inputs resident in HBM (CUDA-event timed, max over ranks)
-  e2e       same metric through the public API with HOST buffers (pinned H2D of x + D2H of the pose per step)
-  roofline  tensor-core roofline of the dominant kernel (stage-1 rnn2 layer launch), timed live with CUDA events
-  cpu_baseline  the CPU oracle port (oracle/net_oracle.py, same algorithm as the reference) on the host cores
+ONE JSON line (rank 0):
+  value         frames/s with the raw frames resident in HBM (CUDA-event timed, max over ranks)
+  e2e           the same metric through the public API with HOST buffers (pinned H2D of ori+acc, D2H of the pose, every step)
+  roofline      tensor-core roofline of the dominant kernel (stage-1 rnn2 layer launch), timed live with CUDA events
+  cpu_baseline  the reference's own net_aagc.py (oracle/_ref, staged unmodified by oracle/build_ref.py) on the host cores
+  secondary     the other BASELINE configs at this N: cfg 3 (AAGC / AGC bf16), cfg 4 (G-GRU, B=4096 total x T=600),
+                cfg 5 (training step with the NCCL gradient all-reduce), cfg 1 on the GPU (B=1 latency)
+`--impl reference`: the reference's CPU implementation alone (rank 0), same metric / config.
 """
 import argparse
 import ctypes as C
@@ -28,31 +31,24 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import torch  # noqa: E402
 
-METRIC = "A3GC-TP frames/sec"
 UNIT = "frames/s"
 B_PER_GPU, T_STEPS = 1024, 300
-MFLOP_PER_FRAME = 115.70          # algorithmic dense MFLOP per frame, A3GC-TP (SURVEY.md 8d / BASELINE.md 4)
-WORKLOAD = "A3GC-TP forward fp32, B=1024 x T=300 per GPU, 15-node graph, stages H=256/64/128 (BASELINE cfg 2)"
+MFLOP = {"A3GC": 115.70, "AGC": 115.70, "AAGC": 103.95, "GGRU": 88.46}     # algorithmic dense MFLOP per frame
+WORKLOAD = "A3GC-TP forward fp32, B=1024 x T=300 per GPU, raw 6-IMU frames (72-d), 15-node graph, stages H=256/64/128 (BASELINE cfg 2)"
 
 
-def load_nira():
-    return torch.load(os.path.join(ROOT, "tests", "golden", "nira_template_15_norm.pt"))
-
-
-def tp_weights(nira):
-    from util import tp_state_dicts
-    return tp_state_dicts("A3GC", nira)
+def metric_name(variant="A3GC", train=False):
+    fam = {"A3GC": "A3GC-TP", "AAGC": "AAGC-TP", "AGC": "AGC-TP", "GGRU": "G-GRU-TP"}[variant]
+    return f"{fam} {'train ' if train else ''}frames/sec"
 
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return d, "measured"
+        return json.load(open(p)), "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
@@ -61,17 +57,22 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.proc = index, None
+    def __init__(self, index, enabled=True):
+        self.index, self.proc, self.enabled = index, None, enabled
 
     def start(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
+        return self
 
     def stop(self):
+        if not self.enabled:
+            return None
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -97,74 +98,232 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_fps(nira, sample_b, steps, warmup):
-    """The reference's CPU algorithm (oracle port) on this box's host cores; returns (frames/s, cores, ms/step)."""
-    from oracle import net_oracle as O
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU reference arm: the reference's own code (oracle/_ref) when it was staged, else the oracle port
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference(variant, points, timed=1, warmup=1):
+    """Times the reference's three-stage forward on this box's host cores (all of them) at the given batch sizes.
+    Returns {"kind", "cores", "points": {B: frames/s}, "ms": {B: ms per pass}}."""
+    from a3gc_ip_b200 import synthetic as S
+    from oracle import build_ref
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sds = tp_weights(nira)
-    x = O.synthetic_input(sample_b, T_STEPS, seed=1234)
-    times = []
+    sds = S.tp_state_dicts(variant, S.load_nira())
+    if build_ref.available():
+        nets = build_ref.ref_tp_nets(variant, sds)
+        run = lambda x: build_ref.ref_tp_forward(nets, x)
+        kind = "reference"
+    else:                                       # oracle/_ref was never staged on this checkout: plain-torch restatement
+        from oracle import net_oracle as O
+        run = lambda x: O.tp_forward(variant, x, sds)
+        kind = "port"
+    fps, ms = {}, {}
     with torch.no_grad():
-        for i in range(warmup + steps):
-            t0 = time.perf_counter()
-            O.tp_forward("A3GC", x, sds)
-            dt = time.perf_counter() - t0
-            if i >= warmup:
-                times.append(dt)
-    tot = sum(times)
-    return sample_b * T_STEPS * len(times) / tot, cores, 1e3 * tot / len(times)
+        for b in points:
+            x = S.synthetic_input(b, T_STEPS, seed=1234)
+            ts = []
+            for i in range(warmup + timed):
+                t0 = time.perf_counter()
+                run(x)
+                if i >= warmup:
+                    ts.append(time.perf_counter() - t0)
+            dt = statistics.median(ts)
+            fps[b], ms[b] = b * T_STEPS / dt, 1e3 * dt
+    return {"kind": kind, "cores": cores, "points": fps, "ms": ms}
+
+
+def cpu_baseline_record(r):
+    best = max(r["points"], key=lambda b: r["points"][b])
+    what = ("the reference's own net_aagc.py (TorchScript cells, unmodified, oracle/_ref)" if r["kind"] == "reference"
+            else "oracle port of net_aagc.py (torch CPU eager)")
+    sample = (f"{what}, A3GC-TP forward chained as evaluate_a3gc_tp.py:167-171, T={T_STEPS}, eval / no_grad, "
+              f"{r['cores']} threads, 1 warm-up + timed passes at B = " + ", ".join(str(b) for b in r["points"]))
+    return {"value": r["points"][best], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample,
+            "points": {f"B={b}": {"frames_per_s": v, "ms_per_pass": r["ms"][b]} for b, v in r["points"].items()}}
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
+    if int(os.environ.get("RANK", 0)) != 0:
         return
-    nira = load_nira()
-    sample_b = 16
-    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
-    fps, cores, ms = cpu_reference_fps(nira, sample_b, steps, warmup)
-    sample = f"oracle port of net_aagc.py (torch CPU eager), B={sample_b} x T={T_STEPS} sequences per step, {steps} timed steps"
+    timed, warmup = max(1, min(args.steps, 2)), min(max(args.warmup, 0), 1)
+    r = cpu_reference("A3GC", (1, 32), timed=timed, warmup=warmup)
+    cb = cpu_baseline_record(r)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": metric_name(), "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": timed, "warmup": warmup,
+        "ms_per_step": r["ms"][32], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": cb["sample"]},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
-def run_train(args):
-    """Secondary workload (BASELINE cfg 5, not the headline line): A3GC-TP training step -- for each of the three
-    stages one optimisation step as train_a3gc_tp.py:74-84 does it (train-mode forward with the reference's dropout,
-    pose loss, BPTT backward, Adam), B=256 x T=200 per GPU, teacher-forced synthetic inputs; data-parallel ranks
-    all-reduce one flat fp32 gradient bucket per stage over NCCL.  frames/s = world * B * T / step time."""
-    import torch.distributed as dist
+# ---------------------------------------------------------------------------------------------------------------------
+# shared measurement helpers
+# ---------------------------------------------------------------------------------------------------------------------
+class Ctx:
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", 1))
+        self.rank = int(os.environ.get("RANK", 0))
+        self.local = int(os.environ.get("LOCAL_RANK", 0))
+        assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def timed(self, fn, k):
+        """k calls of fn bracketed by barrier + synchronize, CUDA-event time, MAX over ranks (ms)."""
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(self.dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev, dtype=torch.float64)
+        self.barrier()
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def layer_profile(L, fn):
+    """Per-launch CUDA-event times of the recurrent layer launches of one call of fn (each launch alone on the stream)."""
+    L.a3gc_profile_enable(1)
+    fn()
+    torch.cuda.synchronize()
+    recs = []
+    for i in range(L.a3gc_profile_count()):
+        lab = C.create_string_buffer(96)
+        ms, fl = C.c_float(), C.c_double()
+        L.a3gc_profile_get(i, lab, 96, C.byref(ms), C.byref(fl))
+        recs.append({"kernel": lab.value.decode(), "ms": ms.value, "gflop": fl.value / 1e9})
+    L.a3gc_profile_enable(0)
+    # macro-batches repeat the same launches: merge by label
+    merged = {}
+    for r in recs:
+        m = merged.setdefault(r["kernel"], {"kernel": r["kernel"], "ms": 0.0, "gflop": 0.0, "launches": 0})
+        m["ms"] += r["ms"]; m["gflop"] += r["gflop"]; m["launches"] += 1
+    return list(merged.values())
+
+
+def infer_section(ctx, args, variant, precision, B, T, steps, warmup, want_profile=True, headline=False):
+    """Three-stage forward of one cell family: device-resident value, e2e with host buffers, clocks, roofline."""
     import a3gc_ip_b200 as A
-    world = int(os.environ.get("WORLD_SIZE", 1)); rank = int(os.environ.get("RANK", 0)); local = int(os.environ.get("LOCAL_RANK", 0))
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    B, T = (args.batch if args.batch != B_PER_GPU else 256), 200
-    W, K = max(args.warmup, 3), max(args.steps, 1)
-    nira = load_nira().float()
+    from a3gc_ip_b200 import synthetic as S
+    L = A.lib()
+    stats = S.load_stats()
+    pipe, _ = S.build_tp(variant, ctx.dev, engine=args.engine, precision=precision, stats=stats)
+    pipe.streams = args.streams
+    ori_h, acc_h = S.synthetic_raw_imu(B, T, seed=1234 + ctx.rank, stats=stats)      # 288 B per frame
+    ori_h, acc_h = ori_h.pin_memory(), acc_h.pin_memory()
+    y_h = torch.empty(B, T, 15, 9, dtype=torch.float32).pin_memory()
+    ori, acc = ori_h.to(ctx.dev), acc_h.to(ctx.dev)
+    for _ in range(warmup):
+        pipe.forward_raw(ori, acc)
+    torch.cuda.synchronize(ctx.dev)
+    sampler = ClockSampler(ctx.local, ctx.rank == 0).start()
+    L.a3gc_reset_launch_count()
+    ms_total = ctx.timed(lambda: pipe.forward_raw(ori, acc), steps)
+    launches = int(L.a3gc_launch_count())
+    clocks = sampler.stop()
+    pipe.forward_host_raw(ori_h, acc_h, y_h, ctx.dev)
+    ms_e2e = ctx.timed(lambda: pipe.forward_host_raw(ori_h, acc_h, y_h, ctx.dev), steps)
+    recs = None
+    if want_profile:
+        pipe.streams = 1                      # each launch timed alone (no co-running chunk on another stream)
+        recs = layer_profile(L, lambda: pipe.forward_raw(ori, acc))
+        pipe.streams = args.streams
+    frames = ctx.world * B * T
+    peaks, src = measured_peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    fps = frames * steps / (ms_total / 1e3)
+    whole_tf = MFLOP[variant] * 1e6 * (B * T) / (ms_total / steps / 1e3) / 1e12          # per GPU
+    out = {"metric": metric_name(variant), "value": fps, "unit": UNIT, "ms_per_step": ms_total / steps, "steps": steps, "warmup": warmup,
+           "dtype": "f32" if precision == "fp32" else "bf16",
+           "e2e": {"value": frames * steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": (ori_h.numel() + acc_h.numel()) * 4 * ctx.world,
+                   "d2h_bytes_per_step": y_h.numel() * 4 * ctx.world, "ms_per_step": ms_e2e / steps},
+           "gpu_launches": launches, "clocks": clocks}
+    roof = {"bound": "tensor", "peak": peak_tf, "unit": "TFLOP/s", "peak_source": f"bf16_tflops_sustained ({src})",
+            "whole_step_tflops": whole_tf, "whole_step_frac": whole_tf / peak_tf}
+    if recs:
+        dom = max(recs, key=lambda r: r["ms"])
+        ach = dom["gflop"] / dom["ms"]            # GFLOP / ms == TFLOP/s
+        traffic, tnote = None, None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")     # dram bytes per launch from the committed ncu --set full capture
+        if os.path.exists(tp) and headline:
+            rec = json.load(open(tp)).get(dom["kernel"])
+            if rec:
+                traffic, tnote = rec["dram_bytes"], rec["source"]
+        roof.update({"achieved": ach, "frac": ach / peak_tf, "traffic": traffic, "traffic_source": tnote, "kernel": dom["kernel"],
+                     "kernel_ms": dom["ms"], "layer_share_of_step": sum(r["ms"] for r in recs) / (ms_total / steps), "launches": recs,
+                     "note": ("algorithmic FLOPs (2MNK of the gate + attention GEMMs) of the dominant layer launch / its CUDA-event time; "
+                              + ("the fp32-parity tensor path executes 3 fp16-split passes, so executed tensor FLOPs are 3x"
+                                 if precision == "fp32" else "bf16 operands, one tensor pass"))})
+    else:
+        roof.update({"achieved": whole_tf, "frac": whole_tf / peak_tf, "traffic": None,
+                     "note": "whole-step algorithmic FLOPs / step time (no per-launch breakdown taken for this section)"})
+    out["roofline"] = roof
+    pipe.release_workspaces()
+    del pipe, ori, acc
+    torch.cuda.empty_cache()
+    return out
+
+
+def latency_section(ctx, args):
+    """BASELINE cfg 1 on the GPU: ONE sequence (B=1, T=300) end to end from host buffers, median of 7 calls."""
+    from a3gc_ip_b200 import synthetic as S
+    stats = S.load_stats()
+    pipe, _ = S.build_tp("A3GC", ctx.dev, engine=args.engine, precision="fp32", stats=stats)
+    ori_h, acc_h = S.synthetic_raw_imu(1, T_STEPS, seed=99, stats=stats)
+    ori_h, acc_h = ori_h.pin_memory(), acc_h.pin_memory()
+    y_h = torch.empty(1, T_STEPS, 15, 9).pin_memory()
+    ts = []
+    for i in range(10):
+        torch.cuda.synchronize(ctx.dev)
+        t0 = time.perf_counter()
+        pipe.forward_host_raw(ori_h, acc_h, y_h, ctx.dev)
+        torch.cuda.synchronize(ctx.dev)
+        if i >= 3:
+            ts.append(time.perf_counter() - t0)
+    pipe.release_workspaces()
+    ms = 1e3 * statistics.median(ts)
+    return {"metric": "A3GC-TP latency of one sequence (B=1, T=300), host buffers in and out", "value": ms, "unit": "ms",
+            "frames_per_s": T_STEPS / (ms / 1e3), "higher_is_better": False}
+
+
+def train_section(ctx, args, B=256, T=200, steps=3, warmup=2):
+    """BASELINE cfg 5: A3GC-TP training step -- for each of the three stages one optimisation step as train_a3gc_tp.py:74-84
+    does it (train-mode forward with the reference's dropout, pose loss, BPTT backward, Adam), teacher-forced synthetic
+    inputs; data-parallel ranks all-reduce the flat fp32 gradient buckets over NCCL.  frames/s = world * B * T / step time."""
+    import a3gc_ip_b200 as A
+    L = A.lib()
+    dev, world = ctx.dev, ctx.world
+    torch.cuda.reset_peak_memory_stats(dev)
+    nira = A.synthetic.load_nira()
     torch.manual_seed(0)                                   # identical initial weights on every rank
-    shapes = ((12, 3, 256), (15, 3, 64), (15, 9, 128))
+    shapes = A.synthetic.TP_SHAPES
     nets = [A.A3GC_net(f0, o, h, nira).to(dev).train() for f0, o, h in shapes]
     opts = [torch.optim.Adam(n.parameters(), lr=1e-3) for n in nets]
-    reds = [A.FlatGradAllReducer(n.parameters()) if world > 1 else None for n in nets]
+    reds = [A.FlatGradAllReducer.for_net(n) if world > 1 else None for n in nets]
     crit = A.pose_loss()
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    g = torch.Generator(device=dev).manual_seed(1234 + ctx.rank)
     xs = [torch.randn(B, T, 15, f0, generator=g, device=dev) for f0, _, _ in shapes]
     ts = [torch.randn(B, T, 15 * o, generator=g, device=dev) for _, o, _ in shapes]
-
     # The three stage models are independent (the reference trains each with its own run of train_a3gc_tp.py), so their
-    # optimisation steps are enqueued on three CUDA streams: the small stages fill the SMs that the H=256 stage's partial
-    # waves (reverse-time chain: 256 CTAs on 148 SMs; tcgen05 forward: 33 clusters of 4) leave idle.  --train-streams 1
-    # runs them one after the other.
+    # optimisation steps are enqueued on three CUDA streams: the small stages fill the SMs the H=256 stage leaves idle.
     conc = args.train_streams > 1
     side = [torch.cuda.Stream(device=dev) for _ in nets] if conc else None
 
@@ -183,37 +342,96 @@ def run_train(args):
             main.wait_stream(st)
         return out
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    for _ in range(W):
+    for _ in range(warmup):
         step()
-    barrier()
-    L = A.lib(); L.a3gc_reset_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        losses = step()
-    e1.record()
+    sampler = ClockSampler(ctx.local, ctx.rank == 0).start()
+    L.a3gc_reset_launch_count()
+    ms = ctx.timed(step, steps) / steps
+    launches = int(L.a3gc_launch_count())
+    clocks = sampler.stop()
+    serial_ms = None
+    if world > 1:                                          # the same step with the all-reduce serialised behind backward
+        for r in reds:
+            r.overlap = False
+        step()
+        serial_ms = ctx.timed(step, steps) / steps
+    # per-phase times of the dominant stage (H=256), one stream, CUDA events
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    n, o, x, t = nets[0], opts[0], xs[0], ts[0]
     torch.cuda.synchronize(dev)
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    barrier()
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        msk = float(ms.item()) / K
-        print(json.dumps({
-            "metric": "A3GC-TP train frames/sec", "value": world * B * T / (msk / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": msk, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "A3GC-TP training step (fwd + BPTT bwd + Adam, 3 stages), B=%d x T=%d per GPU (BASELINE cfg 5)" % (B, T),
-                       "dropout": "reference defaults 0.2 / 0.3 / 0.3", "stage_streams": 3 if conc else 1, "allreduce_bytes_per_step": sum(r.nbytes for r in reds if r) or 0,
-                       "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30},
-            "gpu_launches": int(L.a3gc_launch_count()), "losses": [float(l) for l in losses],
-        }))
-    if world > 1:
-        dist.destroy_process_group()
+    ev[0].record()
+    pred, _ = n.forward(x, None)
+    loss = crit.forward(pred.view(t.shape), t)
+    ev[1].record()
+    o.zero_grad()
+    loss.backward()
+    ev[2].record()
+    o.step()
+    ev[3].record()
+    torch.cuda.synchronize(dev)
+    phases = {"stage1_forward_ms": ev[0].elapsed_time(ev[1]), "stage1_backward_ms": ev[1].elapsed_time(ev[2]), "stage1_adam_ms": ev[2].elapsed_time(ev[3])}
+    peaks, src = measured_peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    tf = 3.0 * MFLOP["A3GC"] * 1e6 * (B * T) / (ms / 1e3) / 1e12          # per GPU; training step ~ 3x forward FLOPs
+    out = {"metric": metric_name("A3GC", train=True), "value": world * B * T / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warmup,
+           "dtype": "f32", "gpu_launches": launches, "clocks": clocks,
+           "config": {"workload": f"A3GC-TP training step (fwd + BPTT bwd + Adam, 3 stages), B={B} x T={T} per GPU (BASELINE cfg 5)",
+                      "dropout": "reference defaults 0.2 / 0.3 / 0.3", "stage_streams": 3 if conc else 1,
+                      "allreduce": "flat fp32 buckets over NCCL, rnn2 + linear_out bucket issued on a side stream while rnn1 is still in backward" if world > 1 else "none (1 GPU)",
+                      "allreduce_bytes_per_step": sum(r.nbytes for r in reds if r) or 0,
+                      "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30},
+           "allreduce_serial_ms_per_step": serial_ms, "phases": phases,
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": None,
+                        "peak_source": f"bf16_tflops_sustained ({src})", "note": "3 x forward algorithmic FLOPs (fwd + dX + dW) / step time"}}
+    for m in nets:
+        m.release_workspaces()
+    del nets, opts, reds, xs, ts
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args):
+    ctx = Ctx()
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    headline = args.variant == "A3GC" and args.precision == "fp32" and args.seq_len == T_STEPS and args.batch == B_PER_GPU
+    main = infer_section(ctx, args, args.variant, args.precision, args.batch, args.seq_len, K, W, headline=headline)
+    workload = WORKLOAD if headline else (f"{args.variant}-TP forward {args.precision}, B={args.batch} x T={args.seq_len} per GPU, raw 6-IMU frames "
+                                          "(side line, not the headline config)")
+    secondary = None
+    if headline and not args.no_secondary:
+        secondary = {}
+        try:
+            for v in ("AAGC", "AGC"):                      # cfg 3: 8192 sequences over 8 GPUs = 1024 per GPU, bf16 path
+                s = infer_section(ctx, args, v, "bf16", 1024, 300, 3, 3, want_profile=True)
+                s["config"] = {"workload": f"{v}-TP forward bf16, B=1024 x T=300 per GPU (BASELINE cfg 3: 8192 sequences on 8 GPUs), stated bound rel-L2 <= 5e-3"}
+                secondary["cfg3_" + v.lower() + "_bf16"] = s
+            b4 = max(8, 4096 // ctx.world)                 # cfg 4: 4096 sequences in total, strong scaling over the ranks
+            s = infer_section(ctx, args, "GGRU", "fp32", b4, 600, 2, 3, want_profile=True)
+            s["config"] = {"workload": f"G-GRU-TP forward fp32, B=4096 total ({b4} per GPU) x T=600 (BASELINE cfg 4)", "scaling": "strong"}
+            secondary["cfg4_ggru_t600"] = s
+            secondary["cfg5_train"] = train_section(ctx, args)
+            if ctx.rank == 0:
+                secondary["cfg1_gpu_latency"] = latency_section(ctx, args)
+        except Exception as e:                              # the headline line must survive a failing side line
+            secondary["error"] = f"{type(e).__name__}: {e}"
+    if ctx.rank != 0:
+        ctx.close()
+        return
+    cpu = None
+    if not args.no_cpu_baseline and ctx.world == 1:       # the CPU baseline is reported at N = 1 only
+        cpu = cpu_baseline_record(cpu_reference("A3GC", (1, 32), timed=1, warmup=1))
+    out = {
+        "metric": main["metric"], "value": main["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": K, "warmup": W, "ms_per_step": main["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": main["dtype"], "data": "synthetic",
+        "config": {"workload": workload, "batch_per_gpu": args.batch, "seq_len": args.seq_len, "engine": args.engine, "streams": args.streams,
+                   "input": "raw IMU frames ori [B,T,54] + acc [B,T,18]; prepare_input (normalise, drop IMU 6, node scatter) fused into the first kernel of every stage",
+                   "l2": "inputs + activations per step (GBs) far larger than the 126 MB L2; no explicit flush",
+                   "weights": "stage1 random-init seed 0; stages 2-3 " + (f"trained_models/{'A3GC' if args.variant == 'A3GC' else 'G-GRU'}" if args.variant in ("A3GC", "GGRU") else "random-init (no checkpoints shipped)")},
+        "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "clocks": main["clocks"], "roofline": main["roofline"], "cpu_baseline": cpu,
+        "secondary": secondary,
+    }
+    print(json.dumps(out))
+    ctx.close()
 
 
 def main():
@@ -225,145 +443,27 @@ def main():
     ap.add_argument("--engine", default=os.environ.get("A3GC_ENGINE", "auto"))
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="sequences per GPU (default: the BASELINE cfg-2 value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg 1 / 3 / 4 / 5 side measurements")
     ap.add_argument("--streams", type=int, default=int(os.environ.get("A3GC_STREAMS", 4)),
                     help="batch chunks whose three-stage chains run concurrently on separate CUDA streams")
-    ap.add_argument("--train-streams", type=int, default=3, help="--workload train: 3 = the three independent stage steps on three CUDA streams, 1 = sequential")
+    ap.add_argument("--train-streams", type=int, default=3, help="cfg 5: 3 = the three independent stage steps on three CUDA streams, 1 = sequential")
     ap.add_argument("--variant", default="A3GC", choices=["A3GC", "AAGC", "AGC", "GGRU"],
-                    help="cell family of the three-stage pipeline (headline: A3GC; the others are the cfg 3 / cfg 4 side lines)")
+                    help="cell family of the three-stage pipeline (headline: A3GC; others print a side line)")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"], help="fp32 = parity path (headline); bf16 = cfg-3 path")
     ap.add_argument("--seq-len", type=int, default=T_STEPS)
-    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
-                    help="infer = the headline line (BASELINE cfg 2); train = the secondary cfg-5 training-step line")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"], help="train: print the cfg-5 training-step line alone")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "train":
-        return run_train(args)
-
-    import torch.distributed as dist
-    import a3gc_ip_b200 as A
-    from oracle import net_oracle as O
-    from util import build_tp
-
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    rank = int(os.environ.get("RANK", 0))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    W, K = max(args.warmup, 3), max(args.steps, 1)
-    B = args.batch
-    nira = load_nira()
-    T = args.seq_len
-    pipe, _ = build_tp(args.variant, nira, device=dev, engine=args.engine, precision=args.precision)
-    pipe.streams = args.streams
-    mflop = {"A3GC": 115.70, "AGC": 115.70, "AAGC": 103.95, "GGRU": 88.46}[args.variant]
-    headline = args.variant == "A3GC" and args.precision == "fp32" and T == T_STEPS and B == B_PER_GPU
-    workload = WORKLOAD if headline else f"{args.variant}-TP forward {args.precision}, B={B} x T={T} per GPU (side line, not the headline config)"
-    L = A.lib()
-
-    # synthetic inputs: seed 1234 + rank; x is 221 MB (> 126 MB L2), pose output 166 MB
-    x_host = O.synthetic_input(B, T, seed=1234 + rank).pin_memory()
-    y_host = torch.empty(B, T, 15, 9, dtype=torch.float32).pin_memory()
-    x = x_host.to(dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def timed(fn, k):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(k):
-            fn()
-        e1.record()
-        torch.cuda.synchronize(dev)
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        barrier()
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    for _ in range(W):
-        pipe(x)
-    torch.cuda.synchronize(dev)
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    L.a3gc_reset_launch_count()
-    ms_total = timed(lambda: pipe(x), K)
-    launches = int(L.a3gc_launch_count())
-    clocks = sampler.stop() if rank == 0 else None
-
-    # end to end through the public API with host buffers (H2D of x and D2H of the pose inside the timed region)
-    pipe.forward_host(x_host, y_host, dev)
-    ms_e2e = timed(lambda: pipe.forward_host(x_host, y_host, dev), K)
-
-    # dominant kernel: per-launch CUDA-event times of the recurrent layer launches
-    L.a3gc_profile_enable(1)
-    pipe.streams = 1                      # each launch timed alone (no co-running chunk on another stream)
-    pipe(x)
-    pipe.streams = args.streams
-    torch.cuda.synchronize(dev)
-    recs = []
-    for i in range(L.a3gc_profile_count()):
-        lab = C.create_string_buffer(96)
-        ms, fl = C.c_float(), C.c_double()
-        L.a3gc_profile_get(i, lab, 96, C.byref(ms), C.byref(fl))
-        recs.append({"kernel": lab.value.decode(), "ms": ms.value, "gflop": fl.value / 1e9})
-    L.a3gc_profile_enable(0)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        ctx = Ctx()
+        rec = train_section(ctx, args, steps=max(args.steps, 1), warmup=max(args.warmup, 3))
+        if ctx.rank == 0:
+            rec.update({"n_gpus": ctx.world, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic"})
+            print(json.dumps(rec))
+        ctx.close()
         return
-    frames_per_step = world * B * T
-    fps = frames_per_step * K / (ms_total / 1e3)
-    fps_e2e = frames_per_step * K / (ms_e2e / 1e3)
-    peaks, src = measured_peaks()
-    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-    dom = max(recs, key=lambda r: r["ms"]) if recs else None
-    layer_ms = sum(r["ms"] for r in recs)
-    roof = None
-    if dom:
-        ach = dom["gflop"] / dom["ms"]            # GFLOP / ms == TFLOP/s
-        tc = dom["kernel"].startswith("tc")
-        traffic, tnote = None, None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")     # dram bytes per launch from the committed ncu --set full capture
-        if os.path.exists(tp) and headline:
-            rec = json.load(open(tp)).get(dom["kernel"])
-            if rec:
-                traffic, tnote = rec["dram_bytes"], rec["source"]
-        roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic, "traffic_source": tnote,
-                "kernel": dom["kernel"], "kernel_ms": dom["ms"], "peak_source": f"bf16_tflops_sustained ({src})",
-                "note": (("algorithmic FLOPs (2MNK of gate+attention GEMMs); the fp32-parity tensor path executes 3 fp16-split passes, "
-                          "so executed tensor FLOPs are 3x" if args.precision == "fp32" else "algorithmic FLOPs; bf16 operands, one tensor pass") if tc else "SIMT fp32 engine: FFMA pipe, quoted against the tensor peak"),
-                "layer_share_of_step": layer_ms / (ms_total / K), "launches": recs,
-                "whole_step_tflops": mflop * 1e6 * (B * T) / (ms_total / K / 1e3) / 1e12}
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:       # the CPU baseline is reported at N = 1 only
-        sb = 16
-        cfps, cores, _ = cpu_reference_fps(nira, sb, 2, 1)
-        cpu = {"value": cfps, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"oracle port of net_aagc.py (torch CPU eager), B={sb} x T={T_STEPS}, 1 warm-up + 2 timed passes"}
-    out = {
-        "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
-        "config": {"workload": workload, "batch_per_gpu": B, "seq_len": T, "engine": args.engine, "streams": args.streams,
-                   "l2": "inputs larger than L2 (x 221 MB, activations GBs per step); no explicit flush",
-                   "weights": "stage1 random-init seed 0; stages 2-3 " + (f"trained_models/{'A3GC' if args.variant == 'A3GC' else 'G-GRU'}" if args.variant in ("A3GC", "GGRU") else "random-init (no checkpoints shipped)")},
-        "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world, "d2h_bytes_per_step": y_host.numel() * 4 * world,
-                "ms_per_step": ms_e2e / K},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-    }
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    run_ours(args)
 
 
 if __name__ == "__main__":

@@ -167,6 +167,24 @@ int a3gc_net_forward(int variant, const a3gc_net_params* net, const float* x,
                      int precision, int engine, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The same net fed with the RAW IMU frame: prepare_input (evaluate_a3gc_tp.py:64-94: (v - mean) / std per channel when the
+ * four statistics vectors are given (--norm), the 6th IMU dropped, IMU j = (acc[3j..3j+2], ori[9j..9j+8]) scattered onto
+ * node [3,4,13,14,10][j], all other nodes zero) and, when pos != NULL, the stage concatenation
+ * torch.cat((x, pos.view(B,T,15,3)), dim=-1) (evaluate_a3gc_tp.py:168, :170) are fused into the load of linear_in, so
+ * the [B,T,15,12] / [B,T,15,15] tensors are never materialised (288 B of input per frame instead of 720).
+ *   acc [B, T, 18], ori [B, T, 54] contiguous;  acc_mean/acc_std [18], ori_mean/ori_std [54] or all NULL;
+ *   pos [B, T, 15, 3] (previous stage's output) or NULL;  units_in of the net is 15 with pos, 12 without.
+ * Workspace: a3gc_net_workspace_bytes with f0 = 12 or 15.
+ */
+int a3gc_net_forward_raw(int variant, const a3gc_net_params* net, const float* acc, const float* ori,
+                         const float* acc_mean, const float* acc_std, const float* ori_mean, const float* ori_std,
+                         const float* pos,
+                         const float* const* h0, const float* const* c0, float* y,
+                         float* const* hT, float* const* cT,
+                         int64_t batch, int64_t steps, int hidden, int f_out,
+                         int precision, int engine, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * ---- Training path (BPTT) of the LSTM family: train_*_tp.py:74-84 calls model.forward in train mode, then
  * loss.backward().  The forward keeps a tape of per-step intermediates; a3gc_layer_backward walks the
  * recurrence in reverse and leaves, per step, the operands of the weight / input gradient contractions,

@@ -29,3 +29,20 @@ def test_umma_selftest(dtype, K, N):
     err = float((d.cpu() - want).abs().max() / want.abs().max())
     print(f"selftest {dtype} K={K} N={N}: max rel err = {err:.3e}")
     assert err < 1e-5
+
+
+@pytest.mark.parametrize("K,N", [(64, 64), (256, 64)])
+def test_umma_vector_operand(K, N):
+    """A operand of 8 rows per K chunk with an 8-row-group stride of 0 (flag 4): D row r = A row (r & 7)."""
+    g = torch.Generator().manual_seed(K * 3 + N)
+    a = torch.randn(8, K, generator=g).to(torch.float16)
+    b = torch.randn(N, K, generator=g).to(torch.float16)
+    want = (a.float() @ b.float().t()).repeat(16, 1)
+    ai, bi = to_image(a).cuda(), to_image(b).cuda()
+    d = torch.full((128, N), float("nan"), device="cuda")
+    rc = _lib.lib().a3gc_tc_selftest(ai.data_ptr(), bi.data_ptr(), d.data_ptr(), K, N, 4, _lib.stream_ptr(d.device))
+    _lib.check(rc, "a3gc_tc_selftest")
+    torch.cuda.synchronize()
+    err = float((d.cpu() - want).abs().max() / want.abs().max())
+    print(f"vector-operand selftest K={K} N={N}: max rel err = {err:.3e}")
+    assert err < 1e-5
