@@ -1,19 +1,21 @@
 // tcgen05 / TMEM engine for the graph-GRU recurrent layers (G_GRU_cell, net_aagc.py:343-368, looped as in :547-568).
 //
-//   msg = P^T-mix (h Wg^T)                      G1: D1[128, 64]  = h[128, H]   * Wg_c[64, H]^T      (tcgen05, N = 64)
-//   r = sig(Wri x + br + Wrh msg)               G2: D2[128, 256] = x[128, F]   * [Wri; Wui; Wci]^T  (N = 192, cols r | u | cx)
-//   u = sig(Wui x + bu + Wuh msg)                               + msg[128, H] * [Wrh; Wuh]^T       (N = 128, cols r | u)
-//   c = tanh(Wci x + bc + r * (Wch msg))                        ,  msg[128, H] * Wch^T             (N = 64,  cols ch)
-//   h' = u h + (1 - u) c                        returns (h', h'): no output activation (:368)
+//   msg = P^T-mix (h Wg^T)                      the node mix acts on the node index, the GEMM on the feature index: they commute,
+//   r = sig(Wri x + br + Wrh msg)               so  W_gh msg = (P^T-mix h) (W_gh Wg)^T  for g in {r, u, c}.  With the fused message
+//   u = sig(Wui x + bu + Wuh msg)               weights W'_g = W_gh Wg (computed once per launch, fp64 accumulation) and the MIXED
+//   c = tanh(Wci x + bc + r * (Wch msg))        state h~ = P^T-mix h in the operand image, a step is ONE recurrent GEMM
+//   h' = u h + (1 - u) c                            D[128, 256] = x[128, F] * [Wri; Wui; Wci]^T   (N = 192, cols r | u | cx)
+//   returns (h', h'): no output activation (:368)              + h~[128, H] * [W'r; W'u]^T        (N = 128, cols r | u)
+//                                                              ,  h~[128, H] * W'c^T              (N = 64,  cols ch)
+//   instead of two dependent GEMMs with a state exchange after each (h -> msg -> h').
 //
 // Same decomposition as the LSTM-family kernel (tc_kernels.cu): a CTA owns 8 sequences (128 accumulator rows) x 64
-// hidden units of one direction for all T steps, a cluster of C = H/64 CTAs covers the hidden dimension, the state
-// operand image lives in shared memory and is all-gathered through DSMEM -- here twice per step, because the message
-// (needed with full K by G2) and the new state alternate in the SAME buffer: h -> msg -> h' -> ...
-// The x part of step t+1 is issued around the two dependent GEMMs of step t (ping-pong accumulator buffers); G1 of
-// step t writes the 64 columns of the OTHER buffer that no x part touches.  The node mix of G1's output runs on the
-// warp-level tensor path exactly like the gate mix of the LSTM kernel; the gate math needs no mix and runs in the
-// TMEM-native layout (thread = row), so the new state goes back to the operand image with 16-byte stores.
+// hidden units of one direction for all T steps, a cluster of C = H/64 CTAs covers the hidden dimension, the operand image of
+// the mixed state lives in shared memory and is all-gathered through DSMEM once per step.  The x part of step t+1 is
+// issued behind the recurrent part of step t (ping-pong accumulator buffers), i.e. while the epilogue warps run the gate
+// math of step t and the exchange is in flight.  The gate math runs in the TMEM-native layout (thread = row, 16 units); the
+// new state h' stays in fp32 registers, and its node mix -- 16 x 16 per sequence on the warp-level tensor path, fp16 hi/lo
+// split, exactly like the gate mix of the LSTM kernel -- produces the next operand.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <cstdlib>
@@ -32,8 +34,7 @@ constexpr int kWstFloats = 8 * 32;
 
 struct GruDir {
   const uint16_t* wx_img;   // [C][F/16][NP][2][192][8]   rows 64*g + unit of dense_{r,u,c}_in.weight
-  const uint16_t* wm_img;   // [C][H/16][NP][2][192][8]   rows 64*g + unit of dense_{r,u,c}_hid.weight
-  const uint16_t* wg_img;   // [C][H/16][NP][2][64][8]    gcn_kernel rows of this chunk
+  const uint16_t* wm_img;   // [C][H/16][NP][2][192][8]   rows 64*g + unit of W'_g = dense_{r,u,c}_hid.weight @ gcn_kernel
   const float* P;           // [16][16] zero padded, msg = P u  (P[n][m] = adjacency[m][n], net_aagc.py:348)
   const float* bias3;       // [H][4]   (b_r, b_u, b_c, 0)
   const float* h0; float* hT;
@@ -44,11 +45,12 @@ struct GruLayerParams {
   const uint16_t* x_img;    // [tiles][T][F/16][NP][2][128][8]
   float* y; int64_t syb, syt, yld;
   uint16_t* y_img; int y_kf;
-  int B, T, F, H, C, S, n1;
+  int B, T, F, H, C, S;
+  int acoll;                // A-operand collector reuse (see ptx::umma_f16_coll)
 };
 
-enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_ACC_FULL = 2 * kMaxStages, BAR_ACC_EMPTY = BAR_ACC_FULL + 2, BAR_G1_FULL = BAR_ACC_EMPTY + 2,
-       BAR_H, BAR_MSG, BAR_HFREE, BAR_MFREE, BAR_COUNT };
+enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_ACC_FULL = 2 * kMaxStages, BAR_ACC_EMPTY = BAR_ACC_FULL + 2, BAR_H = BAR_ACC_EMPTY + 2,
+       BAR_HFREE, BAR_COUNT };
 
 __host__ __device__ inline size_t gru_fixed_smem_bytes() {
   return (size_t)kEpiWarps * kWstFloats * 4 + 256 * 4 + 256 * 4 + 32 * 8 + 16;   // wst, bias, Pfrag, barriers, tmem slot
@@ -64,9 +66,8 @@ tc_gru_layer_kernel(const GruLayerParams p) {
   constexpr int NP = SPLIT ? 2 : 1;
   constexpr uint32_t kXB = NP * 2 * 192 * 16;       // one K=16 block of [Wri; Wui; Wci] (all parts)
   constexpr uint32_t kXA = NP * 2 * 128 * 16;       // one K=16 block of x rows
-  constexpr uint32_t kMB = NP * 2 * 192 * 16;       // one K=16 block of [Wrh; Wuh; Wch]
-  constexpr uint32_t kGB = NP * 2 * 64 * 16;        // one K=16 block of gcn_kernel rows
-  constexpr uint32_t kStageBytes = 2 * kMB;          // ring slot: 2 msg blocks >= 1 x block (B + A) >= 4 G1 blocks
+  constexpr uint32_t kMB = NP * 2 * 192 * 16;       // one K=16 block of [W'r; W'u; W'c]
+  constexpr uint32_t kStageBytes = 2 * kMB;          // ring slot: 2 recurrent blocks >= 1 x block (B + A)
   constexpr uint32_t kHBlock = 8 * kRows * 16;
   extern __shared__ __align__(1024) uint8_t smem[];
 
@@ -76,9 +77,8 @@ tc_gru_layer_kernel(const GruLayerParams p) {
   const GruDir& d = p.d[blockIdx.y];
   const int KF = F / 16, KH = H / 16;
   const int warp = threadIdx.x >> 5;
-  const int n1 = p.n1;
 
-  uint8_t* hbuf = smem;                                              // operand image of h / msg: [NP][H/8][128][8]
+  uint8_t* hbuf = smem;                                              // operand image of the mixed state h~: [NP][H/8][128][8]
   uint8_t* ring = hbuf + (size_t)NP * H * 256;
   float* staging = reinterpret_cast<float*>(ring + (size_t)S * kStageBytes);
   float* biasg = staging + kEpiWarps * kWstFloats;                   // [3][64]  (+ 64 pad)
@@ -87,7 +87,7 @@ tc_gru_layer_kernel(const GruLayerParams p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < BAR_COUNT; ++i) ptx::mbar_init(&bars[i], (i == BAR_HFREE || i == BAR_MFREE) ? (uint32_t)C : 1u);
+    for (int i = 0; i < BAR_COUNT; ++i) ptx::mbar_init(&bars[i], i == BAR_HFREE ? (uint32_t)C : 1u);
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
@@ -126,7 +126,6 @@ tc_gru_layer_kernel(const GruLayerParams p) {
       };
       const uint8_t* wx = reinterpret_cast<const uint8_t*>(d.wx_img) + (size_t)c * KF * kXB;
       const uint8_t* wm = reinterpret_cast<const uint8_t*>(d.wm_img) + (size_t)c * KH * kMB;
-      const uint8_t* wg = reinterpret_cast<const uint8_t*>(d.wg_img) + (size_t)c * KH * kGB;
       const uint8_t* xi = reinterpret_cast<const uint8_t*>(p.x_img);
       auto xblocks = [&](int t, int kb0, int kb1) {
         const int ta = d.reverse ? T - 1 - t : t;
@@ -135,11 +134,8 @@ tc_gru_layer_kernel(const GruLayerParams p) {
       };
       xblocks(0, 0, KF);
       for (int t = 0; t < T; ++t) {
-        const bool nx = t + 1 < T;
-        for (int s4 = 0; s4 < KH / 4; ++s4) load_stage(wg + (size_t)s4 * 4 * kGB, 4 * kGB, 0, nullptr, 0);
-        if (nx) xblocks(t + 1, 0, n1);
         for (int s2 = 0; s2 < KH / 2; ++s2) load_stage(wm + (size_t)s2 * 2 * kMB, 2 * kMB, 0, nullptr, 0);
-        if (nx) xblocks(t + 1, n1, KF);
+        if (t + 1 < T) xblocks(t + 1, 0, KF);
       }
     }
   } else if (warp == 1) {
@@ -163,13 +159,19 @@ tc_gru_layer_kernel(const GruLayerParams p) {
         if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
       };
       const uint64_t dA = ptx::make_smem_desc(0, kRows * 16, 128);
-      const uint64_t dB192 = ptx::make_smem_desc(0, 192 * 16, 128), dB64 = ptx::make_smem_desc(0, 64 * 16, 128);
+      const uint64_t dB192 = ptx::make_smem_desc(0, 192 * 16, 128);
       auto block_mma = [&](uint32_t dcol, uint32_t a0, uint32_t astride, uint32_t b0, uint32_t bstride, uint64_t dB, uint32_t idesc, bool first) {
         const uint64_t ah = dA + ((a0 & 0x3FFFFu) >> 4), bh = dB + ((b0 & 0x3FFFFu) >> 4);
-        ptx::umma_f16(tmem + dcol, ah, bh, idesc, first ? 0u : 1u);
-        if (SPLIT) {
+        if (SPLIT && p.acoll) {
+          ptx::umma_f16_coll(tmem + dcol, ah, bh, idesc, first ? 0u : 1u, 1);
+          ptx::umma_f16_coll(tmem + dcol, ah, bh + (bstride >> 4), idesc, 1u, 3);
           ptx::umma_f16(tmem + dcol, ah + (astride >> 4), bh, idesc, 1u);
-          ptx::umma_f16(tmem + dcol, ah, bh + (bstride >> 4), idesc, 1u);
+        } else {
+          ptx::umma_f16(tmem + dcol, ah, bh, idesc, first ? 0u : 1u);
+          if (SPLIT) {
+            ptx::umma_f16(tmem + dcol, ah + (astride >> 4), bh, idesc, 1u);
+            ptx::umma_f16(tmem + dcol, ah, bh + (bstride >> 4), idesc, 1u);
+          }
         }
       };
       auto xblocks = [&](uint32_t dcol, int kb0, int kb1) {
@@ -183,29 +185,8 @@ tc_gru_layer_kernel(const GruLayerParams p) {
       for (int t = 0; t < T; ++t) {
         const uint32_t b = t & 1, bo = b ^ 1u;
         const bool nx = t + 1 < T;
-        // G1: h Wg^T -> the 64 columns of the other buffer that no x part touches
-        ptx::mbar_wait(&bars[BAR_H], t & 1);
-        ptx::tc_fence_after();
-        for (int s4 = 0; s4 < KH / 4; ++s4) {
-          const uint32_t sa = wait_stage();
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int kb = s4 * 4 + j;
-            block_mma(bo * 256 + 192, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, sa + (uint32_t)j * kGB, kGB / NP, dB64, idesc64, (s4 | j) == 0);
-          }
-          release_stage();
-        }
-        ptx::umma_commit(&bars[BAR_G1_FULL]);
-        if (C > 1) ptx::umma_commit_multicast(&bars[BAR_HFREE], cta_mask); else ptx::umma_commit(&bars[BAR_HFREE]);
-        // x part of step t+1 -> columns [0,192) of the other buffer (free once the gate math of step t-1 has drained it)
-        if (nx && t >= 1) {
-          ptx::mbar_wait(&bars[BAR_ACC_EMPTY + bo], empty_k[bo] & 1u);
-          empty_k[bo] += 1;
-          ptx::tc_fence_after();
-        }
-        if (nx) xblocks(bo * 256, 0, n1);
-        // G2, message part: r | u accumulate onto the x part, ch starts fresh in columns [192,256)
-        ptx::mbar_wait(&bars[BAR_MSG], t & 1);
+        // recurrent part: r | u accumulate onto the x part, ch starts fresh in columns [192,256)
+        ptx::mbar_wait(&bars[BAR_H], t & 1);           // the mixed state of every chunk is in the local image
         ptx::tc_fence_after();
         for (int s2 = 0; s2 < KH / 2; ++s2) {
           const uint32_t sa = wait_stage();
@@ -213,14 +194,35 @@ tc_gru_layer_kernel(const GruLayerParams p) {
           for (int j = 0; j < 2; ++j) {
             const int kb = s2 * 2 + j;
             const uint32_t a0 = hbase + (uint32_t)kb * 2 * kRows * 16, b0 = sa + (uint32_t)j * kMB;
-            block_mma(b * 256, a0, hpart, b0, kMB / NP, dB192, idesc128, false);
-            block_mma(b * 256 + 192, a0, hpart, b0 + 128 * 16, kMB / NP, dB192, idesc64, (s2 | j) == 0);
+            if (SPLIT && p.acoll) {
+              // one A tile (h~ hi, then h~ lo) against r|u (N = 128) and ch (N = 64), hi and lo parts of the weights: the A
+              // operand is read from shared memory once per part and kept in the collector buffer for the other MMAs
+              const uint64_t ah = dA + ((a0 & 0x3FFFFu) >> 4), al = ah + (hpart >> 4);
+              const uint64_t bh = dB192 + ((b0 & 0x3FFFFu) >> 4), bl = bh + ((kMB / NP) >> 4);
+              const uint64_t ch = bh + ((128u * 16u) >> 4), cl = bl + ((128u * 16u) >> 4);
+              const uint32_t first = (s2 | j) == 0 ? 0u : 1u;
+              ptx::umma_f16_coll(tmem + b * 256, ah, bh, idesc128, 1u, 1);
+              ptx::umma_f16_coll(tmem + b * 256, ah, bl, idesc128, 1u, 2);
+              ptx::umma_f16_coll(tmem + b * 256 + 192, ah, ch, idesc64, first, 2);
+              ptx::umma_f16_coll(tmem + b * 256 + 192, ah, cl, idesc64, 1u, 3);
+              ptx::umma_f16_coll(tmem + b * 256, al, bh, idesc128, 1u, 1);
+              ptx::umma_f16_coll(tmem + b * 256 + 192, al, ch, idesc64, 1u, 3);
+            } else {
+              block_mma(b * 256, a0, hpart, b0, kMB / NP, dB192, idesc128, false);
+              block_mma(b * 256 + 192, a0, hpart, b0 + 128 * 16, kMB / NP, dB192, idesc64, (s2 | j) == 0);
+            }
           }
           release_stage();
         }
         ptx::umma_commit(&bars[BAR_ACC_FULL + b]);
-        if (C > 1) ptx::umma_commit_multicast(&bars[BAR_MFREE], cta_mask); else ptx::umma_commit(&bars[BAR_MFREE]);
-        if (nx) xblocks(bo * 256, n1, KF);
+        if (C > 1) ptx::umma_commit_multicast(&bars[BAR_HFREE], cta_mask); else ptx::umma_commit(&bars[BAR_HFREE]);
+        // x part of step t+1 -> columns [0,192) of the other buffer (free once the gate math of step t-1 has drained it)
+        if (nx && t >= 1) {
+          ptx::mbar_wait(&bars[BAR_ACC_EMPTY + bo], empty_k[bo] & 1u);
+          empty_k[bo] += 1;
+          ptx::tc_fence_after();
+        }
+        if (nx) xblocks(bo * 256, 0, KF);
       }
     }
   } else {
@@ -243,26 +245,6 @@ tc_gru_layer_kernel(const GruLayerParams p) {
     for (int i = 0; i < 16; ++i)
       hreg[i] = (rvalid && d.h0 != nullptr) ? d.h0[((size_t)rseq * kNodes + rnode) * H + c * 64 + ubase + i] : 0.f;
 
-    // this thread's 16 units of row `row` -> local operand image (two 16-byte K chunks per part)
-    auto store_row = [&](const float (&v)[16]) {
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t hw[4], lw[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (SPLIT) {
-            ptx::split_pair_f16(v[hf * 8 + 2 * j], v[hf * 8 + 2 * j + 1], hw[j], lw[j]);
-          } else {
-            const __nv_bfloat162 bb = __floats2bfloat162_rn(v[hf * 8 + 2 * j], v[hf * 8 + 2 * j + 1]);
-            hw[j] = *reinterpret_cast<const uint32_t*>(&bb);
-            lw[j] = 0;
-          }
-        }
-        const uint32_t off = img_off((int)c * 64 + ubase + 8 * hf, row);
-        *reinterpret_cast<uint4*>(hbuf + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        if (SPLIT) *reinterpret_cast<uint4*>(hbuf + (size_t)H * 256 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-      }
-    };
     auto publish_block = [&](int bar, int acc_empty, bool tmem_read) {
       ptx::fence_proxy_async();
       if (tmem_read) ptx::tc_fence_before();
@@ -308,64 +290,67 @@ tc_gru_layer_kernel(const GruLayerParams p) {
       }
     };
 
-    store_row(hreg);                                 // h_{-1} = h0
-    publish_block(BAR_H, -1, false);
-
     const uint4* Pfrag4 = reinterpret_cast<const uint4*>(Pfrag);
     const int swz = 8 * (tq & 3);
-
-    for (int t = 0; t < T; ++t) {
-      const uint32_t b = t & 1, bo = b ^ 1u;
-      const int ta = d.reverse ? T - 1 - t : t;
-      // ---------------------------------------------------------------- msg = P (h Wg^T): node mix of G1's output
-      ptx::mbar_wait(&bars[BAR_G1_FULL], t & 1);
-      ptx::mbar_wait(&bars[BAR_HFREE], t & 1);       // every CTA has finished reading h: the image may hold msg now
-      ptx::tc_fence_after();
-      {
-        const uint4 ah4 = Pfrag4[0 * 32 + lane], al4 = Pfrag4[1 * 32 + lane];
-        const uint32_t ah[4] = {ah4.x, ah4.y, ah4.z, ah4.w}, al[4] = {al4.x, al4.y, al4.z, al4.w};
+    // h~ = P h' (16 x 16 node mix per sequence) of this warp's 32 rows x 16 units -> local operand image.  The values go
+    // registers (lane = row) -> warp-private transposition buffer -> B fragments of mma.m16n8k16 (k = node), fp16 hi/lo
+    // split, 3 passes; the C fragment (nodes tq, tq+8 x units 2tr, 2tr+1) is written as packed pairs.
+    auto mix_store = [&](const float (&h)[16]) {
+      const uint4 ah4 = Pfrag4[0 * 32 + lane], al4 = Pfrag4[1 * 32 + lane];
+      const uint32_t ah[4] = {ah4.x, ah4.y, ah4.z, ah4.w}, al[4] = {al4.x, al4.y, al4.z, al4.w};
 #pragma unroll
-        for (int ub = 0; ub < 2; ++ub) {
-          float v[8];
-          ptx::tmem_ld8(tmem_row + bo * 256 + 192 + ubase + 8 * ub, v);
-          __syncwarp();
+      for (int ub = 0; ub < 2; ++ub) {
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) wst[j * 32 + (lane ^ (8 * (j & 3)))] = v[j];
-          __syncwarp();
-          const int k = (int)c * 64 + ubase + 8 * ub + 2 * tr;
+        for (int j = 0; j < 8; ++j) wst[j * 32 + (lane ^ (8 * (j & 3)))] = h[8 * ub + j];
+        __syncwarp();
+        const int k = (int)c * 64 + ubase + 8 * ub + 2 * tr;
 #pragma unroll
-          for (int sq = 0; sq < 2; ++sq) {
-            const float* sp = wst + tq * 32;
-            const float2 u0 = *reinterpret_cast<const float2*>(sp + ((16 * sq + 2 * tr) ^ swz));
-            const float2 u1 = *reinterpret_cast<const float2*>(sp + ((16 * sq + 2 * tr + 8) ^ swz));
+        for (int sq = 0; sq < 2; ++sq) {
+          const float* sp = wst + tq * 32;
+          const float2 u0 = *reinterpret_cast<const float2*>(sp + ((16 * sq + 2 * tr) ^ swz));
+          const float2 u1 = *reinterpret_cast<const float2*>(sp + ((16 * sq + 2 * tr + 8) ^ swz));
+          float z[4] = {0.f, 0.f, 0.f, 0.f};
+          if (SPLIT) {
             uint32_t bh0, bl0, bh1, bl1;
             ptx::split_pair_f16(u0.x, u0.y, bh0, bl0);
             ptx::split_pair_f16(u1.x, u1.y, bh1, bl1);
-            float z[4] = {0.f, 0.f, 0.f, 0.f}, z2[4] = {0.f, 0.f, 0.f, 0.f}, z3[4] = {0.f, 0.f, 0.f, 0.f};
+            float z2[4] = {0.f, 0.f, 0.f, 0.f}, z3[4] = {0.f, 0.f, 0.f, 0.f};
             ptx::mma_16816_f16(z, ah, bh0, bh1);
             ptx::mma_16816_f16(z2, al, bh0, bh1);
             ptx::mma_16816_f16(z3, ah, bl0, bl1);
 #pragma unroll
-            for (int up = 0; up < 2; ++up) {           // C fragment: nodes tq + 8up, units 2tr, 2tr+1 -> operand image
-              const float m0 = z[2 * up] + z2[2 * up] + z3[2 * up], m1 = z[2 * up + 1] + z2[2 * up + 1] + z3[2 * up + 1];
-              uint32_t hi, lo = 0;
-              if (SPLIT) {
-                ptx::split_pair_f16(m0, m1, hi, lo);
-              } else {
-                const __nv_bfloat162 bb = __floats2bfloat162_rn(m0, m1);
-                hi = *reinterpret_cast<const uint32_t*>(&bb);
-              }
-              const uint32_t off = img_off(k, 16 * (2 * qd + sq) + tq + 8 * up);
-              *reinterpret_cast<uint32_t*>(hbuf + off) = hi;
-              if (SPLIT) *reinterpret_cast<uint32_t*>(hbuf + (size_t)H * 256 + off) = lo;
+            for (int j = 0; j < 4; ++j) z[j] += z2[j] + z3[j];
+          } else {
+            const __half2 h0 = __floats2half2_rn(u0.x, u0.y), h1 = __floats2half2_rn(u1.x, u1.y);
+            ptx::mma_16816_f16(z, ah, *reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+          }
+#pragma unroll
+          for (int up = 0; up < 2; ++up) {
+            uint32_t hi, lo = 0;
+            if (SPLIT) {
+              ptx::split_pair_f16(z[2 * up], z[2 * up + 1], hi, lo);
+            } else {
+              const __nv_bfloat162 bb = __floats2bfloat162_rn(z[2 * up], z[2 * up + 1]);
+              hi = *reinterpret_cast<const uint32_t*>(&bb);
             }
+            const uint32_t off = img_off(k, 16 * (2 * qd + sq) + tq + 8 * up);
+            *reinterpret_cast<uint32_t*>(hbuf + off) = hi;
+            if (SPLIT) *reinterpret_cast<uint32_t*>(hbuf + (size_t)H * 256 + off) = lo;
           }
         }
       }
-      publish_block(BAR_MSG, -1, true);
+    };
+
+    mix_store(hreg);                                 // h~_{-1} = P h0
+    publish_block(BAR_H, -1, false);
+
+    for (int t = 0; t < T; ++t) {
+      const uint32_t b = t & 1;
+      const int ta = d.reverse ? T - 1 - t : t;
       // ---------------------------------------------------------------- gates (TMEM-native layout: thread = row)
       ptx::mbar_wait(&bars[BAR_ACC_FULL + b], (t >> 1) & 1);
-      ptx::mbar_wait(&bars[BAR_MFREE], t & 1);       // every CTA has finished reading msg: the image may hold h' now
+      ptx::mbar_wait(&bars[BAR_HFREE], t & 1);       // every CTA has finished reading h~_{t-1}: the image may be rewritten
       ptx::tc_fence_after();
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
@@ -385,7 +370,7 @@ tc_gru_layer_kernel(const GruLayerParams p) {
           hreg[hf * 8 + i] = rvalid ? hn : 0.f;
         }
       }
-      store_row(hreg);
+      mix_store(hreg);
       publish_block(BAR_H, (int)b, true);
       emit(ta, hreg);
     }
@@ -410,7 +395,20 @@ __device__ __forceinline__ uint16_t part_bits(float v, int part, bool split) {
   return __half_as_ushort(__float2half_rn(v - __half2float(hi)));
 }
 
-struct GruPackedTc { uint16_t* wx_img; uint16_t* wm_img; uint16_t* wg_img; float* P; float* bias3; };
+struct GruPackedTc { uint16_t* wx_img; uint16_t* wm_img; float* wfused; float* P; float* bias3; };
+
+// fused message weights W'_g = dense_g_hid.weight @ gcn_kernel  (g = r, u, c; [H, H] each), fp64 accumulation:
+// dense_g_hid(P^T-mix(h gcn_kernel^T)) = (P^T-mix h) W'_g^T   (net_aagc.py:347-348, :353-361)
+__global__ void tc_gru_fuse_kernel(a3gc_cell_params cp, float* __restrict__ wfused, int H) {
+  const int64_t n = (int64_t)3 * H * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % H), j = (int)((i / H) % H), g = (int)(i / ((int64_t)H * H));
+    const float* wh = cp.dense_hid_w[g] + (size_t)j * H;
+    double acc = 0.0;
+    for (int m = 0; m < H; ++m) acc += (double)wh[m] * (double)cp.g_gcn_kernel[(size_t)m * H + k];
+    wfused[i] = (float)acc;
+  }
+}
 
 __global__ void tc_pack_gru_kernel(a3gc_cell_params cp, GruPackedTc out, int F, int H, int split) {
   const int NP = split ? 2 : 1;
@@ -430,17 +428,9 @@ __global__ void tc_pack_gru_kernel(a3gc_cell_params cp, GruPackedTc out, int F, 
       const int part = (int)(rest % NP); rest /= NP;
       const int kb = (int)(rest % KB); const int c = (int)(rest / KB);
       const int g = r >> 6, j = c * 64 + (r & 63), k = kb * 16 + kc * 8 + e;
-      const float* w = which == 0 ? cp.dense_in_w[g] : cp.dense_hid_w[g];
+      const float* w = which == 0 ? cp.dense_in_w[g] : out.wfused + (size_t)g * H * H;
       img[i] = part_bits(w[(size_t)j * K + k], part, split);
     }
-  }
-  const int64_t n_g = (int64_t)C * KH * NP * 2 * 64 * 8;
-  for (int64_t i = tid; i < n_g; i += stride) {
-    const int e = (int)(i & 7), ul = (int)((i >> 3) & 63), kc = (int)((i >> 9) & 1);
-    int64_t rest = i >> 10;
-    const int part = (int)(rest % NP); rest /= NP;
-    const int kb = (int)(rest % KH); const int c = (int)(rest / KH);
-    out.wg_img[i] = part_bits(cp.g_gcn_kernel[(size_t)(c * 64 + ul) * H + kb * 16 + kc * 8 + e], part, split);
   }
   for (int64_t i = tid; i < 256; i += stride) {
     const int n = (int)(i / 16), m = (int)(i % 16);
@@ -456,7 +446,7 @@ size_t gru_dir_bytes(int F, int H, int NP) {
   size_t b = 0;
   b += align_up((size_t)F * 192 * (H / 64) * NP * 2, 256);
   b += align_up((size_t)H * 192 * (H / 64) * NP * 2, 256);
-  b += align_up((size_t)H * H * NP * 2, 256);
+  b += align_up((size_t)3 * H * H * 4, 256);                 // fused message weights W' (fp32)
   b += align_up((size_t)(256 + 4 * H) * 4, 256);
   return b;
 }
@@ -465,7 +455,7 @@ GruPackedTc gru_carve(char* base, int F, int H, int NP) {
   GruPackedTc p;
   p.wx_img = reinterpret_cast<uint16_t*>(base); base += align_up((size_t)F * 192 * (H / 64) * NP * 2, 256);
   p.wm_img = reinterpret_cast<uint16_t*>(base); base += align_up((size_t)H * 192 * (H / 64) * NP * 2, 256);
-  p.wg_img = reinterpret_cast<uint16_t*>(base); base += align_up((size_t)H * H * NP * 2, 256);
+  p.wfused = reinterpret_cast<float*>(base); base += align_up((size_t)3 * H * H * 4, 256);
   float* f = reinterpret_cast<float*>(base);
   p.P = f; p.bias3 = f + 256;
   return p;
@@ -489,22 +479,19 @@ int tc_gru_layer_launch(const LayerArgs& a, const uint16_t* x_img, char* wbase, 
   const size_t dir_bytes = gru_dir_bytes(F, H, NP);
   for (int d = 0; d < a.num_dirs; ++d) {
     GruPackedTc pk = gru_carve(wbase + d * dir_bytes, F, H, NP);
+    tc_gru_fuse_kernel<<<148 * 2, 256, 0, stream>>>(a.cells[d], pk.wfused, H);
+    A3GC_LAUNCH_CHECK("tc_gru_fuse_kernel");
     tc_pack_gru_kernel<<<148, 256, 0, stream>>>(a.cells[d], pk, F, H, split ? 1 : 0);
     A3GC_LAUNCH_CHECK("tc_pack_gru_kernel");
     GruDir& g = p.d[d];
-    g.wx_img = pk.wx_img; g.wm_img = pk.wm_img; g.wg_img = pk.wg_img; g.P = pk.P; g.bias3 = pk.bias3;
+    g.wx_img = pk.wx_img; g.wm_img = pk.wm_img; g.P = pk.P; g.bias3 = pk.bias3;
     g.h0 = a.h0[d]; g.hT = a.hT[d]; g.reverse = a.reverse[d];
   }
   p.x_img = x_img;
   p.y = a.y; p.syb = a.y_stride_b; p.syt = a.y_stride_t; p.yld = a.y_ld;
   p.y_img = a.y_img; p.y_kf = a.y_img_f / 16;
   p.B = (int)a.batch; p.T = (int)a.steps; p.F = F; p.H = H; p.C = C;
-  {
-    const int KF = F / 16;
-    int n1 = (KF + 1) / 2;
-    if (const char* e = getenv("A3GC_TC_SPLIT")) { int x = 0, y = 0; if (sscanf(e, "%d,%d", &x, &y) >= 1) n1 = KF * x / 100; }
-    p.n1 = n1 > KF ? KF : n1;
-  }
+  p.acoll = getenv("A3GC_TC_ACOLL") ? atoi(getenv("A3GC_TC_ACOLL")) : 1;
   int dev = 0, smem_max = 0;
   A3GC_CUDA_TRY(cudaGetDevice(&dev));
   A3GC_CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));

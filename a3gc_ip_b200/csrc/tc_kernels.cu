@@ -83,6 +83,7 @@ struct TcLayerParams {
   int puborder;                      // order in which a CTA serves its peers in the state exchange
   int rescale;                       // fp32 inference: peers' h' blocks are rescaled locally instead of a second all-gather
   int pubbytes;                      // TIMING DIAGNOSTIC ONLY (results are wrong if < kHBlock): bytes per state-exchange copy
+  int acoll;                         // A-operand collector reuse between the hi*hi and hi*lo passes of a K block
   int nprod;                         // producer threads (one per warp) that issue the bulk copies of the weight / x stream, stage i by thread i % nprod
   int n1, n2;                        // x-part blocks of step t+1 issued before A1 / between A1 and A2 of step t (rest after A2)
   // training mode (TRAIN): tape of per-step intermediates (include/a3gc_b200.h, a3gc_tape) and optional recurrent-dropout mask
@@ -284,15 +285,23 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       const uint64_t dA = ptx::make_smem_desc(0, kRows * 16, 128);
       const uint64_t dB256 = ptx::make_smem_desc(0, 256 * 16, 128), dB128 = ptx::make_smem_desc(0, 128 * 16, 128),
                      dB64 = ptx::make_smem_desc(0, 64 * 16, 128);
+      const bool acoll = p.acoll != 0;
       // one K=16 block: D[:, dcol..dcol+N) (+)= A * B^T with the split passes hi*hi + lo*hi + hi*lo
       auto block_mma = [&](uint32_t dcol, uint32_t a0, uint32_t astride, uint32_t b0, uint32_t bstride, uint64_t dB,
                            uint32_t idesc, bool first) {
         // (shared-window addresses of non-zero cluster ranks carry the rank above bit 18: keep the 18-bit offset only)
         const uint64_t ah = dA + ((a0 & 0x3FFFFu) >> 4), bh = dB + ((b0 & 0x3FFFFu) >> 4);
-        ptx::umma_f16(tmem + dcol, ah, bh, idesc, first ? 0u : 1u);
-        if (SPLIT) {
+        if (SPLIT && acoll) {
+          // A_hi is multiplied by B_hi and by B_lo back to back: the second MMA takes it from the collector buffer
+          ptx::umma_f16_coll(tmem + dcol, ah, bh, idesc, first ? 0u : 1u, 1);
+          ptx::umma_f16_coll(tmem + dcol, ah, bh + (bstride >> 4), idesc, 1u, 3);
           ptx::umma_f16(tmem + dcol, ah + (astride >> 4), bh, idesc, 1u);
-          ptx::umma_f16(tmem + dcol, ah, bh + (bstride >> 4), idesc, 1u);
+        } else {
+          ptx::umma_f16(tmem + dcol, ah, bh, idesc, first ? 0u : 1u);
+          if (SPLIT) {
+            ptx::umma_f16(tmem + dcol, ah + (astride >> 4), bh, idesc, 1u);
+            ptx::umma_f16(tmem + dcol, ah, bh + (bstride >> 4), idesc, 1u);
+          }
         }
       };
       // p.xsplit: issue the (off-critical-path) x part as two N = 128 halves instead of one N = 256 MMA.  The warp-level
@@ -1160,6 +1169,7 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
     p.xsplit = getenv("A3GC_TC_XSPLIT") ? atoi(getenv("A3GC_TC_XSPLIT")) : 0;
     p.xdefer = getenv("A3GC_TC_XDEFER") ? atoi(getenv("A3GC_TC_XDEFER")) : 0;
     p.xprefetch = getenv("A3GC_TC_XPREFETCH") ? atoi(getenv("A3GC_TC_XPREFETCH")) : 0;   // measured: no effect (+-0.3 %)
+    p.acoll = getenv("A3GC_TC_ACOLL") ? atoi(getenv("A3GC_TC_ACOLL")) : 1;
     p.nprod = getenv("A3GC_TC_NPROD") ? atoi(getenv("A3GC_TC_NPROD")) : kProducers;
     if (p.nprod < 1) p.nprod = 1;
     if (p.nprod > kProducers) p.nprod = kProducers;

@@ -176,6 +176,20 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// The same MMA with an A-operand collector hint: consecutive MMAs that multiply the SAME A tile by different B tiles can keep A
+// in the tensor core's collector buffer instead of re-reading it from shared memory (SASS UTCHMMA .A_KEEP / .A_REUSE).
+//   mode 0: plain   1: fill (read A, keep it)   2: use (A from the collector, keep it)   3: lastuse (A from the collector, release)
+__device__ __forceinline__ void umma_f16_coll(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate, int mode) {
+#define A3GC_UMMA_COLL(q)                                                                               \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                      \
+               "tcgen05.mma.cta_group::1.kind::f16" q " [%0], %1, %2, %3, p;\n\t}"                      \
+               ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory")
+  if (mode == 1) A3GC_UMMA_COLL(".collector::a::fill");
+  else if (mode == 2) A3GC_UMMA_COLL(".collector::a::use");
+  else if (mode == 3) A3GC_UMMA_COLL(".collector::a::lastuse");
+  else A3GC_UMMA_COLL("");
+#undef A3GC_UMMA_COLL
+}
 // arrive on `bar` (this CTA) once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -15,9 +15,9 @@ T = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 prec = sys.argv[5] if len(sys.argv) > 5 else "fp32"
 variant = sys.argv[6] if len(sys.argv) > 6 else "A3GC"
 nira = torch.load("tests/golden/nira_template_15_norm.pt").float()
-cls = {"A3GC": A.BiA3GC_LSTM, "AAGC": A.BiAAGC_LSTM, "AGC": A.BiAGC_LSTM}[variant]
+cls = {"A3GC": A.BiA3GC_LSTM, "AAGC": A.BiAAGC_LSTM, "AGC": A.BiAGC_LSTM, "GGRU": A.BiG_GRU}[variant]
 KNOBS = ("A3GC_TC_HSEP", "A3GC_TC_SPLIT", "A3GC_TC_STAGES", "A3GC_TC_EARLYPUB", "A3GC_TC_PUBORDER", "A3GC_TC_TRACE", "A3GC_TC_QVEC",
-         "A3GC_TC_XCHG", "A3GC_TC_OPT", "A3GC_TC_NPROD")
+         "A3GC_TC_XCHG", "A3GC_TC_OPT", "A3GC_TC_NPROD", "A3GC_TC_ACOLL")
 names_e = ["start", "acc_full", "ep1_done", "h_free", "pub_hhat", "att_full", "q_sent", "att2_full", "ep3_done", "a_ready", "out_done", "pub_h"]
 names_m = ["start", "h_ready", "hpart_issued", "xpart_issued", "a1_go", "a1_issued", "a2_go", "a2_issued", "x3_issued"]
 for (H, F) in shapes:
@@ -25,7 +25,7 @@ for (H, F) in shapes:
     g = torch.Generator().manual_seed(1)
     x = torch.randn(B, T, 15, F, generator=g).cuda()
     z = torch.zeros(B, 15, H).cuda()
-    st = [(z, z.clone()), (z.clone(), z.clone())]
+    st = [z, z.clone()] if variant == "GGRU" else [(z, z.clone()), (z.clone(), z.clone())]
     ref = None
     for setting in settings:
         for k in KNOBS:
@@ -48,6 +48,8 @@ for (H, F) in shapes:
             ref = y.clone()
         dev = float((y - ref).norm() / ref.norm())
         fl = (2.0 * 15 * (F + H) * 4 * H + (34.0 * H * H + 30 * H if variant != "AAGC" else 0)) * B * T * 2
+        if variant == "GGRU":
+            fl = 2.0 * 15 * (3 * F * H + 4 * H * H) * B * T * 2
         print(f"H={H} F={F} B={B} T={T} {variant}/{prec} [{setting}]: {best:.3f} ms  {best * 1e3 / T:.1f} us/step  {fl / best / 1e9:.1f} TFLOP/s  "
               f"finite={bool(torch.isfinite(y).all())} rel-dev-vs-first={dev:.2e}", flush=True)
         if os.environ.get("A3GC_TC_TRACE"):
