@@ -28,7 +28,8 @@ constexpr int kRows = 128;
 constexpr int kSeqTile = 8;
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = 32 * kEpiWarps;
-constexpr int kThreadsTC = 64 + kEpiThreads;
+constexpr int kProducers = 3;           // warp 0 and the two warps behind the epilogue warps (see tc_kernels.cu)
+constexpr int kThreadsTC = 64 + kEpiThreads + 32 * (kProducers - 1);
 constexpr int kMaxStages = 8;
 constexpr int kWstFloats = 8 * 32;
 
@@ -47,6 +48,7 @@ struct GruLayerParams {
   uint16_t* y_img; int y_kf;
   int B, T, F, H, C, S;
   int acoll;                // A-operand collector reuse (see ptx::umma_f16_coll)
+  int nprod;                // bulk-copy producer threads (1..3)
 };
 
 enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_ACC_FULL = 2 * kMaxStages, BAR_ACC_EMPTY = BAR_ACC_FULL + 2, BAR_H = BAR_ACC_EMPTY + 2,
@@ -87,7 +89,8 @@ tc_gru_layer_kernel(const GruLayerParams p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < BAR_COUNT; ++i) ptx::mbar_init(&bars[i], i == BAR_HFREE ? (uint32_t)C : 1u);
+    for (int i = 0; i < BAR_COUNT; ++i)
+      ptx::mbar_init(&bars[i], i == BAR_HFREE ? (uint32_t)C : (i >= BAR_FULL && i < BAR_FULL + kMaxStages) ? 2u : 1u);
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
@@ -112,16 +115,33 @@ tc_gru_layer_kernel(const GruLayerParams p) {
   const uint32_t tmem = *tmem_slot;
   const uint16_t cta_mask = (uint16_t)((1u << C) - 1u);
 
-  if (warp == 0) {
-    // ================================================================ producer
-    if ((threadIdx.x & 31) == 0) {
-      uint32_t st = 0, ph = 0;
+  if (warp == 0 || warp >= 2 + kEpiWarps) {
+    // ================================================================ producers (same scheme as tc_kernels.cu: the weight (B)
+    // copy of stage i is issued by producer i % 2, the x-image (A) copy of every x stage by the third producer; every FULL
+    // barrier takes two arrivals.  p.nprod = 1 / 2: one / two threads issue both copies of their stages.)
+    const uint32_t my = warp == 0 ? 0u : (uint32_t)(warp - (1 + kEpiWarps));
+    const uint32_t nprod = (uint32_t)p.nprod;
+    const bool split_a = nprod == 3;
+    const uint32_t nb = split_a ? 2u : nprod;
+    if ((threadIdx.x & 31) == 0 && my < nprod) {
+      uint32_t st = 0, ph = 0, turn = 0;
       auto load_stage = [&](const void* bsrc, uint32_t bbytes, uint32_t aoff, const void* asrc, uint32_t abytes) {
-        ptx::mbar_wait(&bars[BAR_EMPTY + st], ph ^ 1u);
-        ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + st], bbytes + abytes);
         uint8_t* dst = ring + st * kStageBytes;
-        ptx::bulk_g2s(dst, bsrc, bbytes, &bars[BAR_FULL + st]);
-        if (abytes) ptx::bulk_g2s(dst + aoff, asrc, abytes, &bars[BAR_FULL + st]);
+        const bool b_side = my < nb && turn == my, a_side = split_a ? my == 2u : b_side;
+        if (b_side || a_side) ptx::mbar_wait(&bars[BAR_EMPTY + st], ph ^ 1u);
+        if (b_side) {
+          ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + st], bbytes);
+          ptx::bulk_g2s(dst, bsrc, bbytes, &bars[BAR_FULL + st]);
+        }
+        if (a_side) {
+          if (abytes) {
+            ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + st], abytes);
+            ptx::bulk_g2s(dst + aoff, asrc, abytes, &bars[BAR_FULL + st]);
+          } else {
+            ptx::mbar_arrive(&bars[BAR_FULL + st]);
+          }
+        }
+        if (++turn == nb) turn = 0;
         if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
       };
       const uint8_t* wx = reinterpret_cast<const uint8_t*>(d.wx_img) + (size_t)c * KF * kXB;
@@ -492,6 +512,9 @@ int tc_gru_layer_launch(const LayerArgs& a, const uint16_t* x_img, char* wbase, 
   p.y_img = a.y_img; p.y_kf = a.y_img_f / 16;
   p.B = (int)a.batch; p.T = (int)a.steps; p.F = F; p.H = H; p.C = C;
   p.acoll = getenv("A3GC_TC_ACOLL") ? atoi(getenv("A3GC_TC_ACOLL")) : 1;
+  p.nprod = getenv("A3GC_TC_NPROD") ? atoi(getenv("A3GC_TC_NPROD")) : kProducers;
+  if (p.nprod < 1) p.nprod = 1;
+  if (p.nprod > kProducers) p.nprod = kProducers;
   int dev = 0, smem_max = 0;
   A3GC_CUDA_TRY(cudaGetDevice(&dev));
   A3GC_CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));

@@ -160,7 +160,8 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
 
   // ------------------------------------------------------------------ setup
   if (threadIdx.x == 0) {
-    for (int i = 0; i < BAR_COUNT; ++i) ptx::mbar_init(&bars[i], (i == BAR_HFREE || i == BAR_A1FREE) ? (uint32_t)C : 1u);
+    for (int i = 0; i < BAR_COUNT; ++i)
+      ptx::mbar_init(&bars[i], (i == BAR_HFREE || i == BAR_A1FREE) ? (uint32_t)C : (i >= BAR_FULL && i < BAR_FULL + kMaxStages) ? 2u : 1u);
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
@@ -194,10 +195,15 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
     // ================================================================ producers: weights / x -> ring
     // One thread issues a bulk copy every ~440 cycles whatever its size (tests/diag_stream_rate.py: 444 cycles per copy for
     // 4 KB .. 48 KB; 222 / 131 cycles with 2 / 4 issuing warps), and an H = 256, F = 512 step needs 92 copies (two per x
-    // stage): 41 k cycles of ONE thread's time for a 44 k-cycle step.  So up to three warps share the stream: all walk the
-    // same static stage sequence, stage i is issued by producer i % nprod.
+    // stage): 41 k cycles of ONE thread's time for a 44 k-cycle step; with three ring slots the two back-to-back copies of
+    // an x stage are also ~900 of the ~2.2 k cycles a slot needs to turn around.  So up to three warps share the stream, all
+    // walking the same static stage sequence:  nprod = 2: stage i is issued by producer i % 2;  nprod = 3: the weight (B)
+    // copy of stage i by producer i % 2 and the x-image (A) copy of every x stage by the third, so the two copies of a stage
+    // are issued concurrently.  Every FULL barrier takes two arrivals (B side, A side).
     const uint32_t my = warp == 0 ? 0u : (uint32_t)(warp - (1 + kEpiWarps));
     const uint32_t nprod = (uint32_t)p.nprod;
+    const bool split_a = nprod == 3;                 // producer 2 = the A side
+    const uint32_t nb = split_a ? 2u : nprod;        // producers that take turns on the stages
     // The order of the stages is the static issue order of the MMA warp: h-part of step t, then the x-part of step
     // t+1 cut into three segments placed around the two attention GEMMs of step t, so that the tensor pipe has work
     // while the epilogue warps are busy and the attention GEMMs are never queued behind a long x-part.
@@ -206,17 +212,25 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       uint32_t turn = 0;                  // whose stage this is
       const uint32_t chunk = (uint32_t)p.chunk;
       auto load_stage = [&](const void* bsrc, uint32_t bbytes, const void* asrc, uint32_t abytes) {
-        if (turn == my) {
-          ptx::mbar_wait(&bars[BAR_EMPTY + st], ph ^ 1u);
-          ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + st], bbytes + abytes);
-          uint8_t* dst = ring + st * kStageBytes;
+        uint8_t* dst = ring + st * kStageBytes;
+        const bool b_side = my < nb && turn == my, a_side = split_a ? my == 2u : b_side;
+        if (b_side || a_side) ptx::mbar_wait(&bars[BAR_EMPTY + st], ph ^ 1u);
+        if (b_side) {
+          ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + st], bbytes);
           // p.chunk (tuning knob) can cut the copies into pieces; measured slower than one copy per operand
           for (uint32_t o = 0; o < bbytes; o += chunk)
             ptx::bulk_g2s(dst + o, static_cast<const uint8_t*>(bsrc) + o, min(chunk, bbytes - o), &bars[BAR_FULL + st]);
-          for (uint32_t o = 0; o < abytes; o += chunk)
-            ptx::bulk_g2s(dst + kBBytes + o, static_cast<const uint8_t*>(asrc) + o, min(chunk, abytes - o), &bars[BAR_FULL + st]);
         }
-        if (++turn == nprod) turn = 0;
+        if (a_side) {
+          if (abytes) {
+            ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + st], abytes);
+            for (uint32_t o = 0; o < abytes; o += chunk)
+              ptx::bulk_g2s(dst + kBBytes + o, static_cast<const uint8_t*>(asrc) + o, min(chunk, abytes - o), &bars[BAR_FULL + st]);
+          } else {
+            ptx::mbar_arrive(&bars[BAR_FULL + st]);
+          }
+        }
+        if (++turn == nb) turn = 0;
         if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
       };
       const uint8_t* wg = reinterpret_cast<const uint8_t*>(d.wg_img) + (size_t)c * (KF + KH) * kBBytes;
