@@ -358,6 +358,12 @@ def train_section(ctx, args, B=256, T=200, steps=3, warmup=2):
     # per-phase times of the dominant stage (H=256), one stream, CUDA events
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     n, o, x, t = nets[0], opts[0], xs[0], ts[0]
+    if reds[0] is not None:
+        for p_ in n.parameters():
+            p_.grad = None                                  # plain (rank-local) step below: no bucket views, no hooks firing into NCCL
+        reds[0].overlap = False
+        reds[0]._pending = 1 << 30
+    A.train_step(n, crit, o, x, t, None)                   # untimed: lets the allocator settle on this stream
     torch.cuda.synchronize(dev)
     ev[0].record()
     pred, _ = n.forward(x, None)
