@@ -91,11 +91,13 @@ class FlatGradAllReducer:
         self.overlap = overlap
         self._pending = 0
         self._back_issued = False
+        self._equal_checked = False
         self._work = []
         self._comm = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self._hooks = []
         if self.split > 0 and self.dist is not None and self.world > 1:
             for p in self.params[self.split:]:
-                p.register_post_accumulate_grad_hook(self._on_grad)
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
 
     @classmethod
     def for_net(cls, net: torch.nn.Module, process_group=None, overlap: bool = True) -> "FlatGradAllReducer":
@@ -103,6 +105,12 @@ class FlatGradAllReducer:
         named = [(n, p) for n, p in net.named_parameters() if p.requires_grad]
         split = sum(1 for n, _ in named if n.startswith(("linear_in.", "rnn1.", "pose_net.linear_in.", "pose_net.rnn1.")))
         return cls([p for _, p in named], process_group, split=split, overlap=overlap)
+
+    def close(self) -> None:
+        """Detach the post-accumulate hooks (a reducer that is replaced by another one on the same parameters)."""
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
 
     @property
     def nbytes(self) -> int:
@@ -148,31 +156,30 @@ class FlatGradAllReducer:
                 p.grad = v
         if self.dist is None or self.world == 1:
             return
-        w = torch.tensor([float(local_batch)], dtype=torch.float64, device=self.bucket.device)
-        tot = w.clone()
+        # total batch weight on the device (no host synchronisation: the stage steps of the three nets stay concurrent)
+        tot = torch.full((1,), float(local_batch), dtype=self.bucket.dtype, device=self.bucket.device)
         if self._back_issued:
             self.bucket[:self.split_off].mul_(float(local_batch))
             self._all_reduce(0, self.split_off)
-            # the back part went out unweighted: correct only when all shards are equal -- checked below
+            # the back part went out unweighted: exact only when all shards are equal -- verified once, below
         else:
             self.bucket.mul_(float(local_batch))
             self._all_reduce(0, self.bucket.numel())
-        cur = torch.cuda.current_stream(self.bucket.device) if self._comm is not None else None
         if self._comm is not None:
+            self._comm.wait_stream(torch.cuda.current_stream(self.bucket.device))
             with torch.cuda.stream(self._comm):
                 self.dist.all_reduce(tot, op=self.dist.ReduceOp.SUM, group=self.group)
-            cur.wait_stream(self._comm)
+            torch.cuda.current_stream(self.bucket.device).wait_stream(self._comm)
         else:
             self.dist.all_reduce(tot, op=self.dist.ReduceOp.SUM, group=self.group)
-        total = float(tot.item())
-        if total <= 0:
-            self.bucket.zero_()
-            return
         if self._back_issued:
-            if abs(total - self.world * float(local_batch)) > 1e-6 * max(total, 1.0):
-                raise RuntimeError("FlatGradAllReducer: overlap=True needs equal per-rank batches (use overlap=False for ragged shards)")
+            if not self._equal_checked:                           # one host read, on the first overlapped step only
+                self._equal_checked = True
+                total = float(tot.item())
+                if abs(total - self.world * float(local_batch)) > 1e-6 * max(total, 1.0):
+                    raise RuntimeError("FlatGradAllReducer: overlap=True needs equal per-rank batches (use overlap=False for ragged shards)")
             self.bucket[self.split_off:].mul_(float(local_batch))
-        self.bucket.div_(total)
+        self.bucket.div_(tot.clamp_min(1e-30))
 
 
 def train_step(model: torch.nn.Module, criterion, optimizer, inputs: torch.Tensor, target: torch.Tensor,

@@ -69,7 +69,11 @@ def _reducer_worker(rank, world, port, ret):
         ok &= red2._back_issued
         red2.reduce(3)
         ok &= bool(torch.allclose(red2.bucket, want6, rtol=1e-5, atol=1e-6))
-        # the overlapped form refuses ragged shards instead of returning a wrong mean
+        # the overlapped form refuses ragged shards instead of returning a wrong mean (checked on its first step)
+        for p_ in net.parameters():
+            p_.grad = None
+        red2.close()
+        red2 = A.FlatGradAllReducer.for_net(net, overlap=True)
         red2.zero_grad()
         ((net(x[bounds[0]:bounds[1]])[0] - t[bounds[0]:bounds[1]]) ** 2).sum(-1).mean().backward()
         try:
