@@ -23,6 +23,7 @@ PRECISION = {"fp32": 0, "bf16": 1}
 ENGINE = {"auto": 0, "simt": 1, "tc": 2}
 
 _f32p = C.POINTER(C.c_float)
+ABI_VERSION = 2          # A3GC_ABI_VERSION of include/a3gc_b200.h this binding was written against
 
 
 class GcParams(C.Structure):
@@ -57,7 +58,7 @@ class TapeGrads(C.Structure):
 
 
 class NetParams(C.Structure):
-    _fields_ = [("linear_in", GcParams), ("rnn", (CellParams * 2) * 2), ("linear_out", GcParams)]
+    _fields_ = [("linear_in", GcParams), ("rnn", (CellParams * 2) * 2), ("linear_out", GcParams), ("packed_rnn", C.c_void_p * 2)]
 
 
 # every symbol include/a3gc_b200.h declares: name -> (restype, argtypes)
@@ -75,6 +76,8 @@ SYMBOLS = {
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                      C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "a3gc_packed_weights_bytes": (C.c_size_t, [C.c_int] * 6),
+    "a3gc_pack_weights": (C.c_int, [C.c_int, C.c_int, C.POINTER(CellParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "a3gc_net_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "a3gc_net_forward": (C.c_int, [C.c_int, C.POINTER(NetParams), C.c_void_p,
                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p,
@@ -154,7 +157,7 @@ def lib() -> C.CDLL:
                     fn = getattr(l, name)
                     fn.restype = res
                     fn.argtypes = args
-                if l.a3gc_abi_version() != 1:
+                if l.a3gc_abi_version() != ABI_VERSION:
                     raise RuntimeError("liba3gc_b200.so ABI version mismatch")
                 _lib = l
     return _lib

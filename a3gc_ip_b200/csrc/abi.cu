@@ -244,6 +244,28 @@ int a3gc_layer_forward(int variant, int num_dirs, const a3gc_cell_params* cells,
   return run_layer(eng, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+size_t a3gc_packed_weights_bytes(int variant, int f_in, int hidden, int num_dirs, int precision, int engine) {
+  if (!variant_ok(variant) || num_dirs < 1 || num_dirs > 2 || f_in <= 0 || hidden <= 0) return 0;
+  if (pick_engine(engine, variant, f_in, hidden, precision) != A3GC_ENGINE_TC) return 0;
+  return tc_packed_weights_bytes(variant, f_in, hidden, num_dirs, precision);
+}
+
+int a3gc_pack_weights(int variant, int num_dirs, const a3gc_cell_params* cells, int f_in, int hidden, int precision,
+                      int engine, void* packed, size_t packed_bytes, void* stream) {
+  if (!variant_ok(variant) || num_dirs < 1 || num_dirs > 2 || !cells || f_in <= 0 || hidden <= 0 || !packed) {
+    set_error("a3gc_pack_weights: invalid argument");
+    return A3GC_ERR_INVALID_ARG;
+  }
+  for (int d = 0; d < num_dirs; ++d) {
+    int rc = check_cell(variant, cells[d], "a3gc_pack_weights");
+    if (rc) return rc;
+  }
+  const size_t need = a3gc_packed_weights_bytes(variant, f_in, hidden, num_dirs, precision, engine);
+  if (need == 0) { set_error("a3gc_pack_weights: this layer does not run on the tensor-core engine (nothing to pack)"); return A3GC_ERR_UNSUPPORTED; }
+  if (packed_bytes < need) { set_error("a3gc_pack_weights: buffer too small (%zu < %zu bytes)", packed_bytes, need); return A3GC_ERR_WORKSPACE; }
+  return tc_pack_weights(variant, num_dirs, cells, f_in, hidden, precision, packed, static_cast<cudaStream_t>(stream));
+}
+
 size_t a3gc_net_workspace_bytes(int variant, int64_t batch, int64_t steps, int f0, int hidden,
                                 int f_out, int precision, int engine) {
   (void)f_out;
@@ -319,11 +341,13 @@ static int net_forward_impl(int variant, const a3gc_net_params* net, const float
   a.batch = batch; a.steps = steps; a.f_in = H; a.hidden = H;
   a.out_act = A3GC_ACT_TANH;   // activation_fn='tanh' for both recurrent layers (net_aagc.py:629-630)
   a.precision = precision;
+  a.packed = p.eng1 == A3GC_ENGINE_TC ? net->packed_rnn[0] : nullptr;
   rc = run_layer(p.eng1, a, ws + p.lws, p.lws_bytes, s);
   if (rc) return rc;
 
   // rnn2, seeded with rnn1's final state (net_aagc.py:642-643)
   a.cells = net->rnn[1];
+  a.packed = p.eng2 == A3GC_ENGINE_TC ? net->packed_rnn[1] : nullptr;
   for (int d = 0; d < 2; ++d) {
     a.h0[d] = h1[d];
     a.c0[d] = gru ? nullptr : c1[d];

@@ -83,6 +83,7 @@ struct LayerArgs {
   uint16_t* y_img;         // if non-null: also write act(h') into the next layer's input image ...
   int y_img_f;             // ... which has this many features (direction d writes columns d*H .. d*H+H-1)
   // training mode of the tensor-core engine (LSTM family, fp32 precision): keep the tape, apply the recurrent-dropout mask
+  const void* packed;      // non-null: weights already packed by tc_pack_weights (the pack kernels are skipped)
   const a3gc_tape* tape;   // null = inference
   const float* hmask;      // [D][B][T][15][H] or null
 };
@@ -139,8 +140,12 @@ bool tc_layer_supported(int variant, int f_in, int hidden, int precision);
 size_t tc_layer_workspace_bytes(int variant, int64_t batch, int64_t steps, int f_in, int hidden, int num_dirs, int precision);
 size_t tc_image_bytes(int64_t batch, int64_t steps, int features, int precision);
 int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t tc_packed_weights_bytes(int variant, int f_in, int hidden, int num_dirs, int precision);
+int tc_pack_weights(int variant, int num_dirs, const a3gc_cell_params* cells, int f_in, int hidden, int precision, void* packed,
+                    cudaStream_t stream);
 // tc_gru_kernels.cu: graph-GRU layers on the tensor-core engine
 size_t tc_gru_weights_bytes(int f_in, int hidden, int num_dirs, int precision);
 int tc_gru_layer_launch(const LayerArgs& a, const uint16_t* x_img, char* weights_ws, cudaStream_t stream);
+int tc_gru_pack_weights(int num_dirs, const a3gc_cell_params* cells, int f_in, int hidden, int precision, char* weights_ws, cudaStream_t stream);
 
 }  // namespace a3gc

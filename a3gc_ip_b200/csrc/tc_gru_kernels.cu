@@ -487,6 +487,21 @@ size_t tc_gru_weights_bytes(int f_in, int hidden, int num_dirs, int precision) {
   return (size_t)num_dirs * gru_dir_bytes(f_in, hidden, precision == A3GC_PREC_FP32 ? 2 : 1);
 }
 
+// fused message weights + operand images + mix matrix + biases of every direction -> weights_ws (tc_gru_weights_bytes)
+int tc_gru_pack_weights(int num_dirs, const a3gc_cell_params* cells, int f_in, int hidden, int precision, char* wbase, cudaStream_t stream) {
+  const bool split = precision == A3GC_PREC_FP32;
+  const int NP = split ? 2 : 1;
+  const size_t dir_bytes = gru_dir_bytes(f_in, hidden, NP);
+  for (int d = 0; d < num_dirs; ++d) {
+    GruPackedTc pk = gru_carve(wbase + d * dir_bytes, f_in, hidden, NP);
+    tc_gru_fuse_kernel<<<148 * 2, 256, 0, stream>>>(cells[d], pk.wfused, hidden);
+    A3GC_LAUNCH_CHECK("tc_gru_fuse_kernel");
+    tc_pack_gru_kernel<<<148, 256, 0, stream>>>(cells[d], pk, f_in, hidden, split ? 1 : 0);
+    A3GC_LAUNCH_CHECK("tc_pack_gru_kernel");
+  }
+  return A3GC_OK;
+}
+
 // G-GRU layer on the tensor-core engine; a.x_img must hold the packed input (tc_layer_forward packs it if needed)
 int tc_gru_layer_launch(const LayerArgs& a, const uint16_t* x_img, char* wbase, cudaStream_t stream) {
   const int F = a.f_in, H = a.hidden;
@@ -497,12 +512,14 @@ int tc_gru_layer_launch(const LayerArgs& a, const uint16_t* x_img, char* wbase, 
   GruLayerParams p;
   memset(&p, 0, sizeof(p));
   const size_t dir_bytes = gru_dir_bytes(F, H, NP);
+  if (a.packed == nullptr) {
+    int rc = tc_gru_pack_weights(a.num_dirs, a.cells, F, H, a.precision, wbase, stream);
+    if (rc) return rc;
+  } else {
+    wbase = const_cast<char*>(static_cast<const char*>(a.packed));
+  }
   for (int d = 0; d < a.num_dirs; ++d) {
     GruPackedTc pk = gru_carve(wbase + d * dir_bytes, F, H, NP);
-    tc_gru_fuse_kernel<<<148 * 2, 256, 0, stream>>>(a.cells[d], pk.wfused, H);
-    A3GC_LAUNCH_CHECK("tc_gru_fuse_kernel");
-    tc_pack_gru_kernel<<<148, 256, 0, stream>>>(a.cells[d], pk, F, H, split ? 1 : 0);
-    A3GC_LAUNCH_CHECK("tc_pack_gru_kernel");
     GruDir& g = p.d[d];
     g.wx_img = pk.wx_img; g.wm_img = pk.wm_img; g.P = pk.P; g.bias3 = pk.bias3;
     g.h0 = a.h0[d]; g.hT = a.hT[d]; g.reverse = a.reverse[d];

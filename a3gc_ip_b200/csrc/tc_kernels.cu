@@ -1108,6 +1108,26 @@ size_t tc_layer_workspace_bytes(int variant, int64_t batch, int64_t steps, int f
   return b + 256;
 }
 
+size_t tc_packed_weights_bytes(int variant, int f_in, int hidden, int num_dirs, int precision) {
+  const int NP = precision == A3GC_PREC_FP32 ? 2 : 1;
+  return variant == A3GC_VARIANT_GGRU ? tc_gru_weights_bytes(f_in, hidden, num_dirs, precision) : (size_t)num_dirs * tc_dir_bytes(f_in, hidden, NP);
+}
+
+// operand images, mix matrices and biases of every direction -> packed (tc_packed_weights_bytes)
+int tc_pack_weights(int variant, int num_dirs, const a3gc_cell_params* cells, int f_in, int hidden, int precision, void* packed,
+                    cudaStream_t stream) {
+  if (variant == A3GC_VARIANT_GGRU) return tc_gru_pack_weights(num_dirs, cells, f_in, hidden, precision, static_cast<char*>(packed), stream);
+  const bool split = precision == A3GC_PREC_FP32;
+  const int NP = split ? 2 : 1;
+  const size_t dir_bytes = tc_dir_bytes(f_in, hidden, NP);
+  for (int d = 0; d < num_dirs; ++d) {
+    TcPacked pk = tc_carve(static_cast<char*>(packed) + d * dir_bytes, f_in, hidden, NP);
+    tc_pack_weights_kernel<<<148, 256, 0, stream>>>(cells[d], pk, f_in, hidden, variant, split ? 1 : 0);
+    A3GC_LAUNCH_CHECK("tc_pack_weights_kernel");
+  }
+  return A3GC_OK;
+}
+
 int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t stream) {
   const int F = a.f_in, H = a.hidden;
   const bool split = a.precision == A3GC_PREC_FP32;
@@ -1140,10 +1160,15 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
   TcLayerParams p;
   memset(&p, 0, sizeof(p));
   const size_t dir_bytes = tc_dir_bytes(F, H, NP);
+  char* wbase = base;
+  if (a.packed == nullptr) {
+    int rc = tc_pack_weights(a.variant, a.num_dirs, a.cells, F, H, a.precision, base, stream);
+    if (rc) return rc;
+  } else {
+    wbase = const_cast<char*>(static_cast<const char*>(a.packed));
+  }
   for (int d = 0; d < a.num_dirs; ++d) {
-    TcPacked pk = tc_carve(base + d * dir_bytes, F, H, NP);
-    tc_pack_weights_kernel<<<148, 256, 0, stream>>>(a.cells[d], pk, F, H, a.variant, split ? 1 : 0);
-    A3GC_LAUNCH_CHECK("tc_pack_weights_kernel");
+    TcPacked pk = tc_carve(wbase + d * dir_bytes, F, H, NP);
     TcDir& td = p.d[d];
     td.wg_img = pk.wg_img; td.a1_img = pk.a1_img; td.a2_img = pk.a2_img; td.P = pk.P; td.bias4 = pk.bias4;
     td.bs = pk.bs; td.u = pk.u; td.bu = pk.bu;

@@ -428,6 +428,52 @@ class _Net(torch.nn.Module, _EngineMixin):
         self.rnn2 = self.bi_cls(units_hidden * 2, units_hidden, adjacency_matrix, activation_fn="tanh", dropout=dropout, recurrent_dropout=dropout)
         self.linear_out = AAGC(units_hidden * 2, units_out, adjacency_matrix, activation_fn="linear", dropout=0.0)
         self._ws = _lib.Workspace()
+        self._pack_cache = False
+
+    def cache_packed_weights(self, on: bool = True):
+        """Opt in to keeping the packed (operand-image) weights of rnn1 / rnn2 across calls instead of re-packing them in
+        every forward (~25 us per layer, i.e. about 1 % of a B = 1 call).  For serving with frozen weights.  The
+        cache is keyed on every parameter's storage pointer and autograd version, so ``load_state_dict``, optimizer steps
+        and ``p.data = ...`` invalidate it; in-place edits through ``p.data`` that keep the storage do not bump the version
+        -- call ``invalidate_packed_weights()`` after those (the default, no cache, is always exact)."""
+        self._pack_cache = bool(on)
+        self.invalidate_packed_weights()
+        return self
+
+    def invalidate_packed_weights(self) -> None:
+        self.__dict__.pop("_packed", None)
+
+    def _packed_ptrs(self, dev):
+        """[ptr or None] * 2 for rnn1, rnn2: packs on the current stream when the key changed, and makes the current
+        stream wait for the packing stream otherwise."""
+        if not self._pack_cache:
+            return [None, None]
+        L = _lib.lib()
+        v, pr, en = _lib.VARIANT[self.variant], _lib.PRECISION[self.precision], _lib.ENGINE[self.engine]
+        H = self.units_hidden
+        cache = self.__dict__.setdefault("_packed", {})
+        out = []
+        for l, (rnn, f_in) in enumerate(((self.rnn1, H), (self.rnn2, 2 * H))):
+            key = (pr, en, str(dev)) + tuple((q.data_ptr(), q._version) for q in rnn.parameters())
+            ent = cache.get(l)
+            if ent is None or ent[0] != key:
+                with torch.cuda.device(dev):
+                    nbytes = L.a3gc_packed_weights_bytes(v, f_in, H, 2, pr, en)
+                    if nbytes == 0:
+                        ent = (key, None, None)
+                    else:
+                        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                        cells = (_lib.CellParams * 2)(*[rnn.directions[d].cell._cell_params() for d in range(2)])
+                        rc = L.a3gc_pack_weights(v, 2, cells, f_in, H, pr, en, buf.data_ptr(), nbytes, _lib.stream_ptr(dev))
+                        _lib.check(rc, "a3gc_pack_weights")
+                        ev = torch.cuda.Event()
+                        ev.record(torch.cuda.current_stream(dev))
+                        ent = (key, buf, ev)
+                cache[l] = ent
+            elif ent[2] is not None:
+                torch.cuda.current_stream(dev).wait_event(ent[2])     # packed on another stream (concurrent batch chunks)
+            out.append(None if ent[1] is None else ent[1].data_ptr())
+        return out
 
     def _workspace(self, slot: int) -> "_lib.Workspace":
         if slot == 0:
@@ -509,6 +555,8 @@ class _Net(torch.nn.Module, _EngineMixin):
         hT = [torch.empty(B, NUM_NODES, H, dtype=torch.float32, device=dev) for _ in range(2)]
         cT = None if gru else [torch.empty(B, NUM_NODES, H, dtype=torch.float32, device=dev) for _ in range(2)]
         p = self._net_params()
+        packed = self._packed_ptrs(dev)
+        p.packed_rnn[0], p.packed_rnn[1] = packed[0], packed[1]
         L = _lib.lib()
         v, pr, en = _lib.VARIANT[self.variant], _lib.PRECISION[self.precision], _lib.ENGINE[self.engine]
         with torch.cuda.device(dev):

@@ -274,6 +274,12 @@ class TPPipeline(torch.nn.Module):
             self._host_chunks(B, T, device, chain)
         return out_host
 
+    def cache_packed_weights(self, on: bool = True):
+        """Serving with frozen weights: keep the packed weights of the three nets across calls (see ``_Net.cache_packed_weights``)."""
+        for n in (self.net1, self.net2, self.net3):
+            n.cache_packed_weights(on)
+        return self
+
     def release_workspaces(self) -> None:
         """Free the scratch memory (operand images, inter-layer activations: ~150 KB per frame in flight) of the three nets."""
         for n in (self.net1, self.net2, self.net3):

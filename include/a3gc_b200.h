@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define A3GC_ABI_VERSION 1
+#define A3GC_ABI_VERSION 2
 #define A3GC_NODES 15
 
 /* Cell family.  Values are part of the ABI. */
@@ -107,6 +107,10 @@ typedef struct a3gc_net_params {
   a3gc_gc_params linear_in;
   a3gc_cell_params rnn[2][2];
   a3gc_gc_params linear_out;
+  /* Optional (NULL = repack on every call, the stateless default): the output of a3gc_pack_weights for rnn1 / rnn2
+   * (both directions), packed from the CURRENT values of rnn[l][*] at the same precision.  The library only reads it;
+   * the caller owns the buffer and re-packs after any parameter update (cached packed weights). */
+  const void* packed_rnn[2];
 } a3gc_net_params;
 
 /* Version of this ABI (A3GC_ABI_VERSION of the library that was built). */
@@ -148,6 +152,16 @@ int a3gc_layer_forward(int variant, int num_dirs, const a3gc_cell_params* cells,
                        float* const* hT, float* const* cT,
                        int64_t batch, int64_t steps, int f_in, int hidden, int out_act,
                        int precision, int engine, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Packed weights of one (bi)layer for the tensor-core engine: operand images of the gate / attention (G-GRU: input and
+ * fused message) weights, mix matrices and biases of `num_dirs` directions, in the form the layer kernel streams.
+ * a3gc_packed_weights_bytes returns 0 when the layer would not run on the tensor-core engine (shape / precision / engine),
+ * i.e. there is nothing to cache.  a3gc_pack_weights enqueues the packing kernels on `stream`.
+ */
+size_t a3gc_packed_weights_bytes(int variant, int f_in, int hidden, int num_dirs, int precision, int engine);
+int a3gc_pack_weights(int variant, int num_dirs, const a3gc_cell_params* cells, int f_in, int hidden, int precision,
+                      int engine, void* packed, size_t packed_bytes, void* stream);
 
 /* Bytes of workspace a3gc_net_forward needs for this shape. */
 size_t a3gc_net_workspace_bytes(int variant, int64_t batch, int64_t steps, int f0, int hidden,

@@ -196,6 +196,42 @@ def test_workspaces_are_not_copied_and_can_be_released(nira):
     assert torch.equal(net(x)[0], y0) and torch.equal(twin(x)[0], y0)
 
 
+@pytest.mark.parametrize("variant", ["A3GC", "GGRU"])
+def test_packed_weight_cache_is_exact_and_invalidates(variant, nira):
+    """Opt-in packed-weight cache: same bits as per-call packing, refreshed after load_state_dict and after an
+    optimizer-style in-place update (parameter version bump), shared safely between the concurrent streams of the pipeline."""
+    sd = O.random_state_dict(variant, 12, 3, 64, nira, seed=21)
+    net = build_net(variant, 12, 3, 64, sd, nira, engine="tc")
+    x = torch.randn(9, 5, 15, 12, generator=torch.Generator().manual_seed(4)).cuda()
+    want, _ = net(x)
+    L = A.lib()
+    net.cache_packed_weights(True)
+    L.a3gc_reset_launch_count(); y1, _ = net(x); n_first = L.a3gc_launch_count()
+    L.a3gc_reset_launch_count(); y2, _ = net(x); n_cached = L.a3gc_launch_count()
+    assert torch.equal(y1, want) and torch.equal(y2, want)
+    assert n_cached == 4 and n_first > n_cached                       # linear_in, rnn1, rnn2, linear_out: no pack kernels
+    with torch.no_grad():                                              # what an optimizer step does
+        for p in net.rnn2.parameters():
+            p.mul_(1.01)
+    fresh = build_net(variant, 12, 3, 64, {k: v.cpu() for k, v in net.state_dict().items()}, nira, engine="tc")
+    assert torch.equal(net(x)[0], fresh(x)[0])
+    net.load_state_dict(sd)
+    assert torch.equal(net(x)[0], want)
+    net.cache_packed_weights(False)
+    assert torch.equal(net(x)[0], want)
+
+
+def test_packed_weight_cache_with_concurrent_chunks(nira):
+    pipe, _ = build_tp("A3GC", nira)
+    x = O.synthetic_input(40, 12, seed=8).cuda()
+    pipe.streams = 1
+    want = pipe(x)[2]
+    pipe.cache_packed_weights(True)
+    pipe.streams = 4
+    for _ in range(2):
+        assert torch.equal(pipe(x)[2], want)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # training glue on the CUDA modules
 # ---------------------------------------------------------------------------------------------------------------
