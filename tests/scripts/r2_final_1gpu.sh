@@ -19,5 +19,9 @@ CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary --str
 $CMD > $O/r02_ncu_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_ncu_launches.csv $CMD > $O/r02_ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:tc_lstm_layer_kernel -s 19 -c 1 -o $O/r02_ncu_lstm_f512_h256 $CMD > $O/r02_ncu_full.log 2>&1
+# the restructured graph-GRU kernel: full capture of its dominant launch (stage-1 rnn2 of G-GRU-TP)
+CMDG="python bench.py --variant GGRU --steps 1 --warmup 3 --no-cpu-baseline --no-secondary --streams 1"
+$CMDG > $O/r02_ncu_plain_ggru.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:tc_gru_layer_kernel -s 19 -c 1 -o $O/r02_ncu_ggru_f512_h256 $CMDG > $O/r02_ncu_full_ggru.log 2>&1
 tail -3 $L
 ls -la $O | tail -12 >> $L
