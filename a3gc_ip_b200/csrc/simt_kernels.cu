@@ -600,6 +600,8 @@ struct BwdGeom {
   a3gc_tape_grads gr;
   const float* hmask;
   int B, T, F, H, out_act, BT;
+  long long* trace;                  // diagnostics: per-phase cycle sums of CTA (0, 0), or nullptr
+  int tcore;                         // blocked kernel: the two weight contractions run on the tensor cores (3xTF32)
 };
 
 template <bool ATT>
@@ -895,12 +897,161 @@ __device__ __forceinline__ void gemv_part(const float* __restrict__ vec, const f
     if (s < BT) *reinterpret_cast<float4*>(scr + ((size_t)kd * BT + s) * H + j4) = make_float4(part[s][0], part[s][1], part[s][2], part[s][3]);
 }
 
+// ---- 3xTF32 tensor-core contraction for the two weight products of the backward chain ---------------------------------
+// D[m][n] += sum_k W[k][m] act[k][n] with m = output unit, n = (sequence, node) row and k the contraction index: the
+// units are the M side of mma.sync.m16n8k8 (row-major A = W^T, read straight from the reference layout in L2: a lane's four
+// A registers are 32-byte segments of four weight rows), the BT * 16 node rows the N side (B fragments from the fp32
+// shared-memory arrays [seq][k][16]).  Both operands are split into tf32 hi + tf32 lo in registers and three products are
+// accumulated (lo x hi, hi x lo, hi x hi; the dropped lo x lo term is 2^-22 relative), the precision the hoisted gradient
+// GEMMs of the training step use as well.  One warp owns MT x NT tiles for the whole contraction: no partial sums meet.
+__device__ __forceinline__ uint32_t tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = tf32_round(x);
+  lo = tf32_round(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// act: shared [seq][k][16] (seq_stride floats per sequence); n tiles nt0 .. nt0 + NT - 1 (tile = 8 rows: sequence tile / 2,
+// nodes 8 (tile % 2) ..);  w: element (k, m) at w[k * ldw + m], m tiles m0 .. m0 + MT - 1;  kcount % 32 == 0
+template <int MT, int NT>
+__device__ __forceinline__ void contract_tf32(float (&acc)[MT][NT][4], const float* __restrict__ act, size_t seq_stride, int nt0,
+                                              const float* __restrict__ w, int ldw, int m0, int kcount) {
+  constexpr int kD = 4;                                   // k tiles of weights in flight per warp (L2 latency)
+  const int lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
+  const float* wp = w + (size_t)c * ldw + m0 * 16 + r;    // a0: (k = c, m = r)  a1: m + 8  a2: k + 4  a3: both
+  const size_t k4 = (size_t)4 * ldw, k8 = (size_t)8 * ldw;
+  float wn[kD][MT][4];
+#pragma unroll
+  for (int i = 0; i < kD; ++i)
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi) {
+      const float* q = wp + i * k8 + mi * 16;
+      wn[i][mi][0] = __ldg(q); wn[i][mi][1] = __ldg(q + 8); wn[i][mi][2] = __ldg(q + k4); wn[i][mi][3] = __ldg(q + k4 + 8);
+    }
+  const float* bp[NT];
+#pragma unroll
+  for (int ni = 0; ni < NT; ++ni) {
+    const int nt = nt0 + ni;
+    bp[ni] = act + (size_t)(nt >> 1) * seq_stride + (nt & 1) * 8 + r + c * kNodesPad;
+  }
+  const int nkt = kcount / 8;
+#pragma unroll 1
+  for (int kt0 = 0; kt0 < nkt; kt0 += kD) {
+#pragma unroll
+    for (int i = 0; i < kD; ++i) {
+      const int kt = kt0 + i;
+      uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) tf32_split(wn[i][mi][e], ah[mi][e], al[mi][e]);
+      if (kt + kD < nkt) {
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi) {
+          const float* q = wp + (size_t)(kt + kD) * k8 + mi * 16;
+          wn[i][mi][0] = __ldg(q); wn[i][mi][1] = __ldg(q + 8); wn[i][mi][2] = __ldg(q + k4); wn[i][mi][3] = __ldg(q + k4 + 8);
+        }
+      }
+      uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+      for (int ni = 0; ni < NT; ++ni) {
+        const float* q = bp[ni] + (size_t)kt * 8 * kNodesPad;
+        tf32_split(q[0], bh[ni][0], bl[ni][0]);
+        tf32_split(q[4 * kNodesPad], bh[ni][1], bl[ni][1]);
+      }
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) mma_tf32(acc[mi][ni], al[mi], bh[ni][0], bh[ni][1]);
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) mma_tf32(acc[mi][ni], ah[mi], bl[ni][0], bl[ni][1]);
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) mma_tf32(acc[mi][ni], ah[mi], bh[ni][0], bh[ni][1]);
+    }
+  }
+}
+
+// phase E on the tensor cores: dhy[n][j] += ds_j + sum_k dep[n][k] Wh[k][j]   (the barrier: v1 = ds is complete)
+template <int MT, int NT>
+__device__ __forceinline__ void bwd_phase_e_tc(const float* dep, size_t HN, const float* __restrict__ Wh, int H, int m0, int nt0,
+                                               float* dh, const float* v1) {
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[mi][ni][e] = 0.f;
+  contract_tf32<MT, NT>(acc, dep, HN, nt0, Wh, H, m0, H);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
+#pragma unroll
+  for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int nt = nt0 + ni, unit = (m0 + mi) * 16 + r + 8 * hf, node = (nt & 1) * 8 + 2 * c;
+        const int task = (nt >> 1) * H + unit;
+        float2* p = reinterpret_cast<float2*>(dh + (size_t)task * kNodesPad + node);
+        float2 cur = *p;
+        const float ds = v1[task];
+        cur.x += acc[mi][ni][2 * hf] + ds;
+        cur.y = node + 1 < kNodes ? cur.y + acc[mi][ni][2 * hf + 1] + ds : 0.f;
+        *p = cur;
+      }
+}
+
+// phase G on the tensor cores: dh'_{prev}[n][k] = sum_g sum_j dzm_g[n][j] W_g[j][F + k], then the recurrent-dropout mask
+template <int MT, int NT>
+__device__ __forceinline__ void bwd_phase_g_tc(const float* dzm, int BT, size_t HN, const BwdDir& d, int F, int H, int m0, int nt0,
+                                               float* dh, const float* hmask_t, int b0, int B, int T) {
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[mi][ni][e] = 0.f;
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) contract_tf32<MT, NT>(acc, dzm + (size_t)q * BT * HN, HN, nt0, d.Wg[q] + F, F + H, m0, H);
+  const int lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
+#pragma unroll
+  for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int nt = nt0 + ni, unit = (m0 + mi) * 16 + r + 8 * hf, node = (nt & 1) * 8 + 2 * c;
+        const int s = nt >> 1, b = b0 + s;
+        float2 v = make_float2(acc[mi][ni][2 * hf], node + 1 < kNodes ? acc[mi][ni][2 * hf + 1] : 0.f);
+        if (hmask_t != nullptr && b < B) {        // hmask_t: mask element (b = 0, this step, node 0, unit 0)
+          const float* mp = hmask_t + ((size_t)b * T * kNodes + node) * H + unit;
+          v.x *= mp[0];
+          if (node + 1 < kNodes) v.y *= mp[H];
+        }
+        *reinterpret_cast<float2*>(dh + ((size_t)s * H + unit) * kNodesPad + node) = v;
+      }
+}
+
 // Same chain as lstm_train_bwd_kernel for H in {64, 128, 256}, arranged around the two weight contractions that
 // dominate it (phase E: dep x Wh, phase G: dzm x W[:, F:]).  BT * H = 512 (or 256): a thread owns 2 sequences x 2
 // units (u, u + H/2) and 1/KS of the contraction range, so the weights cross L2 once per sequence PAIR and every
 // activation float4 read from shared memory feeds 8 FMAs; the KS partial sums meet in shared memory.  dhy overwrites
 // dh' in place and dep lives in dzm[0], which leaves room for two H=256 sequences per CTA.
-template <bool ATT>
+template <bool ATT, bool TCORE>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
   extern __shared__ __align__(16) float smem[];
@@ -927,6 +1078,11 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
   const int UH = H / 2, ntile = UH * (BT / 2), KS = kThreads / ntile;
   const int u = threadIdx.x % UH, s0 = 2 * ((threadIdx.x / UH) % (BT / 2)), kh = threadIdx.x / ntile;
   const int kq = H / KS, k0 = kh * kq, k1 = k0 + kq;
+  // tensor-core phases: warp -> tc_mt unit tiles (16 units) from tc_m0 x tc_nt row tiles (8 rows) from tc_nt0:
+  // H = 256: 2 x 4 (all rows of the CTA's two sequences), H = 128: 1 x 2 BT, H = 64: 1 x BT (warp pairs share a unit tile)
+  const int tc_warp = threadIdx.x >> 5;
+  const int tc_mt = H / 16 >= 8 ? H / 128 : 1, tc_m0 = H / 16 >= 8 ? tc_warp * tc_mt : tc_warp % 4;
+  const int tc_nt = H / 16 >= 8 ? 2 * BT : BT, tc_nt0 = H / 16 >= 8 ? 0 : (tc_warp / 4) * BT;
   // GEMV phases: thread -> (kd, 4 consecutive units jd..jd+3), all BT sequences, 1/KD of the contraction range
   const int KD = 4 * kThreads / H, jd = 4 * (threadIdx.x % (H / 4)), kd = threadIdx.x / (H / 4);
   const int kdq = H / KD;
@@ -934,6 +1090,10 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
   load_state(dh, d.dhT, b0, lg);
   load_state(dc, d.dcT, b0, lg);
   for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) PT[i] = d.PT[i];
+  // diagnostics (A3GC_BWD_TRACE=1): cycles of CTA (0, 0) between the phase barriers, summed over the steps
+  const bool tr = g.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = tr ? clock64() : 0;
+#define BWD_MARK(i) do { if (tr) { const long long now_ = clock64(); tacc[i] += now_ - tlast; tlast = now_; } } while (0)
 
   for (int step = g.T - 1; step >= 0; --step) {
     const int t = d.reverse ? g.T - 1 - step : step;
@@ -981,6 +1141,7 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
     }
     if (ATT) {
       __syncthreads();
+      BWD_MARK(0);
       // ---- B: dalpha[n] = sum_j partial (all threads, then BT*16 of them);  dap = dalpha * a (1 - a)
       {
         const int nI = BT * kNodesPad, parts = kThreads / nI;
@@ -1003,6 +1164,7 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
         }
       }
       __syncthreads();
+      BWD_MARK(1);
       // ---- C: dep[n][j] = dap[n] u_j (1 - e^2);  dqs_j = sum_n dep
       for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
         const int s = task / H, j = task % H, b = b0 + s;
@@ -1024,6 +1186,7 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
         v1[task] = sum;
       }
       __syncthreads();
+      BWD_MARK(2);
       // ---- D: dq_j = sum_k dqs_k Wq[k][j] for all BT sequences at once;  dqp = dq [q > 0]
       if (kdq % 8 == 0) gemv_part<8>(v1, d.Wq, scr, H, BT, jd, kd, kdq); else gemv_part<4>(v1, d.Wq, scr, H, BT, jd, kd, kdq);
       __syncthreads();
@@ -1039,6 +1202,7 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
         v2[task] = r;
       }
       __syncthreads();
+      BWD_MARK(3);
       // ---- D2: ds_j = sum_k dqp_k Wa[k][j]  (-> v1)
       if (kdq % 8 == 0) gemv_part<8>(v2, d.Wa, scr, H, BT, jd, kd, kdq); else gemv_part<4>(v2, d.Wa, scr, H, BT, jd, kd, kdq);
       __syncthreads();
@@ -1047,8 +1211,13 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
         for (int q = 0; q < KD; ++q) ds += scr[(q * BT + task / H) * H + task % H];
         v1[task] = ds;
       }
+      BWD_MARK(4);
       // ---- E: dhy[n][j] += ds_j + sum_k dep[n][k] Wh[k][j]
-      {
+      if constexpr (TCORE) {
+        if (tc_mt == 2) bwd_phase_e_tc<2, 4>(dep, HN, d.Wh, H, tc_m0, tc_nt0, dh, v1);
+        else if (tc_nt == 8) bwd_phase_e_tc<1, 8>(dep, HN, d.Wh, H, tc_m0, tc_nt0, dh, v1);
+        else bwd_phase_e_tc<1, 4>(dep, HN, d.Wh, H, tc_m0, tc_nt0, dh, v1);
+      } else {
         float acc[2][2][16];
 #pragma unroll
         for (int si = 0; si < 2; ++si)
@@ -1079,6 +1248,7 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
       }
     }
     __syncthreads();
+    BWD_MARK(5);
     // ---- F: LSTM pointwise backward, dz (global, in place of the gates) and dzm = P_g^T dz_g
     for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
       const int s = task / H, j = task % H, b = b0 + s;
@@ -1131,8 +1301,14 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
       }
     }
     __syncthreads();
+    BWD_MARK(6);
     // ---- G: dh'_{prev}[n][k] = sum_g sum_j dzm_g[n][j] W_g[j][F + k]   (then the recurrent-dropout mask of this step)
-    {
+    if constexpr (TCORE) {
+      const float* hm = g.hmask != nullptr ? g.hmask + nm0 * H : nullptr;
+      if (tc_mt == 2) bwd_phase_g_tc<2, 4>(dzm, BT, HN, d, F, H, tc_m0, tc_nt0, dh, hm, b0, g.B, g.T);
+      else if (tc_nt == 8) bwd_phase_g_tc<1, 8>(dzm, BT, HN, d, F, H, tc_m0, tc_nt0, dh, hm, b0, g.B, g.T);
+      else bwd_phase_g_tc<1, 4>(dzm, BT, HN, d, F, H, tc_m0, tc_nt0, dh, hm, b0, g.B, g.T);
+    } else {
       float acc[2][2][16];
 #pragma unroll
       for (int si = 0; si < 2; ++si)
@@ -1173,8 +1349,11 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
         if (r + 1 < KS) __syncthreads();
       }
     }
+    BWD_MARK(7);
   }
   __syncthreads();
+  if (tr) for (int i = 0; i < 8; ++i) g.trace[i] = tacc[i];
+#undef BWD_MARK
   store_state(d.dh0, dh, b0, lg);
   store_state(d.dc0, dc, b0, lg);
 }
@@ -1816,15 +1995,34 @@ int simt_train_backward(const TrainBwdArgs& a, void* ws, size_t ws_bytes, cudaSt
   g.dy = a.dy; g.syb = a.dy_stride_b; g.syt = a.dy_stride_t; g.yld = a.dy_ld;
   g.tape = a.tape; g.gr = a.grads; g.hmask = a.hmask;
   g.B = (int)a.batch; g.T = (int)a.steps; g.F = F; g.H = H; g.out_act = a.out_act; g.BT = BT;
+  {
+    // tile shapes the tensor-core phases are instantiated for: (H / 128, 2 BT) in {(2, 4), (1, 8), (1, 4)} or H = 64 with BT in {4, 8}
+    const int nt = H >= 128 ? 2 * BT : BT;
+    const char* e = getenv("A3GC_BWD_MMA");
+    g.tcore = blk && !(e != nullptr && e[0] == '0') && ((H == 256 && nt == 4) || (H <= 128 && (nt == 4 || nt == 8)));
+  }
   dim3 grid((unsigned)((a.batch + BT - 1) / BT), (unsigned)a.num_dirs);
   if (blk) {
     const size_t bsmem = blk_smem_bytes(BT);
-    if (att) {
-      A3GC_CUDA_TRY(cudaFuncSetAttribute(lstm_train_bwd_blk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
-      lstm_train_bwd_blk_kernel<true><<<grid, kThreads, bsmem, stream>>>(bd[0], bd[1], g);
-    } else {
-      A3GC_CUDA_TRY(cudaFuncSetAttribute(lstm_train_bwd_blk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
-      lstm_train_bwd_blk_kernel<false><<<grid, kThreads, bsmem, stream>>>(bd[0], bd[1], g);
+    auto launch = [&](auto kern) -> int {
+      A3GC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+      kern<<<grid, kThreads, bsmem, stream>>>(bd[0], bd[1], g);
+      return A3GC_OK;
+    };
+    g.trace = nullptr;
+    const char* tre = getenv("A3GC_BWD_TRACE");
+    if (tre != nullptr && tre[0] == '1') A3GC_CUDA_TRY(cudaMalloc(&g.trace, 8 * sizeof(long long)));
+    int rc;
+    if (att) rc = g.tcore ? launch(lstm_train_bwd_blk_kernel<true, true>) : launch(lstm_train_bwd_blk_kernel<true, false>);
+    else rc = g.tcore ? launch(lstm_train_bwd_blk_kernel<false, true>) : launch(lstm_train_bwd_blk_kernel<false, false>);
+    if (rc != A3GC_OK) return rc;
+    if (g.trace != nullptr) {
+      long long h[8];
+      A3GC_CUDA_TRY(cudaStreamSynchronize(stream));
+      A3GC_CUDA_TRY(cudaMemcpy(h, g.trace, sizeof(h), cudaMemcpyDeviceToHost));
+      cudaFree(g.trace);
+      fprintf(stderr, "[a3gc bwd trace] H=%d BT=%d T=%d tcore=%d cycles/step: A %lld  B %lld  C %lld  D %lld  D2in %lld  E+D2red %lld  F %lld  G %lld\n",
+              H, BT, g.T, g.tcore, h[0] / g.T, h[1] / g.T, h[2] / g.T, h[3] / g.T, h[4] / g.T, h[5] / g.T, h[6] / g.T, h[7] / g.T);
     }
     A3GC_LAUNCH_CHECK("lstm_train_bwd_blk_kernel");
     return A3GC_OK;

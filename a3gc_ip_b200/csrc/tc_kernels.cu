@@ -82,6 +82,7 @@ struct TcLayerParams {
                                      // (measured -2..4 % per step at H = 256, +1 % at H = 128, where it stays off)
   int puborder;                      // order in which a CTA serves its peers in the state exchange
   int rescale;                       // fp32 inference: peers' h' blocks are rescaled locally instead of a second all-gather
+  int rescale_bf16;                  // the same in bf16 mode (costs a second bf16 rounding of the peers' blocks; experiment knob)
   int pubbytes;                      // TIMING DIAGNOSTIC ONLY (results are wrong if < kHBlock): bytes per state-exchange copy
   int acoll;                         // A-operand collector reuse between the hi*hi and hi*lo passes of a K block
   int nprod;                         // producer threads (one per warp) that issue the bulk copies of the weight / x stream, stage i by thread i % nprod
@@ -915,7 +916,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       if (TRAIN) tape_hp(ta);
       store_units(hreg, tnext);
       if (et == 0) TC_TRACE(0, 10);
-      if (SPLIT && !TRAIN && C > 1 && p.rescale) {
+      if (!TRAIN && C > 1 && (SPLIT ? p.rescale : p.rescale_bf16)) {
         // h' = hy (1 + a) differs from hy by a factor per ROW, and every CTA already holds the hy blocks of its peers (they
         // were exchanged for the attention GEMM) and a[row]: instead of a second all-gather over DSMEM -- measured 8-10 % of
         // the step at H = 256, the copies also delay the weight stream queued behind them -- each CTA rescales the peers'
@@ -932,18 +933,30 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
             uint8_t* ph = hbuf + (size_t)((src * 8 + cg * 2 + h2) * kRows + rr) * 16;
-            uint8_t* pl = ph + (size_t)H * 256;
-            const uint4 hv = *reinterpret_cast<const uint4*>(ph), lv = *reinterpret_cast<const uint4*>(pl);
-            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
-            uint32_t ho[4], lo[4];
+            const uint4 hv = *reinterpret_cast<const uint4*>(ph);
+            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+            uint32_t ho[4];
+            if constexpr (SPLIT) {
+              uint8_t* pl = ph + (size_t)H * 256;
+              const uint4 lv = *reinterpret_cast<const uint4*>(pl);
+              const uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
+              uint32_t lo[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
-              const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
-              ptx::split_pair_f16((hf.x + lf.x) * ar, (hf.y + lf.y) * ar, ho[j], lo[j]);
+              for (int j = 0; j < 4; ++j) {
+                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+                const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
+                ptx::split_pair_f16((hf.x + lf.x) * ar, (hf.y + lf.y) * ar, ho[j], lo[j]);
+              }
+              *reinterpret_cast<uint4*>(pl) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            } else {                                                     // bf16 (opt-in): one extra bf16 rounding per element
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[j]));
+                const __nv_bfloat162 bb = __floats2bfloat162_rn(hf.x * ar, hf.y * ar);
+                ho[j] = *reinterpret_cast<const uint32_t*>(&bb);
+              }
             }
             *reinterpret_cast<uint4*>(ph) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
-            *reinterpret_cast<uint4*>(pl) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
           ptx::fence_proxy_async();
           ptx::named_bar_sync(1, kEpiThreads);
@@ -1215,6 +1228,7 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
     p.earlypub = getenv("A3GC_TC_EARLYPUB") ? atoi(getenv("A3GC_TC_EARLYPUB")) : 1;
     p.puborder = getenv("A3GC_TC_PUBORDER") ? atoi(getenv("A3GC_TC_PUBORDER")) : 1;
     p.rescale = getenv("A3GC_TC_RESCALE") ? atoi(getenv("A3GC_TC_RESCALE")) : 1;
+    p.rescale_bf16 = getenv("A3GC_TC_RESCALE_BF16") ? atoi(getenv("A3GC_TC_RESCALE_BF16")) : 0;
     p.pubbytes = 16384;  // = kHBlock; A3GC_TC_PUBBYTES < 16384 is a timing diagnostic (truncated state exchange, wrong results)
     if (const char* e = getenv("A3GC_TC_PUBBYTES")) { const int v = atoi(e); if (v >= 16 && v <= 16384 && v % 16 == 0) p.pubbytes = v; }
     p.chunk = 1 << 20;   // measured: one bulk copy per operand is fastest (4 KB pieces: -7 %, 2 KB pieces: -30 %)

@@ -1,9 +1,11 @@
 #!/bin/bash
 set -u
-L=gpurun_out/r2_dbg.log
+O=gpurun_out
+L=$O/r2_dbg.log
 : > $L
-for env in "A3GC_TC_STAGES=4" "A3GC_TC_STAGES=5" "A3GC_TC_STAGES=6" "A3GC_TC_STAGES=7" "A3GC_TC_STAGES=8"; do
-  echo "== $env" >> $L
-  env $env timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "net_matches" 2>&1 | grep -E "AssertionError:|passed|failed" | cut -c1-160 >> $L
+for m in 0 1; do
+  A3GC_BWD_TRACE=1 A3GC_BWD_MMA=$m timeout 600 python tests/prof_train.py 256 12 3 256 200 2 2>&1 | grep -E "bwd trace|iter 2" >> $L
+  A3GC_BWD_TRACE=1 A3GC_BWD_MMA=$m timeout 600 python tests/prof_train.py 64 15 9 256 200 2 2>&1 | grep -E "bwd trace|iter 2" >> $L
 done
-tail -3 $L
+timeout 600 python -m pytest tests/test_gpu_train.py -m gpu -q 2>&1 | tail -2 >> $L
+tail -5 $L

@@ -133,8 +133,9 @@ def test_recurrent_dropout_mask_semantics_tc_vs_simt(nira):
 
 @pytest.mark.parametrize("variant,H,B", [("A3GC", 64, 5), ("AAGC", 128, 3), ("AGC", 256, 3)])
 def test_blocked_and_plain_backward_chains_agree(variant, H, B, nira, monkeypatch):
-    """The register-blocked reverse-time chain (H in {64,128,256}; 2 sequences x 2 units x 1/KS of K per thread) against the
-    one-(sequence, unit)-per-thread chain on the same tape, with a recurrent-dropout mask and a ragged batch."""
+    """The blocked reverse-time chain (H in {64,128,256}; its two weight contractions as 3xTF32 mma.sync products) against the
+    one-(sequence, unit)-per-thread fp32 chain on the same tape, with a recurrent-dropout mask and a ragged batch.  Bound 3e-5:
+    the hi/lo TF32 split drops the lo x lo term (2^-22 per product); both chains are within 1e-4 of the oracle separately."""
     from a3gc_ip_b200 import training as TR
     torch.manual_seed(5)
     F, T = 32, 5
@@ -158,8 +159,8 @@ def test_blocked_and_plain_backward_chains_agree(variant, H, B, nira, monkeypatc
         outs[blk] = ([xr.grad.cpu()] + [f.grad.cpu() for f in flat[:4]]
                      + [p_.grad.detach().cpu().clone() for p_ in layer.parameters() if p_.grad is not None])
     assert len(outs["1"]) == len(outs["0"]) > 10
-    for a, b in zip(outs["0"], outs["1"]):
-        assert rel_l2(b, a) <= 1e-5
+    for i, (a, b) in enumerate(zip(outs["0"], outs["1"])):
+        assert rel_l2(b, a) <= 3e-5, f"gradient {i}: rel_l2={rel_l2(b, a):.3e}"
 
 
 def test_tf32_split_and_hprev_operand_builders():
