@@ -600,6 +600,7 @@ struct BwdGeom {
   a3gc_tape_grads gr;
   const float* hmask;
   int B, T, F, H, out_act, BT;
+  int gemv16;                        // blocked kernel: 16 instead of 8 weight loads in flight per thread in the q-chain GEMVs
   long long* trace;                  // diagnostics: per-phase cycle sums of CTA (0, 0), or nullptr
   int tcore;                         // blocked kernel: the two weight contractions run on the tensor cores (3xTF32)
 };
@@ -904,14 +905,12 @@ __device__ __forceinline__ void gemv_part(const float* __restrict__ vec, const f
 // shared-memory arrays [seq][k][16]).  Both operands are split into tf32 hi + tf32 lo in registers and three products are
 // accumulated (lo x hi, hi x lo, hi x hi; the dropped lo x lo term is 2^-22 relative), the precision the hoisted gradient
 // GEMMs of the training step use as well.  One warp owns MT x NT tiles for the whole contraction: no partial sums meet.
-__device__ __forceinline__ uint32_t tf32_round(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// hi = x rounded to TF32 (nearest, ties away: add half an ulp of the 10-bit mantissa to the magnitude and clear the 13 low
+// bits -- two integer instructions; cvt.rna.tf32.f32 expands to a ten-instruction sequence on sm_100 and made the contraction
+// loops ALU-bound), lo = x - hi exactly; the tensor core ignores the 13 low mantissa bits of lo (2^-11 of lo = 2^-22 of x).
 __device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
-  hi = tf32_round(x);
-  lo = tf32_round(x - __uint_as_float(hi));
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -919,9 +918,24 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(uint32_t lo_bits, uint32_t hi_bits) {      // {bf16(lo) in bits 0..15, bf16(hi) in 16..31}
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi_bits)), "f"(__uint_as_float(lo_bits)));
+  return r;
+}
+
 // act: shared [seq][k][16] (seq_stride floats per sequence); n tiles nt0 .. nt0 + NT - 1 (tile = 8 rows: sequence tile / 2,
 // nodes 8 (tile % 2) ..);  w: element (k, m) at w[k * ldw + m], m tiles m0 .. m0 + MT - 1;  kcount % 32 == 0
-template <int MT, int NT>
+// MIXED: the two correction products (lo x hi, hi x lo) of a PAIR of k tiles run as one bf16 m16n8k16 product each (their
+// operands rounded to bf16: 2^-9 on a term that is 2^-11 of the product), the hi x hi product stays TF32 -- 4 tensor
+// instructions per 16 contraction steps instead of 6.  The k16 slots {2c, 2c+1, 2c+8, 2c+9} of lane c carry the contraction
+// indices {c, c+4, c+8, c+12} it already holds for the two TF32 tiles, on the A and the B side alike.
+template <int MT, int NT, bool MIXED>
 __device__ __forceinline__ void contract_tf32(float (&acc)[MT][NT][4], const float* __restrict__ act, size_t seq_stride, int nt0,
                                               const float* __restrict__ w, int ldw, int m0, int kcount) {
   constexpr int kD = 4;                                   // k tiles of weights in flight per warp (L2 latency)
@@ -943,48 +957,101 @@ __device__ __forceinline__ void contract_tf32(float (&acc)[MT][NT][4], const flo
     bp[ni] = act + (size_t)(nt >> 1) * seq_stride + (nt & 1) * 8 + r + c * kNodesPad;
   }
   const int nkt = kcount / 8;
+  auto refill = [&](int i, int kt) {
+    if (kt < nkt) {
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi) {
+        const float* q = wp + (size_t)kt * k8 + mi * 16;
+        wn[i][mi][0] = __ldg(q); wn[i][mi][1] = __ldg(q + 8); wn[i][mi][2] = __ldg(q + k4); wn[i][mi][3] = __ldg(q + k4 + 8);
+      }
+    }
+  };
 #pragma unroll 1
   for (int kt0 = 0; kt0 < nkt; kt0 += kD) {
+    if constexpr (!MIXED) {
 #pragma unroll
-    for (int i = 0; i < kD; ++i) {
-      const int kt = kt0 + i;
-      uint32_t ah[MT][4], al[MT][4];
+      for (int i = 0; i < kD; ++i) {
+        const int kt = kt0 + i;
+        uint32_t ah[MT][4], al[MT][4];
 #pragma unroll
-      for (int mi = 0; mi < MT; ++mi)
+        for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) tf32_split(wn[i][mi][e], ah[mi][e], al[mi][e]);
-      if (kt + kD < nkt) {
+          for (int e = 0; e < 4; ++e) tf32_split(wn[i][mi][e], ah[mi][e], al[mi][e]);
+        refill(i, kt + kD);
+        uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) {
+          const float* q = bp[ni] + (size_t)kt * 8 * kNodesPad;
+          tf32_split(q[0], bh[ni][0], bl[ni][0]);
+          tf32_split(q[4 * kNodesPad], bh[ni][1], bl[ni][1]);
+        }
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < NT; ++ni) mma_tf32(acc[mi][ni], al[mi], bh[ni][0], bh[ni][1]);
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < NT; ++ni) mma_tf32(acc[mi][ni], ah[mi], bl[ni][0], bl[ni][1]);
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < NT; ++ni) mma_tf32(acc[mi][ni], ah[mi], bh[ni][0], bh[ni][1]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kD; i += 2) {
+        const int kt = kt0 + i;
+        uint32_t ah[2][MT][4], ahb[MT][4], alb[MT][4];       // TF32 heads of the two tiles; bf16 pairs of heads / tails
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi) {
-          const float* q = wp + (size_t)(kt + kD) * k8 + mi * 16;
-          wn[i][mi][0] = __ldg(q); wn[i][mi][1] = __ldg(q + 8); wn[i][mi][2] = __ldg(q + k4); wn[i][mi][3] = __ldg(q + k4 + 8);
+          uint32_t al[2][4];
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) tf32_split(wn[i + j][mi][e], ah[j][mi][e], al[j][e]);
+          // k16 A registers: (row r, slots 2c, 2c+1) (row r+8, same) (row r, slots 2c+8, 2c+9) (row r+8, same)
+          ahb[mi][0] = pack_bf16(ah[0][mi][0], ah[0][mi][2]); ahb[mi][1] = pack_bf16(ah[0][mi][1], ah[0][mi][3]);
+          ahb[mi][2] = pack_bf16(ah[1][mi][0], ah[1][mi][2]); ahb[mi][3] = pack_bf16(ah[1][mi][1], ah[1][mi][3]);
+          alb[mi][0] = pack_bf16(al[0][0], al[0][2]); alb[mi][1] = pack_bf16(al[0][1], al[0][3]);
+          alb[mi][2] = pack_bf16(al[1][0], al[1][2]); alb[mi][3] = pack_bf16(al[1][1], al[1][3]);
         }
+        refill(i, kt + kD);
+        refill(i + 1, kt + 1 + kD);
+        uint32_t bh[2][NT][2], bhb[NT][2], blb[NT][2];
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) {
+          uint32_t bl[2][2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const float* q = bp[ni] + (size_t)(kt + j) * 8 * kNodesPad;
+            tf32_split(q[0], bh[j][ni][0], bl[j][0]);
+            tf32_split(q[4 * kNodesPad], bh[j][ni][1], bl[j][1]);
+          }
+          bhb[ni][0] = pack_bf16(bh[0][ni][0], bh[0][ni][1]); bhb[ni][1] = pack_bf16(bh[1][ni][0], bh[1][ni][1]);
+          blb[ni][0] = pack_bf16(bl[0][0], bl[0][1]); blb[ni][1] = pack_bf16(bl[1][0], bl[1][1]);
+        }
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < NT; ++ni) mma_bf16(acc[mi][ni], alb[mi], bhb[ni][0], bhb[ni][1]);
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < NT; ++ni) mma_bf16(acc[mi][ni], ahb[mi], blb[ni][0], blb[ni][1]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < NT; ++ni) mma_tf32(acc[mi][ni], ah[j][mi], bh[j][ni][0], bh[j][ni][1]);
       }
-      uint32_t bh[NT][2], bl[NT][2];
-#pragma unroll
-      for (int ni = 0; ni < NT; ++ni) {
-        const float* q = bp[ni] + (size_t)kt * 8 * kNodesPad;
-        tf32_split(q[0], bh[ni][0], bl[ni][0]);
-        tf32_split(q[4 * kNodesPad], bh[ni][1], bl[ni][1]);
-      }
-#pragma unroll
-      for (int mi = 0; mi < MT; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < NT; ++ni) mma_tf32(acc[mi][ni], al[mi], bh[ni][0], bh[ni][1]);
-#pragma unroll
-      for (int mi = 0; mi < MT; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < NT; ++ni) mma_tf32(acc[mi][ni], ah[mi], bl[ni][0], bl[ni][1]);
-#pragma unroll
-      for (int mi = 0; mi < MT; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < NT; ++ni) mma_tf32(acc[mi][ni], ah[mi], bh[ni][0], bh[ni][1]);
     }
   }
 }
 
 // phase E on the tensor cores: dhy[n][j] += ds_j + sum_k dep[n][k] Wh[k][j]   (the barrier: v1 = ds is complete)
-template <int MT, int NT>
+template <int MT, int NT, bool MIXED>
 __device__ __forceinline__ void bwd_phase_e_tc(const float* dep, size_t HN, const float* __restrict__ Wh, int H, int m0, int nt0,
                                                float* dh, const float* v1) {
   float acc[MT][NT][4];
@@ -994,7 +1061,7 @@ __device__ __forceinline__ void bwd_phase_e_tc(const float* dep, size_t HN, cons
     for (int ni = 0; ni < NT; ++ni)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[mi][ni][e] = 0.f;
-  contract_tf32<MT, NT>(acc, dep, HN, nt0, Wh, H, m0, H);
+  contract_tf32<MT, NT, MIXED>(acc, dep, HN, nt0, Wh, H, m0, H);
   __syncthreads();
   const int lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
 #pragma unroll
@@ -1015,7 +1082,7 @@ __device__ __forceinline__ void bwd_phase_e_tc(const float* dep, size_t HN, cons
 }
 
 // phase G on the tensor cores: dh'_{prev}[n][k] = sum_g sum_j dzm_g[n][j] W_g[j][F + k], then the recurrent-dropout mask
-template <int MT, int NT>
+template <int MT, int NT, bool MIXED>
 __device__ __forceinline__ void bwd_phase_g_tc(const float* dzm, int BT, size_t HN, const BwdDir& d, int F, int H, int m0, int nt0,
                                                float* dh, const float* hmask_t, int b0, int B, int T) {
   float acc[MT][NT][4];
@@ -1025,9 +1092,10 @@ __device__ __forceinline__ void bwd_phase_g_tc(const float* dzm, int BT, size_t 
     for (int ni = 0; ni < NT; ++ni)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[mi][ni][e] = 0.f;
-#pragma unroll 1
-  for (int q = 0; q < 4; ++q) contract_tf32<MT, NT>(acc, dzm + (size_t)q * BT * HN, HN, nt0, d.Wg[q] + F, F + H, m0, H);
   const int lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
+  // the recurrent-dropout mask of this step for the thread's outputs is fetched before the contraction (hmask_t: mask
+  // element (b = 0, this step, node 0, unit 0)), not after it
+  float mk[MT][NT][4];
 #pragma unroll
   for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
@@ -1035,13 +1103,25 @@ __device__ __forceinline__ void bwd_phase_g_tc(const float* dzm, int BT, size_t 
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int nt = nt0 + ni, unit = (m0 + mi) * 16 + r + 8 * hf, node = (nt & 1) * 8 + 2 * c;
-        const int s = nt >> 1, b = b0 + s;
-        float2 v = make_float2(acc[mi][ni][2 * hf], node + 1 < kNodes ? acc[mi][ni][2 * hf + 1] : 0.f);
-        if (hmask_t != nullptr && b < B) {        // hmask_t: mask element (b = 0, this step, node 0, unit 0)
+        const int b = b0 + (nt >> 1);
+        mk[mi][ni][2 * hf] = 1.0f; mk[mi][ni][2 * hf + 1] = 1.0f;
+        if (hmask_t != nullptr && b < B) {
           const float* mp = hmask_t + ((size_t)b * T * kNodes + node) * H + unit;
-          v.x *= mp[0];
-          if (node + 1 < kNodes) v.y *= mp[H];
+          mk[mi][ni][2 * hf] = __ldg(mp);
+          if (node + 1 < kNodes) mk[mi][ni][2 * hf + 1] = __ldg(mp + H);
         }
+      }
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) contract_tf32<MT, NT, MIXED>(acc, dzm + (size_t)q * BT * HN, HN, nt0, d.Wg[q] + F, F + H, m0, H);
+#pragma unroll
+  for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int nt = nt0 + ni, unit = (m0 + mi) * 16 + r + 8 * hf, node = (nt & 1) * 8 + 2 * c;
+        const int s = nt >> 1;
+        float2 v = make_float2(acc[mi][ni][2 * hf] * mk[mi][ni][2 * hf], node + 1 < kNodes ? acc[mi][ni][2 * hf + 1] * mk[mi][ni][2 * hf + 1] : 0.f);
         *reinterpret_cast<float2*>(dh + ((size_t)s * H + unit) * kNodesPad + node) = v;
       }
 }
@@ -1051,7 +1131,7 @@ __device__ __forceinline__ void bwd_phase_g_tc(const float* dzm, int BT, size_t 
 // units (u, u + H/2) and 1/KS of the contraction range, so the weights cross L2 once per sequence PAIR and every
 // activation float4 read from shared memory feeds 8 FMAs; the KS partial sums meet in shared memory.  dhy overwrites
 // dh' in place and dep lives in dzm[0], which leaves room for two H=256 sequences per CTA.
-template <bool ATT, bool TCORE>
+template <bool ATT, int TCORE>      // TCORE: 0 = FFMA contractions, 1 = 3xTF32 mma.sync, 2 = TF32 head + bf16 corrections
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
   extern __shared__ __align__(16) float smem[];
@@ -1117,11 +1197,18 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
       if (b < g.B) {
         const float* hpp = tp.hp + (nm0 + (size_t)b * g.T * kNodes) * H + j;
         const float* yp = g.dy + (size_t)b * g.syb + (size_t)t * g.syt + y_off + j;
+        // all 30 loads are issued before the first use (one DRAM latency per task instead of one per node)
+        float gy[kNodes], hv[kNodes];
 #pragma unroll
-        for (int n = 0; n < kNodes; ++n) {
-          const float gy = __ldg(yp + (size_t)n * g.yld);
-          if (g.out_act == A3GC_ACT_TANH) { const float y = fast_tanh(hpp[(size_t)n * H]); dv[n] = fmaf(gy, 1.0f - y * y, dv[n]); }
-          else dv[n] += gy;
+        for (int n = 0; n < kNodes; ++n) gy[n] = __ldg(yp + (size_t)n * g.yld);
+        if (g.out_act == A3GC_ACT_TANH) {
+#pragma unroll
+          for (int n = 0; n < kNodes; ++n) hv[n] = __ldg(hpp + (size_t)n * H);
+#pragma unroll
+          for (int n = 0; n < kNodes; ++n) { const float y = fast_tanh(hv[n]); dv[n] = fmaf(gy[n], 1.0f - y * y, dv[n]); }
+        } else {
+#pragma unroll
+          for (int n = 0; n < kNodes; ++n) dv[n] += gy[n];
         }
         dv[15] = 0.f;
         if (ATT) {
@@ -1188,7 +1275,8 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
       __syncthreads();
       BWD_MARK(2);
       // ---- D: dq_j = sum_k dqs_k Wq[k][j] for all BT sequences at once;  dqp = dq [q > 0]
-      if (kdq % 8 == 0) gemv_part<8>(v1, d.Wq, scr, H, BT, jd, kd, kdq); else gemv_part<4>(v1, d.Wq, scr, H, BT, jd, kd, kdq);
+      if (g.gemv16 && kdq % 16 == 0) gemv_part<16>(v1, d.Wq, scr, H, BT, jd, kd, kdq);
+      else if (kdq % 8 == 0) gemv_part<8>(v1, d.Wq, scr, H, BT, jd, kd, kdq); else gemv_part<4>(v1, d.Wq, scr, H, BT, jd, kd, kdq);
       __syncthreads();
       for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
         const int s = task / H, j = task % H, b = b0 + s;
@@ -1204,7 +1292,8 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
       __syncthreads();
       BWD_MARK(3);
       // ---- D2: ds_j = sum_k dqp_k Wa[k][j]  (-> v1)
-      if (kdq % 8 == 0) gemv_part<8>(v2, d.Wa, scr, H, BT, jd, kd, kdq); else gemv_part<4>(v2, d.Wa, scr, H, BT, jd, kd, kdq);
+      if (g.gemv16 && kdq % 16 == 0) gemv_part<16>(v2, d.Wa, scr, H, BT, jd, kd, kdq);
+      else if (kdq % 8 == 0) gemv_part<8>(v2, d.Wa, scr, H, BT, jd, kd, kdq); else gemv_part<4>(v2, d.Wa, scr, H, BT, jd, kd, kdq);
       __syncthreads();
       for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
         float ds = 0.f;
@@ -1213,10 +1302,10 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
       }
       BWD_MARK(4);
       // ---- E: dhy[n][j] += ds_j + sum_k dep[n][k] Wh[k][j]
-      if constexpr (TCORE) {
-        if (tc_mt == 2) bwd_phase_e_tc<2, 4>(dep, HN, d.Wh, H, tc_m0, tc_nt0, dh, v1);
-        else if (tc_nt == 8) bwd_phase_e_tc<1, 8>(dep, HN, d.Wh, H, tc_m0, tc_nt0, dh, v1);
-        else bwd_phase_e_tc<1, 4>(dep, HN, d.Wh, H, tc_m0, tc_nt0, dh, v1);
+      if constexpr (TCORE != 0) {
+        if (tc_mt == 2) bwd_phase_e_tc<2, 4, TCORE == 2>(dep, HN, d.Wh, H, tc_m0, tc_nt0, dh, v1);
+        else if (tc_nt == 8) bwd_phase_e_tc<1, 8, TCORE == 2>(dep, HN, d.Wh, H, tc_m0, tc_nt0, dh, v1);
+        else bwd_phase_e_tc<1, 4, TCORE == 2>(dep, HN, d.Wh, H, tc_m0, tc_nt0, dh, v1);
       } else {
         float acc[2][2][16];
 #pragma unroll
@@ -1303,11 +1392,11 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
     __syncthreads();
     BWD_MARK(6);
     // ---- G: dh'_{prev}[n][k] = sum_g sum_j dzm_g[n][j] W_g[j][F + k]   (then the recurrent-dropout mask of this step)
-    if constexpr (TCORE) {
+    if constexpr (TCORE != 0) {
       const float* hm = g.hmask != nullptr ? g.hmask + nm0 * H : nullptr;
-      if (tc_mt == 2) bwd_phase_g_tc<2, 4>(dzm, BT, HN, d, F, H, tc_m0, tc_nt0, dh, hm, b0, g.B, g.T);
-      else if (tc_nt == 8) bwd_phase_g_tc<1, 8>(dzm, BT, HN, d, F, H, tc_m0, tc_nt0, dh, hm, b0, g.B, g.T);
-      else bwd_phase_g_tc<1, 4>(dzm, BT, HN, d, F, H, tc_m0, tc_nt0, dh, hm, b0, g.B, g.T);
+      if (tc_mt == 2) bwd_phase_g_tc<2, 4, TCORE == 2>(dzm, BT, HN, d, F, H, tc_m0, tc_nt0, dh, hm, b0, g.B, g.T);
+      else if (tc_nt == 8) bwd_phase_g_tc<1, 8, TCORE == 2>(dzm, BT, HN, d, F, H, tc_m0, tc_nt0, dh, hm, b0, g.B, g.T);
+      else bwd_phase_g_tc<1, 4, TCORE == 2>(dzm, BT, HN, d, F, H, tc_m0, tc_nt0, dh, hm, b0, g.B, g.T);
     } else {
       float acc[2][2][16];
 #pragma unroll
@@ -1999,7 +2088,10 @@ int simt_train_backward(const TrainBwdArgs& a, void* ws, size_t ws_bytes, cudaSt
     // tile shapes the tensor-core phases are instantiated for: (H / 128, 2 BT) in {(2, 4), (1, 8), (1, 4)} or H = 64 with BT in {4, 8}
     const int nt = H >= 128 ? 2 * BT : BT;
     const char* e = getenv("A3GC_BWD_MMA");
-    g.tcore = blk && !(e != nullptr && e[0] == '0') && ((H == 256 && nt == 4) || (H <= 128 && (nt == 4 || nt == 8)));
+    const int mode = e != nullptr ? atoi(e) : 2;
+    const char* e16 = getenv("A3GC_BWD_GEMV16");
+    g.gemv16 = e16 != nullptr ? atoi(e16) : 1;
+    g.tcore = (blk && ((H == 256 && nt == 4) || (H <= 128 && (nt == 4 || nt == 8)))) ? (mode < 0 || mode > 2 ? 2 : mode) : 0;
   }
   dim3 grid((unsigned)((a.batch + BT - 1) / BT), (unsigned)a.num_dirs);
   if (blk) {
@@ -2013,8 +2105,10 @@ int simt_train_backward(const TrainBwdArgs& a, void* ws, size_t ws_bytes, cudaSt
     const char* tre = getenv("A3GC_BWD_TRACE");
     if (tre != nullptr && tre[0] == '1') A3GC_CUDA_TRY(cudaMalloc(&g.trace, 8 * sizeof(long long)));
     int rc;
-    if (att) rc = g.tcore ? launch(lstm_train_bwd_blk_kernel<true, true>) : launch(lstm_train_bwd_blk_kernel<true, false>);
-    else rc = g.tcore ? launch(lstm_train_bwd_blk_kernel<false, true>) : launch(lstm_train_bwd_blk_kernel<false, false>);
+    if (att) rc = g.tcore == 2 ? launch(lstm_train_bwd_blk_kernel<true, 2>) : g.tcore == 1 ? launch(lstm_train_bwd_blk_kernel<true, 1>)
+                                                                                            : launch(lstm_train_bwd_blk_kernel<true, 0>);
+    else rc = g.tcore == 2 ? launch(lstm_train_bwd_blk_kernel<false, 2>) : g.tcore == 1 ? launch(lstm_train_bwd_blk_kernel<false, 1>)
+                                                                                         : launch(lstm_train_bwd_blk_kernel<false, 0>);
     if (rc != A3GC_OK) return rc;
     if (g.trace != nullptr) {
       long long h[8];
