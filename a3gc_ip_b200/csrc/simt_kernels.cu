@@ -204,6 +204,15 @@ __device__ __forceinline__ void load16(float (&v)[16], const float* src) {
   }
 }
 
+// store16 with the two 8-float halves exchanged when swz: the tensor-core phases of the backward chain read the [k][16]
+// arrays as mma B fragments (lane -> k = c, c + 4; node = r), and rows k, k + 2 would otherwise share their banks
+__device__ __forceinline__ void store16_swz(float* dst, const float (&v)[16], bool swz) {
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  const int o = swz ? 2 : 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) d4[q ^ o] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
 struct DirPtrs {
   const float* h0; const float* c0; float* hT; float* cT; int reverse;
 };
@@ -589,6 +598,7 @@ struct BwdDir {
   const float* Wa;         // attention_w  [H][H]
   const float* u;          // attention_u  [H]
   const float* PT;         // [4][16][16]  PT_g[n][m] = P_g[m][n]  (zero padded)
+  const uint4* wfrag;      // blocked kernel, mode 3: the five H x H weight blocks as ready-made mma.sync A fragments (pack_bwd_frag_kernel)
   const float* c0;         // [B][15][H] initial cell state (nullptr = zeros)
   const float* dhT; const float* dcT;   // [B][15][H] gradients of the final state (nullptr = zeros)
   float* dh0; float* dc0;               // [B][15][H] gradients of the initial state (nullptr = skip)
@@ -935,9 +945,10 @@ __device__ __forceinline__ uint32_t pack_bf16(uint32_t lo_bits, uint32_t hi_bits
 // operands rounded to bf16: 2^-9 on a term that is 2^-11 of the product), the hi x hi product stays TF32 -- 4 tensor
 // instructions per 16 contraction steps instead of 6.  The k16 slots {2c, 2c+1, 2c+8, 2c+9} of lane c carry the contraction
 // indices {c, c+4, c+8, c+12} it already holds for the two TF32 tiles, on the A and the B side alike.
+// accc: accumulators of the correction products (MIXED); the callers pass acc itself (a separate set was measured: no faster).
 template <int MT, int NT, bool MIXED>
-__device__ __forceinline__ void contract_tf32(float (&acc)[MT][NT][4], const float* __restrict__ act, size_t seq_stride, int nt0,
-                                              const float* __restrict__ w, int ldw, int m0, int kcount) {
+__device__ __forceinline__ void contract_tf32(float (&acc)[MT][NT][4], float (&accc)[MT][NT][4], const float* __restrict__ act,
+                                              size_t seq_stride, int nt0, const float* __restrict__ w, int ldw, int m0, int kcount) {
   constexpr int kD = 4;                                   // k tiles of weights in flight per warp (L2 latency)
   const int lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
   const float* wp = w + (size_t)c * ldw + m0 * 16 + r;    // a0: (k = c, m = r)  a1: m + 8  a2: k + 4  a3: both
@@ -954,7 +965,7 @@ __device__ __forceinline__ void contract_tf32(float (&acc)[MT][NT][4], const flo
 #pragma unroll
   for (int ni = 0; ni < NT; ++ni) {
     const int nt = nt0 + ni;
-    bp[ni] = act + (size_t)(nt >> 1) * seq_stride + (nt & 1) * 8 + r + c * kNodesPad;
+    bp[ni] = act + (size_t)(nt >> 1) * seq_stride + (((nt & 1) ^ ((c >> 1) & 1)) * 8) + r + c * kNodesPad;   // writer: store16_swz
   }
   const int nkt = kcount / 8;
   auto refill = [&](int i, int kt) {
@@ -1034,11 +1045,11 @@ __device__ __forceinline__ void contract_tf32(float (&acc)[MT][NT][4], const flo
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
-          for (int ni = 0; ni < NT; ++ni) mma_bf16(acc[mi][ni], alb[mi], bhb[ni][0], bhb[ni][1]);
+          for (int ni = 0; ni < NT; ++ni) mma_bf16(accc[mi][ni], alb[mi], bhb[ni][0], bhb[ni][1]);
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
-          for (int ni = 0; ni < NT; ++ni) mma_bf16(acc[mi][ni], ahb[mi], blb[ni][0], blb[ni][1]);
+          for (int ni = 0; ni < NT; ++ni) mma_bf16(accc[mi][ni], ahb[mi], blb[ni][0], blb[ni][1]);
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -1050,9 +1061,259 @@ __device__ __forceinline__ void contract_tf32(float (&acc)[MT][NT][4], const flo
   }
 }
 
+// The same contraction as contract_tf32<.., MIXED = true> with the weight side prepared once per launch: per (unit tile, 16
+// contraction steps) four 16-byte words per lane -- the TF32 heads of the two k8 tiles, the bf16 pairs of the heads, the bf16
+// pairs of the tails (pack_bwd_frag_kernel) -- so the loop neither splits nor packs weights and fetches them with four
+// coalesced 128-bit loads instead of sixteen 32-bit ones.  Bit-identical to the in-register form (same split, same products).
+// FULL = false: the fragments hold the fp32 weights themselves in fragment order (two words per lane, the bytes of the
+// reference layout: at H = 256 the full form doubles the L2 traffic of every step and is slower); heads, tails and bf16 pairs
+// are then formed in registers as in contract_tf32, but the fetch is two coalesced 128-bit loads instead of eight 32-bit
+// loads that touch four lines each (the L1 tag stage was the busiest unit of the kernel).
+template <int MT, int NT, bool FULL>
+__device__ __forceinline__ void contract_packed(float (&acc)[MT][NT][4], float (&accc)[MT][NT][4], const float* __restrict__ act,
+                                                size_t seq_stride, int nt0, const uint4* __restrict__ wpk, int nk16, int m0) {
+  constexpr int kD = 2;                                   // 16-step groups of weights in flight per warp
+  constexpr int kW = FULL ? 4 : 2;                        // 16-byte words per lane and (unit tile, 16 steps)
+  const int lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
+  const uint4* wp = wpk + (size_t)m0 * nk16 * (kW * 32) + lane;   // tile (mi, k16), word w: wp[((mi * nk16 + k16) * kW + w) * 32]
+  uint4 wn[kD][MT][kW];
+#pragma unroll
+  for (int i = 0; i < kD; ++i)
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+      for (int w = 0; w < kW; ++w) wn[i][mi][w] = __ldg(wp + ((size_t)(mi * nk16 + i) * kW + w) * 32);
+  const float* bp[NT];
+#pragma unroll
+  for (int ni = 0; ni < NT; ++ni) {
+    const int nt = nt0 + ni;
+    bp[ni] = act + (size_t)(nt >> 1) * seq_stride + (((nt & 1) ^ ((c >> 1) & 1)) * 8) + r + c * kNodesPad;   // writer: store16_swz
+  }
+#pragma unroll 1
+  for (int k0 = 0; k0 < nk16; k0 += kD) {
+#pragma unroll
+    for (int i = 0; i < kD; ++i) {
+      const int k16 = k0 + i;
+      uint32_t ah[2][MT][4], ahb[MT][4], alb[MT][4];
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi) {
+        if constexpr (FULL) {
+          ah[0][mi][0] = wn[i][mi][0].x; ah[0][mi][1] = wn[i][mi][0].y; ah[0][mi][2] = wn[i][mi][0].z; ah[0][mi][3] = wn[i][mi][0].w;
+          ah[1][mi][0] = wn[i][mi][1].x; ah[1][mi][1] = wn[i][mi][1].y; ah[1][mi][2] = wn[i][mi][1].z; ah[1][mi][3] = wn[i][mi][1].w;
+          ahb[mi][0] = wn[i][mi][2].x; ahb[mi][1] = wn[i][mi][2].y; ahb[mi][2] = wn[i][mi][2].z; ahb[mi][3] = wn[i][mi][2].w;
+          alb[mi][0] = wn[i][mi][3].x; alb[mi][1] = wn[i][mi][3].y; alb[mi][2] = wn[i][mi][3].z; alb[mi][3] = wn[i][mi][3].w;
+        } else {
+          uint32_t al[2][4];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            tf32_split(__uint_as_float(wn[i][mi][j].x), ah[j][mi][0], al[j][0]);
+            tf32_split(__uint_as_float(wn[i][mi][j].y), ah[j][mi][1], al[j][1]);
+            tf32_split(__uint_as_float(wn[i][mi][j].z), ah[j][mi][2], al[j][2]);
+            tf32_split(__uint_as_float(wn[i][mi][j].w), ah[j][mi][3], al[j][3]);
+          }
+          ahb[mi][0] = pack_bf16(ah[0][mi][0], ah[0][mi][2]); ahb[mi][1] = pack_bf16(ah[0][mi][1], ah[0][mi][3]);
+          ahb[mi][2] = pack_bf16(ah[1][mi][0], ah[1][mi][2]); ahb[mi][3] = pack_bf16(ah[1][mi][1], ah[1][mi][3]);
+          alb[mi][0] = pack_bf16(al[0][0], al[0][2]); alb[mi][1] = pack_bf16(al[0][1], al[0][3]);
+          alb[mi][2] = pack_bf16(al[1][0], al[1][2]); alb[mi][3] = pack_bf16(al[1][1], al[1][3]);
+        }
+      }
+      if (k16 + kD < nk16) {
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+          for (int w = 0; w < kW; ++w) wn[i][mi][w] = __ldg(wp + ((size_t)(mi * nk16 + k16 + kD) * kW + w) * 32);
+      }
+      uint32_t bh[2][NT][2], bhb[NT][2], blb[NT][2];
+#pragma unroll
+      for (int ni = 0; ni < NT; ++ni) {
+        uint32_t bl[2][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float* q = bp[ni] + (size_t)(2 * k16 + j) * 8 * kNodesPad;
+          tf32_split(q[0], bh[j][ni][0], bl[j][0]);
+          tf32_split(q[4 * kNodesPad], bh[j][ni][1], bl[j][1]);
+        }
+        bhb[ni][0] = pack_bf16(bh[0][ni][0], bh[0][ni][1]); bhb[ni][1] = pack_bf16(bh[1][ni][0], bh[1][ni][1]);
+        blb[ni][0] = pack_bf16(bl[0][0], bl[0][1]); blb[ni][1] = pack_bf16(bl[1][0], bl[1][1]);
+      }
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) mma_bf16(accc[mi][ni], alb[mi], bhb[ni][0], bhb[ni][1]);
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) mma_bf16(accc[mi][ni], ahb[mi], blb[ni][0], blb[ni][1]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < NT; ++ni) mma_tf32(acc[mi][ni], ah[j][mi], bh[j][ni][0], bh[j][ni][1]);
+    }
+  }
+}
+
+// Weight blocks of the backward chain as mma.sync A fragments: block 0..3 = W_g[:, F:] (contraction index j = row of
+// gcn_kernel_g, unit = column F + m), blocks 4, 5, 6 = attention_wh, attention_wq, attention_w (ATT).  One warp per (block,
+// unit tile, 16 contraction steps).
+__global__ void pack_bwd_frag_kernel(BwdDir d, uint4* __restrict__ out, int F, int H, int nblocks, int full) {
+  const int nt = H / 16, lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
+  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tile >= nblocks * nt * nt) return;
+  const int blk = tile / (nt * nt), mt = (tile / nt) % nt, k16 = tile % nt;
+  const float* w = blk < 4 ? d.Wg[blk] + F : blk == 4 ? d.Wh : blk == 5 ? d.Wq : d.Wa;
+  const int ld = blk < 4 ? F + H : H;
+  uint32_t hi[2][4], lo[2][4];
+  float raw[2][4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float* q = w + (size_t)(k16 * 16 + 8 * j + c) * ld + mt * 16 + r;
+    raw[j][0] = q[0]; raw[j][1] = q[8]; raw[j][2] = q[(size_t)4 * ld]; raw[j][3] = q[(size_t)4 * ld + 8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) tf32_split(raw[j][e], hi[j][e], lo[j][e]);
+  }
+  if (!full) {                       // the fp32 weights in fragment order
+    float4* o4 = reinterpret_cast<float4*>(out) + (size_t)tile * 64 + lane;
+    o4[0] = make_float4(raw[0][0], raw[0][1], raw[0][2], raw[0][3]);
+    o4[32] = make_float4(raw[1][0], raw[1][1], raw[1][2], raw[1][3]);
+    return;
+  }
+  uint4* o = out + (size_t)tile * 128 + lane;
+  o[0] = make_uint4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);
+  o[32] = make_uint4(hi[1][0], hi[1][1], hi[1][2], hi[1][3]);
+  o[64] = make_uint4(pack_bf16(hi[0][0], hi[0][2]), pack_bf16(hi[0][1], hi[0][3]), pack_bf16(hi[1][0], hi[1][2]), pack_bf16(hi[1][1], hi[1][3]));
+  o[96] = make_uint4(pack_bf16(lo[0][0], lo[0][2]), pack_bf16(lo[0][1], lo[0][3]), pack_bf16(lo[1][0], lo[1][2]), pack_bf16(lo[1][1], lo[1][3]));
+}
+
+// The two H x H vector products of the q chain (phases D, D2) as tensor-core products: out[m][n] = sum_k W[k][m] vec[n][k] with
+// the sequences on the N side (n < BT <= 8, one n tile) -- a handful of mma instructions; the point is the weight fetch: each
+// warp owns MT unit tiles for the whole contraction and keeps KD k8 tiles of weights in flight (the FFMA form reached
+// 20 B/clk/SM on a 256 KB matrix).  Same TF32 head + bf16 correction scheme as contract_tf32<.., true>.
+// acc[mi]: {(unit r, seq 2c), (unit r, seq 2c+1), (unit r+8, seq 2c), (unit r+8, seq 2c+1)}
+template <int MT, int KD, bool PACKED>
+__device__ __forceinline__ void gemv_tc(float (&acc)[MT][4], const float* __restrict__ vec, int BT, int H,
+                                        const float* __restrict__ w, const uint4* __restrict__ wpk, int m0) {
+  const int lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
+  const int nkt = H / 8, nk16 = H / 16;
+  // PACKED: the fp32 weights in fragment order (pack_bwd_frag_kernel, full = 0): word j of (unit tile, 16 steps) = k8 tile j
+  const float* wp = w + (size_t)c * H + m0 * 16 + r;
+  const uint4* wq = wpk + (size_t)m0 * nk16 * 64 + lane;
+  const size_t k4 = (size_t)4 * H, k8 = (size_t)8 * H;
+  float wn[KD][MT][4];
+  auto fetch = [&](int i, int kt) {
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi) {
+      if constexpr (PACKED) {
+        const uint4 v = __ldg(wq + ((size_t)(mi * nk16 + (kt >> 1)) * 2 + (kt & 1)) * 32);
+        wn[i][mi][0] = __uint_as_float(v.x); wn[i][mi][1] = __uint_as_float(v.y);
+        wn[i][mi][2] = __uint_as_float(v.z); wn[i][mi][3] = __uint_as_float(v.w);
+      } else {
+        const float* q = wp + (size_t)kt * k8 + mi * 16;
+        wn[i][mi][0] = __ldg(q); wn[i][mi][1] = __ldg(q + 8); wn[i][mi][2] = __ldg(q + k4); wn[i][mi][3] = __ldg(q + k4 + 8);
+      }
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < KD; ++i) fetch(i, i);
+  float accc[MT][4];
+#pragma unroll
+  for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { acc[mi][e] = 0.f; accc[mi][e] = 0.f; }
+  const float* bp = vec + (size_t)(r < BT ? r : 0) * H + c;
+  const bool bv = r < BT;
+#pragma unroll 1
+  for (int kt0 = 0; kt0 < nkt; kt0 += KD) {
+#pragma unroll
+    for (int i = 0; i < KD; i += 2) {
+      const int kt = kt0 + i;
+      uint32_t ah[2][MT][4], ahb[MT][4], alb[MT][4];
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi) {
+        uint32_t al[2][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) tf32_split(wn[i + j][mi][e], ah[j][mi][e], al[j][e]);
+        ahb[mi][0] = pack_bf16(ah[0][mi][0], ah[0][mi][2]); ahb[mi][1] = pack_bf16(ah[0][mi][1], ah[0][mi][3]);
+        ahb[mi][2] = pack_bf16(ah[1][mi][0], ah[1][mi][2]); ahb[mi][3] = pack_bf16(ah[1][mi][1], ah[1][mi][3]);
+        alb[mi][0] = pack_bf16(al[0][0], al[0][2]); alb[mi][1] = pack_bf16(al[0][1], al[0][3]);
+        alb[mi][2] = pack_bf16(al[1][0], al[1][2]); alb[mi][3] = pack_bf16(al[1][1], al[1][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (kt + j + KD < nkt) fetch(i + j, kt + j + KD);
+      uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float x0 = bv ? bp[(kt + j) * 8] : 0.f, x1 = bv ? bp[(kt + j) * 8 + 4] : 0.f;
+        tf32_split(x0, bh[j][0], bl[j][0]);
+        tf32_split(x1, bh[j][1], bl[j][1]);
+      }
+      const uint32_t bhb0 = pack_bf16(bh[0][0], bh[0][1]), bhb1 = pack_bf16(bh[1][0], bh[1][1]);
+      const uint32_t blb0 = pack_bf16(bl[0][0], bl[0][1]), blb1 = pack_bf16(bl[1][0], bl[1][1]);
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi) mma_bf16(accc[mi], alb[mi], bhb0, bhb1);
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi) mma_bf16(accc[mi], ahb[mi], blb0, blb1);
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi) mma_tf32(acc[mi], ah[j][mi], bh[j][0], bh[j][1]);
+    }
+  }
+#pragma unroll
+  for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[mi][e] += accc[mi][e];
+}
+
+// phases D and D2 on the tensor cores: dq = dqs Wq, dqp = dq [q > 0] (-> v2, gr.dqp);  ds = dqp Wa (-> v1)
+template <int MT, bool PACKED>
+__device__ __forceinline__ void bwd_phase_d_tc(float* v1, float* v2, int BT, int H, const BwdDir& d, int m0, bool active,
+                                               const float* __restrict__ tq, float* __restrict__ dqp, int nvalid) {
+  const int lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
+  float acc[MT][4];
+  if (active) {
+    // the relu mask's operand is fetched before the contraction
+    float qv[MT][4];
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int unit = (m0 + mi) * 16 + r + 8 * (e >> 1), sq = 2 * c + (e & 1);
+        qv[mi][e] = sq < nvalid ? __ldg(tq + (size_t)sq * H + unit) : 0.f;
+      }
+    gemv_tc<MT, 8, PACKED>(acc, v1, BT, H, d.Wq, d.wfrag + (size_t)5 * (H / 16) * (H / 16) * 64, m0);
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int unit = (m0 + mi) * 16 + r + 8 * (e >> 1), sq = 2 * c + (e & 1);
+        if (sq < BT) {
+          const float rv = (sq < nvalid && qv[mi][e] > 0.f) ? acc[mi][e] : 0.f;
+          if (sq < nvalid) dqp[(size_t)sq * H + unit] = rv;
+          v2[sq * H + unit] = rv;
+        }
+      }
+  }
+  __syncthreads();
+  if (active) {
+    gemv_tc<MT, 8, PACKED>(acc, v2, BT, H, d.Wa, d.wfrag + (size_t)6 * (H / 16) * (H / 16) * 64, m0);
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int unit = (m0 + mi) * 16 + r + 8 * (e >> 1), sq = 2 * c + (e & 1);
+        if (sq < BT) v1[sq * H + unit] = acc[mi][e];
+      }
+  }
+}
+
 // phase E on the tensor cores: dhy[n][j] += ds_j + sum_k dep[n][k] Wh[k][j]   (the barrier: v1 = ds is complete)
-template <int MT, int NT, bool MIXED>
-__device__ __forceinline__ void bwd_phase_e_tc(const float* dep, size_t HN, const float* __restrict__ Wh, int H, int m0, int nt0,
+template <int MT, int NT, int MODE>
+__device__ __forceinline__ void bwd_phase_e_tc(const float* dep, size_t HN, const BwdDir& d, int H, int m0, int nt0,
                                                float* dh, const float* v1) {
   float acc[MT][NT][4];
 #pragma unroll
@@ -1061,7 +1322,8 @@ __device__ __forceinline__ void bwd_phase_e_tc(const float* dep, size_t HN, cons
     for (int ni = 0; ni < NT; ++ni)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[mi][ni][e] = 0.f;
-  contract_tf32<MT, NT, MIXED>(acc, dep, HN, nt0, Wh, H, m0, H);
+  if constexpr (MODE >= 3) contract_packed<MT, NT, MODE == 3>(acc, acc, dep, HN, nt0, d.wfrag + (size_t)4 * (H / 16) * (H / 16) * (MODE == 3 ? 128 : 64), H / 16, m0);
+  else contract_tf32<MT, NT, MODE == 2>(acc, acc, dep, HN, nt0, d.Wh, H, m0, H);
   __syncthreads();
   const int lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
 #pragma unroll
@@ -1082,7 +1344,7 @@ __device__ __forceinline__ void bwd_phase_e_tc(const float* dep, size_t HN, cons
 }
 
 // phase G on the tensor cores: dh'_{prev}[n][k] = sum_g sum_j dzm_g[n][j] W_g[j][F + k], then the recurrent-dropout mask
-template <int MT, int NT, bool MIXED>
+template <int MT, int NT, int MODE>
 __device__ __forceinline__ void bwd_phase_g_tc(const float* dzm, int BT, size_t HN, const BwdDir& d, int F, int H, int m0, int nt0,
                                                float* dh, const float* hmask_t, int b0, int B, int T) {
   float acc[MT][NT][4];
@@ -1112,7 +1374,10 @@ __device__ __forceinline__ void bwd_phase_g_tc(const float* dzm, int BT, size_t 
         }
       }
 #pragma unroll 1
-  for (int q = 0; q < 4; ++q) contract_tf32<MT, NT, MIXED>(acc, dzm + (size_t)q * BT * HN, HN, nt0, d.Wg[q] + F, F + H, m0, H);
+  for (int q = 0; q < 4; ++q) {
+    if constexpr (MODE >= 3) contract_packed<MT, NT, MODE == 3>(acc, acc, dzm + (size_t)q * BT * HN, HN, nt0, d.wfrag + (size_t)q * (H / 16) * (H / 16) * (MODE == 3 ? 128 : 64), H / 16, m0);
+    else contract_tf32<MT, NT, MODE == 2>(acc, acc, dzm + (size_t)q * BT * HN, HN, nt0, d.Wg[q] + F, F + H, m0, H);
+  }
 #pragma unroll
   for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
@@ -1131,7 +1396,7 @@ __device__ __forceinline__ void bwd_phase_g_tc(const float* dzm, int BT, size_t 
 // units (u, u + H/2) and 1/KS of the contraction range, so the weights cross L2 once per sequence PAIR and every
 // activation float4 read from shared memory feeds 8 FMAs; the KS partial sums meet in shared memory.  dhy overwrites
 // dh' in place and dep lives in dzm[0], which leaves room for two H=256 sequences per CTA.
-template <bool ATT, int TCORE>      // TCORE: 0 = FFMA contractions, 1 = 3xTF32 mma.sync, 2 = TF32 head + bf16 corrections
+template <bool ATT, int TCORE>      // TCORE: 0 = FFMA contractions, 1 = 3xTF32 mma.sync, 2 = TF32 head + bf16 corrections, 3 = 2 with pre-built weight fragments, 4 = 2 with the fp32 weights in fragment order
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
   extern __shared__ __align__(16) float smem[];
@@ -1269,43 +1534,53 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
 #pragma unroll
           for (int n = 0; n < 16; ++n) o[n] = 0.f;
         }
-        store16(dep + (size_t)task * kNodesPad, o);
+        store16_swz(dep + (size_t)task * kNodesPad, o, TCORE != 0 && ((j >> 1) & 1));
         v1[task] = sum;
       }
       __syncthreads();
       BWD_MARK(2);
-      // ---- D: dq_j = sum_k dqs_k Wq[k][j] for all BT sequences at once;  dqp = dq [q > 0]
-      if (g.gemv16 && kdq % 16 == 0) gemv_part<16>(v1, d.Wq, scr, H, BT, jd, kd, kdq);
-      else if (kdq % 8 == 0) gemv_part<8>(v1, d.Wq, scr, H, BT, jd, kd, kdq); else gemv_part<4>(v1, d.Wq, scr, H, BT, jd, kd, kdq);
-      __syncthreads();
-      for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
-        const int s = task / H, j = task % H, b = b0 + s;
-        float dq = 0.f;
-        for (int q = 0; q < KD; ++q) dq += scr[(q * BT + s) * H + j];
-        float r = 0.f;
-        if (b < g.B) {
-          r = tp.q[(rec0 + b) * H + j] > 0.f ? dq : 0.f;
-          gr.dqp[(rec0 + b) * H + j] = r;
+      if constexpr (TCORE >= 2) {
+        // ---- D, D2 on the tensor cores (v1 = dqs -> v2 = dqp -> v1 = ds); the reads of v1 end before the barrier inside
+        const int nval = g.B - b0 < BT ? g.B - b0 : BT;
+        const float* tq = tp.q + (rec0 + b0) * H;
+        float* dqp = gr.dqp + (rec0 + b0) * H;
+        if (H >= 256) bwd_phase_d_tc<2, TCORE == 4>(v1, v2, BT, H, d, 2 * tc_warp, true, tq, dqp, nval);
+        else bwd_phase_d_tc<1, TCORE == 4>(v1, v2, BT, H, d, tc_warp, tc_warp < H / 16, tq, dqp, nval);
+        BWD_MARK(3);
+      } else {
+        // ---- D: dq_j = sum_k dqs_k Wq[k][j] for all BT sequences at once;  dqp = dq [q > 0]
+        if (g.gemv16 && kdq % 16 == 0) gemv_part<16>(v1, d.Wq, scr, H, BT, jd, kd, kdq);
+        else if (kdq % 8 == 0) gemv_part<8>(v1, d.Wq, scr, H, BT, jd, kd, kdq); else gemv_part<4>(v1, d.Wq, scr, H, BT, jd, kd, kdq);
+        __syncthreads();
+        for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+          const int s = task / H, j = task % H, b = b0 + s;
+          float dq = 0.f;
+          for (int q = 0; q < KD; ++q) dq += scr[(q * BT + s) * H + j];
+          float r = 0.f;
+          if (b < g.B) {
+            r = tp.q[(rec0 + b) * H + j] > 0.f ? dq : 0.f;
+            gr.dqp[(rec0 + b) * H + j] = r;
+          }
+          v2[task] = r;
         }
-        v2[task] = r;
-      }
-      __syncthreads();
-      BWD_MARK(3);
-      // ---- D2: ds_j = sum_k dqp_k Wa[k][j]  (-> v1)
-      if (g.gemv16 && kdq % 16 == 0) gemv_part<16>(v2, d.Wa, scr, H, BT, jd, kd, kdq);
-      else if (kdq % 8 == 0) gemv_part<8>(v2, d.Wa, scr, H, BT, jd, kd, kdq); else gemv_part<4>(v2, d.Wa, scr, H, BT, jd, kd, kdq);
-      __syncthreads();
-      for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
-        float ds = 0.f;
-        for (int q = 0; q < KD; ++q) ds += scr[(q * BT + task / H) * H + task % H];
-        v1[task] = ds;
+        __syncthreads();
+        BWD_MARK(3);
+        // ---- D2: ds_j = sum_k dqp_k Wa[k][j]  (-> v1)
+        if (g.gemv16 && kdq % 16 == 0) gemv_part<16>(v2, d.Wa, scr, H, BT, jd, kd, kdq);
+        else if (kdq % 8 == 0) gemv_part<8>(v2, d.Wa, scr, H, BT, jd, kd, kdq); else gemv_part<4>(v2, d.Wa, scr, H, BT, jd, kd, kdq);
+        __syncthreads();
+        for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+          float ds = 0.f;
+          for (int q = 0; q < KD; ++q) ds += scr[(q * BT + task / H) * H + task % H];
+          v1[task] = ds;
+        }
       }
       BWD_MARK(4);
       // ---- E: dhy[n][j] += ds_j + sum_k dep[n][k] Wh[k][j]
       if constexpr (TCORE != 0) {
-        if (tc_mt == 2) bwd_phase_e_tc<2, 4, TCORE == 2>(dep, HN, d.Wh, H, tc_m0, tc_nt0, dh, v1);
-        else if (tc_nt == 8) bwd_phase_e_tc<1, 8, TCORE == 2>(dep, HN, d.Wh, H, tc_m0, tc_nt0, dh, v1);
-        else bwd_phase_e_tc<1, 4, TCORE == 2>(dep, HN, d.Wh, H, tc_m0, tc_nt0, dh, v1);
+        if (tc_mt == 2) bwd_phase_e_tc<2, 4, TCORE>(dep, HN, d, H, tc_m0, tc_nt0, dh, v1);
+        else if (tc_nt == 8) bwd_phase_e_tc<1, 8, TCORE>(dep, HN, d, H, tc_m0, tc_nt0, dh, v1);
+        else bwd_phase_e_tc<1, 4, TCORE>(dep, HN, d, H, tc_m0, tc_nt0, dh, v1);
       } else {
         float acc[2][2][16];
 #pragma unroll
@@ -1381,7 +1656,7 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
       for (int q = 0; q < 4; ++q) {
         float m[16];
         mix15(dz[q], PT + q * 256, m);
-        store16(dzm + ((size_t)q * BT * H + task) * kNodesPad, m);
+        store16_swz(dzm + ((size_t)q * BT * H + task) * kNodesPad, m, TCORE != 0 && ((j >> 1) & 1));
         if (b < g.B) {
           float* zp = gr.dzm + (nm0 + (size_t)b * g.T * kNodes) * 4 * H + (size_t)q * H + j;
 #pragma unroll
@@ -1394,9 +1669,9 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
     // ---- G: dh'_{prev}[n][k] = sum_g sum_j dzm_g[n][j] W_g[j][F + k]   (then the recurrent-dropout mask of this step)
     if constexpr (TCORE != 0) {
       const float* hm = g.hmask != nullptr ? g.hmask + nm0 * H : nullptr;
-      if (tc_mt == 2) bwd_phase_g_tc<2, 4, TCORE == 2>(dzm, BT, HN, d, F, H, tc_m0, tc_nt0, dh, hm, b0, g.B, g.T);
-      else if (tc_nt == 8) bwd_phase_g_tc<1, 8, TCORE == 2>(dzm, BT, HN, d, F, H, tc_m0, tc_nt0, dh, hm, b0, g.B, g.T);
-      else bwd_phase_g_tc<1, 4, TCORE == 2>(dzm, BT, HN, d, F, H, tc_m0, tc_nt0, dh, hm, b0, g.B, g.T);
+      if (tc_mt == 2) bwd_phase_g_tc<2, 4, TCORE>(dzm, BT, HN, d, F, H, tc_m0, tc_nt0, dh, hm, b0, g.B, g.T);
+      else if (tc_nt == 8) bwd_phase_g_tc<1, 8, TCORE>(dzm, BT, HN, d, F, H, tc_m0, tc_nt0, dh, hm, b0, g.B, g.T);
+      else bwd_phase_g_tc<1, 4, TCORE>(dzm, BT, HN, d, F, H, tc_m0, tc_nt0, dh, hm, b0, g.B, g.T);
     } else {
       float acc[2][2][16];
 #pragma unroll
@@ -1894,7 +2169,9 @@ int simt_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream
 // ------------------------------------------------------------------------------------------
 size_t simt_train_workspace_bytes(int variant, int f_in, int hidden, int num_dirs) {
   const size_t packed = variant == A3GC_VARIANT_GGRU ? gru_packed_floats(f_in, hidden) : lstm_packed_floats(f_in, hidden);
-  const size_t per = align_up(packed * sizeof(float), 256) + 4 * 256 * sizeof(float);
+  // + (LSTM family) the seven H x H weight blocks of the backward chain as mma.sync fragments: up to 8 bytes per weight
+  const size_t frag = variant == A3GC_VARIANT_GGRU ? 0 : align_up((size_t)7 * hidden * hidden * 8, 256);
+  const size_t per = align_up(packed * sizeof(float), 256) + 4 * 256 * sizeof(float) + frag;
   return (size_t)num_dirs * per;
 }
 
@@ -2076,6 +2353,7 @@ int simt_train_backward(const TrainBwdArgs& a, void* ws, size_t ws_bytes, cudaSt
     for (int q = 0; q < 4; ++q) bd[d].Wg[q] = a.cells[d].gcn_kernel[q];
     bd[d].Wh = a.cells[d].attention_wh; bd[d].Wq = a.cells[d].attention_wq; bd[d].Wa = a.cells[d].attention_w;
     bd[d].u = a.cells[d].attention_u; bd[d].PT = pt;
+    bd[d].wfrag = reinterpret_cast<const uint4*>(pt + 4 * 256);
     bd[d].c0 = a.c0[d]; bd[d].dhT = a.dhT[d]; bd[d].dcT = a.dcT[d]; bd[d].dh0 = a.dh0[d]; bd[d].dc0 = a.dc0[d];
     bd[d].reverse = a.reverse[d];
   }
@@ -2088,10 +2366,10 @@ int simt_train_backward(const TrainBwdArgs& a, void* ws, size_t ws_bytes, cudaSt
     // tile shapes the tensor-core phases are instantiated for: (H / 128, 2 BT) in {(2, 4), (1, 8), (1, 4)} or H = 64 with BT in {4, 8}
     const int nt = H >= 128 ? 2 * BT : BT;
     const char* e = getenv("A3GC_BWD_MMA");
-    const int mode = e != nullptr ? atoi(e) : 2;
+    const int mode = e != nullptr ? atoi(e) : 4;
     const char* e16 = getenv("A3GC_BWD_GEMV16");
     g.gemv16 = e16 != nullptr ? atoi(e16) : 1;
-    g.tcore = (blk && ((H == 256 && nt == 4) || (H <= 128 && (nt == 4 || nt == 8)))) ? (mode < 0 || mode > 2 ? 2 : mode) : 0;
+    g.tcore = (blk && ((H == 256 && nt == 4) || (H <= 128 && (nt == 4 || nt == 8)))) ? (mode < 0 || mode > 4 ? 4 : mode) : 0;
   }
   dim3 grid((unsigned)((a.batch + BT - 1) / BT), (unsigned)a.num_dirs);
   if (blk) {
@@ -2105,10 +2383,19 @@ int simt_train_backward(const TrainBwdArgs& a, void* ws, size_t ws_bytes, cudaSt
     const char* tre = getenv("A3GC_BWD_TRACE");
     if (tre != nullptr && tre[0] == '1') A3GC_CUDA_TRY(cudaMalloc(&g.trace, 8 * sizeof(long long)));
     int rc;
-    if (att) rc = g.tcore == 2 ? launch(lstm_train_bwd_blk_kernel<true, 2>) : g.tcore == 1 ? launch(lstm_train_bwd_blk_kernel<true, 1>)
-                                                                                            : launch(lstm_train_bwd_blk_kernel<true, 0>);
-    else rc = g.tcore == 2 ? launch(lstm_train_bwd_blk_kernel<false, 2>) : g.tcore == 1 ? launch(lstm_train_bwd_blk_kernel<false, 1>)
-                                                                                         : launch(lstm_train_bwd_blk_kernel<false, 0>);
+    if (g.tcore >= 3) {
+      const int nblk = att ? 7 : 4, ntile = nblk * (H / 16) * (H / 16);
+      for (int d = 0; d < a.num_dirs; ++d) {
+        pack_bwd_frag_kernel<<<(ntile + 7) / 8, 256, 0, stream>>>(bd[d], const_cast<uint4*>(bd[d].wfrag), F, H, nblk, g.tcore == 3);
+        A3GC_LAUNCH_CHECK("pack_bwd_frag_kernel");
+      }
+    }
+    if (att) rc = g.tcore == 4 ? launch(lstm_train_bwd_blk_kernel<true, 4>) : g.tcore == 3 ? launch(lstm_train_bwd_blk_kernel<true, 3>)
+                : g.tcore == 2 ? launch(lstm_train_bwd_blk_kernel<true, 2>) : g.tcore == 1 ? launch(lstm_train_bwd_blk_kernel<true, 1>)
+                                                                              : launch(lstm_train_bwd_blk_kernel<true, 0>);
+    else rc = g.tcore == 4 ? launch(lstm_train_bwd_blk_kernel<false, 4>) : g.tcore == 3 ? launch(lstm_train_bwd_blk_kernel<false, 3>)
+              : g.tcore == 2 ? launch(lstm_train_bwd_blk_kernel<false, 2>) : g.tcore == 1 ? launch(lstm_train_bwd_blk_kernel<false, 1>)
+                                                                            : launch(lstm_train_bwd_blk_kernel<false, 0>);
     if (rc != A3GC_OK) return rc;
     if (g.trace != nullptr) {
       long long h[8];

@@ -25,7 +25,7 @@ def main():
         xr = x.clone().requires_grad_(True)
         y, _ = O.net_forward(variant, xr, sdr, None)
         torch.mean(torch.sum(torch.square(target - y.reshape(target.shape)), -1)).backward()
-        for mode in ("0", "1", "2"):
+        for mode in ("0", "1", "2", "4"):
             os.environ["A3GC_BWD_MMA"] = mode
             net = getattr(A, NET_CLS_NAMES[variant])(f0, out, hidden, nira, linear_dropout=0.0, dropout=0.0, recurrent_dropout=0.0)
             net.load_state_dict(sd, strict=True)
