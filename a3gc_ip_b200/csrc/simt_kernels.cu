@@ -204,6 +204,22 @@ __device__ __forceinline__ void load16(float (&v)[16], const float* src) {
   }
 }
 
+// 64-byte rows of the tape in global memory as two 256-bit accesses (sm_100: LDG.256 / STG.256): a warp's 32 rows are 64
+// bytes apart, so every access touches 16 lines whatever its width, and the backward chain's pointwise phases are bound by
+// exactly those L1 tag lookups -- half as many instructions, half as many lookups.  Rows are 64-byte aligned.
+__device__ __forceinline__ void load16g(float (&v)[16], const float* src) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(src));
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]) : "l"(src + 8));
+}
+__device__ __forceinline__ void store16g(float* dst, const float (&v)[16]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(dst + 8), "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]) : "memory");
+}
+
 // store16 with the two 8-float halves exchanged when swz: the tensor-core phases of the backward chain read the [k][16]
 // arrays as mma B fragments (lane -> k = c, c + 4; node = r), and rows k, k + 2 would otherwise share their banks
 __device__ __forceinline__ void store16_swz(float* dst, const float (&v)[16], bool swz) {
@@ -1478,7 +1494,7 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
         dv[15] = 0.f;
         if (ATT) {
           float hh[16], pa[16], av[16];
-          load16(hh, tp.hh + ((rec0 + b) * H + j) * kNodesPad);
+          load16g(hh, tp.hh + ((rec0 + b) * H + j) * kNodesPad);
           load16(av, al + (size_t)s * kNodesPad);
 #pragma unroll
           for (int n = 0; n < 16; ++n) { pa[n] = dv[n] * hh[n]; dv[n] *= 1.0f + av[n]; }
@@ -1523,12 +1539,12 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
         float e[16], av[16], o[16];
         float sum = 0.f;
         if (b < g.B) {
-          load16(e, tp.e + ((rec0 + b) * H + j) * kNodesPad);
+          load16g(e, tp.e + ((rec0 + b) * H + j) * kNodesPad);
           load16(av, abuf + (size_t)s * kNodesPad);
           const float uj = d.u[j];
 #pragma unroll
           for (int n = 0; n < 16; ++n) { o[n] = av[n] * uj * (1.0f - e[n] * e[n]); sum += o[n]; }
-          store16(gr.dep + ((rec0 + b) * H + j) * kNodesPad, o);
+          store16g(gr.dep + ((rec0 + b) * H + j) * kNodesPad, o);
           gr.dqs[(rec0 + b) * H + j] = sum;
         } else {
 #pragma unroll
@@ -1621,9 +1637,9 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
       if (b < g.B) {
         float gi[16], gf[16], gg[16], go[16], cc[16], cp[16], dv[16];
         float* gp = tp.gates + ((rec0 + b) * 4 * H + j) * kNodesPad;
-        load16(gi, gp); load16(gf, gp + HN); load16(gg, gp + 2 * HN); load16(go, gp + 3 * HN);
-        load16(cc, tp.c + ((rec0 + b) * H + j) * kNodesPad);
-        if (step > 0) load16(cp, tp.c + ((recp0 + b) * H + j) * kNodesPad);
+        load16g(gi, gp); load16g(gf, gp + HN); load16g(gg, gp + 2 * HN); load16g(go, gp + 3 * HN);
+        load16g(cc, tp.c + ((rec0 + b) * H + j) * kNodesPad);
+        if (step > 0) load16g(cp, tp.c + ((recp0 + b) * H + j) * kNodesPad);
         else {
 #pragma unroll
           for (int n = 0; n < 16; ++n) cp[n] = (d.c0 != nullptr && n < kNodes) ? d.c0[((size_t)b * kNodes + n) * H + j] : 0.f;
@@ -1641,7 +1657,7 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
           dcv[n] = dcn * gf[n];
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { dz[q][15] = 0.f; store16(gp + q * HN, dz[q]); }
+        for (int q = 0; q < 4; ++q) { dz[q][15] = 0.f; store16g(gp + q * HN, dz[q]); }
         dcv[15] = 0.f;
       } else {
 #pragma unroll
