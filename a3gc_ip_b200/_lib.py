@@ -23,7 +23,7 @@ PRECISION = {"fp32": 0, "bf16": 1}
 ENGINE = {"auto": 0, "simt": 1, "tc": 2}
 
 _f32p = C.POINTER(C.c_float)
-ABI_VERSION = 2          # A3GC_ABI_VERSION of include/a3gc_b200.h this binding was written against
+ABI_VERSION = 3          # A3GC_ABI_VERSION of include/a3gc_b200.h this binding was written against
 
 
 class GcParams(C.Structure):
@@ -108,6 +108,9 @@ SYMBOLS = {
     "a3gc_train_split_tf32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "a3gc_train_hprev_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                          C.c_int, C.c_int, C.c_void_p]),
+    "a3gc_train_split_mixed": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "a3gc_train_hprev_split_mixed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                               C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
     "a3gc_profile_enable": (C.c_int, [C.c_int]),
     "a3gc_profile_count": (C.c_int, []),
     "a3gc_profile_get": (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double)]),

@@ -527,6 +527,30 @@ int a3gc_train_hprev_split(const float* hp, const float* h0, const float* mask, 
   return train_hprev_split(hp, h0, mask, hi, lo, batch, steps, hidden, reverse, static_cast<cudaStream_t>(stream));
 }
 
+int a3gc_train_split_mixed(const float* x, int64_t rows, int cols, float* hi, uint16_t* hi16, uint16_t* lo16, int64_t ld, int64_t col0,
+                           void* stream) {
+  if (rows < 0 || cols < 0 || cols % 4 != 0 || ld % 4 != 0 || col0 % 4 != 0 || col0 < 0 || col0 + cols > ld ||
+      (rows * cols > 0 && (!x || !hi || !hi16 || !lo16))) {
+    set_error("a3gc_train_split_mixed: invalid argument (cols, ld and col0 must be multiples of 4, col0 + cols <= ld)");
+    return A3GC_ERR_INVALID_ARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi)) & 15 || (reinterpret_cast<uintptr_t>(hi16) | reinterpret_cast<uintptr_t>(lo16)) & 7) {
+    set_error("a3gc_train_split_mixed: x / hi must be 16-byte aligned, hi16 / lo16 8-byte aligned");
+    return A3GC_ERR_INVALID_ARG;
+  }
+  return train_split_mixed(x, rows, cols, hi, hi16, lo16, ld, col0, static_cast<cudaStream_t>(stream));
+}
+
+int a3gc_train_hprev_split_mixed(const float* hp, const float* h0, const float* mask, float* hi, uint16_t* hi16, uint16_t* lo16,
+                                 int64_t batch, int64_t steps, int hidden, int64_t ld, int64_t col0, int reverse, void* stream) {
+  if (batch < 0 || steps < 0 || hidden <= 0 || hidden % 4 != 0 || ld % 4 != 0 || col0 % 4 != 0 || col0 < 0 || col0 + hidden > ld ||
+      (batch * steps > 0 && (!hp || !hi || !hi16 || !lo16))) {
+    set_error("a3gc_train_hprev_split_mixed: invalid argument (hidden, ld and col0 must be multiples of 4, col0 + hidden <= ld)");
+    return A3GC_ERR_INVALID_ARG;
+  }
+  return train_hprev_split_mixed(hp, h0, mask, hi, hi16, lo16, batch, steps, hidden, ld, col0, reverse, static_cast<cudaStream_t>(stream));
+}
+
 int a3gc_concat_stage_input(const float* x, const float* pos, float* dst, int64_t frames, void* stream) {
   if (frames < 0 || (frames > 0 && (!x || !pos || !dst))) { set_error("a3gc_concat_stage_input: invalid argument"); return A3GC_ERR_INVALID_ARG; }
   return simt_concat_stage_input(x, pos, dst, frames, static_cast<cudaStream_t>(stream));

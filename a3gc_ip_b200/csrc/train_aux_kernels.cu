@@ -4,6 +4,12 @@
 // The hoisted GEMMs run on the tensor cores as three TF32 passes (hi*hi + lo*hi + hi*lo): every fp32 operand is cut
 // into a head that is exactly representable in TF32 (cvt.rna, 11 significand bits) and the fp32 remainder, so the
 // library's TF32 conversion of the head is exact and the dropped lo*lo term is 2^-22 relative.
+//
+// "Mixed" form (round 2): only the hi*hi product needs TF32; the two correction products carry 2^-11 of the result, so
+// their operands may be rounded to bf16 (2^-9 of a 2^-11 term) and run at the bf16 tensor rate -- measured 4-5x the
+// TF32 rate of the library on these shapes (tests/diag_dw_gemm.py).  The builders below therefore emit hi (fp32,
+// TF32-exact), bf16(hi) and bf16(lo) in one pass, into row-strided buffers so that x and h_prev land side by side
+// in one S = [x | h_prev] operand (one GEMM instead of two per weight-gradient block).
 #include "common.cuh"
 
 namespace a3gc {
@@ -55,6 +61,52 @@ __global__ void __launch_bounds__(256) hprev_split_kernel(const float4* __restri
   }
 }
 
+__device__ __forceinline__ uint2 bf16x4(float a, float b, float c, float d) {
+  uint2 r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.x) : "f"(b), "f"(a));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.y) : "f"(d), "f"(c));
+  return r;
+}
+
+__device__ __forceinline__ void emit_mixed(const float4& v, float4* hi, uint2* hi16, uint2* lo16, int64_t o4) {
+  float4 h;
+  h.x = tf32_head(v.x); h.y = tf32_head(v.y); h.z = tf32_head(v.z); h.w = tf32_head(v.w);
+  hi[o4] = h;
+  hi16[o4] = bf16x4(h.x, h.y, h.z, h.w);
+  lo16[o4] = bf16x4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+
+// x [rows][cols] -> hi / hi16 / lo16 [rows][ld] at column col0 (all in units of 4 elements)
+__global__ void __launch_bounds__(256) split_mixed_kernel(const float4* __restrict__ x, float4* __restrict__ hi, uint2* __restrict__ hi16,
+                                                          uint2* __restrict__ lo16, int64_t rows, int cols4, int64_t ld4, int64_t col04) {
+  const int64_t n4 = rows * cols4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / cols4;
+    emit_mixed(__ldg(x + i), hi, hi16, lo16, row * ld4 + col04 + (i - row * cols4));
+  }
+}
+
+// hprev_split_kernel in mixed form; output rows are (b, t, node), H/4 units each, at column col0 of a [rows][ld] buffer
+__global__ void __launch_bounds__(256) hprev_split_mixed_kernel(const float4* __restrict__ hp, const float4* __restrict__ h0,
+                                                                const float4* __restrict__ mask, float4* __restrict__ hi,
+                                                                uint2* __restrict__ hi16, uint2* __restrict__ lo16, int B, int T,
+                                                                int h4, int64_t ld4, int64_t col04, int reverse) {
+  const int row4 = kNodes * h4;
+  const int64_t n4 = (int64_t)B * T * row4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bt = i / row4;
+    const int r = (int)(i - bt * row4);
+    const int b = (int)(bt / T), t = (int)(bt - (int64_t)b * T);
+    const int tp = reverse ? t + 1 : t - 1;
+    float4 v;
+    if (tp < 0 || tp >= T) v = h0 != nullptr ? __ldg(h0 + (int64_t)b * row4 + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+    else v = __ldg(hp + ((int64_t)b * T + tp) * row4 + r);
+    if (mask != nullptr) { const float4 m = __ldg(mask + i); v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w; }
+    const int64_t row = i / h4;                                  // (b, t, node)
+    emit_mixed(v, hi, hi16, lo16, row * ld4 + col04 + (i - row * h4));
+  }
+}
+
 }  // namespace
 
 int train_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream) {
@@ -83,6 +135,31 @@ int train_hprev_split(const float* hp, const float* h0, const float* mask, float
       reinterpret_cast<const float4*>(hp), reinterpret_cast<const float4*>(h0), reinterpret_cast<const float4*>(mask),
       reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo), (int)batch, (int)steps, row4, reverse);
   A3GC_LAUNCH_CHECK("hprev_split_kernel");
+  return A3GC_OK;
+}
+
+int train_split_mixed(const float* x, int64_t rows, int cols, float* hi, uint16_t* hi16, uint16_t* lo16, int64_t ld, int64_t col0,
+                      cudaStream_t stream) {
+  if (rows == 0 || cols == 0) return A3GC_OK;
+  const int64_t n4 = rows * (cols / 4);
+  const int64_t blocks = (n4 + 255) / 256;
+  split_mixed_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(hi), reinterpret_cast<uint2*>(hi16), reinterpret_cast<uint2*>(lo16),
+      rows, cols / 4, ld / 4, col0 / 4);
+  A3GC_LAUNCH_CHECK("split_mixed_kernel");
+  return A3GC_OK;
+}
+
+int train_hprev_split_mixed(const float* hp, const float* h0, const float* mask, float* hi, uint16_t* hi16, uint16_t* lo16,
+                            int64_t batch, int64_t steps, int hidden, int64_t ld, int64_t col0, int reverse, cudaStream_t stream) {
+  if (batch == 0 || steps == 0) return A3GC_OK;
+  const int64_t n4 = batch * steps * kNodes * (hidden / 4);
+  const int64_t blocks = (n4 + 255) / 256;
+  hprev_split_mixed_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(hp), reinterpret_cast<const float4*>(h0), reinterpret_cast<const float4*>(mask),
+      reinterpret_cast<float4*>(hi), reinterpret_cast<uint2*>(hi16), reinterpret_cast<uint2*>(lo16), (int)batch, (int)steps, hidden / 4,
+      ld / 4, col0 / 4, reverse);
+  A3GC_LAUNCH_CHECK("hprev_split_mixed_kernel");
   return A3GC_OK;
 }
 

@@ -40,27 +40,49 @@ LSTM_PARAM_NAMES = {
 # hoisted GEMMs: fp32 accuracy from three TF32 tensor-core passes
 # ----------------------------------------------------------------------------------------------------------------------
 def _gemm_mode() -> str:
-    mode = os.environ.get("A3GC_TRAIN_GEMM", "tf32x3")
-    if mode not in ("tf32x3", "fp32"):
-        raise ValueError(f"A3GC_TRAIN_GEMM must be tf32x3 or fp32, got {mode!r}")
+    mode = os.environ.get("A3GC_TRAIN_GEMM", "mixed")
+    if mode not in ("mixed", "tf32x3", "fp32"):
+        raise ValueError(f"A3GC_TRAIN_GEMM must be mixed, tf32x3 or fp32, got {mode!r}")
     return mode
 
 
 class _Split:
-    """An fp32 matrix as (hi, lo): hi exactly representable in TF32, lo = x - hi.  In fp32 mode hi = x, lo = None."""
-    __slots__ = ("hi", "lo")
+    """An fp32 matrix as (hi, lo): hi exactly representable in TF32, lo = x - hi.  In fp32 mode hi = x, lo = None.
+    Mixed mode: hi (fp32) plus bf16 copies hi16 = bf16(hi), lo16 = bf16(lo) for the two correction products (lo = None)."""
+    __slots__ = ("hi", "lo", "hi16", "lo16")
 
-    def __init__(self, hi: Tensor, lo: Optional[Tensor]):
-        self.hi, self.lo = hi, lo
+    def __init__(self, hi: Tensor, lo: Optional[Tensor], hi16: Optional[Tensor] = None, lo16: Optional[Tensor] = None):
+        self.hi, self.lo, self.hi16, self.lo16 = hi, lo, hi16, lo16
 
     def cols(self, a: int, b: int) -> "_Split":
-        return _Split(self.hi[:, a:b], None if self.lo is None else self.lo[:, a:b])
+        cut = lambda t: None if t is None else t[:, a:b]
+        return _Split(self.hi[:, a:b], cut(self.lo), cut(self.hi16), cut(self.lo16))
+
+
+def _mixed_buffers(rows: int, ld: int, device) -> _Split:
+    return _Split(torch.empty(rows, ld, dtype=torch.float32, device=device), None,
+                  torch.empty(rows, ld, dtype=torch.bfloat16, device=device), torch.empty(rows, ld, dtype=torch.bfloat16, device=device))
+
+
+def _split_into(dst: _Split, x: Tensor, col0: int) -> None:
+    """Mixed split of x [rows, cols] into columns col0.. of the row-major buffers of dst (a3gc_train_split_mixed)."""
+    x = x.contiguous()
+    rows, cols = x.shape
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().a3gc_train_split_mixed(x.data_ptr(), rows, cols, dst.hi.data_ptr(), dst.hi16.data_ptr(), dst.lo16.data_ptr(),
+                                               dst.hi.shape[1], col0, _lib.stream_ptr(x.device))
+    _lib.check(rc, "a3gc_train_split_mixed")
 
 
 def _split(x: Tensor) -> _Split:
     x = x.contiguous()
-    if _gemm_mode() == "fp32":
+    mode = _gemm_mode()
+    if mode == "fp32":
         return _Split(x, None)
+    if mode == "mixed" and x.dim() == 2 and x.shape[1] % 4 == 0:
+        out = _mixed_buffers(x.shape[0], x.shape[1], x.device)
+        _split_into(out, x, 0)
+        return out
     hi, lo = torch.empty_like(x), torch.empty_like(x)
     with torch.cuda.device(x.device):
         rc = _lib.lib().a3gc_train_split_tf32(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _lib.stream_ptr(x.device))
@@ -68,14 +90,25 @@ def _split(x: Tensor) -> _Split:
     return _Split(hi, lo)
 
 
-def _hprev_split(hp: Tensor, h0: Optional[Tensor], mask: Optional[Tensor], reverse: int) -> _Split:
-    """Rows of the h half of S = [x | h_prev] of one direction, [B*T*15, H] (see a3gc_train_hprev_split)."""
+def _hprev_split(hp: Tensor, h0: Optional[Tensor], mask: Optional[Tensor], reverse: int, into: Optional[_Split] = None,
+                 col0: int = 0) -> _Split:
+    """Rows of the h half of S = [x | h_prev] of one direction, [B*T*15, H] (see a3gc_train_hprev_split); with `into`
+    (mixed mode) they are written into columns col0.. of an existing S buffer instead."""
     B, T, _, H = hp.shape
+    if into is not None:
+        with torch.cuda.device(hp.device):
+            rc = _lib.lib().a3gc_train_hprev_split_mixed(hp.data_ptr(), _lib.ptr(h0), _lib.ptr(mask), into.hi.data_ptr(),
+                                                         into.hi16.data_ptr(), into.lo16.data_ptr(), B, T, H, into.hi.shape[1], col0,
+                                                         int(reverse), _lib.stream_ptr(hp.device))
+        _lib.check(rc, "a3gc_train_hprev_split_mixed")
+        return into
     if _gemm_mode() == "fp32" or H % 4 != 0:
         hprev = torch.cat((hp[:, 1:], h0.unsqueeze(1)), dim=1) if reverse else torch.cat((h0.unsqueeze(1), hp[:, :-1]), dim=1)
         if mask is not None:
             hprev = hprev * mask
         return _split(hprev.reshape(B * T * NUM_NODES, H))
+    if _gemm_mode() == "mixed":
+        return _hprev_split(hp, h0, mask, reverse, _mixed_buffers(B * T * NUM_NODES, H, hp.device), 0)
     hi, lo = torch.empty(B * T * NUM_NODES, H, dtype=torch.float32, device=hp.device), torch.empty(B * T * NUM_NODES, H, dtype=torch.float32, device=hp.device)
     with torch.cuda.device(hp.device):
         rc = _lib.lib().a3gc_train_hprev_split(hp.data_ptr(), _lib.ptr(h0), _lib.ptr(mask), hi.data_ptr(), lo.data_ptr(),
@@ -96,8 +129,22 @@ class _tf32_passes:
         return False
 
 
+def _pair_forms(a: _Split, b: _Split) -> None:
+    """A mixed operand meeting a three-pass one (a width that is not a multiple of 4): give the latter bf16 copies too."""
+    for s_, o_ in ((a, b), (b, a)):
+        if s_.hi16 is None and s_.lo is not None and o_.hi16 is not None:
+            s_.hi16, s_.lo16 = s_.hi.bfloat16(), s_.lo.bfloat16()
+
+
 def _mm_tn(a: _Split, b: _Split) -> Tensor:
     """a^T @ b for row-aligned a [R, M], b [R, N]."""
+    _pair_forms(a, b)
+    if a.hi16 is not None and b.hi16 is not None:
+        out = torch.mm(a.lo16.t(), b.hi16, out_dtype=torch.float32)
+        out += torch.mm(a.hi16.t(), b.lo16, out_dtype=torch.float32)
+        with _tf32_passes():
+            out.addmm_(a.hi.t(), b.hi)
+        return out
     if a.lo is None:
         return a.hi.t() @ b.hi
     with _tf32_passes():
@@ -109,6 +156,13 @@ def _mm_tn(a: _Split, b: _Split) -> Tensor:
 
 def _addmm_nn(out: Tensor, a: _Split, b: _Split) -> None:
     """out += a @ b for a [R, K], b [K, N]."""
+    _pair_forms(a, b)
+    if a.hi16 is not None and b.hi16 is not None:
+        out += torch.mm(a.lo16, b.hi16, out_dtype=torch.float32)
+        out += torch.mm(a.hi16, b.lo16, out_dtype=torch.float32)
+        with _tf32_passes():
+            out.addmm_(a.hi, b.hi)
+        return
     if a.lo is None:
         out.addmm_(a.hi, b.hi)
         return
@@ -233,21 +287,32 @@ class _LayerTrainFn(torch.autograd.Function):
 
         # ---- hoisted contractions over all (t, b): plain GEMMs (torch / cuBLAS fp32 on the current stream)
         R = B * T * NUM_NODES
-        x2d = _split(x.reshape(R, F))
+        # mixed mode: x and h_prev side by side in one S = [x | h_prev] operand, so dW = dzm^T S is one GEMM per precision
+        one_s = _gemm_mode() == "mixed" and F % 4 == 0 and H % 4 == 0
+        if one_s:
+            S = _mixed_buffers(R, F + H, dev)
+            _split_into(S, x.reshape(R, F), 0)
+        else:
+            x2d = _split(x.reshape(R, F))
         dx = torch.zeros(R, F, **f32)
         grads: List[Optional[Tensor]] = []
         for d in range(nd):
             ps = dict(zip(names, params[d]))
             dzm2d = _split(gr["dzm"][d].reshape(R, 4 * H))
             # S = [x | h_prev]: h_prev is h' of the previous step of this direction (h0 at its first step), masked
-            hprev = _hprev_split(tape["hp"][d], h0[d], None if hmask is None else hmask[d], reverse[d])
-            dWx = _mm_tn(dzm2d, x2d)                                     # [4H, F]
-            dWh = _mm_tn(dzm2d, hprev)                                   # [4H, H]
-            del hprev
+            if one_s:
+                _hprev_split(tape["hp"][d], h0[d], None if hmask is None else hmask[d], reverse[d], into=S, col0=F)
+                dW = _mm_tn(dzm2d, S)                                    # [4H, F + H]
+                gW = [dW[i * H:(i + 1) * H] for i in range(4)]
+            else:
+                hprev = _hprev_split(tape["hp"][d], h0[d], None if hmask is None else hmask[d], reverse[d])
+                dWx = _mm_tn(dzm2d, x2d)                                 # [4H, F]
+                dWh = _mm_tn(dzm2d, hprev)                               # [4H, H]
+                del hprev
+                gW = [torch.cat((dWx[i * H:(i + 1) * H], dWh[i * H:(i + 1) * H]), dim=1) for i in range(4)]
             Wx = torch.cat([ps[f"gcn_kernel_{g}"][:, :F] for g in "ifco"], dim=0)   # [4H, F]
             _addmm_nn(dx, dzm2d, _split(Wx))
             del dzm2d
-            gW = [torch.cat((dWx[i * H:(i + 1) * H], dWh[i * H:(i + 1) * H]), dim=1) for i in range(4)]
             dz = tape["gates"][d].reshape(T * B, 4, H, 16)               # the backward left dz here
             ones = torch.ones(1, T * B, **f32)
             gb = (ones @ dz.reshape(T * B, 4 * H * 16)).reshape(4, H, 16).sum(2)     # [4, H]; one bandwidth-bound pass

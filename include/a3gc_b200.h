@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define A3GC_ABI_VERSION 2
+#define A3GC_ABI_VERSION 3
 #define A3GC_NODES 15
 
 /* Cell family.  Values are part of the ABI. */
@@ -298,6 +298,18 @@ int a3gc_reduced_to_full_local(const float* pose, float* out, int64_t frames, in
 int a3gc_train_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
 int a3gc_train_hprev_split(const float* hp, const float* h0, const float* mask, float* hi, float* lo, int64_t batch,
                            int64_t steps, int hidden, int reverse, void* stream);
+
+/*
+ * The same builders in "mixed" form (ABI 3): the hi*hi product stays TF32, the two correction products run on bf16 copies
+ * of their operands (a correction is 2^-11 of the result, bf16 rounding 2^-9 of that).  One pass writes hi (fp32, exactly
+ * representable in TF32), hi16 = bf16(hi) and lo16 = bf16(x - hi) into row-major buffers of row length ld at column col0,
+ * so that x (cols = F, col0 = 0) and h_prev (col0 = F) form one S = [x | h_prev] operand of row length F + H:
+ * dW = dzm^T S is then one GEMM per precision instead of two.  x is [rows, cols] contiguous; cols, ld, col0 multiples of 4.
+ */
+int a3gc_train_split_mixed(const float* x, int64_t rows, int cols, float* hi, uint16_t* hi16, uint16_t* lo16, int64_t ld, int64_t col0,
+                           void* stream);
+int a3gc_train_hprev_split_mixed(const float* hp, const float* h0, const float* mask, float* hi, uint16_t* hi16, uint16_t* lo16,
+                                 int64_t batch, int64_t steps, int hidden, int64_t ld, int64_t col0, int reverse, void* stream);
 
 /*
  * Optional per-launch timing of the recurrent-layer kernels (used by bench.py for the roofline):

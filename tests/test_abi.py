@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string():
     L = _lib.lib()
-    assert L.a3gc_abi_version() == _lib.ABI_VERSION == 2
+    assert L.a3gc_abi_version() == _lib.ABI_VERSION == 3
     assert isinstance(L.a3gc_last_error(), bytes)
 
 

@@ -163,10 +163,11 @@ def test_blocked_and_plain_backward_chains_agree(variant, H, B, nira, monkeypatc
         assert rel_l2(b, a) <= 3e-5, f"gradient {i}: rel_l2={rel_l2(b, a):.3e}"
 
 
-def test_tf32_split_and_hprev_operand_builders():
+def test_tf32_split_and_hprev_operand_builders(monkeypatch):
     """a3gc_train_split_tf32: hi is exactly representable in TF32 (13 low significand bits zero), hi + lo == x bit for bit;
     a3gc_train_hprev_split: the shifted, masked h_prev operand equals the torch construction (net_aagc.py:181-182)."""
     from a3gc_ip_b200 import training as TR
+    monkeypatch.setenv("A3GC_TRAIN_GEMM", "tf32x3")
     torch.manual_seed(11)
     x = (torch.randn(1027, 33, device="cuda") * torch.logspace(-20, 6, 33, device="cuda")).contiguous()
     sp = TR._split(x)
@@ -187,3 +188,36 @@ def test_tf32_split_and_hprev_operand_builders():
                     want = want * m
                 assert torch.equal((got.hi + got.lo).reshape(B, T, 15, H), want)
                 assert int((got.hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+
+
+def test_mixed_operand_builders_and_gemms():
+    """a3gc_train_split_mixed / a3gc_train_hprev_split_mixed (ABI 3): hi is TF32-exact, hi16 = bf16(hi), lo16 = bf16(x - hi), written
+    at a column offset of a wider row-major buffer (x and h_prev side by side); the mixed products (TF32 hi x hi + two bf16
+    correction GEMMs) agree with an fp64 product to fp32-level accuracy."""
+    from a3gc_ip_b200 import training as TR
+    torch.manual_seed(12)
+    R, F, H = 4 * 6 * 15, 24, 64
+    x = torch.randn(R, F, device="cuda") * torch.logspace(-6, 3, F, device="cuda")
+    B, T = 4, 6
+    hp = torch.randn(B, T, 15, H, device="cuda")
+    h0 = torch.randn(B, 15, H, device="cuda")
+    mask = (torch.rand(B, T, 15, H, device="cuda") >= 0.3).float() / 0.7
+    S = TR._mixed_buffers(R, F + H, "cuda")
+    TR._split_into(S, x, 0)
+    TR._hprev_split(hp, h0, mask, 1, into=S, col0=F)
+    want = torch.cat((x, (torch.cat((hp[:, 1:], h0.unsqueeze(1)), dim=1) * mask).reshape(R, H)), dim=1)
+    assert int((S.hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    assert torch.equal(S.hi16, S.hi.bfloat16())
+    assert torch.equal(S.lo16, (want - S.hi).bfloat16())
+    assert float(((want - S.hi).abs() > S.hi.abs() * 2.0 ** -10).sum()) == 0
+    a = torch.randn(R, 96, device="cuda")
+    got = TR._mm_tn(TR._split(a), S)
+    ref = (a.double().t() @ want.double()).float()
+    assert rel_l2(got.cpu(), ref.cpu()) <= 2e-6
+    w = torch.randn(F + H, 40, device="cuda")
+    out = torch.zeros(R, 40, device="cuda")
+    TR._addmm_nn(out, S, TR._split(w))
+    assert rel_l2(out.cpu(), (want.double() @ w.double()).float().cpu()) <= 2e-6
+    odd = torch.randn(R, 15, device="cuda")                       # a width the vectorised builder does not take: three-pass form
+    got = TR._mm_tn(TR._split(a), TR._split(odd))
+    assert rel_l2(got.cpu(), (a.double().t() @ odd.double()).float().cpu()) <= 2e-6
