@@ -614,7 +614,7 @@ struct BwdDir {
   const float* Wa;         // attention_w  [H][H]
   const float* u;          // attention_u  [H]
   const float* PT;         // [4][16][16]  PT_g[n][m] = P_g[m][n]  (zero padded)
-  const uint4* wfrag;      // blocked kernel, mode 3: the five H x H weight blocks as ready-made mma.sync A fragments (pack_bwd_frag_kernel)
+  const uint4* wfrag;      // blocked kernel, modes 3 / 4: the seven H x H weight blocks in mma.sync A-fragment order (pack_bwd_frag_kernel)
   const float* c0;         // [B][15][H] initial cell state (nullptr = zeros)
   const float* dhT; const float* dcT;   // [B][15][H] gradients of the final state (nullptr = zeros)
   float* dh0; float* dc0;               // [B][15][H] gradients of the initial state (nullptr = skip)
@@ -626,9 +626,8 @@ struct BwdGeom {
   a3gc_tape_grads gr;
   const float* hmask;
   int B, T, F, H, out_act, BT;
-  int gemv16;                        // blocked kernel: 16 instead of 8 weight loads in flight per thread in the q-chain GEMVs
   long long* trace;                  // diagnostics: per-phase cycle sums of CTA (0, 0), or nullptr
-  int tcore;                         // blocked kernel: the two weight contractions run on the tensor cores (3xTF32)
+  int tcore;                         // blocked kernel: how the weight products run (A3GC_BWD_MMA: 0 FFMA, 1..4 mma.sync forms; default 4)
 };
 
 template <bool ATT>
@@ -1408,7 +1407,9 @@ __device__ __forceinline__ void bwd_phase_g_tc(const float* dzm, int BT, size_t 
 }
 
 // Same chain as lstm_train_bwd_kernel for H in {64, 128, 256}, arranged around the two weight contractions that
-// dominate it (phase E: dep x Wh, phase G: dzm x W[:, F:]).  BT * H = 512 (or 256): a thread owns 2 sequences x 2
+// dominate it (phase E: dep x Wh, phase G: dzm x W[:, F:]).  TCORE != 0 (the default, 4): those two and the q chain's
+// vector products run as mma.sync tensor-core products (contract_tf32 / contract_packed / gemv_tc above); the rest of
+// this comment describes the FFMA form (TCORE = 0), which stays as the A/B reference.  BT * H = 512 (or 256): a thread owns 2 sequences x 2
 // units (u, u + H/2) and 1/KS of the contraction range, so the weights cross L2 once per sequence PAIR and every
 // activation float4 read from shared memory feeds 8 FMAs; the KS partial sums meet in shared memory.  dhy overwrites
 // dh' in place and dep lives in dzm[0], which leaves room for two H=256 sequences per CTA.
@@ -1565,8 +1566,7 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
         BWD_MARK(3);
       } else {
         // ---- D: dq_j = sum_k dqs_k Wq[k][j] for all BT sequences at once;  dqp = dq [q > 0]
-        if (g.gemv16 && kdq % 16 == 0) gemv_part<16>(v1, d.Wq, scr, H, BT, jd, kd, kdq);
-        else if (kdq % 8 == 0) gemv_part<8>(v1, d.Wq, scr, H, BT, jd, kd, kdq); else gemv_part<4>(v1, d.Wq, scr, H, BT, jd, kd, kdq);
+        if (kdq % 8 == 0) gemv_part<8>(v1, d.Wq, scr, H, BT, jd, kd, kdq); else gemv_part<4>(v1, d.Wq, scr, H, BT, jd, kd, kdq);
         __syncthreads();
         for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
           const int s = task / H, j = task % H, b = b0 + s;
@@ -1582,8 +1582,7 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
         __syncthreads();
         BWD_MARK(3);
         // ---- D2: ds_j = sum_k dqp_k Wa[k][j]  (-> v1)
-        if (g.gemv16 && kdq % 16 == 0) gemv_part<16>(v2, d.Wa, scr, H, BT, jd, kd, kdq);
-        else if (kdq % 8 == 0) gemv_part<8>(v2, d.Wa, scr, H, BT, jd, kd, kdq); else gemv_part<4>(v2, d.Wa, scr, H, BT, jd, kd, kdq);
+        if (kdq % 8 == 0) gemv_part<8>(v2, d.Wa, scr, H, BT, jd, kd, kdq); else gemv_part<4>(v2, d.Wa, scr, H, BT, jd, kd, kdq);
         __syncthreads();
         for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
           float ds = 0.f;
@@ -2383,8 +2382,6 @@ int simt_train_backward(const TrainBwdArgs& a, void* ws, size_t ws_bytes, cudaSt
     const int nt = H >= 128 ? 2 * BT : BT;
     const char* e = getenv("A3GC_BWD_MMA");
     const int mode = e != nullptr ? atoi(e) : 4;
-    const char* e16 = getenv("A3GC_BWD_GEMV16");
-    g.gemv16 = e16 != nullptr ? atoi(e16) : 1;
     g.tcore = (blk && ((H == 256 && nt == 4) || (H <= 128 && (nt == 4 || nt == 8)))) ? (mode < 0 || mode > 4 ? 4 : mode) : 0;
   }
   dim3 grid((unsigned)((a.batch + BT - 1) / BT), (unsigned)a.num_dirs);
