@@ -111,6 +111,7 @@ SYMBOLS = {
     "a3gc_train_split_mixed": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "a3gc_train_hprev_split_mixed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                                C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
+    "a3gc_train_adjacency_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "a3gc_profile_enable": (C.c_int, [C.c_int]),
     "a3gc_profile_count": (C.c_int, []),
     "a3gc_profile_get": (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double)]),

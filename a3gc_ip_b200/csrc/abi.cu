@@ -551,6 +551,19 @@ int a3gc_train_hprev_split_mixed(const float* hp, const float* h0, const float* 
   return train_hprev_split_mixed(hp, h0, mask, hi, hi16, lo16, batch, steps, hidden, ld, col0, reverse, static_cast<cudaStream_t>(stream));
 }
 
+int a3gc_train_adjacency_grad(const float* dz, const float* u, int64_t records, int hidden, float* partial, int nblocks, float* dP,
+                              void* stream) {
+  if (records < 0 || hidden <= 0 || hidden % 16 != 0 || nblocks <= 0 || !dz || !u || !partial || !dP) {
+    set_error("a3gc_train_adjacency_grad: invalid argument (hidden must be a positive multiple of 16, nblocks > 0)");
+    return A3GC_ERR_INVALID_ARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(u)) & 15) {
+    set_error("a3gc_train_adjacency_grad: dz / u must be 16-byte aligned");
+    return A3GC_ERR_INVALID_ARG;
+  }
+  return train_adjacency_grad(dz, u, records, hidden, partial, nblocks, dP, static_cast<cudaStream_t>(stream));
+}
+
 int a3gc_concat_stage_input(const float* x, const float* pos, float* dst, int64_t frames, void* stream) {
   if (frames < 0 || (frames > 0 && (!x || !pos || !dst))) { set_error("a3gc_concat_stage_input: invalid argument"); return A3GC_ERR_INVALID_ARG; }
   return simt_concat_stage_input(x, pos, dst, frames, static_cast<cudaStream_t>(stream));

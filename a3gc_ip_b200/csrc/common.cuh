@@ -116,6 +116,8 @@ int simt_reduced_to_full_local(const float* pose, float* out, int64_t frames, in
 int train_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream);
 int train_hprev_split(const float* hp, const float* h0, const float* mask, float* hi, float* lo, int64_t batch,
                       int64_t steps, int hidden, int reverse, cudaStream_t stream);
+int train_adjacency_grad(const float* dz, const float* u, int64_t records, int hidden, float* partial, int nblocks, float* dP,
+                         cudaStream_t stream);
 int train_split_mixed(const float* x, int64_t rows, int cols, float* hi, uint16_t* hi16, uint16_t* lo16, int64_t ld, int64_t col0,
                       cudaStream_t stream);
 int train_hprev_split_mixed(const float* hp, const float* h0, const float* mask, float* hi, uint16_t* hi16, uint16_t* lo16,

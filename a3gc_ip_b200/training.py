@@ -322,10 +322,20 @@ class _LayerTrainFn(torch.autograd.Function):
                 out["adjacency"] = None                                  # frozen (requires_grad=False, net_aagc.py:238)
             else:
                 u = tape["u"][d].reshape(T * B, 4, H, 16)
-                for i, g in enumerate("ifco"):
-                    # dP_g[m][n] = sum dz_g[., j, m] u_g[., j, n];  adjacency_g is stored as P_g (used as P_g @ S)
-                    dP = torch.bmm(dz[:, i].transpose(1, 2), u[:, i]).sum(0)
-                    out[f"adjacency_{g}"] = dP[:NUM_NODES, :NUM_NODES].contiguous()
+                # dP_g[m][n] = sum dz_g[., j, m] u_g[., j, n];  adjacency_g is stored as P_g (used as P_g @ S)
+                if H % 16 == 0 and os.environ.get("A3GC_TRAIN_ADJ", "fused") == "fused":
+                    nblk = 4 * torch.cuda.get_device_properties(dev).multi_processor_count
+                    part, dP4 = torch.empty(nblk, 1024, **f32), torch.empty(4, 16, 16, **f32)
+                    with torch.cuda.device(dev):
+                        rc = L.a3gc_train_adjacency_grad(dz.data_ptr(), u.data_ptr(), T * B, H, part.data_ptr(), nblk, dP4.data_ptr(),
+                                                         _lib.stream_ptr(dev))
+                    _lib.check(rc, "a3gc_train_adjacency_grad")
+                    for i, g in enumerate("ifco"):
+                        out[f"adjacency_{g}"] = dP4[i, :NUM_NODES, :NUM_NODES].contiguous()
+                else:
+                    for i, g in enumerate("ifco"):
+                        dP = torch.bmm(dz[:, i].transpose(1, 2), u[:, i]).sum(0)
+                        out[f"adjacency_{g}"] = dP[:NUM_NODES, :NUM_NODES].contiguous()
             if att:
                 dep = gr["dep"][d].reshape(T * B, H, 16)
                 hh = tape["hh"][d].reshape(T * B, H, 16)

@@ -312,6 +312,16 @@ int a3gc_train_hprev_split_mixed(const float* hp, const float* h0, const float* 
                                  int64_t batch, int64_t steps, int hidden, int64_t ld, int64_t col0, int reverse, void* stream);
 
 /*
+ * Adjacency gradients of one direction of an A3GC / AAGC layer (ABI 3; the bmm + sum autograd nodes of loss.backward(),
+ * train_a3gc_tp.py:83): dP[g][m][n] = sum over records r and units j of dz[r][g][j][m] * u[r][g][j][n], with dz the gate
+ * pre-activation gradients a3gc_layer_backward left in tape.gates and u = tape.u, both [records][4][hidden][16].
+ * One pass over the two arrays; partial is scratch of nblocks * 1024 floats (nblocks: a few per SM), dP is [4][16][16]
+ * (rows / columns 15 are padding).  The sum order is fixed: the result is deterministic.
+ */
+int a3gc_train_adjacency_grad(const float* dz, const float* u, int64_t records, int hidden, float* partial, int nblocks, float* dP,
+                              void* stream);
+
+/*
  * Optional per-launch timing of the recurrent-layer kernels (used by bench.py for the roofline):
  * while enabled, every layer launch is bracketed by CUDA events on the launching stream.
  * a3gc_profile_get must be called after the stream has been synchronised; it returns the launch's

@@ -221,3 +221,23 @@ def test_mixed_operand_builders_and_gemms():
     odd = torch.randn(R, 15, device="cuda")                       # a width the vectorised builder does not take: three-pass form
     got = TR._mm_tn(TR._split(a), TR._split(odd))
     assert rel_l2(got.cpu(), (a.double().t() @ odd.double()).float().cpu()) <= 2e-6
+
+
+def test_fused_adjacency_gradient_kernel():
+    """a3gc_train_adjacency_grad against the bmm + sum it replaces (training.py), fp64 reference; deterministic across calls."""
+    from a3gc_ip_b200 import _lib
+    torch.manual_seed(13)
+    R, H = 333, 64
+    dz = torch.randn(R, 4, H, 16, device="cuda")
+    u = torch.randn(R, 4, H, 16, device="cuda")
+    want = torch.einsum("rgjm,rgjn->gmn", dz.double(), u.double()).float()
+    outs = []
+    for nblk in (7, 64):
+        part, dP = torch.empty(nblk, 1024, device="cuda"), torch.empty(4, 16, 16, device="cuda")
+        rc = A.lib().a3gc_train_adjacency_grad(dz.data_ptr(), u.data_ptr(), R, H, part.data_ptr(), nblk, dP.data_ptr(), _lib.stream_ptr(dz.device))
+        _lib.check(rc, "a3gc_train_adjacency_grad")
+        assert rel_l2(dP.cpu(), want.cpu()) <= 2e-6
+        outs.append(dP.clone())
+    part, dP = torch.empty(64, 1024, device="cuda"), torch.empty(4, 16, 16, device="cuda")
+    A.lib().a3gc_train_adjacency_grad(dz.data_ptr(), u.data_ptr(), R, H, part.data_ptr(), 64, dP.data_ptr(), _lib.stream_ptr(dz.device))
+    assert torch.equal(dP, outs[1])
