@@ -110,50 +110,65 @@ __global__ void __launch_bounds__(256) hprev_split_mixed_kernel(const float4* __
 // Adjacency gradients of one direction: dP_g[m][n] = sum over records r and units j of dz[r][g][j][m] * u[r][g][j][n]
 // (the autograd bmm + sum of training.py; dz is what the backward chain left in place of the gates, u the pre-mix
 // accumulators of the tape, both [records][4][H][16]).  One pass over the two arrays at HBM speed instead of four batched
-// 16 x H x 16 GEMMs: a block walks records blockIdx.x, blockIdx.x + gridDim.x, ...; thread (js, mb, nb) owns the 4 x 4 block
-// (m = 4 mb.., n = 4 nb..) of all four gates for the units j = js (mod 16); the 16 unit slices meet in shared memory and
-// the blocks' partial results are summed in a fixed order by adjacency_grad_reduce_kernel (deterministic).
+// 16 x H x 16 GEMMs: block (x, g) walks records x, x + gridDim.x, ... of gate g; the two H x 16 tiles of a record (16 KB each
+// at H = 256, contiguous) are staged in shared memory by cp.async, double buffered -- a first version that read them
+// straight into registers had 16 KB per SM in flight and reached a third of the HBM rate; thread (js, mb, nb) owns the
+// 4 x 4 block (m = 4 mb.., n = 4 nb..) for the units j = js (mod 16); the 16 unit slices meet in shared memory and the
+// blocks' partial results are summed in a fixed order by adjacency_grad_reduce_kernel (deterministic).
 __global__ void __launch_bounds__(256) adjacency_grad_kernel(const float4* __restrict__ dz, const float4* __restrict__ u,
                                                              float* __restrict__ partial, int64_t records, int H) {
-  extern __shared__ __align__(16) float red[];            // [16 slices][4 gates][256]
+  extern __shared__ __align__(16) float4 stage[];         // [2 buffers][dz tile | u tile], H * 4 float4 per tile
+  const int g = blockIdx.y, tile4 = H * 4;
   const int js = threadIdx.x >> 4, mb = (threadIdx.x >> 2) & 3, nb = threadIdx.x & 3;
-  float acc[4][4][4];
+  float acc[4][4];
 #pragma unroll
-  for (int g = 0; g < 4; ++g)
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[g][a][b] = 0.f;
-  const int64_t rec4 = (int64_t)4 * H * 4;                // float4 per record
-  for (int64_t r = blockIdx.x; r < records; r += gridDim.x) {
-    const float4* dr = dz + r * rec4;
-    const float4* ur = u + r * rec4;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-#pragma unroll 4
-      for (int j = js; j < H; j += 16) {
-        const float4 a = __ldg(dr + ((int64_t)g * H + j) * 4 + mb);
-        const float4 b = __ldg(ur + ((int64_t)g * H + j) * 4 + nb);
-        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-          for (int y = 0; y < 4; ++y) acc[g][x][y] = fmaf(av[x], bv[y], acc[g][x][y]);
-      }
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  auto fetch = [&](int64_t r, int buf) {
+    const float4* dr = dz + (r * 4 + g) * tile4;
+    const float4* ur = u + (r * 4 + g) * tile4;
+    float4* sd = stage + (size_t)buf * 2 * tile4;
+    for (int i = threadIdx.x; i < tile4; i += blockDim.x) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sd + i)), "l"(dr + i));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sd + tile4 + i)), "l"(ur + i));
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int buf = 0;
+  if ((int64_t)blockIdx.x < records) fetch(blockIdx.x, 0);
+  for (int64_t r = blockIdx.x; r < records; r += gridDim.x) {
+    const int64_t rn = r + gridDim.x;
+    if (rn < records) {
+      fetch(rn, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float4* sd = stage + (size_t)buf * 2 * tile4;
+    const float4* su = sd + tile4;
+#pragma unroll 4
+    for (int j = js; j < H; j += 16) {
+      const float4 a = sd[j * 4 + mb], b = su[j * 4 + nb];
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(av[x], bv[y], acc[x][y]);
+    }
+    __syncthreads();                                       // the buffer is refilled two iterations later
+    buf ^= 1;
   }
+  float* red = reinterpret_cast<float*>(stage);            // [16 slices][256]
 #pragma unroll
-  for (int g = 0; g < 4; ++g)
+  for (int x = 0; x < 4; ++x)
 #pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-      for (int y = 0; y < 4; ++y) red[(js * 4 + g) * 256 + (4 * mb + x) * 16 + 4 * nb + y] = acc[g][x][y];
+    for (int y = 0; y < 4; ++y) red[js * 256 + (4 * mb + x) * 16 + 4 * nb + y] = acc[x][y];
   __syncthreads();
-  for (int o = threadIdx.x; o < 4 * 256; o += blockDim.x) {
-    float sum = 0.f;
-    for (int sl = 0; sl < 16; ++sl) sum += red[(sl * 4 + o / 256) * 256 + o % 256];
-    partial[(size_t)blockIdx.x * 1024 + o] = sum;
-  }
+  float sum = 0.f;
+  for (int sl = 0; sl < 16; ++sl) sum += red[sl * 256 + threadIdx.x];
+  partial[((size_t)blockIdx.x * 4 + g) * 256 + threadIdx.x] = sum;
 }
 
 __global__ void adjacency_grad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dP, int nblocks) {
@@ -222,9 +237,10 @@ int train_hprev_split_mixed(const float* hp, const float* h0, const float* mask,
 
 int train_adjacency_grad(const float* dz, const float* u, int64_t records, int hidden, float* partial, int nblocks, float* dP,
                          cudaStream_t stream) {
-  const size_t smem = (size_t)16 * 4 * 256 * sizeof(float);
+  size_t smem = (size_t)2 * 2 * hidden * 16 * sizeof(float);           // two buffers of (dz tile | u tile)
+  if (smem < (size_t)16 * 256 * sizeof(float)) smem = (size_t)16 * 256 * sizeof(float);
   A3GC_CUDA_TRY(cudaFuncSetAttribute(adjacency_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  adjacency_grad_kernel<<<nblocks, 256, smem, stream>>>(reinterpret_cast<const float4*>(dz), reinterpret_cast<const float4*>(u), partial,
+  adjacency_grad_kernel<<<dim3((unsigned)nblocks, 4), 256, smem, stream>>>(reinterpret_cast<const float4*>(dz), reinterpret_cast<const float4*>(u), partial,
                                                         records, hidden);
   A3GC_LAUNCH_CHECK("adjacency_grad_kernel");
   adjacency_grad_reduce_kernel<<<4, 256, 0, stream>>>(partial, dP, nblocks);
