@@ -54,7 +54,7 @@ class Tape(C.Structure):
 
 
 class TapeGrads(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("dzm", "dep", "dqs", "dqp", "dap")]
+    _fields_ = [(n, C.c_void_p) for n in ("dzm", "dep", "dqs", "dqp", "dap", "dzm_hi16", "dzm_lo16")]
 
 
 class NetParams(C.Structure):

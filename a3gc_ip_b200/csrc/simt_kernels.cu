@@ -8,6 +8,7 @@
 // the 16 node values of feature k as four broadcast 128-bit loads and owns all 15 nodes of its
 // column -- which makes the 15x15 adjacency mix a purely in-register operation.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace a3gc {
 namespace {
@@ -620,6 +621,18 @@ struct BwdDir {
   float* dh0; float* dc0;               // [B][15][H] gradients of the initial state (nullptr = skip)
   int reverse;
 };
+// One element of grads.dzm: plain fp32, or -- when the caller passed the bf16 arrays (the "mixed" form of the hoisted GEMMs,
+// include/a3gc_b200.h) -- the TF32-exact head in dzm plus bf16(head) and bf16(remainder), which saves the separate split
+// pass over the largest operand of the training step.  (Packing the bf16 halves of a unit pair into one 32-bit store through a
+// lane shuffle was measured: phase F 38 k -> 56 k cycles per step, not kept.)
+__device__ __forceinline__ void emit_dzm(const a3gc_tape_grads& gr, size_t idx, float v) {
+  if (gr.dzm_hi16 == nullptr) { gr.dzm[idx] = v; return; }
+  const float h = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+  gr.dzm[idx] = h;
+  gr.dzm_hi16[idx] = __bfloat16_as_ushort(__float2bfloat16_rn(h));
+  gr.dzm_lo16[idx] = __bfloat16_as_ushort(__float2bfloat16_rn(v - h));
+}
+
 struct BwdGeom {
   const float* dy; int64_t syb, syt, yld;   // dY element (b, t, n, d*H + j)
   a3gc_tape tape;
@@ -811,9 +824,9 @@ lstm_train_bwd_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
         mix15(dz[q], PT + q * 256, m);
         store16(dzm + ((size_t)q * BT * H + task) * kNodesPad, m);
         if (b < g.B) {   // [D][B][T][15][4H], column q*H + j: rows match x [B,T,15,F], so dW and dX are plain GEMMs
-          float* zp = gr.dzm + (nm0 + (size_t)b * g.T * kNodes) * 4 * H + (size_t)q * H + j;
+          const size_t zi = (nm0 + (size_t)b * g.T * kNodes) * 4 * H + (size_t)q * H + j;
 #pragma unroll
-          for (int n = 0; n < kNodes; ++n) zp[(size_t)n * 4 * H] = m[n];
+          for (int n = 0; n < kNodes; ++n) emit_dzm(gr, zi + (size_t)n * 4 * H, m[n]);
         }
       }
     }
@@ -1673,9 +1686,9 @@ lstm_train_bwd_blk_kernel(BwdDir d0, BwdDir d1, BwdGeom g) {
         mix15(dz[q], PT + q * 256, m);
         store16_swz(dzm + ((size_t)q * BT * H + task) * kNodesPad, m, TCORE != 0 && ((j >> 1) & 1));
         if (b < g.B) {
-          float* zp = gr.dzm + (nm0 + (size_t)b * g.T * kNodes) * 4 * H + (size_t)q * H + j;
+          const size_t zi = (nm0 + (size_t)b * g.T * kNodes) * 4 * H + (size_t)q * H + j;
 #pragma unroll
-          for (int n = 0; n < kNodes; ++n) zp[(size_t)n * 4 * H] = m[n];
+          for (int n = 0; n < kNodes; ++n) emit_dzm(gr, zi + (size_t)n * 4 * H, m[n]);
         }
       }
     }

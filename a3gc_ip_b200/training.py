@@ -267,12 +267,17 @@ class _LayerTrainFn(torch.autograd.Function):
             "dqp": torch.empty(nd, T, B, H, **f32) if att else None,
             "dap": torch.empty(nd, T, B, 16, **f32) if att else None,
         }
+        # mixed mode: the backward writes dzm directly as (TF32-exact head, bf16 head, bf16 remainder) -- no split pass over it
+        dzm_mixed = _gemm_mode() == "mixed"
+        if dzm_mixed:
+            gr["dzm_hi16"] = torch.empty(nd, B, T, NUM_NODES, 4 * H, dtype=torch.bfloat16, device=dev)
+            gr["dzm_lo16"] = torch.empty(nd, B, T, NUM_NODES, 4 * H, dtype=torch.bfloat16, device=dev)
         dh0 = [torch.empty(B, NUM_NODES, H, **f32) for _ in range(nd)]
         dc0 = [torch.empty(B, NUM_NODES, H, **f32) for _ in range(nd)]
         cells = (_lib.CellParams * nd)(*[_cell_params_struct(variant, params[d]) for d in range(nd)])
         rev = (C.c_int * nd)(*[int(r) for r in reverse])
         tp = _lib.Tape(*[_lib.ptr(tape[k]) for k in ("gates", "u", "c", "hh", "e", "hp", "a", "q", "s")])
-        tg = _lib.TapeGrads(*[_lib.ptr(gr[k]) for k in ("dzm", "dep", "dqs", "dqp", "dap")])
+        tg = _lib.TapeGrads(*[_lib.ptr(gr.get(k)) for k in ("dzm", "dep", "dqs", "dqp", "dap", "dzm_hi16", "dzm_lo16")])
         L = _lib.lib()
         v = _lib.VARIANT[variant]
         with torch.cuda.device(dev):
@@ -298,7 +303,10 @@ class _LayerTrainFn(torch.autograd.Function):
         grads: List[Optional[Tensor]] = []
         for d in range(nd):
             ps = dict(zip(names, params[d]))
-            dzm2d = _split(gr["dzm"][d].reshape(R, 4 * H))
+            if dzm_mixed:
+                dzm2d = _Split(gr["dzm"][d].reshape(R, 4 * H), None, gr["dzm_hi16"][d].reshape(R, 4 * H), gr["dzm_lo16"][d].reshape(R, 4 * H))
+            else:
+                dzm2d = _split(gr["dzm"][d].reshape(R, 4 * H))
             # S = [x | h_prev]: h_prev is h' of the previous step of this direction (h0 at its first step), masked
             if one_s:
                 _hprev_split(tape["hp"][d], h0[d], None if hmask is None else hmask[d], reverse[d], into=S, col0=F)
@@ -457,7 +465,7 @@ class _GruLayerTrainFn(torch.autograd.Function):
         cells = (_lib.CellParams * nd)(*[_gru_params_struct(params[d]) for d in range(nd)])
         rev = (C.c_int * nd)(*[int(r) for r in reverse])
         tp = _lib.Tape(_lib.ptr(tape["gates"]), None, _lib.ptr(tape["c"]), _lib.ptr(tape["hh"]), None, _lib.ptr(tape["hp"]), None, None, None)
-        tg = _lib.TapeGrads(_lib.ptr(gr["dzm"]), _lib.ptr(gr["dep"]), _lib.ptr(gr["dqs"]), None, None)
+        tg = _lib.TapeGrads(_lib.ptr(gr["dzm"]), _lib.ptr(gr["dep"]), _lib.ptr(gr["dqs"]), None, None, None, None)
         L = _lib.lib()
         v = _lib.VARIANT["GGRU"]
         with torch.cuda.device(dev):

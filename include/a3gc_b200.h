@@ -230,6 +230,11 @@ typedef struct a3gc_tape_grads {
   float* dqs;   /* [D][T][B][H]        node sums of dep (dWq)                                */
   float* dqp;   /* [D][T][B][H]        grads of the relu pre-activation of q_t (dWa)         */
   float* dap;   /* [D][T][B][16]       grads of the sigmoid pre-activation of a_t (du, dbu)  */
+  /* ABI 3, LSTM family, optional (NULL = dzm is plain fp32): dzm in the "mixed" form of the hoisted GEMMs, written by the
+     backward itself -- dzm then holds the TF32-exact head, these two bf16(head) and bf16(value - head), same shape.
+     The graph-GRU backward ignores them. */
+  uint16_t* dzm_hi16;
+  uint16_t* dzm_lo16;
 } a3gc_tape_grads;
 
 /* Workspace for a3gc_layer_train_forward AND a3gc_layer_backward of this shape (the larger of the two). */
