@@ -54,8 +54,9 @@ struct GruLayerParams {
 enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_ACC_FULL = 2 * kMaxStages, BAR_ACC_EMPTY = BAR_ACC_FULL + 2, BAR_H = BAR_ACC_EMPTY + 2,
        BAR_HFREE, BAR_COUNT };
 
-__host__ __device__ inline size_t gru_fixed_smem_bytes() {
-  return (size_t)kEpiWarps * kWstFloats * 4 + 256 * 4 + 256 * 4 + 32 * 8 + 16;   // wst, bias, Pfrag, barriers, tmem slot
+// fp32-split mode: no separate transposition buffers (each warp borrows 2 x 512 bytes of the state image, see `wst`)
+__host__ __device__ inline size_t gru_fixed_smem_bytes(bool split) {
+  return (split ? (size_t)0 : (size_t)kEpiWarps * kWstFloats * 4) + 256 * 4 + 256 * 4 + 32 * 8 + 16;   // wst, bias, Pfrag, barriers, tmem slot
 }
 
 __device__ __forceinline__ uint32_t img_off(int k, int row) {
@@ -83,7 +84,7 @@ tc_gru_layer_kernel(const GruLayerParams p) {
   uint8_t* hbuf = smem;                                              // operand image of the mixed state h~: [NP][H/8][128][8]
   uint8_t* ring = hbuf + (size_t)NP * H * 256;
   float* staging = reinterpret_cast<float*>(ring + (size_t)S * kStageBytes);
-  float* biasg = staging + kEpiWarps * kWstFloats;                   // [3][64]  (+ 64 pad)
+  float* biasg = staging + (SPLIT ? 0 : kEpiWarps * kWstFloats);     // [3][64]  (+ 64 pad)
   uint32_t* Pfrag = reinterpret_cast<uint32_t*>(biasg + 256);        // [hi, lo][32 lanes][4 regs]
   uint64_t* bars = reinterpret_cast<uint64_t*>(Pfrag + 256);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
@@ -253,7 +254,18 @@ tc_gru_layer_kernel(const GruLayerParams p) {
     const int ug = ew >> 2;
     const int ubase = 16 * ug;                       // this warp's 16 units of the CTA's 64
     const int tq = lane >> 2, tr = lane & 3;
+    // Warp-private transposition buffer (8 columns x 32 rows fp32, as two 512-byte halves: columns 0..3 at wst, 4..7 at wst2).
+    // bf16 mode: a separate allocation.  fp32-split mode: rows 32qd..32qd+31 of K chunk 2ug+1 of the CTA's own block of the
+    // state image, hi and lo part -- the bytes that this warp itself rewrites last in mix_store (unit block 1), and that
+    // nobody reads between BAR_HFREE (every MMA on h~_{t-1} has completed, so every outgoing copy has landed) and the next
+    // publish.  The 16 KB this saves are a fourth ring slot at H = 256.
     float* wst = staging + ew * kWstFloats;
+    float* wst2 = wst + 4 * 32;
+    if (SPLIT) {
+      wst = reinterpret_cast<float*>(hbuf + ((size_t)((int)c * 8 + 2 * ug + 1) * kRows + 32 * qd) * 16);
+      wst2 = wst + (size_t)H * 64;
+    }
+    const float* wsp = (tq < 4 ? wst : wst2) + (tq & 3) * 32;        // column tq (B-fragment reads)
     const uint32_t tmem_row = tmem + ((uint32_t)(qd * 32) << 16);
     const int ycol = blockIdx.y * H + (int)c * 64;
     // gate-math ownership (TMEM-native): this thread = accumulator row `row`, units ubase .. ubase+15
@@ -322,19 +334,23 @@ tc_gru_layer_kernel(const GruLayerParams p) {
       for (int ub = 0; ub < 2; ++ub) {
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) wst[j * 32 + (lane ^ (8 * (j & 3)))] = h[8 * ub + j];
+        for (int j = 0; j < 8; ++j) (j < 4 ? wst : wst2)[(j & 3) * 32 + (lane ^ (8 * (j & 3)))] = h[8 * ub + j];
         __syncwarp();
         const int k = (int)c * 64 + ubase + 8 * ub + 2 * tr;
+        float2 u0[2], u1[2];
 #pragma unroll
         for (int sq = 0; sq < 2; ++sq) {
-          const float* sp = wst + tq * 32;
-          const float2 u0 = *reinterpret_cast<const float2*>(sp + ((16 * sq + 2 * tr) ^ swz));
-          const float2 u1 = *reinterpret_cast<const float2*>(sp + ((16 * sq + 2 * tr + 8) ^ swz));
+          u0[sq] = *reinterpret_cast<const float2*>(wsp + ((16 * sq + 2 * tr) ^ swz));
+          u1[sq] = *reinterpret_cast<const float2*>(wsp + ((16 * sq + 2 * tr + 8) ^ swz));
+        }
+        if (SPLIT && ub == 1) __syncwarp();          // the results of unit block 1 go to the bytes the buffer borrows
+#pragma unroll
+        for (int sq = 0; sq < 2; ++sq) {
           float z[4] = {0.f, 0.f, 0.f, 0.f};
           if (SPLIT) {
             uint32_t bh0, bl0, bh1, bl1;
-            ptx::split_pair_f16(u0.x, u0.y, bh0, bl0);
-            ptx::split_pair_f16(u1.x, u1.y, bh1, bl1);
+            ptx::split_pair_f16(u0[sq].x, u0[sq].y, bh0, bl0);
+            ptx::split_pair_f16(u1[sq].x, u1[sq].y, bh1, bl1);
             float z2[4] = {0.f, 0.f, 0.f, 0.f}, z3[4] = {0.f, 0.f, 0.f, 0.f};
             ptx::mma_16816_f16(z, ah, bh0, bh1);
             ptx::mma_16816_f16(z2, al, bh0, bh1);
@@ -342,7 +358,7 @@ tc_gru_layer_kernel(const GruLayerParams p) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) z[j] += z2[j] + z3[j];
           } else {
-            const __half2 h0 = __floats2half2_rn(u0.x, u0.y), h1 = __floats2half2_rn(u1.x, u1.y);
+            const __half2 h0 = __floats2half2_rn(u0[sq].x, u0[sq].y), h1 = __floats2half2_rn(u1[sq].x, u1[sq].y);
             ptx::mma_16816_f16(z, ah, *reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
           }
 #pragma unroll
@@ -536,7 +552,7 @@ int tc_gru_layer_launch(const LayerArgs& a, const uint16_t* x_img, char* wbase, 
   A3GC_CUDA_TRY(cudaGetDevice(&dev));
   A3GC_CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const size_t stage_bytes = (size_t)2 * NP * 2 * 192 * 16;
-  const size_t fixed = (size_t)NP * H * 256 + gru_fixed_smem_bytes();
+  const size_t fixed = (size_t)NP * H * 256 + gru_fixed_smem_bytes(split);
   int S = kMaxStages;
   if (const char* e = getenv("A3GC_TC_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= kMaxStages) S = v; }
   while (S > 1 && fixed + (size_t)S * stage_bytes > (size_t)smem_max) --S;

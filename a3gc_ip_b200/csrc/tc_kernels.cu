@@ -73,7 +73,8 @@ struct TcLayerParams {
   const uint16_t* x_img;    // [tiles][T][F/16][NP][2][128][8]
   float* y; int64_t syb, syt, yld;   // fp32 output (may be null)
   uint16_t* y_img; int y_kf;         // next layer's operand image (may be null) and its K/16
-  int B, T, F, H, out_act, C, S, trace;
+  int B, T, F, H, out_act, C, S, trace;   // S = slots of the weight ring
+  int SX;                            // slots of the x-image ring
   int chunk;                         // bytes per bulk copy of the weight / x stream
   int xsplit;                        // x part as two N=128 MMAs per K block
   int xdefer;                        // first x segment only after the gate phase of the step
@@ -95,13 +96,17 @@ struct TcLayerParams {
 // barrier slots in shared memory
 // BAR_H / BAR_HHAT / BAR_Q are ARRAYS of 4 barriers, one per source CTA of the cluster: the MMA warp consumes the K range
 // of a chunk as soon as THAT chunk has arrived, its own chunk (available without any DSMEM transfer) first
-enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_ACC_FULL = 2 * kMaxStages, BAR_ATT_FULL = BAR_ACC_FULL + 2, BAR_ATT2_FULL,
+// BAR_FULL / BAR_EMPTY: slots of the weight ring (every stage); BAR_XFULL / BAR_XEMPTY: slots of the x-image ring (x stages only)
+enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_XFULL = 2 * kMaxStages, BAR_XEMPTY = 3 * kMaxStages,
+       BAR_ACC_FULL = 4 * kMaxStages, BAR_ATT_FULL = BAR_ACC_FULL + 2, BAR_ATT2_FULL,
        BAR_ACC_EMPTY, BAR_A = BAR_ACC_EMPTY + 2, BAR_HFREE, BAR_A1FREE, BAR_H, BAR_HHAT = BAR_H + 4, BAR_Q = BAR_HHAT + 4,
        BAR_COUNT = BAR_Q + 4 };
-constexpr int kBarSlots = 40;
+constexpr int kBarSlots = 56;
 
-__host__ __device__ inline size_t tc_fixed_smem_bytes(int C) {
-  return (size_t)kEpiWarps * kWstFloats * 4   // wst
+// fp32-split mode: the warp-private transposition buffers are not a separate allocation -- each warp uses the 2 x 512 bytes of
+// the state operand image it will itself overwrite at the end of the gate phase (see `wst` in the epilogue)
+__host__ __device__ inline size_t tc_fixed_smem_bytes(int C, bool split) {
+  return (split ? (size_t)0 : (size_t)kEpiWarps * kWstFloats * 4)   // wst
          + (size_t)C * 128 * 4                // apart
          + 4 * 128 * 4                        // ahalf
          + 256 * 4 + 64 * 4 * 2 + 16 * 4      // biasg, bs, u, bu
@@ -132,7 +137,6 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
   constexpr int NP = SPLIT ? 2 : 1;
   constexpr uint32_t kBBytes = NP * 2 * 256 * 16;     // one K=16 block of gate weights (all parts)
   constexpr uint32_t kABytes = NP * 2 * 128 * 16;     // one K=16 block of x rows
-  constexpr uint32_t kStageBytes = kBBytes + kABytes;
   constexpr uint32_t kA1Block = NP * 2 * 128 * 16;    // one K=16 block of [Wh ; Wa] rows
   constexpr uint32_t kA2Block = NP * 2 * 64 * 16;     // one K=16 block of Wq rows
   constexpr uint32_t kHBlock = 8 * kRows * 16;         // this CTA's 64 units of one operand part: 8 K-chunks
@@ -146,10 +150,17 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
   const int warp = threadIdx.x >> 5;
   const int n1 = p.n1, n2 = p.n2;
 
+  // Two rings instead of one ring of (weights + x) slots: every stage takes a 16 KB (fp32-split) weight slot, only the x
+  // stages take an 8 KB x-image slot.  The ring is latency-bound (a slot turns around in ~2 k cycles: copy ~1 k, its MMAs,
+  // the commit -> producer hand-off), so its rate is (bytes in flight) / turn: at H = 256 the 128 KB state image left room
+  // for three 24 KB slots; with the transposition buffers aliased into the state image (below) the same shared memory holds
+  // four weight slots + three x slots, and the recurrent / attention stages no longer occupy x space they do not use.
+  const int SX = p.SX;
   uint8_t* hbuf = smem;
-  uint8_t* ring = hbuf + (size_t)NP * H * 256;
-  float* staging = reinterpret_cast<float*>(ring + (size_t)S * kStageBytes);   // [16 warps][8][32]
-  float* apart = staging + kEpiWarps * kWstFloats;   // [C][128]
+  uint8_t* ring = hbuf + (size_t)NP * H * 256;                // weight slots
+  uint8_t* xring = ring + (size_t)S * kBBytes;                // x-image slots
+  float* staging = reinterpret_cast<float*>(xring + (size_t)SX * kABytes);   // [16 warps][8][32]  (bf16 mode only)
+  float* apart = staging + (SPLIT ? 0 : kEpiWarps * kWstFloats);   // [C][128]
   float* ahalf = apart + C * 128;            // [4][128]
   float* biasg = ahalf + 4 * 128;            // [4 gates][64 units]
   float* bss = biasg + 256;                  // [64]
@@ -162,7 +173,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
   // ------------------------------------------------------------------ setup
   if (threadIdx.x == 0) {
     for (int i = 0; i < BAR_COUNT; ++i)
-      ptx::mbar_init(&bars[i], (i == BAR_HFREE || i == BAR_A1FREE) ? (uint32_t)C : (i >= BAR_FULL && i < BAR_FULL + kMaxStages) ? 2u : 1u);
+      ptx::mbar_init(&bars[i], (i == BAR_HFREE || i == BAR_A1FREE) ? (uint32_t)C : 1u);
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
@@ -196,11 +207,10 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
     // ================================================================ producers: weights / x -> ring
     // One thread issues a bulk copy every ~440 cycles whatever its size (tests/diag_stream_rate.py: 444 cycles per copy for
     // 4 KB .. 48 KB; 222 / 131 cycles with 2 / 4 issuing warps), and an H = 256, F = 512 step needs 92 copies (two per x
-    // stage): 41 k cycles of ONE thread's time for a 44 k-cycle step; with three ring slots the two back-to-back copies of
-    // an x stage are also ~900 of the ~2.2 k cycles a slot needs to turn around.  So up to three warps share the stream, all
-    // walking the same static stage sequence:  nprod = 2: stage i is issued by producer i % 2;  nprod = 3: the weight (B)
-    // copy of stage i by producer i % 2 and the x-image (A) copy of every x stage by the third, so the two copies of a stage
-    // are issued concurrently.  Every FULL barrier takes two arrivals (B side, A side).
+    // stage): 41 k cycles of ONE thread's time for a 44 k-cycle step.  So up to three warps share the stream, all walking the
+    // same static stage sequence:  nprod = 2: stage i is issued by producer i % 2;  nprod = 3: the weight (B) copy of stage i
+    // by producer i % 2 and the x-image (A) copy of every x stage by the third, which follows its own ring and therefore runs
+    // ahead of the weight stream across the recurrent / attention stages.
     const uint32_t my = warp == 0 ? 0u : (uint32_t)(warp - (1 + kEpiWarps));
     const uint32_t nprod = (uint32_t)p.nprod;
     const bool split_a = nprod == 3;                 // producer 2 = the A side
@@ -209,30 +219,30 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
     // t+1 cut into three segments placed around the two attention GEMMs of step t, so that the tensor pipe has work
     // while the epilogue warps are busy and the attention GEMMs are never queued behind a long x-part.
     if ((threadIdx.x & 31) == 0 && my < nprod) {
-      uint32_t st = 0, ph = 0;            // ring slot and the parity of its current fill (no div / mod in the loop)
+      uint32_t ws = 0, wph = 0;           // weight-ring slot and the parity of its current fill (no div / mod in the loop)
+      uint32_t xs = 0, xph = 0;           // the same for the x-image ring
       uint32_t turn = 0;                  // whose stage this is
       const uint32_t chunk = (uint32_t)p.chunk;
       auto load_stage = [&](const void* bsrc, uint32_t bbytes, const void* asrc, uint32_t abytes) {
-        uint8_t* dst = ring + st * kStageBytes;
-        const bool b_side = my < nb && turn == my, a_side = split_a ? my == 2u : b_side;
-        if (b_side || a_side) ptx::mbar_wait(&bars[BAR_EMPTY + st], ph ^ 1u);
+        const bool b_side = my < nb && turn == my, a_side = abytes != 0 && (split_a ? my == 2u : b_side);
         if (b_side) {
-          ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + st], bbytes);
+          uint8_t* dst = ring + ws * kBBytes;
+          ptx::mbar_wait(&bars[BAR_EMPTY + ws], wph ^ 1u);
+          ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + ws], bbytes);
           // p.chunk (tuning knob) can cut the copies into pieces; measured slower than one copy per operand
           for (uint32_t o = 0; o < bbytes; o += chunk)
-            ptx::bulk_g2s(dst + o, static_cast<const uint8_t*>(bsrc) + o, min(chunk, bbytes - o), &bars[BAR_FULL + st]);
+            ptx::bulk_g2s(dst + o, static_cast<const uint8_t*>(bsrc) + o, min(chunk, bbytes - o), &bars[BAR_FULL + ws]);
         }
         if (a_side) {
-          if (abytes) {
-            ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + st], abytes);
-            for (uint32_t o = 0; o < abytes; o += chunk)
-              ptx::bulk_g2s(dst + kBBytes + o, static_cast<const uint8_t*>(asrc) + o, min(chunk, abytes - o), &bars[BAR_FULL + st]);
-          } else {
-            ptx::mbar_arrive(&bars[BAR_FULL + st]);
-          }
+          uint8_t* dst = xring + xs * kABytes;
+          ptx::mbar_wait(&bars[BAR_XEMPTY + xs], xph ^ 1u);
+          ptx::mbar_arrive_expect_tx(&bars[BAR_XFULL + xs], abytes);
+          for (uint32_t o = 0; o < abytes; o += chunk)
+            ptx::bulk_g2s(dst + o, static_cast<const uint8_t*>(asrc) + o, min(chunk, abytes - o), &bars[BAR_XFULL + xs]);
         }
         if (++turn == nb) turn = 0;
-        if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
+        if (++ws == (uint32_t)S) { ws = 0; wph ^= 1u; }
+        if (abytes != 0 && ++xs == (uint32_t)SX) { xs = 0; xph ^= 1u; }
       };
       const uint8_t* wg = reinterpret_cast<const uint8_t*>(d.wg_img) + (size_t)c * (KF + KH) * kBBytes;
       const uint8_t* a1 = reinterpret_cast<const uint8_t*>(d.a1_img) + (size_t)c * KH * kA1Block;
@@ -285,17 +295,26 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       const uint32_t hpart = (uint32_t)H * 256;
       // The issue loop runs on ONE thread whose dependent-instruction latency bounds the MMA rate, so it is kept
       // lean: ring slot / parity are counters (no div / mod), descriptors are a constant plus (address >> 4).
-      uint32_t st = 0, ph = 0;
+      uint32_t ws = 0, wph = 0, xs = 0, xph = 0;
       uint32_t empty_k[2] = {0, 0};     // completions of BAR_ACC_EMPTY[b] consumed so far (no-attention variant)
-      const uint32_t ring_addr = ptx::smem_u32(ring);
-      auto wait_stage = [&]() -> uint32_t {
-        ptx::mbar_wait(&bars[BAR_FULL + st], ph);
+      const uint32_t ring_addr = ptx::smem_u32(ring), xring_addr = ptx::smem_u32(xring);
+      auto wait_stage = [&]() -> uint32_t {          // next weight slot
+        ptx::mbar_wait(&bars[BAR_FULL + ws], wph);
         ptx::tc_fence_after();
-        return ring_addr + st * kStageBytes;
+        return ring_addr + ws * kBBytes;
+      };
+      auto wait_xstage = [&]() -> uint32_t {         // next x-image slot
+        ptx::mbar_wait(&bars[BAR_XFULL + xs], xph);
+        ptx::tc_fence_after();
+        return xring_addr + xs * kABytes;
       };
       auto release_stage = [&]() {
-        ptx::umma_commit(&bars[BAR_EMPTY + st]);
-        if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
+        ptx::umma_commit(&bars[BAR_EMPTY + ws]);
+        if (++ws == (uint32_t)S) { ws = 0; wph ^= 1u; }
+      };
+      auto release_xstage = [&]() {
+        ptx::umma_commit(&bars[BAR_XEMPTY + xs]);
+        if (++xs == (uint32_t)SX) { xs = 0; xph ^= 1u; }
       };
       const uint64_t dA = ptx::make_smem_desc(0, kRows * 16, 128);
       const uint64_t dB256 = ptx::make_smem_desc(0, 256 * 16, 128), dB128 = ptx::make_smem_desc(0, 128 * 16, 128),
@@ -325,14 +344,16 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       const bool xsplit = p.xsplit != 0;
       auto xblocks = [&](uint32_t dcol, int kb0, int kb1) {
         for (int kb = kb0; kb < kb1; ++kb) {
+          const uint32_t xa = wait_xstage();
           const uint32_t sa = wait_stage();
           if (xsplit) {
-            block_mma(dcol, sa + kBBytes, kABytes / NP, sa, kBBytes / NP, dB256, idesc128, kb == 0);
-            block_mma(dcol + 128, sa + kBBytes, kABytes / NP, sa + 128 * 16, kBBytes / NP, dB256, idesc128, kb == 0);
+            block_mma(dcol, xa, kABytes / NP, sa, kBBytes / NP, dB256, idesc128, kb == 0);
+            block_mma(dcol + 128, xa, kABytes / NP, sa + 128 * 16, kBBytes / NP, dB256, idesc128, kb == 0);
           } else {
-            block_mma(dcol, sa + kBBytes, kABytes / NP, sa, kBBytes / NP, dB256, idesc256, kb == 0);
+            block_mma(dcol, xa, kABytes / NP, sa, kBBytes / NP, dB256, idesc256, kb == 0);
           }
           release_stage();
+          release_xstage();
         }
       };
       xblocks(0, 0, KF);
@@ -433,7 +454,6 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
     const int ug = ew >> 2;
     const int tq = lane >> 2, tr = lane & 3;
     const bool pad_hi = tq == 7;
-    float* wst = staging + ew * kWstFloats;
     const uint32_t tmem_row = tmem + ((uint32_t)(qd * 32) << 16);
     const int ycol = blockIdx.y * H + (int)c * 64;
     const int ubase = 16 * ug;                       // attention outputs: first unit (within the CTA's 64) of this warp
@@ -444,6 +464,21 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
     // its tape stores are measurably faster with 16 contiguous units per warp: 34 vs 40 ms per stage-1 step.)
     constexpr int kUbs = TRAIN ? 8 : 32;             // unit distance between the two unit blocks of a warp
     const int gbase = TRAIN ? 16 * ug : 8 * ug;
+    // Warp-private transposition buffer: 8 accumulator columns x 32 rows fp32 = 1 KB, as two 512-byte halves (columns 0..3 at
+    // wst, columns 4..7 at wst2).  bf16 mode: a separate allocation.  fp32-split mode: the rows 32qd..32qd+31 of the K chunk of
+    // this warp's SECOND unit block in the CTA's own block of the state image, hi part and lo part -- 2 x 512 bytes that only
+    // this warp writes, and only at the end of its gate phase (store_units of unit block 1, after the last use of the buffer,
+    // rewrites every byte).  The region is dead during the gate phase: the phase starts after BAR_HFREE (every MMA of the
+    // cluster that reads h'_{t-1} has completed, and therefore every outgoing copy of the block has landed), peers never
+    // write into a CTA's own block, and this CTA's q rows are written after the gate phase.
+    float* wst = staging + ew * kWstFloats;
+    float* wst2 = wst + 4 * 32;
+    if (SPLIT) {
+      const int ch1 = (gbase + kUbs) >> 3;
+      wst = reinterpret_cast<float*>(hbuf + ((size_t)((int)c * 8 + ch1) * kRows + 32 * qd) * 16);
+      wst2 = wst + (size_t)H * 64;                   // the lo part of the image is H * 256 bytes further on
+    }
+    const float* wsp = (tq < 4 ? wst : wst2) + (tq & 3) * 32;      // column tq of the buffer (B-fragment reads)
     int bseq[2]; bool valid[2];
 #pragma unroll
     for (int sq = 0; sq < 2; ++sq) { bseq[sq] = tile * kSeqTile + 2 * qd + sq; valid[sq] = bseq[sq] < p.B; }
@@ -644,7 +679,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
             }
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) wst[j * 32 + (lane ^ (8 * (j & 3)))] = v[j];
+            for (int j = 0; j < 8; ++j) (j < 4 ? wst : wst2)[(j & 3) * 32 + (lane ^ (8 * (j & 3)))] = v[j];
             __syncwarp();
           }
           // z[16 nodes x 8 units] = P_g (16x16) . U (16 nodes x 8 units) per sequence on the warp-level tensor path,
@@ -654,9 +689,8 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
           const float2 bias = *reinterpret_cast<const float2*>(biasg + g * 64 + gbase + kUbs * ub + 2 * tr);
 #pragma unroll
           for (int sq = 0; sq < 2; ++sq) {
-            const float* sp = wst + tq * 32;
-            const float2 u0 = *reinterpret_cast<const float2*>(sp + ((16 * sq + 2 * tr) ^ swz));        // nodes 2tr, 2tr+1 of unit column tq
-            const float2 u1 = *reinterpret_cast<const float2*>(sp + ((16 * sq + 2 * tr + 8) ^ swz));    // nodes 2tr+8, 2tr+9
+            const float2 u0 = *reinterpret_cast<const float2*>(wsp + ((16 * sq + 2 * tr) ^ swz));        // nodes 2tr, 2tr+1 of unit column tq
+            const float2 u1 = *reinterpret_cast<const float2*>(wsp + ((16 * sq + 2 * tr + 8) ^ swz));    // nodes 2tr+8, 2tr+9
             float z[4] = {bias.x, bias.y, bias.x, bias.y};
             if (SPLIT) {
               uint32_t bh0, bl0, bh1, bl1;
@@ -1238,17 +1272,30 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
   int dev = 0, smem_max = 0;
   A3GC_CUDA_TRY(cudaGetDevice(&dev));
   A3GC_CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const size_t stage_bytes = (size_t)NP * (2 * 256 * 16 + 2 * 128 * 16);
-  const size_t fixed = (size_t)NP * H * 256 + tc_fixed_smem_bytes(C);
+  // two rings (weights: every stage; x image: x stages only): as many slot PAIRS as fit, then the remainder goes to single
+  // slots (H = 256, fp32: 4 weight slots of 16 KB + 3 x slots of 8 KB next to the 128 KB state image)
+  const size_t wslot = (size_t)NP * 2 * 256 * 16, xslot = (size_t)NP * 2 * 128 * 16;
+  const size_t fixed = (size_t)NP * H * 256 + tc_fixed_smem_bytes(C, split);
   int S = kMaxStages;
   if (const char* e = getenv("A3GC_TC_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= kMaxStages) S = v; }
-  while (S > 1 && fixed + (size_t)S * stage_bytes > (size_t)smem_max) --S;
-  if (fixed + (size_t)S * stage_bytes > (size_t)smem_max || S < 2) {
+  while (S > 1 && fixed + (size_t)S * (wslot + xslot) > (size_t)smem_max) --S;
+  if (fixed + (size_t)S * (wslot + xslot) > (size_t)smem_max || S < 2) {
     set_error("tc engine: shared memory budget exceeded (hidden=%d)", H);
     return A3GC_ERR_UNSUPPORTED;
   }
-  p.S = S;
-  const size_t smem = fixed + (size_t)S * stage_bytes;
+  int SW = S, SX = S;
+  if (getenv("A3GC_TC_STAGES") == nullptr) {
+    while (SW < kMaxStages && fixed + (size_t)(SW + 1) * wslot + (size_t)SX * xslot <= (size_t)smem_max) ++SW;
+    while (SX < kMaxStages && fixed + (size_t)SW * wslot + (size_t)(SX + 1) * xslot <= (size_t)smem_max) ++SX;
+  }
+  if (const char* e = getenv("A3GC_TC_WSTAGES")) { const int v = atoi(e); if (v >= 2 && v <= kMaxStages) SW = v; }
+  if (const char* e = getenv("A3GC_TC_XSTAGES")) { const int v = atoi(e); if (v >= 2 && v <= kMaxStages) SX = v; }
+  if (fixed + (size_t)SW * wslot + (size_t)SX * xslot > (size_t)smem_max) {
+    set_error("tc engine: A3GC_TC_WSTAGES / A3GC_TC_XSTAGES exceed the shared memory budget (hidden=%d)", H);
+    return A3GC_ERR_INVALID_ARG;
+  }
+  p.S = SW; p.SX = SX;
+  const size_t smem = fixed + (size_t)SW * wslot + (size_t)SX * xslot;
 
   const bool train = a.tape != nullptr;
   if (train) { p.tape = *a.tape; p.hmask = a.hmask; }
