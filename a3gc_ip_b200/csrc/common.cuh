@@ -153,5 +153,6 @@ int tc_pack_weights(int variant, int num_dirs, const a3gc_cell_params* cells, in
 size_t tc_gru_weights_bytes(int f_in, int hidden, int num_dirs, int precision);
 int tc_gru_layer_launch(const LayerArgs& a, const uint16_t* x_img, char* weights_ws, cudaStream_t stream);
 int tc_gru_pack_weights(int num_dirs, const a3gc_cell_params* cells, int f_in, int hidden, int precision, char* weights_ws, cudaStream_t stream);
+int tc_gru_read_trace(unsigned long long* host_out);
 
 }  // namespace a3gc

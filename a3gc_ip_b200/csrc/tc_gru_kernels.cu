@@ -33,6 +33,13 @@ constexpr int kThreadsTC = 64 + kEpiThreads + 32 * (kProducers - 1);
 constexpr int kMaxStages = 8;
 constexpr int kWstFloats = 8 * 32;
 
+// optional per-phase timeline of CTA (0,0) (A3GC_TC_TRACE=gru): [role 0 = epilogue, 1 = mma][step < 16][slot < 16] clock64
+__device__ unsigned long long g_gru_trace[2][16][16];
+#define GRU_TRACE(role, slot)                                                                \
+  do {                                                                                       \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t < 16) g_gru_trace[role][t][slot] = clock64(); \
+  } while (0)
+
 struct GruDir {
   const uint16_t* wx_img;   // [C][F/16][NP][2][192][8]   rows 64*g + unit of dense_{r,u,c}_in.weight
   const uint16_t* wm_img;   // [C][H/16][NP][2][192][8]   rows 64*g + unit of W'_g = dense_{r,u,c}_hid.weight @ gcn_kernel
@@ -49,6 +56,7 @@ struct GruLayerParams {
   int B, T, F, H, C, S;
   int acoll;                // A-operand collector reuse (see ptx::umma_f16_coll)
   int nprod;                // bulk-copy producer threads (1..3)
+  int trace;
 };
 
 enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_ACC_FULL = 2 * kMaxStages, BAR_ACC_EMPTY = BAR_ACC_FULL + 2, BAR_H = BAR_ACC_EMPTY + 2,
@@ -126,10 +134,16 @@ tc_gru_layer_kernel(const GruLayerParams p) {
     const uint32_t nb = split_a ? 2u : nprod;
     if ((threadIdx.x & 31) == 0 && my < nprod) {
       uint32_t st = 0, ph = 0, turn = 0;
+      const bool tr_on = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
+      unsigned long long w_empty = 0, t_begin = tr_on ? clock64() : 0;      // trace: cycles this producer waited for a free slot
       auto load_stage = [&](const void* bsrc, uint32_t bbytes, uint32_t aoff, const void* asrc, uint32_t abytes) {
         uint8_t* dst = ring + st * kStageBytes;
         const bool b_side = my < nb && turn == my, a_side = split_a ? my == 2u : b_side;
-        if (b_side || a_side) ptx::mbar_wait(&bars[BAR_EMPTY + st], ph ^ 1u);
+        if (b_side || a_side) {
+          const unsigned long long t0 = tr_on ? clock64() : 0;
+          ptx::mbar_wait(&bars[BAR_EMPTY + st], ph ^ 1u);
+          if (tr_on) w_empty += clock64() - t0;
+        }
         if (b_side) {
           ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + st], bbytes);
           ptx::bulk_g2s(dst, bsrc, bbytes, &bars[BAR_FULL + st]);
@@ -158,6 +172,7 @@ tc_gru_layer_kernel(const GruLayerParams p) {
         for (int s2 = 0; s2 < KH / 2; ++s2) load_stage(wm + (size_t)s2 * 2 * kMB, 2 * kMB, 0, nullptr, 0);
         if (t + 1 < T) xblocks(t + 1, 0, KF);
       }
+      if (tr_on) { g_gru_trace[0][15][2 * my] = w_empty; g_gru_trace[0][15][2 * my + 1] = clock64() - t_begin; }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (one thread)
@@ -170,8 +185,12 @@ tc_gru_layer_kernel(const GruLayerParams p) {
       uint32_t st = 0, ph = 0;
       uint32_t empty_k[2] = {0, 0};
       const uint32_t ring_addr = ptx::smem_u32(ring);
+      const bool tr_on = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
+      unsigned long long w_full = 0, w_h = 0, t_begin = tr_on ? clock64() : 0;   // trace: cycles waited for a full slot / for BAR_H
       auto wait_stage = [&]() -> uint32_t {
+        const unsigned long long t0 = tr_on ? clock64() : 0;
         ptx::mbar_wait(&bars[BAR_FULL + st], ph);
+        if (tr_on) w_full += clock64() - t0;
         ptx::tc_fence_after();
         return ring_addr + st * kStageBytes;
       };
@@ -207,8 +226,14 @@ tc_gru_layer_kernel(const GruLayerParams p) {
         const uint32_t b = t & 1, bo = b ^ 1u;
         const bool nx = t + 1 < T;
         // recurrent part: r | u accumulate onto the x part, ch starts fresh in columns [192,256)
-        ptx::mbar_wait(&bars[BAR_H], t & 1);           // the mixed state of every chunk is in the local image
+        GRU_TRACE(1, 0);
+        {
+          const unsigned long long t0 = tr_on ? clock64() : 0;
+          ptx::mbar_wait(&bars[BAR_H], t & 1);         // the mixed state of every chunk is in the local image
+          if (tr_on) w_h += clock64() - t0;
+        }
         ptx::tc_fence_after();
+        GRU_TRACE(1, 1);
         for (int s2 = 0; s2 < KH / 2; ++s2) {
           const uint32_t sa = wait_stage();
 #pragma unroll
@@ -237,14 +262,18 @@ tc_gru_layer_kernel(const GruLayerParams p) {
         }
         ptx::umma_commit(&bars[BAR_ACC_FULL + b]);
         if (C > 1) ptx::umma_commit_multicast(&bars[BAR_HFREE], cta_mask); else ptx::umma_commit(&bars[BAR_HFREE]);
+        GRU_TRACE(1, 2);
         // x part of step t+1 -> columns [0,192) of the other buffer (free once the gate math of step t-1 has drained it)
         if (nx && t >= 1) {
           ptx::mbar_wait(&bars[BAR_ACC_EMPTY + bo], empty_k[bo] & 1u);
           empty_k[bo] += 1;
           ptx::tc_fence_after();
         }
+        GRU_TRACE(1, 3);
         if (nx) xblocks(bo * 256, 0, KF);
+        GRU_TRACE(1, 4);
       }
+      if (tr_on) { g_gru_trace[1][15][0] = w_full; g_gru_trace[1][15][1] = w_h; g_gru_trace[1][15][2] = clock64() - t_begin; }
     }
   } else {
     // ================================================================ epilogue warps
@@ -385,9 +414,12 @@ tc_gru_layer_kernel(const GruLayerParams p) {
       const uint32_t b = t & 1;
       const int ta = d.reverse ? T - 1 - t : t;
       // ---------------------------------------------------------------- gates (TMEM-native layout: thread = row)
+      if (et == 0) GRU_TRACE(0, 0);
       ptx::mbar_wait(&bars[BAR_ACC_FULL + b], (t >> 1) & 1);
+      if (et == 0) GRU_TRACE(0, 1);
       ptx::mbar_wait(&bars[BAR_HFREE], t & 1);       // every CTA has finished reading h~_{t-1}: the image may be rewritten
       ptx::tc_fence_after();
+      if (et == 0) GRU_TRACE(0, 2);
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         float zr[8], zu[8], zx[8], zh[8];
@@ -406,9 +438,13 @@ tc_gru_layer_kernel(const GruLayerParams p) {
           hreg[hf * 8 + i] = rvalid ? hn : 0.f;
         }
       }
+      if (et == 0) GRU_TRACE(0, 3);
       mix_store(hreg);
+      if (et == 0) GRU_TRACE(0, 4);
       publish_block(BAR_H, (int)b, true);
+      if (et == 0) GRU_TRACE(0, 5);
       emit(ta, hreg);
+      if (et == 0) GRU_TRACE(0, 6);
     }
     if (rvalid && d.hT != nullptr) {
 #pragma unroll
@@ -548,6 +584,7 @@ int tc_gru_layer_launch(const LayerArgs& a, const uint16_t* x_img, char* wbase, 
   p.nprod = getenv("A3GC_TC_NPROD") ? atoi(getenv("A3GC_TC_NPROD")) : kProducers;
   if (p.nprod < 1) p.nprod = 1;
   if (p.nprod > kProducers) p.nprod = kProducers;
+  p.trace = (getenv("A3GC_TC_TRACE") != nullptr && strcmp(getenv("A3GC_TC_TRACE"), "gru") == 0) ? 1 : 0;
   int dev = 0, smem_max = 0;
   A3GC_CUDA_TRY(cudaGetDevice(&dev));
   A3GC_CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -576,6 +613,12 @@ int tc_gru_layer_launch(const LayerArgs& a, const uint16_t* x_img, char* wbase, 
   cfg.attrs = attr; cfg.numAttrs = 1;
   A3GC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
   A3GC_LAUNCH_CHECK("tc_gru_layer_kernel");
+  return A3GC_OK;
+}
+
+// debug: the per-phase timeline of CTA (0,0) of the last traced G-GRU launch (see a3gc_debug_read_tc_trace)
+int tc_gru_read_trace(unsigned long long* host_out) {
+  A3GC_CUDA_TRY(cudaMemcpyFromSymbol(host_out, g_gru_trace, sizeof(unsigned long long) * 2 * 16 * 16));
   return A3GC_OK;
 }
 

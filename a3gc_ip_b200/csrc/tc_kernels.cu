@@ -1328,6 +1328,7 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
 extern "C" int a3gc_debug_read_tc_trace(unsigned long long* host_out) {
   using namespace a3gc;
   if (!host_out) return A3GC_ERR_INVALID_ARG;
+  if (const char* e = getenv("A3GC_TC_TRACE")) if (strcmp(e, "gru") == 0) return tc_gru_read_trace(host_out);
   A3GC_CUDA_TRY(cudaMemcpyFromSymbol(host_out, g_tc_trace, sizeof(unsigned long long) * 2 * 16 * 16));
   return A3GC_OK;
 }
