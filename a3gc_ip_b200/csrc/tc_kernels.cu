@@ -632,13 +632,15 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
 
     // tape.hp [D][B][T][15][H] (node-major like x): h'_t of this thread's elements
     auto tape_hp = [&](int ta) {
+      float* hp0 = p.tape.hp + ((((size_t)blockIdx.y * p.B + bseq[0]) * T + ta) * kNodes + tq) * H + (int)c * 64 + gbase + 2 * tr;
+      const size_t seq_stride = (size_t)T * kNodes * H;
 #pragma unroll
       for (int sq = 0; sq < 2; ++sq) {
         if (!valid[sq]) continue;
 #pragma unroll
         for (int up = 0; up < 2; ++up) {
           if (tq + 8 * up >= kNodes) continue;
-          float* hp = p.tape.hp + ((((size_t)blockIdx.y * p.B + bseq[sq]) * T + ta) * kNodes + tq + 8 * up) * H + (int)c * 64 + gbase + 2 * tr;
+          float* hp = hp0 + sq * seq_stride + (size_t)up * 8 * H;
 #pragma unroll
           for (int ub = 0; ub < 2; ++ub) *reinterpret_cast<float2*>(hp + kUbs * ub) = make_float2(hreg[sq][ub][2 * up], hreg[sq][ub][2 * up + 1]);
         }
@@ -660,6 +662,16 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       ptx::tc_fence_after();
       if (et == 0) TC_TRACE(0, 1);
       if (et == 0) TC_TRACE_NS(0, 15);
+      // training: per-step bases of the tape rows this thread writes in the gate phase, so that the 128 stores of the phase
+      // take an immediate offset each instead of a 64-bit index computation (they were a third of the phase's instructions)
+      const size_t H16 = (size_t)H * 16;
+      float* tape_g0 = nullptr; float* tape_u0 = nullptr;
+      if (TRAIN) {
+        const size_t rec_t = (size_t)blockIdx.y * T + ta;
+        tape_g0 = p.tape.gates + (rec_t * p.B + bseq[0]) * 4 * H16 + (size_t)((int)c * 64 + gbase + 2 * tr) * 16 + tq;
+        if (p.tape.u != nullptr)
+          tape_u0 = p.tape.u + (rec_t * p.B + (tile * kSeqTile + 2 * qd + (lane >> 4))) * 4 * H16 + (size_t)((int)c * 64 + gbase) * 16 + (lane & 15);
+      }
 #pragma unroll
       for (int ub = 0; ub < 2; ++ub) {
         float e1[2][4], e2[2][4];
@@ -671,8 +683,8 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
             if (TRAIN) {
               // tape.u [rec][gate][unit][16]: this lane = accumulator row = (sequence, node); node slot 15 holds an exact 0
               const int rs = tile * kSeqTile + 2 * qd + (lane >> 4);
-              if (p.tape.u != nullptr && rs < p.B) {
-                float* up = p.tape.u + ((((size_t)blockIdx.y * T + ta) * p.B + rs) * 4 + g) * H * 16 + (size_t)((int)c * 64 + gbase + kUbs * ub) * 16 + (lane & 15);
+              if (tape_u0 != nullptr && rs < p.B) {
+                float* up = tape_u0 + (size_t)g * H16 + kUbs * ub * 16;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) up[j * 16] = v[j];
               }
@@ -709,6 +721,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
               const __half2 h0 = __floats2half2_rn(u0.x, u0.y), h1 = __floats2half2_rn(u1.x, u1.y);
               ptx::mma_16816_f16(z, ah, *reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
             }
+            float* tape_gp = TRAIN ? tape_g0 + (size_t)(4 * sq + g) * H16 + kUbs * ub * 16 : nullptr;   // + (j & 1) * 16 + 8 * (j >> 1)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const bool ok = valid[sq] && !(pad_hi && j >= 2);
@@ -748,10 +761,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
                 if (TRAIN) gv = rcp_ftz(eo);
                 hreg[sq][ub][j] = ok ? hy : 0.f;
               }
-              if (TRAIN && valid[sq]) {
-                const int unit = (int)c * 64 + gbase + kUbs * ub + 2 * tr + (j & 1), node = tq + 8 * (j >> 1);
-                p.tape.gates[((((size_t)blockIdx.y * T + ta) * p.B + bseq[sq]) * 4 + g) * H * 16 + (size_t)unit * 16 + node] = ok ? gv : 0.f;
-              }
+              if (TRAIN && valid[sq]) tape_gp[(j & 1) * 16 + 8 * (j >> 1)] = ok ? gv : 0.f;   // [rec][gate][unit][node]
             }
           }
         }
