@@ -155,11 +155,15 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
   // the commit -> producer hand-off), so its rate is (bytes in flight) / turn: at H = 256 the 128 KB state image left room
   // for three 24 KB slots; with the transposition buffers aliased into the state image (below) the same shared memory holds
   // four weight slots + three x slots, and the recurrent / attention stages no longer occupy x space they do not use.
+  // bf16 mode keeps ONE ring of (weights + x) slots: its stages are a single 129-cycle MMA, and the second barrier wait and
+  // second commit per x stage of the two-ring form cost more than the decoupling gains (AAGC bf16: -9 %, measured).
+  constexpr bool kTwoRings = SPLIT;
+  constexpr uint32_t kSlotStride = kTwoRings ? kBBytes : kBBytes + kABytes;
   const int SX = p.SX;
   uint8_t* hbuf = smem;
-  uint8_t* ring = hbuf + (size_t)NP * H * 256;                // weight slots
-  uint8_t* xring = ring + (size_t)S * kBBytes;                // x-image slots
-  float* staging = reinterpret_cast<float*>(xring + (size_t)SX * kABytes);   // [16 warps][8][32]  (bf16 mode only)
+  uint8_t* ring = hbuf + (size_t)NP * H * 256;                // weight slots (bf16: weight + x slots)
+  uint8_t* xring = ring + (size_t)S * kBBytes;                // x-image slots (fp32 mode)
+  float* staging = reinterpret_cast<float*>(kTwoRings ? xring + (size_t)SX * kABytes : ring + (size_t)S * kSlotStride);   // [16 warps][8][32]  (bf16 mode only)
   float* apart = staging + (SPLIT ? 0 : kEpiWarps * kWstFloats);   // [C][128]
   float* ahalf = apart + C * 128;            // [4][128]
   float* biasg = ahalf + 4 * 128;            // [4 gates][64 units]
@@ -173,7 +177,8 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
   // ------------------------------------------------------------------ setup
   if (threadIdx.x == 0) {
     for (int i = 0; i < BAR_COUNT; ++i)
-      ptx::mbar_init(&bars[i], (i == BAR_HFREE || i == BAR_A1FREE) ? (uint32_t)C : 1u);
+      ptx::mbar_init(&bars[i], (i == BAR_HFREE || i == BAR_A1FREE) ? (uint32_t)C
+                                   : (!kTwoRings && i >= BAR_FULL && i < BAR_FULL + kMaxStages) ? 2u : 1u);   // one ring: B side + A side
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
@@ -224,21 +229,42 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       uint32_t turn = 0;                  // whose stage this is
       const uint32_t chunk = (uint32_t)p.chunk;
       auto load_stage = [&](const void* bsrc, uint32_t bbytes, const void* asrc, uint32_t abytes) {
-        const bool b_side = my < nb && turn == my, a_side = abytes != 0 && (split_a ? my == 2u : b_side);
-        if (b_side) {
-          uint8_t* dst = ring + ws * kBBytes;
-          ptx::mbar_wait(&bars[BAR_EMPTY + ws], wph ^ 1u);
-          ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + ws], bbytes);
-          // p.chunk (tuning knob) can cut the copies into pieces; measured slower than one copy per operand
-          for (uint32_t o = 0; o < bbytes; o += chunk)
-            ptx::bulk_g2s(dst + o, static_cast<const uint8_t*>(bsrc) + o, min(chunk, bbytes - o), &bars[BAR_FULL + ws]);
-        }
-        if (a_side) {
-          uint8_t* dst = xring + xs * kABytes;
-          ptx::mbar_wait(&bars[BAR_XEMPTY + xs], xph ^ 1u);
-          ptx::mbar_arrive_expect_tx(&bars[BAR_XFULL + xs], abytes);
-          for (uint32_t o = 0; o < abytes; o += chunk)
-            ptx::bulk_g2s(dst + o, static_cast<const uint8_t*>(asrc) + o, min(chunk, abytes - o), &bars[BAR_XFULL + xs]);
+        if (kTwoRings) {
+          const bool b_side = my < nb && turn == my, a_side = abytes != 0 && (split_a ? my == 2u : b_side);
+          if (b_side) {
+            uint8_t* dst = ring + ws * kBBytes;
+            ptx::mbar_wait(&bars[BAR_EMPTY + ws], wph ^ 1u);
+            ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + ws], bbytes);
+            // p.chunk (tuning knob) can cut the copies into pieces; measured slower than one copy per operand
+            for (uint32_t o = 0; o < bbytes; o += chunk)
+              ptx::bulk_g2s(dst + o, static_cast<const uint8_t*>(bsrc) + o, min(chunk, bbytes - o), &bars[BAR_FULL + ws]);
+          }
+          if (a_side) {
+            uint8_t* dst = xring + xs * kABytes;
+            ptx::mbar_wait(&bars[BAR_XEMPTY + xs], xph ^ 1u);
+            ptx::mbar_arrive_expect_tx(&bars[BAR_XFULL + xs], abytes);
+            for (uint32_t o = 0; o < abytes; o += chunk)
+              ptx::bulk_g2s(dst + o, static_cast<const uint8_t*>(asrc) + o, min(chunk, abytes - o), &bars[BAR_XFULL + xs]);
+          }
+        } else {
+          // one ring: every FULL barrier takes two arrivals (B side, A side)
+          uint8_t* dst = ring + ws * kSlotStride;
+          const bool b_side = my < nb && turn == my, a_side = split_a ? my == 2u : b_side;
+          if (b_side || a_side) ptx::mbar_wait(&bars[BAR_EMPTY + ws], wph ^ 1u);
+          if (b_side) {
+            ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + ws], bbytes);
+            for (uint32_t o = 0; o < bbytes; o += chunk)
+              ptx::bulk_g2s(dst + o, static_cast<const uint8_t*>(bsrc) + o, min(chunk, bbytes - o), &bars[BAR_FULL + ws]);
+          }
+          if (a_side) {
+            if (abytes) {
+              ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + ws], abytes);
+              for (uint32_t o = 0; o < abytes; o += chunk)
+                ptx::bulk_g2s(dst + kBBytes + o, static_cast<const uint8_t*>(asrc) + o, min(chunk, abytes - o), &bars[BAR_FULL + ws]);
+            } else {
+              ptx::mbar_arrive(&bars[BAR_FULL + ws]);
+            }
+          }
         }
         if (++turn == nb) turn = 0;
         if (++ws == (uint32_t)S) { ws = 0; wph ^= 1u; }
@@ -301,7 +327,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       auto wait_stage = [&]() -> uint32_t {          // next weight slot
         ptx::mbar_wait(&bars[BAR_FULL + ws], wph);
         ptx::tc_fence_after();
-        return ring_addr + ws * kBBytes;
+        return ring_addr + ws * kSlotStride;
       };
       auto wait_xstage = [&]() -> uint32_t {         // next x-image slot
         ptx::mbar_wait(&bars[BAR_XFULL + xs], xph);
@@ -344,8 +370,8 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       const bool xsplit = p.xsplit != 0;
       auto xblocks = [&](uint32_t dcol, int kb0, int kb1) {
         for (int kb = kb0; kb < kb1; ++kb) {
-          const uint32_t xa = wait_xstage();
           const uint32_t sa = wait_stage();
+          const uint32_t xa = kTwoRings ? wait_xstage() : sa + kBBytes;
           if (xsplit) {
             block_mma(dcol, xa, kABytes / NP, sa, kBBytes / NP, dB256, idesc128, kb == 0);
             block_mma(dcol + 128, xa, kABytes / NP, sa + 128 * 16, kBBytes / NP, dB256, idesc128, kb == 0);
@@ -353,7 +379,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
             block_mma(dcol, xa, kABytes / NP, sa, kBBytes / NP, dB256, idesc256, kb == 0);
           }
           release_stage();
-          release_xstage();
+          if (kTwoRings) release_xstage();
         }
       };
       xblocks(0, 0, KF);
@@ -1294,12 +1320,14 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
     return A3GC_ERR_UNSUPPORTED;
   }
   int SW = S, SX = S;
-  if (getenv("A3GC_TC_STAGES") == nullptr) {
+  if (split && getenv("A3GC_TC_STAGES") == nullptr) {   // bf16 mode: one ring of S (weights + x) slots
     while (SW < kMaxStages && fixed + (size_t)(SW + 1) * wslot + (size_t)SX * xslot <= (size_t)smem_max) ++SW;
     while (SX < kMaxStages && fixed + (size_t)SW * wslot + (size_t)(SX + 1) * xslot <= (size_t)smem_max) ++SX;
   }
-  if (const char* e = getenv("A3GC_TC_WSTAGES")) { const int v = atoi(e); if (v >= 2 && v <= kMaxStages) SW = v; }
-  if (const char* e = getenv("A3GC_TC_XSTAGES")) { const int v = atoi(e); if (v >= 2 && v <= kMaxStages) SX = v; }
+  if (split) {
+    if (const char* e = getenv("A3GC_TC_WSTAGES")) { const int v = atoi(e); if (v >= 2 && v <= kMaxStages) SW = v; }
+    if (const char* e = getenv("A3GC_TC_XSTAGES")) { const int v = atoi(e); if (v >= 2 && v <= kMaxStages) SX = v; }
+  }
   if (fixed + (size_t)SW * wslot + (size_t)SX * xslot > (size_t)smem_max) {
     set_error("tc engine: A3GC_TC_WSTAGES / A3GC_TC_XSTAGES exceed the shared memory budget (hidden=%d)", H);
     return A3GC_ERR_INVALID_ARG;
