@@ -175,8 +175,11 @@ tc_gru_layer_kernel(const GruLayerParams p) {
       if (tr_on) { g_gru_trace[0][15][2 * my] = w_empty; g_gru_trace[0][15][2 * my + 1] = clock64() - t_begin; }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer (one thread)
-    if ((threadIdx.x & 31) == 0) {
+    // ================================================================ MMA issuer: the whole warp walks the stage sequence
+    // (uniform control flow and operands), one elected lane issues the MMAs and commits of a stage (see ptx::elect_one)
+    {
+      const bool lane0 = (threadIdx.x & 31) == 0;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t idesc192 = ptx::make_idesc_f16(128, 192, !SPLIT);
       const uint32_t idesc128 = ptx::make_idesc_f16(128, 128, !SPLIT);
       const uint32_t idesc64 = ptx::make_idesc_f16(128, 64, !SPLIT);
@@ -194,31 +197,34 @@ tc_gru_layer_kernel(const GruLayerParams p) {
         ptx::tc_fence_after();
         return ring_addr + st * kStageBytes;
       };
-      auto release_stage = [&]() {
-        ptx::umma_commit(&bars[BAR_EMPTY + st]);
-        if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
-      };
+      auto next_stage = [&]() { if (++st == (uint32_t)S) { st = 0; ph ^= 1u; } };
       const uint64_t dA = ptx::make_smem_desc(0, kRows * 16, 128);
       const uint64_t dB192 = ptx::make_smem_desc(0, 192 * 16, 128);
+      const bool acoll = SPLIT && p.acoll;
+      // one K=16 block: D[:, dcol..dcol+N) (+)= A * B^T with the split passes hi*hi + hi*lo + lo*hi  (elected lane only)
       auto block_mma = [&](uint32_t dcol, uint32_t a0, uint32_t astride, uint32_t b0, uint32_t bstride, uint64_t dB, uint32_t idesc, bool first) {
         const uint64_t ah = dA + ((a0 & 0x3FFFFu) >> 4), bh = dB + ((b0 & 0x3FFFFu) >> 4);
-        if (SPLIT && p.acoll) {
-          ptx::umma_f16_coll(tmem + dcol, ah, bh, idesc, first ? 0u : 1u, 1);
-          ptx::umma_f16_coll(tmem + dcol, ah, bh + (bstride >> 4), idesc, 1u, 3);
-          ptx::umma_f16(tmem + dcol, ah + (astride >> 4), bh, idesc, 1u);
+        if (acoll) {
+          ptx::umma_f16_coll(tmem_u + dcol, ah, bh, idesc, first ? 0u : 1u, 1);
+          ptx::umma_f16_coll(tmem_u + dcol, ah, bh + (bstride >> 4), idesc, 1u, 3);
+          ptx::umma_f16(tmem_u + dcol, ah + (astride >> 4), bh, idesc, 1u);
         } else {
-          ptx::umma_f16(tmem + dcol, ah, bh, idesc, first ? 0u : 1u);
+          ptx::umma_f16(tmem_u + dcol, ah, bh, idesc, first ? 0u : 1u);
           if (SPLIT) {
-            ptx::umma_f16(tmem + dcol, ah + (astride >> 4), bh, idesc, 1u);
-            ptx::umma_f16(tmem + dcol, ah, bh + (bstride >> 4), idesc, 1u);
+            ptx::umma_f16(tmem_u + dcol, ah + (astride >> 4), bh, idesc, 1u);
+            ptx::umma_f16(tmem_u + dcol, ah, bh + (bstride >> 4), idesc, 1u);
           }
         }
       };
       auto xblocks = [&](uint32_t dcol, int kb0, int kb1) {
         for (int kb = kb0; kb < kb1; ++kb) {
           const uint32_t sa = wait_stage();
-          block_mma(dcol, sa + kXB, kXA / NP, sa, kXB / NP, dB192, idesc192, kb == 0);
-          release_stage();
+          if (ptx::elect_one()) {
+            block_mma(dcol, sa + kXB, kXA / NP, sa, kXB / NP, dB192, idesc192, kb == 0);
+            ptx::umma_commit(&bars[BAR_EMPTY + st]);
+          }
+          __syncwarp();
+          next_stage();
         }
       };
       xblocks(0, 0, KF);
@@ -226,54 +232,60 @@ tc_gru_layer_kernel(const GruLayerParams p) {
         const uint32_t b = t & 1, bo = b ^ 1u;
         const bool nx = t + 1 < T;
         // recurrent part: r | u accumulate onto the x part, ch starts fresh in columns [192,256)
-        GRU_TRACE(1, 0);
+        if (lane0) GRU_TRACE(1, 0);
         {
           const unsigned long long t0 = tr_on ? clock64() : 0;
           ptx::mbar_wait(&bars[BAR_H], t & 1);         // the mixed state of every chunk is in the local image
           if (tr_on) w_h += clock64() - t0;
         }
         ptx::tc_fence_after();
-        GRU_TRACE(1, 1);
+        if (lane0) GRU_TRACE(1, 1);
         for (int s2 = 0; s2 < KH / 2; ++s2) {
           const uint32_t sa = wait_stage();
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int kb = s2 * 2 + j;
-            const uint32_t a0 = hbase + (uint32_t)kb * 2 * kRows * 16, b0 = sa + (uint32_t)j * kMB;
-            if (SPLIT && p.acoll) {
-              // one A tile (h~ hi, then h~ lo) against r|u (N = 128) and ch (N = 64), hi and lo parts of the weights: the A
-              // operand is read from shared memory once per part and kept in the collector buffer for the other MMAs
-              const uint64_t ah = dA + ((a0 & 0x3FFFFu) >> 4), al = ah + (hpart >> 4);
-              const uint64_t bh = dB192 + ((b0 & 0x3FFFFu) >> 4), bl = bh + ((kMB / NP) >> 4);
-              const uint64_t ch = bh + ((128u * 16u) >> 4), cl = bl + ((128u * 16u) >> 4);
-              const uint32_t first = (s2 | j) == 0 ? 0u : 1u;
-              ptx::umma_f16_coll(tmem + b * 256, ah, bh, idesc128, 1u, 1);
-              ptx::umma_f16_coll(tmem + b * 256, ah, bl, idesc128, 1u, 2);
-              ptx::umma_f16_coll(tmem + b * 256 + 192, ah, ch, idesc64, first, 2);
-              ptx::umma_f16_coll(tmem + b * 256 + 192, ah, cl, idesc64, 1u, 3);
-              ptx::umma_f16_coll(tmem + b * 256, al, bh, idesc128, 1u, 1);
-              ptx::umma_f16_coll(tmem + b * 256 + 192, al, ch, idesc64, 1u, 3);
-            } else {
-              block_mma(b * 256, a0, hpart, b0, kMB / NP, dB192, idesc128, false);
-              block_mma(b * 256 + 192, a0, hpart, b0 + 128 * 16, kMB / NP, dB192, idesc64, (s2 | j) == 0);
+            for (int j = 0; j < 2; ++j) {
+              const int kb = s2 * 2 + j;
+              const uint32_t a0 = hbase + (uint32_t)kb * 2 * kRows * 16, b0 = sa + (uint32_t)j * kMB;
+              if (acoll) {
+                // one A tile (h~ hi, then h~ lo) against r|u (N = 128) and ch (N = 64), hi and lo parts of the weights: the A
+                // operand is read from shared memory once per part and kept in the collector buffer for the other MMAs
+                const uint64_t ah = dA + ((a0 & 0x3FFFFu) >> 4), al = ah + (hpart >> 4);
+                const uint64_t bh = dB192 + ((b0 & 0x3FFFFu) >> 4), bl = bh + ((kMB / NP) >> 4);
+                const uint64_t ch = bh + ((128u * 16u) >> 4), cl = bl + ((128u * 16u) >> 4);
+                const uint32_t first = (s2 | j) == 0 ? 0u : 1u;
+                ptx::umma_f16_coll(tmem_u + b * 256, ah, bh, idesc128, 1u, 1);
+                ptx::umma_f16_coll(tmem_u + b * 256, ah, bl, idesc128, 1u, 2);
+                ptx::umma_f16_coll(tmem_u + b * 256 + 192, ah, ch, idesc64, first, 2);
+                ptx::umma_f16_coll(tmem_u + b * 256 + 192, ah, cl, idesc64, 1u, 3);
+                ptx::umma_f16_coll(tmem_u + b * 256, al, bh, idesc128, 1u, 1);
+                ptx::umma_f16_coll(tmem_u + b * 256 + 192, al, ch, idesc64, 1u, 3);
+              } else {
+                block_mma(b * 256, a0, hpart, b0, kMB / NP, dB192, idesc128, false);
+                block_mma(b * 256 + 192, a0, hpart, b0 + 128 * 16, kMB / NP, dB192, idesc64, (s2 | j) == 0);
+              }
+            }
+            ptx::umma_commit(&bars[BAR_EMPTY + st]);
+            if (s2 == KH / 2 - 1) {
+              ptx::umma_commit(&bars[BAR_ACC_FULL + b]);
+              if (C > 1) ptx::umma_commit_multicast(&bars[BAR_HFREE], cta_mask); else ptx::umma_commit(&bars[BAR_HFREE]);
             }
           }
-          release_stage();
+          __syncwarp();
+          next_stage();
         }
-        ptx::umma_commit(&bars[BAR_ACC_FULL + b]);
-        if (C > 1) ptx::umma_commit_multicast(&bars[BAR_HFREE], cta_mask); else ptx::umma_commit(&bars[BAR_HFREE]);
-        GRU_TRACE(1, 2);
+        if (lane0) GRU_TRACE(1, 2);
         // x part of step t+1 -> columns [0,192) of the other buffer (free once the gate math of step t-1 has drained it)
         if (nx && t >= 1) {
           ptx::mbar_wait(&bars[BAR_ACC_EMPTY + bo], empty_k[bo] & 1u);
           empty_k[bo] += 1;
           ptx::tc_fence_after();
         }
-        GRU_TRACE(1, 3);
+        if (lane0) GRU_TRACE(1, 3);
         if (nx) xblocks(bo * 256, 0, KF);
-        GRU_TRACE(1, 4);
+        if (lane0) GRU_TRACE(1, 4);
       }
-      if (tr_on) { g_gru_trace[1][15][0] = w_full; g_gru_trace[1][15][1] = w_h; g_gru_trace[1][15][2] = clock64() - t_begin; }
+      if (tr_on && lane0) { g_gru_trace[1][15][0] = w_full; g_gru_trace[1][15][1] = w_h; g_gru_trace[1][15][2] = clock64() - t_begin; }
     }
   } else {
     // ================================================================ epilogue warps

@@ -168,6 +168,16 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, bool bf16) {
   return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
+// One lane of a CONVERGED warp.  The MMA warp runs its issue loop on all 32 lanes (every lane computes the same slot indices,
+// phases and descriptors, so the compiler keeps them in uniform registers) and issues the tcgen05 instructions from the
+// elected lane: the UTCHMMA / UTCBAR instructions of a stage are then emitted back to back.  The same loop under
+// `if (lane == 0)` makes every operand a per-thread value: each UTCHMMA is wrapped in an ELECT / R2UR / BRA.U.ANY
+// "waterfall" and the stage costs ~600 cycles of issue latency on one thread -- more than its MMAs take to execute.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
