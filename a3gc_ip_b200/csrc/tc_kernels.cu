@@ -312,16 +312,21 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer (one thread)
-    if ((threadIdx.x & 31) == 0) {
+    // ================================================================ MMA issuer
+    // The whole warp walks the static stage sequence -- slot indices, phases and descriptors are the same in every lane, so
+    // they live in uniform registers -- and ONE elected lane issues the MMAs and commits of a stage, back to back
+    // (ptx::elect_one).  Under `if (lane == 0)` every tcgen05 instruction was wrapped in an ELECT / R2UR / BRA.U.ANY waterfall and
+    // a stage cost ~400-600 cycles of issue latency on that one thread -- more than its three MMAs take to execute, and the
+    // real reason why ring depth, producer count and the restructurings of the chain changed so little.
+    {
+      const bool lane0 = (threadIdx.x & 31) == 0;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t idesc256 = ptx::make_idesc_f16(128, 256, !SPLIT);
       const uint32_t idesc128 = ptx::make_idesc_f16(128, 128, !SPLIT);
       const uint32_t idesc64 = ptx::make_idesc_f16(128, 64, !SPLIT);
       const uint32_t hbase = ptx::smem_u32(hbuf);
       const uint32_t hpart = (uint32_t)H * 256;
-      // The issue loop runs on ONE thread whose dependent-instruction latency bounds the MMA rate, so it is kept
-      // lean: ring slot / parity are counters (no div / mod), descriptors are a constant plus (address >> 4).
-      uint32_t ws = 0, wph = 0, xs = 0, xph = 0;
+      uint32_t ws = 0, wph = 0, xs = 0, xph = 0;     // ring slots and the parities of their current fills (no div / mod)
       uint32_t empty_k[2] = {0, 0};     // completions of BAR_ACC_EMPTY[b] consumed so far (no-attention variant)
       const uint32_t ring_addr = ptx::smem_u32(ring), xring_addr = ptx::smem_u32(xring);
       auto wait_stage = [&]() -> uint32_t {          // next weight slot
@@ -334,33 +339,27 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         ptx::tc_fence_after();
         return xring_addr + xs * kABytes;
       };
-      auto release_stage = [&]() {
-        ptx::umma_commit(&bars[BAR_EMPTY + ws]);
-        if (++ws == (uint32_t)S) { ws = 0; wph ^= 1u; }
-      };
-      auto release_xstage = [&]() {
-        ptx::umma_commit(&bars[BAR_XEMPTY + xs]);
-        if (++xs == (uint32_t)SX) { xs = 0; xph ^= 1u; }
-      };
+      auto next_stage = [&]() { if (++ws == (uint32_t)S) { ws = 0; wph ^= 1u; } };
+      auto next_xstage = [&]() { if (++xs == (uint32_t)SX) { xs = 0; xph ^= 1u; } };
       const uint64_t dA = ptx::make_smem_desc(0, kRows * 16, 128);
       const uint64_t dB256 = ptx::make_smem_desc(0, 256 * 16, 128), dB128 = ptx::make_smem_desc(0, 128 * 16, 128),
                      dB64 = ptx::make_smem_desc(0, 64 * 16, 128);
       const bool acoll = p.acoll != 0;
-      // one K=16 block: D[:, dcol..dcol+N) (+)= A * B^T with the split passes hi*hi + lo*hi + hi*lo
+      // one K=16 block: D[:, dcol..dcol+N) (+)= A * B^T with the split passes hi*hi + lo*hi + hi*lo   (elected lane only)
       auto block_mma = [&](uint32_t dcol, uint32_t a0, uint32_t astride, uint32_t b0, uint32_t bstride, uint64_t dB,
                            uint32_t idesc, bool first) {
         // (shared-window addresses of non-zero cluster ranks carry the rank above bit 18: keep the 18-bit offset only)
         const uint64_t ah = dA + ((a0 & 0x3FFFFu) >> 4), bh = dB + ((b0 & 0x3FFFFu) >> 4);
         if (SPLIT && acoll) {
           // A_hi is multiplied by B_hi and by B_lo back to back: the second MMA takes it from the collector buffer
-          ptx::umma_f16_coll(tmem + dcol, ah, bh, idesc, first ? 0u : 1u, 1);
-          ptx::umma_f16_coll(tmem + dcol, ah, bh + (bstride >> 4), idesc, 1u, 3);
-          ptx::umma_f16(tmem + dcol, ah + (astride >> 4), bh, idesc, 1u);
+          ptx::umma_f16_coll(tmem_u + dcol, ah, bh, idesc, first ? 0u : 1u, 1);
+          ptx::umma_f16_coll(tmem_u + dcol, ah, bh + (bstride >> 4), idesc, 1u, 3);
+          ptx::umma_f16(tmem_u + dcol, ah + (astride >> 4), bh, idesc, 1u);
         } else {
-          ptx::umma_f16(tmem + dcol, ah, bh, idesc, first ? 0u : 1u);
+          ptx::umma_f16(tmem_u + dcol, ah, bh, idesc, first ? 0u : 1u);
           if (SPLIT) {
-            ptx::umma_f16(tmem + dcol, ah + (astride >> 4), bh, idesc, 1u);
-            ptx::umma_f16(tmem + dcol, ah, bh + (bstride >> 4), idesc, 1u);
+            ptx::umma_f16(tmem_u + dcol, ah + (astride >> 4), bh, idesc, 1u);
+            ptx::umma_f16(tmem_u + dcol, ah, bh + (bstride >> 4), idesc, 1u);
           }
         }
       };
@@ -372,14 +371,19 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         for (int kb = kb0; kb < kb1; ++kb) {
           const uint32_t sa = wait_stage();
           const uint32_t xa = kTwoRings ? wait_xstage() : sa + kBBytes;
-          if (xsplit) {
-            block_mma(dcol, xa, kABytes / NP, sa, kBBytes / NP, dB256, idesc128, kb == 0);
-            block_mma(dcol + 128, xa, kABytes / NP, sa + 128 * 16, kBBytes / NP, dB256, idesc128, kb == 0);
-          } else {
-            block_mma(dcol, xa, kABytes / NP, sa, kBBytes / NP, dB256, idesc256, kb == 0);
+          if (ptx::elect_one()) {
+            if (xsplit) {
+              block_mma(dcol, xa, kABytes / NP, sa, kBBytes / NP, dB256, idesc128, kb == 0);
+              block_mma(dcol + 128, xa, kABytes / NP, sa + 128 * 16, kBBytes / NP, dB256, idesc128, kb == 0);
+            } else {
+              block_mma(dcol, xa, kABytes / NP, sa, kBBytes / NP, dB256, idesc256, kb == 0);
+            }
+            ptx::umma_commit(&bars[BAR_EMPTY + ws]);
+            if (kTwoRings) ptx::umma_commit(&bars[BAR_XEMPTY + xs]);
           }
-          release_stage();
-          if (kTwoRings) release_xstage();
+          __syncwarp();
+          next_stage();
+          if (kTwoRings) next_xstage();
         }
       };
       xblocks(0, 0, KF);
@@ -387,21 +391,28 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         const uint32_t b = t & 1, bo = b ^ 1u, dcol = b * 256;
         const bool nx = t + 1 < T;
         // h-part of step t (needs h'_{t-1} of every chunk in local shared memory)
-        TC_TRACE(1, 0);
+        if (lane0) TC_TRACE(1, 0);
         for (int i = 0; i < C; ++i) {
           const int src = ((int)c + i) % C;
           ptx::mbar_wait(&bars[BAR_H + src], t & 1);
           ptx::tc_fence_after();
-          if (i == 0) TC_TRACE(1, 1);
+          if (i == 0 && lane0) TC_TRACE(1, 1);
           for (int kb = 4 * src; kb < 4 * src + 4; ++kb) {
             const uint32_t sa = wait_stage();
-            block_mma(dcol, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, sa, kBBytes / NP, dB256, idesc256, false);
-            release_stage();
+            if (ptx::elect_one()) {
+              block_mma(dcol, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, sa, kBBytes / NP, dB256, idesc256, false);
+              ptx::umma_commit(&bars[BAR_EMPTY + ws]);
+            }
+            __syncwarp();
+            next_stage();
           }
         }
-        ptx::umma_commit(&bars[BAR_ACC_FULL + b]);
-        if (C > 1) ptx::umma_commit_multicast(&bars[BAR_HFREE], cta_mask); else ptx::umma_commit(&bars[BAR_HFREE]);
-        TC_TRACE(1, 2);
+        if (ptx::elect_one()) {
+          ptx::umma_commit(&bars[BAR_ACC_FULL + b]);
+          if (C > 1) ptx::umma_commit_multicast(&bars[BAR_HFREE], cta_mask); else ptx::umma_commit(&bars[BAR_HFREE]);
+        }
+        __syncwarp();
+        if (lane0) TC_TRACE(1, 2);
         // x-part of step t+1 goes into the other buffer (free once the epilogue of step t-1 has drained it)
         if (nx && t >= 1) {
           if (ATT) ptx::mbar_wait(&bars[BAR_ACC_EMPTY + bo], 1u);
@@ -410,7 +421,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         }
         if (!ATT) {
           if (nx) xblocks(bo * 256, 0, KF);
-          TC_TRACE(1, 3);
+          if (lane0) TC_TRACE(1, 3);
           continue;
         }
         // p.xdefer (tuning knob, default off): hold the first x segment back until the gate phase of this step is over.  The
@@ -418,31 +429,40 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         // ~7 k cycles at H=256 but the x part then delays the attention GEMM by as much: no net gain (measured).
         if (p.xdefer) { ptx::mbar_wait(&bars[BAR_ACC_EMPTY + b], 0u); ptx::tc_fence_after(); }
         if (nx) xblocks(bo * 256, 0, n1);
-        TC_TRACE(1, 3);
+        if (lane0) TC_TRACE(1, 3);
         // A1: [Wh hy | Wa (hy, node-sum in row 15)] -> columns [0,128) of the drained buffer
         ptx::mbar_wait(&bars[BAR_ACC_EMPTY + b], 0u);
         for (int i = 0; i < C; ++i) {
           const int src = ((int)c + i) % C;
           ptx::mbar_wait(&bars[BAR_HHAT + src], t & 1);
           ptx::tc_fence_after();
-          if (i == 0) TC_TRACE(1, 4);
-          if (i == 1) TC_TRACE(1, 9);
-          if (i == 2) TC_TRACE(1, 10);
-          if (i == 3) TC_TRACE(1, 11);
+          if (lane0) {
+            if (i == 0) TC_TRACE(1, 4);
+            if (i == 1) TC_TRACE(1, 9);
+            if (i == 2) TC_TRACE(1, 10);
+            if (i == 3) TC_TRACE(1, 11);
+          }
           for (int s2 = 2 * src; s2 < 2 * src + 2; ++s2) {
             const uint32_t sa = wait_stage();
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int kb = s2 * 2 + j;
-              block_mma(dcol, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, sa + (uint32_t)j * kA1Block, kA1Block / NP, dB128, idesc128,
-                        i == 0 && s2 == 2 * src && j == 0);
+              for (int j = 0; j < 2; ++j) {
+                const int kb = s2 * 2 + j;
+                block_mma(dcol, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, sa + (uint32_t)j * kA1Block, kA1Block / NP, dB128, idesc128,
+                          i == 0 && s2 == 2 * src && j == 0);
+              }
+              ptx::umma_commit(&bars[BAR_EMPTY + ws]);
             }
-            release_stage();
+            __syncwarp();
+            next_stage();
           }
         }
-        ptx::umma_commit(&bars[BAR_ATT_FULL]);
-        if (C > 1) ptx::umma_commit_multicast(&bars[BAR_A1FREE], cta_mask); else ptx::umma_commit(&bars[BAR_A1FREE]);
-        TC_TRACE(1, 5);
+        if (ptx::elect_one()) {
+          ptx::umma_commit(&bars[BAR_ATT_FULL]);
+          if (C > 1) ptx::umma_commit_multicast(&bars[BAR_A1FREE], cta_mask); else ptx::umma_commit(&bars[BAR_A1FREE]);
+        }
+        __syncwarp();
+        if (lane0) TC_TRACE(1, 5);
         if (nx) xblocks(bo * 256, n1, n1 + n2);
         // A2: Wq q (q sits in row 15 of every sequence) -> columns [128,192)
         for (int i = 0; i < C; ++i) {
@@ -450,20 +470,25 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
           ptx::mbar_wait_cluster(&bars[BAR_Q + src], t & 1);
           ptx::fence_proxy_async();
           ptx::tc_fence_after();
-          if (i == 0) TC_TRACE(1, 6);
+          if (i == 0 && lane0) TC_TRACE(1, 6);
           const uint32_t sa = wait_stage();
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int kb = src * 4 + j;
-            block_mma(dcol + 128, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, sa + (uint32_t)j * kA2Block, kA2Block / NP, dB64, idesc64,
-                      i == 0 && j == 0);
+            for (int j = 0; j < 4; ++j) {
+              const int kb = src * 4 + j;
+              block_mma(dcol + 128, hbase + (uint32_t)kb * 2 * kRows * 16, hpart, sa + (uint32_t)j * kA2Block, kA2Block / NP, dB64, idesc64,
+                        i == 0 && j == 0);
+            }
+            ptx::umma_commit(&bars[BAR_EMPTY + ws]);
           }
-          release_stage();
+          __syncwarp();
+          next_stage();
         }
-        ptx::umma_commit(&bars[BAR_ATT2_FULL]);
-        TC_TRACE(1, 7);
+        if (ptx::elect_one()) ptx::umma_commit(&bars[BAR_ATT2_FULL]);
+        __syncwarp();
+        if (lane0) TC_TRACE(1, 7);
         if (nx) xblocks(bo * 256, n1 + n2, KF);
-        TC_TRACE(1, 8);
+        if (lane0) TC_TRACE(1, 8);
       }
     }
   } else {
