@@ -329,15 +329,27 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       uint32_t ws = 0, wph = 0, xs = 0, xph = 0;     // ring slots and the parities of their current fills (no div / mod)
       uint32_t empty_k[2] = {0, 0};     // completions of BAR_ACC_EMPTY[b] consumed so far (no-attention variant)
       const uint32_t ring_addr = ptx::smem_u32(ring), xring_addr = ptx::smem_u32(xring);
+      // trace: cycles this warp waited for a full weight slot / x slot / anything else (state blocks, q, accumulators)
+      const bool tr_on = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
+      unsigned long long w_full = 0, w_xfull = 0, w_other = 0, t_begin = tr_on ? clock64() : 0;
       auto wait_stage = [&]() -> uint32_t {          // next weight slot
+        const unsigned long long t0 = tr_on ? clock64() : 0;
         ptx::mbar_wait(&bars[BAR_FULL + ws], wph);
+        if (tr_on) w_full += clock64() - t0;
         ptx::tc_fence_after();
         return ring_addr + ws * kSlotStride;
       };
       auto wait_xstage = [&]() -> uint32_t {         // next x-image slot
+        const unsigned long long t0 = tr_on ? clock64() : 0;
         ptx::mbar_wait(&bars[BAR_XFULL + xs], xph);
+        if (tr_on) w_xfull += clock64() - t0;
         ptx::tc_fence_after();
         return xring_addr + xs * kABytes;
+      };
+      auto wait_other = [&](uint64_t* bar, uint32_t parity) {
+        const unsigned long long t0 = tr_on ? clock64() : 0;
+        ptx::mbar_wait(bar, parity);
+        if (tr_on) w_other += clock64() - t0;
       };
       auto next_stage = [&]() { if (++ws == (uint32_t)S) { ws = 0; wph ^= 1u; } };
       auto next_xstage = [&]() { if (++xs == (uint32_t)SX) { xs = 0; xph ^= 1u; } };
@@ -394,7 +406,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         if (lane0) TC_TRACE(1, 0);
         for (int i = 0; i < C; ++i) {
           const int src = ((int)c + i) % C;
-          ptx::mbar_wait(&bars[BAR_H + src], t & 1);
+          wait_other(&bars[BAR_H + src], t & 1);
           ptx::tc_fence_after();
           if (i == 0 && lane0) TC_TRACE(1, 1);
           for (int kb = 4 * src; kb < 4 * src + 4; ++kb) {
@@ -415,8 +427,8 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         if (lane0) TC_TRACE(1, 2);
         // x-part of step t+1 goes into the other buffer (free once the epilogue of step t-1 has drained it)
         if (nx && t >= 1) {
-          if (ATT) ptx::mbar_wait(&bars[BAR_ACC_EMPTY + bo], 1u);
-          else { ptx::mbar_wait(&bars[BAR_ACC_EMPTY + bo], empty_k[bo] & 1u); empty_k[bo] += 1; }
+          if (ATT) wait_other(&bars[BAR_ACC_EMPTY + bo], 1u);
+          else { wait_other(&bars[BAR_ACC_EMPTY + bo], empty_k[bo] & 1u); empty_k[bo] += 1; }
           ptx::tc_fence_after();
         }
         if (!ATT) {
@@ -431,10 +443,10 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         if (nx) xblocks(bo * 256, 0, n1);
         if (lane0) TC_TRACE(1, 3);
         // A1: [Wh hy | Wa (hy, node-sum in row 15)] -> columns [0,128) of the drained buffer
-        ptx::mbar_wait(&bars[BAR_ACC_EMPTY + b], 0u);
+        wait_other(&bars[BAR_ACC_EMPTY + b], 0u);
         for (int i = 0; i < C; ++i) {
           const int src = ((int)c + i) % C;
-          ptx::mbar_wait(&bars[BAR_HHAT + src], t & 1);
+          wait_other(&bars[BAR_HHAT + src], t & 1);
           ptx::tc_fence_after();
           if (lane0) {
             if (i == 0) TC_TRACE(1, 4);
@@ -467,7 +479,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         // A2: Wq q (q sits in row 15 of every sequence) -> columns [128,192)
         for (int i = 0; i < C; ++i) {
           const int src = ((int)c + i) % C;           // q of chunk src sits in row 15 of K blocks 4 src .. 4 src + 3
-          ptx::mbar_wait_cluster(&bars[BAR_Q + src], t & 1);
+          { const unsigned long long t0 = tr_on ? clock64() : 0; ptx::mbar_wait_cluster(&bars[BAR_Q + src], t & 1); if (tr_on) w_other += clock64() - t0; }
           ptx::fence_proxy_async();
           ptx::tc_fence_after();
           if (i == 0 && lane0) TC_TRACE(1, 6);
@@ -489,6 +501,9 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         if (lane0) TC_TRACE(1, 7);
         if (nx) xblocks(bo * 256, n1 + n2, KF);
         if (lane0) TC_TRACE(1, 8);
+      }
+      if (tr_on && lane0) {
+        g_tc_trace[1][15][0] = w_full; g_tc_trace[1][15][1] = w_xfull; g_tc_trace[1][15][2] = w_other; g_tc_trace[1][15][3] = clock64() - t_begin;
       }
     }
   } else {
@@ -1302,10 +1317,11 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
     // epilogue warps run the gate phase, ~35 % during the q hand-off, the rest during e.u / h' / the state exchange
     const int KF = F / 16;
     int n1 = (KF * 45 + 99) / 100, n2 = KF * 35 / 100;   // measured best all-round split (45 % / 35 % / 20 %)
-    // per-shape optimum of the sweep in tests/sweep_split.sh (the curve is flat: 1-3 % between the best and 45/35)
-    if (H == 256 && F >= 512) { n1 = KF * 60 / 100; n2 = KF * 20 / 100; }
-    else if (H == 256) { n1 = KF * 35 / 100; n2 = KF * 45 / 100; }
-    else if (H == 128) { n1 = KF * 30 / 100; n2 = KF * 30 / 100; }
+    // per-shape optimum of the sweep with the lean MMA issue loop (profiles/r02_knob_sweep_lean_issue.log; the curve is flat:
+    // 1-3 % between the best and 45/35)
+    if (H == 256 && F < 512) { n1 = KF * 35 / 100; n2 = KF * 45 / 100; }
+    else if (H == 128 && F < 256) { n1 = KF * 20 / 100; n2 = KF * 40 / 100; }
+    else if (H == 64) { n1 = KF * 10 / 100; n2 = KF * 30 / 100; }
     if (const char* e = getenv("A3GC_TC_SPLIT")) {
       int a = 0, b = 0;
       if (sscanf(e, "%d,%d", &a, &b) == 2) { n1 = KF * a / 100; n2 = KF * b / 100; }
@@ -1315,7 +1331,9 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
     p.n1 = n1; p.n2 = n2;
     p.xsplit = getenv("A3GC_TC_XSPLIT") ? atoi(getenv("A3GC_TC_XSPLIT")) : 0;
     p.xdefer = getenv("A3GC_TC_XDEFER") ? atoi(getenv("A3GC_TC_XDEFER")) : 0;
-    p.xprefetch = getenv("A3GC_TC_XPREFETCH") ? atoi(getenv("A3GC_TC_XPREFETCH")) : 0;   // measured: no effect (+-0.3 %)
+    // L2 prefetch of the next step's x image: no effect while the issue thread was the bottleneck, -3.7 % at F512:H256 and
+    // -1.6 % at F256:H128 since (neutral elsewhere)
+    p.xprefetch = getenv("A3GC_TC_XPREFETCH") ? atoi(getenv("A3GC_TC_XPREFETCH")) : 1;
     p.acoll = getenv("A3GC_TC_ACOLL") ? atoi(getenv("A3GC_TC_ACOLL")) : 1;
     p.nprod = getenv("A3GC_TC_NPROD") ? atoi(getenv("A3GC_TC_NPROD")) : kProducers;
     if (p.nprod < 1) p.nprod = 1;

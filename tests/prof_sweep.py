@@ -17,7 +17,7 @@ variant = sys.argv[6] if len(sys.argv) > 6 else "A3GC"
 nira = torch.load("tests/golden/nira_template_15_norm.pt").float()
 cls = {"A3GC": A.BiA3GC_LSTM, "AAGC": A.BiAAGC_LSTM, "AGC": A.BiAGC_LSTM, "GGRU": A.BiG_GRU}[variant]
 KNOBS = ("A3GC_TC_HSEP", "A3GC_TC_SPLIT", "A3GC_TC_STAGES", "A3GC_TC_EARLYPUB", "A3GC_TC_PUBORDER", "A3GC_TC_TRACE", "A3GC_TC_QVEC",
-         "A3GC_TC_XCHG", "A3GC_TC_OPT", "A3GC_TC_NPROD", "A3GC_TC_ACOLL", "A3GC_TC_WSTAGES", "A3GC_TC_XSTAGES")
+         "A3GC_TC_XCHG", "A3GC_TC_OPT", "A3GC_TC_NPROD", "A3GC_TC_ACOLL", "A3GC_TC_WSTAGES", "A3GC_TC_XSTAGES", "A3GC_TC_XPREFETCH", "A3GC_TC_XSPLIT", "A3GC_TC_XDEFER")
 names_e = ["start", "acc_full", "ep1_done", "h_free", "pub_hhat", "att_full", "q_sent", "att2_full", "ep3_done", "a_ready", "out_done", "pub_h"]
 names_m = ["start", "h_ready", "hpart_issued", "xpart_issued", "a1_go", "a1_issued", "a2_go", "a2_issued", "x3_issued"]
 for (H, F) in shapes:
@@ -64,3 +64,7 @@ for (H, F) in shapes:
                 print(f"           mma " + " ".join(f"{n}={v - e[0]}" for n, v in zip(names_m, mm)))
             cyc = int(buf[0, 12, 1]) - int(buf[0, 2, 1])
             print(f"   steps 2..12: {cyc / 10:.0f} cycles per step", flush=True)
+            w = [int(v) for v in buf[1, 15, :4]]
+            if variant != "GGRU" and w[3]:
+                print(f"   MMA warp over the launch: {w[3]} cycles; waiting for a full weight slot {100 * w[0] / w[3]:.0f} %, x slot {100 * w[1] / w[3]:.0f} %, "
+                      f"state blocks / q / accumulators {100 * w[2] / w[3]:.0f} %, issuing {100 * (w[3] - w[0] - w[1] - w[2]) / w[3]:.0f} %", flush=True)
