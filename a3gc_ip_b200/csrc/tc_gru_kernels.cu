@@ -128,11 +128,12 @@ tc_gru_layer_kernel(const GruLayerParams p) {
     // ================================================================ producers (same scheme as tc_kernels.cu: the weight (B)
     // copy of stage i is issued by producer i % 2, the x-image (A) copy of every x stage by the third producer; every FULL
     // barrier takes two arrivals.  p.nprod = 1 / 2: one / two threads issue both copies of their stages.)
-    const uint32_t my = warp == 0 ? 0u : (uint32_t)(warp - (1 + kEpiWarps));
+    // (whole warp, elected lane issues: see the MMA warp)
+    const uint32_t my = __shfl_sync(0xffffffffu, warp == 0 ? 0u : (uint32_t)(warp - (1 + kEpiWarps)), 0);
     const uint32_t nprod = (uint32_t)p.nprod;
     const bool split_a = nprod == 3;
     const uint32_t nb = split_a ? 2u : nprod;
-    if ((threadIdx.x & 31) == 0 && my < nprod) {
+    if (my < nprod) {
       uint32_t st = 0, ph = 0, turn = 0;
       const bool tr_on = p.trace && blockIdx.x == 0 && blockIdx.y == 0;
       unsigned long long w_empty = 0, t_begin = tr_on ? clock64() : 0;      // trace: cycles this producer waited for a free slot
@@ -144,18 +145,21 @@ tc_gru_layer_kernel(const GruLayerParams p) {
           ptx::mbar_wait(&bars[BAR_EMPTY + st], ph ^ 1u);
           if (tr_on) w_empty += clock64() - t0;
         }
-        if (b_side) {
-          ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + st], bbytes);
-          ptx::bulk_g2s(dst, bsrc, bbytes, &bars[BAR_FULL + st]);
-        }
-        if (a_side) {
-          if (abytes) {
-            ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + st], abytes);
-            ptx::bulk_g2s(dst + aoff, asrc, abytes, &bars[BAR_FULL + st]);
-          } else {
-            ptx::mbar_arrive(&bars[BAR_FULL + st]);
+        if ((b_side || a_side) && ptx::elect_one()) {
+          if (b_side) {
+            ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + st], bbytes);
+            ptx::bulk_g2s(dst, bsrc, bbytes, &bars[BAR_FULL + st]);
+          }
+          if (a_side) {
+            if (abytes) {
+              ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + st], abytes);
+              ptx::bulk_g2s(dst + aoff, asrc, abytes, &bars[BAR_FULL + st]);
+            } else {
+              ptx::mbar_arrive(&bars[BAR_FULL + st]);
+            }
           }
         }
+        __syncwarp();
         if (++turn == nb) turn = 0;
         if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
       };
@@ -172,7 +176,7 @@ tc_gru_layer_kernel(const GruLayerParams p) {
         for (int s2 = 0; s2 < KH / 2; ++s2) load_stage(wm + (size_t)s2 * 2 * kMB, 2 * kMB, 0, nullptr, 0);
         if (t + 1 < T) xblocks(t + 1, 0, KF);
       }
-      if (tr_on) { g_gru_trace[0][15][2 * my] = w_empty; g_gru_trace[0][15][2 * my + 1] = clock64() - t_begin; }
+      if (tr_on && (threadIdx.x & 31) == 0) { g_gru_trace[0][15][2 * my] = w_empty; g_gru_trace[0][15][2 * my + 1] = clock64() - t_begin; }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer: the whole warp walks the stage sequence

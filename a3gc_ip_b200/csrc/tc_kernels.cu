@@ -216,14 +216,15 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
     // same static stage sequence:  nprod = 2: stage i is issued by producer i % 2;  nprod = 3: the weight (B) copy of stage i
     // by producer i % 2 and the x-image (A) copy of every x stage by the third, which follows its own ring and therefore runs
     // ahead of the weight stream across the recurrent / attention stages.
-    const uint32_t my = warp == 0 ? 0u : (uint32_t)(warp - (1 + kEpiWarps));
+    // Like the MMA warp, a producer warp walks the sequence on all 32 lanes (uniform operands) and one elected lane issues.
+    const uint32_t my = __shfl_sync(0xffffffffu, warp == 0 ? 0u : (uint32_t)(warp - (1 + kEpiWarps)), 0);
     const uint32_t nprod = (uint32_t)p.nprod;
     const bool split_a = nprod == 3;                 // producer 2 = the A side
     const uint32_t nb = split_a ? 2u : nprod;        // producers that take turns on the stages
     // The order of the stages is the static issue order of the MMA warp: h-part of step t, then the x-part of step
     // t+1 cut into three segments placed around the two attention GEMMs of step t, so that the tensor pipe has work
     // while the epilogue warps are busy and the attention GEMMs are never queued behind a long x-part.
-    if ((threadIdx.x & 31) == 0 && my < nprod) {
+    if (my < nprod) {
       uint32_t ws = 0, wph = 0;           // weight-ring slot and the parity of its current fill (no div / mod in the loop)
       uint32_t xs = 0, xph = 0;           // the same for the x-image ring
       uint32_t turn = 0;                  // whose stage this is
@@ -234,37 +235,46 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
           if (b_side) {
             uint8_t* dst = ring + ws * kBBytes;
             ptx::mbar_wait(&bars[BAR_EMPTY + ws], wph ^ 1u);
-            ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + ws], bbytes);
-            // p.chunk (tuning knob) can cut the copies into pieces; measured slower than one copy per operand
-            for (uint32_t o = 0; o < bbytes; o += chunk)
-              ptx::bulk_g2s(dst + o, static_cast<const uint8_t*>(bsrc) + o, min(chunk, bbytes - o), &bars[BAR_FULL + ws]);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + ws], bbytes);
+              // p.chunk (tuning knob) can cut the copies into pieces; measured slower than one copy per operand
+              for (uint32_t o = 0; o < bbytes; o += chunk)
+                ptx::bulk_g2s(dst + o, static_cast<const uint8_t*>(bsrc) + o, min(chunk, bbytes - o), &bars[BAR_FULL + ws]);
+            }
+            __syncwarp();
           }
           if (a_side) {
             uint8_t* dst = xring + xs * kABytes;
             ptx::mbar_wait(&bars[BAR_XEMPTY + xs], xph ^ 1u);
-            ptx::mbar_arrive_expect_tx(&bars[BAR_XFULL + xs], abytes);
-            for (uint32_t o = 0; o < abytes; o += chunk)
-              ptx::bulk_g2s(dst + o, static_cast<const uint8_t*>(asrc) + o, min(chunk, abytes - o), &bars[BAR_XFULL + xs]);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(&bars[BAR_XFULL + xs], abytes);
+              for (uint32_t o = 0; o < abytes; o += chunk)
+                ptx::bulk_g2s(dst + o, static_cast<const uint8_t*>(asrc) + o, min(chunk, abytes - o), &bars[BAR_XFULL + xs]);
+            }
+            __syncwarp();
           }
         } else {
           // one ring: every FULL barrier takes two arrivals (B side, A side)
           uint8_t* dst = ring + ws * kSlotStride;
           const bool b_side = my < nb && turn == my, a_side = split_a ? my == 2u : b_side;
           if (b_side || a_side) ptx::mbar_wait(&bars[BAR_EMPTY + ws], wph ^ 1u);
-          if (b_side) {
-            ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + ws], bbytes);
-            for (uint32_t o = 0; o < bbytes; o += chunk)
-              ptx::bulk_g2s(dst + o, static_cast<const uint8_t*>(bsrc) + o, min(chunk, bbytes - o), &bars[BAR_FULL + ws]);
-          }
-          if (a_side) {
-            if (abytes) {
-              ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + ws], abytes);
-              for (uint32_t o = 0; o < abytes; o += chunk)
-                ptx::bulk_g2s(dst + kBBytes + o, static_cast<const uint8_t*>(asrc) + o, min(chunk, abytes - o), &bars[BAR_FULL + ws]);
-            } else {
-              ptx::mbar_arrive(&bars[BAR_FULL + ws]);
+          if ((b_side || a_side) && ptx::elect_one()) {
+            if (b_side) {
+              ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + ws], bbytes);
+              for (uint32_t o = 0; o < bbytes; o += chunk)
+                ptx::bulk_g2s(dst + o, static_cast<const uint8_t*>(bsrc) + o, min(chunk, bbytes - o), &bars[BAR_FULL + ws]);
+            }
+            if (a_side) {
+              if (abytes) {
+                ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + ws], abytes);
+                for (uint32_t o = 0; o < abytes; o += chunk)
+                  ptx::bulk_g2s(dst + kBBytes + o, static_cast<const uint8_t*>(asrc) + o, min(chunk, abytes - o), &bars[BAR_FULL + ws]);
+              } else {
+                ptx::mbar_arrive(&bars[BAR_FULL + ws]);
+              }
             }
           }
+          __syncwarp();
         }
         if (++turn == nb) turn = 0;
         if (++ws == (uint32_t)S) { ws = 0; wph ^= 1u; }
@@ -282,7 +292,8 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         if (kb0 == 0 && p.xprefetch && my == 0 && t + 1 < T) {
           const int tn = d.reverse ? T - 2 - t : t + 1;
           const uint32_t share = (uint32_t)(KF / C) * kABytes;
-          ptx::bulk_prefetch_l2(xi + ((size_t)tile * T + tn) * KF * kABytes + (size_t)c * share, share);
+          if (ptx::elect_one()) ptx::bulk_prefetch_l2(xi + ((size_t)tile * T + tn) * KF * kABytes + (size_t)c * share, share);
+          __syncwarp();
         }
         for (int kb = kb0; kb < kb1; ++kb) load_stage(wg + (size_t)kb * kBBytes, kBBytes, xs + (size_t)kb * kABytes, kABytes);
       };
