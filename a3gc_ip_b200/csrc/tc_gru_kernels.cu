@@ -57,6 +57,7 @@ struct GruLayerParams {
   int acoll;                // A-operand collector reuse (see ptx::umma_f16_coll)
   int nprod;                // bulk-copy producer threads (1..3)
   int trace;
+  int xprefetch;            // L2 prefetch of the next step's x image
 };
 
 enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_ACC_FULL = 2 * kMaxStages, BAR_ACC_EMPTY = BAR_ACC_FULL + 2, BAR_H = BAR_ACC_EMPTY + 2,
@@ -169,6 +170,13 @@ tc_gru_layer_kernel(const GruLayerParams p) {
       auto xblocks = [&](int t, int kb0, int kb1) {
         const int ta = d.reverse ? T - 1 - t : t;
         const uint8_t* xs = xi + ((size_t)tile * T + ta) * KF * kXA;
+        // the x operand image comes from HBM: this CTA's share of the NEXT step's image is pulled into L2 one step ahead
+        if (p.xprefetch && my == 0 && t + 1 < T) {
+          const int tn = d.reverse ? T - 2 - t : t + 1;
+          const uint32_t share = (uint32_t)(KF / C) * kXA;
+          if (ptx::elect_one()) ptx::bulk_prefetch_l2(xi + ((size_t)tile * T + tn) * KF * kXA + (size_t)c * share, share);
+          __syncwarp();
+        }
         for (int kb = kb0; kb < kb1; ++kb) load_stage(wx + (size_t)kb * kXB, kXB, kXB, xs + (size_t)kb * kXA, kXA);
       };
       xblocks(0, 0, KF);
@@ -600,6 +608,7 @@ int tc_gru_layer_launch(const LayerArgs& a, const uint16_t* x_img, char* wbase, 
   p.nprod = getenv("A3GC_TC_NPROD") ? atoi(getenv("A3GC_TC_NPROD")) : kProducers;
   if (p.nprod < 1) p.nprod = 1;
   if (p.nprod > kProducers) p.nprod = kProducers;
+  p.xprefetch = getenv("A3GC_TC_XPREFETCH") ? atoi(getenv("A3GC_TC_XPREFETCH")) : 1;
   p.trace = (getenv("A3GC_TC_TRACE") != nullptr && strcmp(getenv("A3GC_TC_TRACE"), "gru") == 0) ? 1 : 0;
   int dev = 0, smem_max = 0;
   A3GC_CUDA_TRY(cudaGetDevice(&dev));
