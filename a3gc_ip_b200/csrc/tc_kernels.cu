@@ -548,6 +548,9 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
     // rewrites every byte).  The region is dead during the gate phase: the phase starts after BAR_HFREE (every MMA of the
     // cluster that reads h'_{t-1} has completed, and therefore every outgoing copy of the block has landed), peers never
     // write into a CTA's own block, and this CTA's q rows are written after the gate phase.
+    // the first epilogue warp issues the hand-offs (bulk copies to the peers, remote barrier arrives): warp-uniform flag, so that
+    // the operands of those instructions are uniform and one elected lane issues them without a per-instruction waterfall
+    const bool warp0 = __shfl_sync(0xffffffffu, ew, 0) == 0;
     float* wst = staging + ew * kWstFloats;
     float* wst2 = wst + 4 * 32;
     if (SPLIT) {
@@ -613,7 +616,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       ptx::fence_proxy_async();
       if (acc_empty >= 0) ptx::tc_fence_before();
       ptx::named_bar_sync(1, kEpiThreads);
-      if (et == 0) {
+      if (warp0 && ptx::elect_one()) {
         if (acc_empty >= 0) ptx::mbar_arrive(&bars[BAR_ACC_EMPTY + acc_empty]);
         ptx::mbar_arrive(&bars[bar + c]);                               // own chunk: usable at once
         // Send order: CTA c serves c-1 first, then c-2, ...: a receiver walks the sources own, r+1, r+2, ... (rotated K order),
@@ -637,7 +640,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       ptx::fence_proxy_async();
       if (acc_empty >= 0) ptx::tc_fence_before();
       ptx::named_bar_sync(1, kEpiThreads);
-      if (et == 0) {
+      if (warp0 && ptx::elect_one()) {
         constexpr uint32_t kHalf = kHBlock / 2;
         for (uint32_t i = 1; i < (uint32_t)C; ++i) {
           const uint32_t peer = (c + (uint32_t)C - i) % (uint32_t)C;
@@ -972,7 +975,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       ptx::named_bar_sync(1, kEpiThreads);
-      if (et == 0) {
+      if (warp0 && ptx::elect_one()) {
         // one cluster-scope release fence, then relaxed arrives (a release arrive per peer costs a MEMBAR.GPU each)
         if (C > 1) ptx::fence_acq_rel_cluster();
         for (uint32_t peer = 0; peer < (uint32_t)C; ++peer) ptx::mbar_arrive_remote_relaxed(&bars[BAR_Q + c], peer);
@@ -1004,7 +1007,7 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       if (et < 128) apart[c * 128 + et] = (ahalf[et] + ahalf[128 + et]) + (ahalf[256 + et] + ahalf[384 + et]);
       ptx::fence_proxy_async();
       ptx::named_bar_sync(1, kEpiThreads);
-      if (et == 0) {
+      if (warp0 && ptx::elect_one()) {
         for (uint32_t peer = 0; peer < (uint32_t)C; ++peer)
           if (peer != c) ptx::bulk_s2remote(apart + c * 128, 512, &bars[BAR_A], peer);
         ptx::mbar_arrive_expect_tx(&bars[BAR_A], (uint32_t)(C - 1) * 512);
