@@ -10,7 +10,7 @@ import json
 import os
 import re
 
-RAW = "r02b_ncu_raw_lstm_f512_h256.csv"   # the capture of the final tree (two rings); r02_ncu_raw_* = before that change
+RAW = "r02c_ncu_raw_lstm_f512_h256.csv"   # the capture of the final tree; r02b_ = two rings, before the lean issue loop; r02_ = start of the session
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 P = os.path.join(ROOT, "profiles")
 
