@@ -36,6 +36,8 @@ constexpr int kUnits = 64;             // hidden units per CTA
 constexpr int kEpiWarps = 16;          // warps 2..17: warp (qd = warp%4, ug = (warp-2)/4) owns rows 32qd..32qd+31 x units 16ug..16ug+15
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kProducers = 3;           // warp 0 and the two warps behind the epilogue warps (18, 19)
+constexpr int kXchgWarp = 2 + kEpiWarps + (kProducers - 2);   // warp 19: the third producer, or the state exchange through L2 (p.xchg;
+                                                               // a 21st warp would cut the register budget from 96 to 80 per thread)
 constexpr int kThreadsTC = 64 + kEpiThreads + 32 * (kProducers - 1);
 constexpr int kMaxStages = 8;
 constexpr int kWstFloats = 8 * 32;     // warp-private transposition buffer: 8 accumulator columns x 32 rows
@@ -85,6 +87,8 @@ struct TcLayerParams {
   int rescale;                       // fp32 inference: peers' h' blocks are rescaled locally instead of a second all-gather
   int rescale_bf16;                  // the same in bf16 mode (costs a second bf16 rounding of the peers' blocks; experiment knob)
   int pubbytes;                      // TIMING DIAGNOSTIC ONLY (results are wrong if < kHBlock): bytes per state-exchange copy
+  int xchg;                          // state exchange through L2: bulk store of the CTA's block, then ONE multicast bulk load into the peers
+  uint8_t* xchg_buf;                 // [direction][tile][C][NP][16 KB] scratch of that exchange (caller's workspace)
   int acoll;                         // A-operand collector reuse between the hi*hi and hi*lo passes of a K block
   int nprod;                         // producer threads (one per warp) that issue the bulk copies of the weight / x stream, stage i by thread i % nprod
   int n1, n2;                        // x-part blocks of step t+1 issued before A1 / between A1 and A2 of step t (rest after A2)
@@ -100,7 +104,8 @@ struct TcLayerParams {
 enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_XFULL = 2 * kMaxStages, BAR_XEMPTY = 3 * kMaxStages,
        BAR_ACC_FULL = 4 * kMaxStages, BAR_ATT_FULL = BAR_ACC_FULL + 2, BAR_ATT2_FULL,
        BAR_ACC_EMPTY, BAR_A = BAR_ACC_EMPTY + 2, BAR_HFREE, BAR_A1FREE, BAR_H, BAR_HHAT = BAR_H + 4, BAR_Q = BAR_HHAT + 4,
-       BAR_COUNT = BAR_Q + 4 };
+       BAR_XRDY = BAR_Q + 4,     // [2] halves of this CTA's block are in its image: the exchange warp may store them (p.xchg)
+       BAR_COUNT = BAR_XRDY + 2 };
 constexpr int kBarSlots = 56;
 
 // fp32-split mode: the warp-private transposition buffers are not a separate allocation -- each warp uses the 2 x 512 bytes of
@@ -208,7 +213,37 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
   const uint32_t tmem = *tmem_slot;
   const uint16_t cta_mask = (uint16_t)((1u << C) - 1u);
 
-  if (warp == 0 || warp >= 2 + kEpiWarps) {
+  const bool xchg_warp_on = p.xchg && !TRAIN && C > 2 && p.earlypub;   // (the host then runs two producers: p.nprod <= 2)
+  if (warp == kXchgWarp && xchg_warp_on) {
+    // ================================================================ exchange warp (p.xchg, 4-CTA clusters, inference): the
+    // CTA's 64-unit block of hy goes to the peers through L2 -- a bulk store of each half as soon as the epilogue warps have
+    // written it (BAR_XRDY), then ONE multicast bulk load per part drops it into every peer and completes on the peers'
+    // barriers of source c.  The DSMEM copies it replaces move ~13 B/cycle per SM (the three peer blocks land 4.4 / 5.8 / 7.2 k
+    // cycles after the hand-off) and read the block three times; this path needs ~2.5 k cycles per half and its wait for the
+    // store blocks only this warp.
+    {
+      constexpr uint32_t kHalf = kHBlock / 2;
+      uint8_t* mine = p.xchg_buf + ((((size_t)blockIdx.y * (gridDim.x / C) + tile) * C + c) * NP) * kHBlock;
+      const int bar = ATT ? BAR_HHAT : BAR_H;
+      const uint16_t peers = (uint16_t)(cta_mask & ~(1u << c));
+      for (int t = 0; t < T; ++t) {
+        for (int half = 0; half < 2; ++half) {
+          ptx::mbar_wait(&bars[BAR_XRDY + half], t & 1);
+          if (ptx::elect_one()) {
+            for (int part = 0; part < NP; ++part)
+              ptx::bulk_s2g(mine + (size_t)part * kHBlock + (size_t)half * kHalf,
+                            hbuf + (size_t)part * H * 256 + (size_t)c * kHBlock + (size_t)half * kHalf, kHalf);
+            ptx::bulk_commit_group();
+            ptx::bulk_wait_group0();
+            for (int part = 0; part < NP; ++part)
+              ptx::bulk_g2s_multicast(hbuf + (size_t)part * H * 256 + (size_t)c * kHBlock + (size_t)half * kHalf,
+                                      mine + (size_t)part * kHBlock + (size_t)half * kHalf, kHalf, &bars[bar + c], peers);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 0 || warp >= 2 + kEpiWarps) {
     // ================================================================ producers: weights / x -> ring
     // One thread issues a bulk copy every ~440 cycles whatever its size (tests/diag_stream_rate.py: 444 cycles per copy for
     // 4 KB .. 48 KB; 222 / 131 cycles with 2 / 4 issuing warps), and an H = 256, F = 512 step needs 92 copies (two per x
@@ -612,6 +647,9 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
     // all epilogue threads have written their part of the local operand image: make it visible to the async proxy,
     // then send this CTA's 64-unit block to every peer; `bar` completes in each CTA when all C blocks have landed.
     // `acc_empty` >= 0: the accumulator buffer has been drained as well (tcgen05 loads fenced before the barrier).
+    // this CTA's slot of the L2 exchange scratch: [direction][tile][chunk][part][16 KB]
+    uint8_t* xchg_mine = p.xchg_buf == nullptr ? nullptr
+        : p.xchg_buf + ((((size_t)blockIdx.y * (gridDim.x / C) + tile) * C + c) * NP) * kHBlock;
     auto publish_block = [&](int bar, int acc_empty) {
       ptx::fence_proxy_async();
       if (acc_empty >= 0) ptx::tc_fence_before();
@@ -621,6 +659,17 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
         ptx::mbar_arrive(&bars[bar + c]);                               // own chunk: usable at once
         // Send order: CTA c serves c-1 first, then c-2, ...: a receiver walks the sources own, r+1, r+2, ... (rotated K order),
         // so the block it needs first is the one every sender pushes first (p.puborder 0 = fixed order 0, 1, 2, ...; 2 = c+1 first)
+        if (p.xchg && C > 1) {
+          // through L2: store the block once, then one multicast load per part drops it into every peer (and completes on the
+          // peers' barriers of source c) -- the DSMEM copies move ~13 B/cycle per SM and read the block three times
+          for (int part = 0; part < NP; ++part)
+            ptx::bulk_s2g(xchg_mine + (size_t)part * kHBlock, hbuf + (size_t)part * H * 256 + (size_t)c * kHBlock, kHBlock);
+          ptx::bulk_commit_group();
+          ptx::bulk_wait_group0();
+          for (int part = 0; part < NP; ++part)
+            ptx::bulk_g2s_multicast(hbuf + (size_t)part * H * 256 + (size_t)c * kHBlock, xchg_mine + (size_t)part * kHBlock, kHBlock, &bars[bar + c],
+                                    (uint16_t)(cta_mask & ~(1u << c)));
+        } else
         for (uint32_t i = 1; i < (uint32_t)C; ++i) {
           const uint32_t peer = p.puborder == 1 ? (c + (uint32_t)C - i) % (uint32_t)C
                               : p.puborder == 2 ? (c + i) % (uint32_t)C
@@ -642,6 +691,9 @@ tc_lstm_layer_kernel(const TcLayerParams p) {
       ptx::named_bar_sync(1, kEpiThreads);
       if (warp0 && ptx::elect_one()) {
         constexpr uint32_t kHalf = kHBlock / 2;
+        if (p.xchg) {
+          ptx::mbar_arrive(&bars[BAR_XRDY + half]);                      // the exchange warp stores / multicasts this half
+        } else
         for (uint32_t i = 1; i < (uint32_t)C; ++i) {
           const uint32_t peer = (c + (uint32_t)C - i) % (uint32_t)C;
           for (int part = 0; part < NP; ++part)
@@ -1242,6 +1294,10 @@ size_t tc_layer_workspace_bytes(int variant, int64_t batch, int64_t steps, int f
   size_t b = variant == A3GC_VARIANT_GGRU ? tc_gru_weights_bytes(f_in, hidden, num_dirs, precision)
                                           : (size_t)num_dirs * tc_dir_bytes(f_in, hidden, NP);
   b += tc_image_bytes(batch, steps, f_in, precision);   // x image (unused when the caller hands one in)
+  if (variant != A3GC_VARIANT_GGRU) {                    // scratch of the state exchange through L2 (LSTM family, clusters only)
+    const int64_t tiles = (batch + kSeqTile - 1) / kSeqTile;
+    b += (size_t)num_dirs * tiles * (hidden / 64) * NP * (8 * kRows * 16);
+  }
   return b + 256;
 }
 
@@ -1356,6 +1412,11 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
     p.puborder = getenv("A3GC_TC_PUBORDER") ? atoi(getenv("A3GC_TC_PUBORDER")) : 1;
     p.rescale = getenv("A3GC_TC_RESCALE") ? atoi(getenv("A3GC_TC_RESCALE")) : 1;
     p.rescale_bf16 = getenv("A3GC_TC_RESCALE_BF16") ? atoi(getenv("A3GC_TC_RESCALE_BF16")) : 0;
+    // state exchange through L2 with the third producer warp as exchange warp: on for the 4-CTA clusters of the inference path
+    // (-1 % at H = 256 for A3GC / AGC, -3..4 % for AAGC; neutral for 2-CTA clusters, not used by the training forward)
+    p.xchg = getenv("A3GC_TC_XCHG") ? atoi(getenv("A3GC_TC_XCHG")) : ((C > 2 && a.tape == nullptr) ? 1 : 0);
+    p.xchg_buf = reinterpret_cast<uint8_t*>(base + a.num_dirs * dir_bytes + tc_image_bytes(a.batch, a.steps, F, a.precision));
+    if (p.xchg && a.tape == nullptr && C > 2 && p.earlypub && p.nprod > 2) p.nprod = 2;   // the third producer warp runs the exchange
     p.pubbytes = 16384;  // = kHBlock; A3GC_TC_PUBBYTES < 16384 is a timing diagnostic (truncated state exchange, wrong results)
     if (const char* e = getenv("A3GC_TC_PUBBYTES")) { const int v = atoi(e); if (v >= 16 && v <= 16384 && v % 16 == 0) p.pubbytes = v; }
     p.chunk = 1 << 20;   // measured: one bulk copy per operand is fastest (4 KB pieces: -7 %, 2 KB pieces: -30 %)

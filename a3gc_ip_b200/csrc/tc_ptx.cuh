@@ -94,6 +94,19 @@ __device__ __forceinline__ void bulk_s2remote(void* smem_ptr, uint32_t bytes, ui
                ::"r"(rdst), "r"(smem_u32(smem_ptr)), "r"(bytes), "r"(rbar) : "memory");
 }
 
+// this CTA's shared memory -> global memory (bulk async-group of the issuing thread)
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk async-groups of this thread have COMPLETED (their global writes are performed, not only their source reads)
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// global -> the same CTA-relative offset in every CTA of `cta_mask`; completion on the barrier at the same offset in each of them
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
 // ---------------------------------------------------------------- cluster
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
