@@ -1412,9 +1412,10 @@ int tc_layer_forward(const LayerArgs& a, void* ws, size_t ws_bytes, cudaStream_t
     p.puborder = getenv("A3GC_TC_PUBORDER") ? atoi(getenv("A3GC_TC_PUBORDER")) : 1;
     p.rescale = getenv("A3GC_TC_RESCALE") ? atoi(getenv("A3GC_TC_RESCALE")) : 1;
     p.rescale_bf16 = getenv("A3GC_TC_RESCALE_BF16") ? atoi(getenv("A3GC_TC_RESCALE_BF16")) : 0;
-    // state exchange through L2 with the third producer warp as exchange warp: on for the 4-CTA clusters of the inference path
-    // (-1 % at H = 256 for A3GC / AGC, -3..4 % for AAGC; neutral for 2-CTA clusters, not used by the training forward)
-    p.xchg = getenv("A3GC_TC_XCHG") ? atoi(getenv("A3GC_TC_XCHG")) : ((C > 2 && a.tape == nullptr) ? 1 : 0);
+    // state exchange through L2: on for 4-CTA clusters.  Inference: the third producer warp is the exchange warp (-1 % at H = 256
+    // for A3GC / AGC, -3..5 % for AAGC); training forward (two all-gathers per step, issued in line by the first epilogue warp):
+    // -8 % per H = 256 step.  Neutral for 2-CTA clusters, which keep the DSMEM copies.
+    p.xchg = getenv("A3GC_TC_XCHG") ? atoi(getenv("A3GC_TC_XCHG")) : (C > 2 ? 1 : 0);
     p.xchg_buf = reinterpret_cast<uint8_t*>(base + a.num_dirs * dir_bytes + tc_image_bytes(a.batch, a.steps, F, a.precision));
     if (p.xchg && a.tape == nullptr && C > 2 && p.earlypub && p.nprod > 2) p.nprod = 2;   // the third producer warp runs the exchange
     p.pubbytes = 16384;  // = kHBlock; A3GC_TC_PUBBYTES < 16384 is a timing diagnostic (truncated state exchange, wrong results)
