@@ -48,6 +48,18 @@ gc_in_kernel(a3gc_gc_params p, const float* __restrict__ x, GcRawInput raw, floa
   float* xs = bias + O;              // [8][15][K]
   const int KP = K | 1;              // odd row stride: consecutive rows of xm fall into different banks
   float* xm = xs + 8 * kNodes * K;   // [128][KP]  (adj @ x), row 15 of each frame zero
+  float* nrm = xm + 128 * KP;        // RAW: [72] mean, [72] std in the order of the raw frame (18 acc, 54 ori)
+  if (RAW) {
+    for (int i = threadIdx.x; i < 72; i += blockDim.x) {
+      if (i < 18) {
+        nrm[i] = raw.acc_mean != nullptr ? raw.acc_mean[i] : 0.f;
+        nrm[72 + i] = raw.acc_std != nullptr ? raw.acc_std[i] : 1.f;
+      } else {
+        nrm[i] = raw.ori_mean != nullptr ? raw.ori_mean[i - 18] : 0.f;
+        nrm[72 + i] = raw.ori_std != nullptr ? raw.ori_std[i - 18] : 1.f;
+      }
+    }
+  }
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     const int m = i >> 4, n = i & 15;
     adj[i] = (m < kNodes && n < kNodes) ? p.adj[m * kNodes + n] : 0.f;
@@ -62,40 +74,71 @@ gc_in_kernel(a3gc_gc_params p, const float* __restrict__ x, GcRawInput raw, floa
     // ---- load the 8 frames of this group
     int64_t tile = 0; int t = 0;
     if (IMG) { tile = grp / T; t = (int)(grp % T); }
-    for (int i = threadIdx.x; i < 8 * per_frame; i += blockDim.x) {
-      const int fr = i / per_frame, r = i % per_frame;
-      float v = 0.f;
-      int64_t f = -1;                                   // frame index in [B*T) order, -1: beyond the batch
-      if (IMG) {
-        const int64_t b = tile * 8 + fr;
-        if (b < B) f = b * T + t;
-      } else {
-        if (grp * 8 + fr < frames) f = grp * 8 + fr;
-      }
-      if (f >= 0) {
-        if (RAW) {
-          const int n = r / K, k = r % K;
-          if (k >= 12) {
-            v = __ldg(raw.pos + (size_t)f * (kNodes * 3) + n * 3 + (k - 12));
+    if (RAW) {
+      // coalesced: the 72 raw floats of each frame (18 acc + 54 ori) are read once, normalised from the shared-memory copy of
+      // the statistics and scattered to (node, feature); IMU 6 is dropped.  The ten zero nodes' IMU features are never
+      // written: the mix below reads nodes 3, 4, 10, 13, 14 only for k < 12.  Three independent loads per thread.
+#pragma unroll
+      for (int it = 0; it < 3; ++it) {
+        const int i = (int)threadIdx.x + it * kGcThreads;
+        if (i < 8 * 72) {
+          const int fr = i / 72, c = i % 72;
+          int64_t f = -1;
+          if (IMG) {
+            const int64_t b = tile * 8 + fr;
+            if (b < B) f = b * T + t;
           } else {
-            const int imu = c_node_imu[n];
-            if (imu >= 0) {
-              if (k < 3) {
-                const int ch = imu * 3 + k;
-                v = __ldg(raw.acc + (size_t)f * 18 + ch);
-                if (raw.acc_mean != nullptr) v = (v - raw.acc_mean[ch]) / raw.acc_std[ch];
-              } else {
-                const int ch = imu * 9 + (k - 3);
-                v = __ldg(raw.ori + (size_t)f * 54 + ch);
-                if (raw.ori_mean != nullptr) v = (v - raw.ori_mean[ch]) / raw.ori_std[ch];
-              }
+            if (grp * 8 + fr < frames) f = grp * 8 + fr;
+          }
+          float v = 0.f;
+          int imu, k;
+          if (c < 18) {
+            imu = c / 3; k = c % 3;
+            if (f >= 0) {
+              v = __ldg(raw.acc + (size_t)f * 18 + c);
+              if (raw.acc_mean != nullptr) v = (v - nrm[c]) / nrm[72 + c];
+            }
+          } else {
+            const int ch = c - 18;
+            imu = ch / 9; k = 3 + ch % 9;
+            if (f >= 0) {
+              v = __ldg(raw.ori + (size_t)f * 54 + ch);
+              if (raw.ori_mean != nullptr) v = (v - nrm[c]) / nrm[72 + c];
             }
           }
-        } else {
-          v = __ldg(x + (size_t)f * per_frame + r);
+          if (imu < 5 && k < K) {
+            const int node = imu == 0 ? 3 : imu == 1 ? 4 : imu == 2 ? 13 : imu == 3 ? 14 : 10;   // input_joints (evaluate_a3gc_tp.py:65)
+            xs[fr * per_frame + node * K + k] = v;
+          }
         }
       }
-      xs[i] = v;
+      const int PK = K - 12;                              // features taken from the previous stage's output (0 or 3)
+      if (PK > 0) {
+        const int per = kNodes * PK;
+        for (int i = threadIdx.x; i < 8 * per; i += blockDim.x) {
+          const int fr = i / per, e = i % per, n = e / PK, j = e % PK;
+          int64_t f = -1;
+          if (IMG) {
+            const int64_t b = tile * 8 + fr;
+            if (b < B) f = b * T + t;
+          } else {
+            if (grp * 8 + fr < frames) f = grp * 8 + fr;
+          }
+          xs[fr * per_frame + n * K + 12 + j] = f >= 0 ? __ldg(raw.pos + (size_t)f * (kNodes * 3) + n * 3 + j) : 0.f;
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < 8 * per_frame; i += blockDim.x) {
+        const int fr = i / per_frame, r = i % per_frame;
+        int64_t f = -1;                                   // frame index in [B*T) order, -1: beyond the batch
+        if (IMG) {
+          const int64_t b = tile * 8 + fr;
+          if (b < B) f = b * T + t;
+        } else {
+          if (grp * 8 + fr < frames) f = grp * 8 + fr;
+        }
+        xs[i] = f >= 0 ? __ldg(x + (size_t)f * per_frame + r) : 0.f;
+      }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 128 * K; i += blockDim.x) {
@@ -177,6 +220,36 @@ gc_in_kernel(a3gc_gc_params p, const float* __restrict__ x, GcRawInput raw, floa
   }
 }
 
+
+// Sum N per-lane values over the 32 lanes of a warp.  Stage MASK: lanes with the bit clear keep the lower half of the values and
+// receive the partner's, lanes with the bit set keep the upper half -- (N+1)/2 values remain.  After the last stage value j of
+// a lane is the complete sum of the original value butterfly_index(j, lane).
+template <int N, int MASK>
+__device__ __forceinline__ void xor_butterfly(float* v, int lane) {
+  constexpr int H = (N + 1) / 2;
+  const bool up = (lane & MASK) != 0;
+#pragma unroll
+  for (int i = 0; i < H; ++i) {
+    const float a = v[i];
+    const float b = (i + H < N) ? v[i + H] : 0.f;
+    const float send = up ? a : b, keep = up ? b : a;
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
+  }
+  if constexpr (MASK > 1) xor_butterfly<H, MASK / 2>(v, lane);
+}
+__host__ __device__ constexpr int butterfly_count(int n, int mask) { return mask == 0 ? n : butterfly_count((n + 1) / 2, mask / 2); }
+template <int N, int MASK>
+__device__ __forceinline__ int butterfly_index(int j, int lane) {
+  constexpr int H = (N + 1) / 2;
+  int pos = j;
+  if constexpr (MASK > 1) {
+    pos = butterfly_index<H, MASK / 2>(j, lane);
+    if (pos < 0) return -1;
+  }
+  pos += (lane & MASK) ? H : 0;
+  return pos < N ? pos : -1;
+}
+
 // ------------------------------------------------------------------------------------------
 // gc_out: f_in % 128 == 0, f_out <= 16.  Block = 16 frames (240 rows); each warp takes 8 rows at a time.
 // ------------------------------------------------------------------------------------------
@@ -219,18 +292,15 @@ gc_out_kernel(a3gc_gc_params p, const float* __restrict__ x, float* __restrict__
           }
         }
       }
+      // transposing butterfly: every stage halves the values a lane carries (71 shuffles for 8 x 9 sums instead of 360); the
+      // pairing tree per sum is the xor butterfly 16, 8, 4, 2, 1 as before, so the results are unchanged bit for bit
+      float* flat = &acc[0][0];
+      xor_butterfly<8 * OMAX, 16>(flat, lane);
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
-#pragma unroll
-        for (int o = 0; o < OMAX; ++o) {
-          float s = acc[r][o];
-          s += __shfl_xor_sync(0xffffffffu, s, 16);
-          s += __shfl_xor_sync(0xffffffffu, s, 8);
-          s += __shfl_xor_sync(0xffffffffu, s, 4);
-          s += __shfl_xor_sync(0xffffffffu, s, 2);
-          s += __shfl_xor_sync(0xffffffffu, s, 1);
-          if (lane == 0 && r8 + r < nrows) v[(size_t)(r8 + r) * OMAX + o] = s;
-        }
+      for (int j = 0; j < butterfly_count(8 * OMAX, 16); ++j) {
+        const int idx = butterfly_index<8 * OMAX, 16>(j, lane);          // = r * OMAX + o of the sum this lane holds
+        if (idx >= 0 && r8 + idx / OMAX < nrows) v[(size_t)r8 * OMAX + idx] = flat[j];
+      }
     }
     __syncthreads();
     // y[f][m][o] = sum_n adj[m][n] v[f][n][o] + b[o]
@@ -261,7 +331,7 @@ int gc_forward_fast(const a3gc_gc_params* p, const float* x, float* y, int64_t f
   if (frames == 0) { *handled = 1; return A3GC_OK; }
   const int sms = sm_count();
   if (f_in <= 32) {
-    const size_t smem = (256 + (size_t)f_in * f_out + f_out + 8 * kNodes * f_in + 128 * (f_in | 1)) * sizeof(float);
+    const size_t smem = (256 + (size_t)f_in * f_out + f_out + 8 * kNodes * f_in + 128 * (f_in | 1) + 144) * sizeof(float);
     if (smem > 160 * 1024) return A3GC_OK;
     int64_t groups = (frames + 7) / 8;
     int64_t blocks = groups < (int64_t)sms * 8 ? groups : (int64_t)sms * 8;
@@ -296,7 +366,7 @@ int gc_forward_image(const a3gc_gc_params* p, const float* x, const GcRawInput* 
                      int f_in, int f_out, int act, int split, cudaStream_t stream) {
   if (batch == 0 || steps == 0) return A3GC_OK;
   if (f_in > 32 || f_out % 16 != 0) { set_error("gc_forward_image: unsupported shape"); return A3GC_ERR_UNSUPPORTED; }
-  const size_t smem = (256 + (size_t)f_in * f_out + f_out + 8 * kNodes * f_in + 128 * (f_in | 1)) * sizeof(float);
+  const size_t smem = (256 + (size_t)f_in * f_out + f_out + 8 * kNodes * f_in + 128 * (f_in | 1) + 144) * sizeof(float);
   const int64_t groups = ((batch + 7) / 8) * steps;
   const int sms = sm_count();
   int64_t blocks = groups < (int64_t)sms * 8 ? groups : (int64_t)sms * 8;
@@ -315,7 +385,7 @@ int gc_forward_image(const a3gc_gc_params* p, const float* x, const GcRawInput* 
 int gc_forward_raw(const a3gc_gc_params* p, const GcRawInput* raw, float* y, int64_t frames, int f_in, int f_out, int act,
                    cudaStream_t stream) {
   if (frames == 0) return A3GC_OK;
-  const size_t smem = (256 + (size_t)f_in * f_out + f_out + 8 * kNodes * f_in + 128 * (f_in | 1)) * sizeof(float);
+  const size_t smem = (256 + (size_t)f_in * f_out + f_out + 8 * kNodes * f_in + 128 * (f_in | 1) + 144) * sizeof(float);
   if (f_in > 32 || smem > 160 * 1024) { set_error("gc_forward_raw: unsupported shape"); return A3GC_ERR_UNSUPPORTED; }
   const int sms = sm_count();
   int64_t groups = (frames + 7) / 8;
