@@ -25,9 +25,6 @@ __device__ __forceinline__ void split16(float v, bool split, uint16_t& hi, uint1
   }
 }
 
-// node -> IMU index of prepare_input: input_joints = [3, 4, 13, 14, 10] (evaluate_a3gc_tp.py:65), -1 = zero node
-__constant__ int c_node_imu[16] = {-1, -1, -1, 0, 1, -1, -1, -1, -1, -1, 4, -1, -1, 2, 3, -1};
-
 // ------------------------------------------------------------------------------------------
 // gc_in: f_in <= 32.  Block = 8 frames.  IMG = false: frames f0..f0+7 -> y fp32.
 // RAW = true: the input is not a materialised [frames,15,K] tensor but the raw IMU frame (GcRawInput, common.cuh):
@@ -37,10 +34,13 @@ __constant__ int c_node_imu[16] = {-1, -1, -1, 0, 1, -1, -1, -1, -1, -1, 4, -1, 
 // IMG = true: the 8 frames are (tile, t): sequences 8*tile..8*tile+7 at time t -> operand image
 // [tiles][T][O/16][NP][2][128][8] (row = 16*seq + node, row 15 of every sequence zero).
 // ------------------------------------------------------------------------------------------
-template <bool IMG, bool RAW>
-__global__ void __launch_bounds__(kGcThreads)
+// KC > 0: f_in known at compile time (12 = raw IMU frame, 15 = + the previous stage's positions): the projection loops unroll
+// fully and the index arithmetic divides by constants; KC = 0: any f_in <= 32.  Same operations in the same order either way.
+template <bool IMG, bool RAW, int KC>
+__global__ void __launch_bounds__(kGcThreads, 4)
 gc_in_kernel(a3gc_gc_params p, const float* __restrict__ x, GcRawInput raw, float* __restrict__ y, uint16_t* __restrict__ img,
-             int64_t frames, int B, int T, int K, int O, int act, int split) {
+             int64_t frames, int B, int T, int Krt, int O, int act, int split) {
+  const int K = KC > 0 ? KC : Krt;
   extern __shared__ __align__(16) float smem[];
   float* adj = smem;                 // [16][16]
   float* wt = adj + 256;             // [K][O]   W transposed
@@ -112,8 +112,8 @@ gc_in_kernel(a3gc_gc_params p, const float* __restrict__ x, GcRawInput raw, floa
           }
         }
       }
-      const int PK = K - 12;                              // features taken from the previous stage's output (0 or 3)
-      if (PK > 0) {
+      const int PK = K > 12 ? K - 12 : 1;                 // features taken from the previous stage's output (3; none at K = 12)
+      if (K > 12) {
         const int per = kNodes * PK;
         for (int i = threadIdx.x; i < 8 * per; i += blockDim.x) {
           const int fr = i / per, e = i % per, n = e / PK, j = e % PK;
@@ -171,6 +171,7 @@ gc_in_kernel(a3gc_gc_params p, const float* __restrict__ x, GcRawInput raw, floa
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = bias[ch * 8 + j];
+#pragma unroll
         for (int k = 0; k < K; ++k) {
           const float av = a[k];
           const float4 w0 = *reinterpret_cast<const float4*>(wt + (size_t)k * O + ch * 8);
@@ -201,6 +202,7 @@ gc_in_kernel(a3gc_gc_params p, const float* __restrict__ x, GcRawInput raw, floa
         float acc[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[j] = (qd * 4 + j < O) ? bias[qd * 4 + j] : 0.f;
+#pragma unroll
         for (int k = 0; k < K; ++k) {
           const float av = a[k];
 #pragma unroll
@@ -316,6 +318,21 @@ gc_out_kernel(a3gc_gc_params p, const float* __restrict__ x, float* __restrict__
   }
 }
 
+template <bool IMG, bool RAW>
+int launch_gc_in(int64_t blocks, size_t smem, cudaStream_t stream, const a3gc_gc_params& p, const float* x, const GcRawInput& raw,
+                 float* y, uint16_t* img, int64_t frames, int B, int T, int K, int O, int act, int split) {
+#define A3GC_GC_IN(KC)                                                                                                             \
+  do {                                                                                                                             \
+    A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_in_kernel<IMG, RAW, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    gc_in_kernel<IMG, RAW, KC><<<(unsigned)blocks, kGcThreads, smem, stream>>>(p, x, raw, y, img, frames, B, T, K, O, act, split); \
+  } while (0)
+  if (K == 12) A3GC_GC_IN(12);
+  else if (K == 15) A3GC_GC_IN(15);
+  else A3GC_GC_IN(0);
+#undef A3GC_GC_IN
+  return A3GC_OK;
+}
+
 int sm_count() {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -335,8 +352,7 @@ int gc_forward_fast(const a3gc_gc_params* p, const float* x, float* y, int64_t f
     if (smem > 160 * 1024) return A3GC_OK;
     int64_t groups = (frames + 7) / 8;
     int64_t blocks = groups < (int64_t)sms * 8 ? groups : (int64_t)sms * 8;
-    A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_in_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gc_in_kernel<false, false><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, x, GcRawInput{}, y, nullptr, frames, 0, 0, f_in, f_out, act, 0);
+    { const int rc = launch_gc_in<false, false>(blocks, smem, stream, *p, x, GcRawInput{}, y, nullptr, frames, 0, 0, f_in, f_out, act, 0); if (rc != A3GC_OK) return rc; }
     A3GC_LAUNCH_CHECK("gc_in_kernel");
     *handled = 1;
   } else if (f_out <= 16 && f_in % 128 == 0) {
@@ -371,11 +387,11 @@ int gc_forward_image(const a3gc_gc_params* p, const float* x, const GcRawInput* 
   const int sms = sm_count();
   int64_t blocks = groups < (int64_t)sms * 8 ? groups : (int64_t)sms * 8;
   if (raw != nullptr) {
-    A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_in_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gc_in_kernel<true, true><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, nullptr, *raw, nullptr, img, batch * steps, (int)batch, (int)steps, f_in, f_out, act, split);
+    const int rc = launch_gc_in<true, true>(blocks, smem, stream, *p, nullptr, *raw, nullptr, img, batch * steps, (int)batch, (int)steps, f_in, f_out, act, split);
+    if (rc != A3GC_OK) return rc;
   } else {
-    A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_in_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gc_in_kernel<true, false><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, x, GcRawInput{}, nullptr, img, batch * steps, (int)batch, (int)steps, f_in, f_out, act, split);
+    const int rc = launch_gc_in<true, false>(blocks, smem, stream, *p, x, GcRawInput{}, nullptr, img, batch * steps, (int)batch, (int)steps, f_in, f_out, act, split);
+    if (rc != A3GC_OK) return rc;
   }
   A3GC_LAUNCH_CHECK("gc_in_kernel<img>");
   return A3GC_OK;
@@ -390,8 +406,7 @@ int gc_forward_raw(const a3gc_gc_params* p, const GcRawInput* raw, float* y, int
   const int sms = sm_count();
   int64_t groups = (frames + 7) / 8;
   int64_t blocks = groups < (int64_t)sms * 8 ? groups : (int64_t)sms * 8;
-  A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_in_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gc_in_kernel<false, true><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, nullptr, *raw, y, nullptr, frames, 0, 0, f_in, f_out, act, 0);
+  { const int rc = launch_gc_in<false, true>(blocks, smem, stream, *p, nullptr, *raw, y, nullptr, frames, 0, 0, f_in, f_out, act, 0); if (rc != A3GC_OK) return rc; }
   A3GC_LAUNCH_CHECK("gc_in_kernel<raw>");
   return A3GC_OK;
 }
