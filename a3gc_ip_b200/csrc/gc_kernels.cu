@@ -162,33 +162,46 @@ gc_in_kernel(a3gc_gc_params p, const float* __restrict__ x, GcRawInput raw, floa
     }
     __syncthreads();
     if (IMG) {
-      // item = (8 consecutive outputs, row): one 16-byte chunk of the image per part
+      // item = (8 consecutive outputs, rows r and r + 64): the weights of a k are read once for QR = 2 rows (2 shared-memory
+      // wavefronts per row and k instead of 3; QR = 4 spills under the 64-register cap); per row one 16-byte chunk of the image per part
+      constexpr int QR = 2, RS = 128 / QR;
       const int chunks = O / 8;
       uint8_t* base = reinterpret_cast<uint8_t*>(img) + ((size_t)tile * T + t) * (size_t)O * 128 * NP * 2;
-      for (int i = threadIdx.x; i < chunks * 128; i += blockDim.x) {
-        const int row = i & 127, ch = i >> 7;
-        const float* a = xm + (size_t)row * KP;
-        float acc[8];
+      for (int i = threadIdx.x; i < chunks * RS; i += blockDim.x) {
+        const int r = i % RS, ch = i / RS;
+        const float* a = xm + (size_t)r * KP;
+        float acc[QR][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = bias[ch * 8 + j];
+        for (int j = 0; j < 8; ++j) {
+          const float bj = bias[ch * 8 + j];
+#pragma unroll
+          for (int q = 0; q < QR; ++q) acc[q][j] = bj;
+        }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          const float av = a[k];
           const float4 w0 = *reinterpret_cast<const float4*>(wt + (size_t)k * O + ch * 8);
           const float4 w1 = *reinterpret_cast<const float4*>(wt + (size_t)k * O + ch * 8 + 4);
-          acc[0] = fmaf(av, w0.x, acc[0]); acc[1] = fmaf(av, w0.y, acc[1]); acc[2] = fmaf(av, w0.z, acc[2]); acc[3] = fmaf(av, w0.w, acc[3]);
-          acc[4] = fmaf(av, w1.x, acc[4]); acc[5] = fmaf(av, w1.y, acc[5]); acc[6] = fmaf(av, w1.z, acc[6]); acc[7] = fmaf(av, w1.w, acc[7]);
-        }
-        uint16_t hi[8], lo[8];
-        const bool live = (row & 15) < kNodes;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) split16(live ? apply_act(acc[j], act) : 0.f, split != 0, hi[j], lo[j]);
-        // image offset: [kb = ch/2][part][kc = ch%2][row][8]
-        const size_t off = ((((size_t)(ch >> 1) * NP + 0) * 2 + (ch & 1)) * 128 + row) * 16;
-        *reinterpret_cast<uint4*>(base + off) = make_uint4((uint32_t)hi[0] | ((uint32_t)hi[1] << 16), (uint32_t)hi[2] | ((uint32_t)hi[3] << 16), (uint32_t)hi[4] | ((uint32_t)hi[5] << 16), (uint32_t)hi[6] | ((uint32_t)hi[7] << 16));
-        if (split)
-          *reinterpret_cast<uint4*>(base + off + (size_t)2 * 128 * 16) =
-              make_uint4((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16), (uint32_t)lo[4] | ((uint32_t)lo[5] << 16), (uint32_t)lo[6] | ((uint32_t)lo[7] << 16));
+          for (int q = 0; q < QR; ++q) {
+            const float av = a[(size_t)q * RS * KP + k];
+            acc[q][0] = fmaf(av, w0.x, acc[q][0]); acc[q][1] = fmaf(av, w0.y, acc[q][1]); acc[q][2] = fmaf(av, w0.z, acc[q][2]); acc[q][3] = fmaf(av, w0.w, acc[q][3]);
+            acc[q][4] = fmaf(av, w1.x, acc[q][4]); acc[q][5] = fmaf(av, w1.y, acc[q][5]); acc[q][6] = fmaf(av, w1.z, acc[q][6]); acc[q][7] = fmaf(av, w1.w, acc[q][7]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < QR; ++q) {
+          const int row = r + RS * q;
+          uint16_t hi[8], lo[8];
+          const bool live = (row & 15) < kNodes;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) split16(live ? apply_act(acc[q][j], act) : 0.f, split != 0, hi[j], lo[j]);
+          // image offset: [kb = ch/2][part][kc = ch%2][row][8]
+          const size_t off = ((((size_t)(ch >> 1) * NP + 0) * 2 + (ch & 1)) * 128 + row) * 16;
+          *reinterpret_cast<uint4*>(base + off) = make_uint4((uint32_t)hi[0] | ((uint32_t)hi[1] << 16), (uint32_t)hi[2] | ((uint32_t)hi[3] << 16), (uint32_t)hi[4] | ((uint32_t)hi[5] << 16), (uint32_t)hi[6] | ((uint32_t)hi[7] << 16));
+          if (split)
+            *reinterpret_cast<uint4*>(base + off + (size_t)2 * 128 * 16) =
+                make_uint4((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16), (uint32_t)lo[4] | ((uint32_t)lo[5] << 16), (uint32_t)lo[6] | ((uint32_t)lo[7] << 16));
+        }
       }
     } else {
       // item = (4 consecutive outputs, frame-row): float4 stores, consecutive threads -> consecutive addresses
@@ -253,10 +266,11 @@ __device__ __forceinline__ int butterfly_index(int j, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------
-// gc_out: f_in % 128 == 0, f_out <= 16.  Block = 16 frames (240 rows); each warp takes 8 rows at a time.
+// gc_out: f_in % 128 == 0, f_out <= 16.  Block = 16 frames (240 rows); each warp takes R rows at a time (8 at f_out <= 4; 4 above:
+// half the accumulators, twice the resident warps -- the loads of one warp overlap the reduction of another).
 // ------------------------------------------------------------------------------------------
-template <int OMAX>
-__global__ void __launch_bounds__(kGcThreads)
+template <int OMAX, int R>
+__global__ void __launch_bounds__(kGcThreads, (R == 4 && OMAX <= 9) ? 3 : 2)
 gc_out_kernel(a3gc_gc_params p, const float* __restrict__ x, float* __restrict__ y, int64_t frames, int K, int O, int act) {
   extern __shared__ __align__(16) float smem[];
   float* adj = smem;                         // [16][16]
@@ -273,23 +287,23 @@ gc_out_kernel(a3gc_gc_params p, const float* __restrict__ x, float* __restrict__
     const int64_t row0 = grp * 16 * kNodes;
     const int64_t nrows = ((frames - grp * 16) < 16 ? (frames - grp * 16) : 16) * kNodes;
     __syncthreads();
-    for (int r8 = warp * 8; r8 < nrows; r8 += 8 * (kGcThreads / 32)) {
-      float acc[8][OMAX];
+    for (int r8 = warp * R; r8 < nrows; r8 += R * (kGcThreads / 32)) {
+      float acc[R][OMAX];
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
+      for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int o = 0; o < OMAX; ++o) acc[r][o] = 0.f;
       for (int k0 = lane * 4; k0 < K; k0 += 128) {
-        float4 xv[8];
+        float4 xv[R];
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int r = 0; r < R; ++r)
           xv[r] = (r8 + r < nrows) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)(row0 + r8 + r) * K + k0)) : make_float4(0, 0, 0, 0);
 #pragma unroll
         for (int o = 0; o < OMAX; ++o) {
           if (o < O) {
             const float4 w = *reinterpret_cast<const float4*>(ws + (size_t)o * K + k0);
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
+            for (int r = 0; r < R; ++r)
               acc[r][o] = fmaf(xv[r].x, w.x, fmaf(xv[r].y, w.y, fmaf(xv[r].z, w.z, fmaf(xv[r].w, w.w, acc[r][o]))));
           }
         }
@@ -297,10 +311,10 @@ gc_out_kernel(a3gc_gc_params p, const float* __restrict__ x, float* __restrict__
       // transposing butterfly: every stage halves the values a lane carries (71 shuffles for 8 x 9 sums instead of 360); the
       // pairing tree per sum is the xor butterfly 16, 8, 4, 2, 1 as before, so the results are unchanged bit for bit
       float* flat = &acc[0][0];
-      xor_butterfly<8 * OMAX, 16>(flat, lane);
+      xor_butterfly<R * OMAX, 16>(flat, lane);
 #pragma unroll
-      for (int j = 0; j < butterfly_count(8 * OMAX, 16); ++j) {
-        const int idx = butterfly_index<8 * OMAX, 16>(j, lane);          // = r * OMAX + o of the sum this lane holds
+      for (int j = 0; j < butterfly_count(R * OMAX, 16); ++j) {
+        const int idx = butterfly_index<R * OMAX, 16>(j, lane);          // = r * OMAX + o of the sum this lane holds
         if (idx >= 0 && r8 + idx / OMAX < nrows) v[(size_t)r8 * OMAX + idx] = flat[j];
       }
     }
@@ -359,16 +373,17 @@ int gc_forward_fast(const a3gc_gc_params* p, const float* x, float* y, int64_t f
     const size_t smem = (256 + (size_t)f_out * f_in + 16 * kNodes * 16) * sizeof(float);
     if (smem > 200 * 1024) return A3GC_OK;
     int64_t groups = (frames + 15) / 16;
-    int64_t blocks = groups < (int64_t)sms * 4 ? groups : (int64_t)sms * 4;
+    const int per_sm = (f_out > 4 && f_out <= 9) ? 6 : 4;          // two waves of the 3 (gc_out<9, 4>) or 2 resident CTAs per SM
+    int64_t blocks = groups < (int64_t)sms * per_sm ? groups : (int64_t)sms * per_sm;
     if (f_out <= 4) {
-      A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_out_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      gc_out_kernel<4><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, x, y, frames, f_in, f_out, act);
+      A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_out_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      gc_out_kernel<4, 8><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, x, y, frames, f_in, f_out, act);
     } else if (f_out <= 9) {
-      A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_out_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      gc_out_kernel<9><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, x, y, frames, f_in, f_out, act);
+      A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_out_kernel<9, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      gc_out_kernel<9, 4><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, x, y, frames, f_in, f_out, act);
     } else {
-      A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_out_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      gc_out_kernel<16><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, x, y, frames, f_in, f_out, act);
+      A3GC_CUDA_TRY(cudaFuncSetAttribute(gc_out_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      gc_out_kernel<16, 4><<<(unsigned)blocks, kGcThreads, smem, stream>>>(*p, x, y, frames, f_in, f_out, act);
     }
     A3GC_LAUNCH_CHECK("gc_out_kernel");
     *handled = 1;
