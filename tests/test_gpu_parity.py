@@ -96,11 +96,14 @@ def test_time_major_layers_match_oracle(variant, nira):
 
 def test_aagc_graph_conv_matches_oracle(nira):
     g = torch.Generator().manual_seed(4)
-    for f_in, f_out, act in ((12, 32, "linear"), (64, 9, "tanh"), (15, 256, "linear"), (512, 3, "linear")):
+    # gc_in with f_in known at compile time (12, 15) and generic (20), the generic kernel (64 -> 9), gc_out with 8 rows per warp
+    # (f_out <= 4) and 4 rows per warp (f_out = 9 and 16)
+    for f_in, f_out, act in ((12, 32, "linear"), (64, 9, "tanh"), (15, 256, "linear"), (512, 3, "linear"), (20, 32, "tanh"),
+                             (256, 9, "linear"), (128, 16, "tanh"), (128, 3, "linear")):
         m = A.AAGC(f_in, f_out, nira.float(), activation_fn=act)
         m.gcn_bias.data = torch.randn(f_out, generator=g)
         m.adj.data += 0.1 * torch.randn(15, 15, generator=g)
-        x = torch.randn(3, 5, 15, f_in, generator=g)
+        x = torch.randn(3, 7, 15, f_in, generator=g)                     # 21 frames: a ragged last group of 8 / 16
         sd = {"m." + k: v.clone() for k, v in m.state_dict().items()}
         want = O.aagc_forward(x, sd, "m.", act)
         assert_close(m.cuda().eval()(x.cuda()), want, what=f"AAGC {f_in}->{f_out}")
